@@ -1,0 +1,151 @@
+/* include/lscqp.h -- C ABI of the B200 batched agent-QP path (liblscqp.so).
+ *
+ * Drop-in boundary for the reference's per-agent planning hot path.  The reference has no FFI
+ * layer; the boundary there is two C++ classes owned by TrajPlanner
+ * (/root/reference/include/traj_planner.hpp:104,110):
+ *     TrajOptimizer::solve            include/traj_optimizer.hpp:25-30, src/traj_optimizer.cpp:18-156
+ *     CollisionConstraints (LSC/SFC)  include/collision_constraints.hpp:98-201
+ * and the LSC generators TrajPlanner::generateLSC / generateCLSC / generateBVC
+ * (src/traj_planner.cpp:611-736).  include/lscqp_shim.hpp re-creates those classes on top of
+ * this ABI; INTEGRATION.md shows the patch a maintainer applies.
+ *
+ * Conventions
+ *   - POD only, caller-owned buffers, no exceptions across the boundary.
+ *   - Every function returns 0 on success or a negative LSCQP_E_* code (nothing written).
+ *     Per-agent solver outcomes are reported through status_out only.
+ *   - Buffers are DEVICE pointers for the *_batch entry points and HOST pointers for the *_host
+ *     entry points (which stage through pinned memory owned by the handle and include the
+ *     host<->device copies).  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - One handle per (device, host thread); calls on a handle are stream-ordered, not re-entrant.
+ *   - No CPU fallback exists: without a CUDA device lscqp_create fails with LSCQP_E_NODEVICE.
+ */
+#ifndef LSCQP_H
+#define LSCQP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSCQP_E_INVALID     (-1)   /* bad argument / unsupported configuration            */
+#define LSCQP_E_NODEVICE    (-2)   /* no usable CUDA device                                */
+#define LSCQP_E_CUDA        (-3)   /* CUDA runtime error (see lscqp_last_error)            */
+#define LSCQP_E_CAPACITY    (-4)   /* n_agents / obstacle count above the handle's capacity */
+
+/* per-agent status_out values */
+#define LSCQP_OK            0
+#define LSCQP_MAX_ITER      1
+#define LSCQP_INFEASIBLE    2
+#define LSCQP_NUMERICAL     3
+
+/* PlannerMode, include/sp_const.hpp:19-26 (same integer values) */
+#define LSCQP_MODE_DLSC 0
+#define LSCQP_MODE_LSC  1
+#define LSCQP_MODE_BVC  2
+
+/* LSC generator selected by TrajPlanner::constructLSC, src/traj_planner.cpp:552-569 */
+#define LSCQP_GEN_LSC   0          /* generateLSC  :611-657 */
+#define LSCQP_GEN_CLSC  1          /* generateCLSC :659-706 (mode lsc + grid_based_planner) */
+#define LSCQP_GEN_BVC   2          /* generateBVC  :708-736 */
+
+/* The fields of Param / Mission the QP reads (src/param.cpp:5-173). */
+typedef struct lscqp_config {
+    int M, n, phi, dim;            /* segments (5|10), degree (5), phi (3), world_dimension (2|3) */
+    double dt, w_control, w_terminal;   /* param.dt, control_input_weight, terminal_weight    */
+    int planner_mode;              /* LSCQP_MODE_*; LSC adds the terminal-stop equalities      */
+    int use_sfc;                   /* param.world_use_octomap: box constraints from `sfc`      */
+    double comm_range;             /* param.communication_range; must be <= 0 in this release  */
+    double world_min[3], world_max[3], z_2d;   /* mission.world_min/max, param.world_z_2d      */
+    int max_obs;                   /* capacity: obstacles per agent (<= 40)                    */
+    int max_agents;                /* capacity of the staging buffers for the *_host calls     */
+    int max_iter;                  /* interior-point iteration cap (0 = default 60)            */
+    double tol;                    /* complementarity / primal tolerance (0 = default 1e-10)   */
+} lscqp_config;
+
+typedef struct lscqp_handle lscqp_handle;
+
+/* Packed LSC half-spaces: row (oi, m, i) reads  normal[oi][m] . c[m][i] >= rhs[oi][m][i]
+ * (rhs = n . obs_control_point + d, the constant of traj_optimizer.cpp:413-429). */
+typedef struct lscqp_planes {
+    const int*    obs_offsets;     /* [n_agents+1] CSR offsets into the obstacle axis          */
+    double*       normals;         /* [sum K][M][3]                                            */
+    double*       rhs;             /* [sum K][M][6]                                            */
+} lscqp_planes;
+
+const char* lscqp_version(void);
+const char* lscqp_last_error(void);
+
+int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** out);
+int lscqp_destroy(lscqp_handle* h);
+
+/* Number of doubles per agent in dual_out (layout: [max_obs_padded][M][6] LSC rows, then
+ * [dim*M*6][6] box rows = lb, ub, vel+, vel-, acc+, acc- of the variable's stencil). */
+int lscqp_dual_stride(const lscqp_handle* h);
+int lscqp_max_obs_padded(const lscqp_handle* h);
+
+/* LSC assembly for agent-type obstacles: generateLSC / generateCLSC / generateBVC
+ * (src/traj_planner.cpp:611-736; normals by GJK as normalVectorBetweenPolys :1179-1205).
+ * All pointers are device pointers. */
+int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents,
+        const float* own_traj,      /* [n_agents][M][6][3]  initial_traj                        */
+        const float* agent_meta,    /* [n_agents][4]        radius, downwash, -, -              */
+        const float* agent_goal,    /* [n_agents][3]        current_goal_point (CLSC, LSC fallback) */
+        const int*   obs_offsets,   /* [n_agents+1]                                              */
+        const float* obs_traj,      /* [sum K][M][6][3]     obs_pred_trajs                      */
+        const float* obs_meta,      /* [sum K][4]           radius, downwash, -, -              */
+        const float* obs_goal,      /* [sum K][3]           obstacle goal_point (CLSC)          */
+        const float* obs_position,  /* [sum K][3]           obstacle position (LSC fallback)    */
+        double* normals_out,        /* [sum K][M][3]                                             */
+        double* rhs_out,            /* [sum K][M][6]                                             */
+        void* stream);
+
+/* Batched QP solve (TrajOptimizer::solve for every agent of the batch).  Device pointers. */
+int lscqp_solve_batch(lscqp_handle* h, int n_agents,
+        const float*  state,        /* [n_agents][9]  position, velocity, acceleration          */
+        const float*  goal,         /* [n_agents][3]  current_goal_point                        */
+        const double* limits,       /* [n_agents][8]  max_vel[3], max_acc[3], radius, nominal_velocity */
+        const float*  sfc,          /* [n_agents][M][6] box_min, box_max (use_sfc) or NULL      */
+        const int*    obs_offsets,  /* [n_agents+1]                                              */
+        const double* normals,      /* [sum K][M][3]                                             */
+        const double* rhs,          /* [sum K][M][6]                                             */
+        double* ctrl_out,           /* [n_agents][dim][M][6]  index order of traj_optimizer.cpp:241 */
+        double* cost_out,           /* [n_agents]  objective incl. constant (cplex.getObjValue) */
+        int*    status_out,         /* [n_agents]  LSCQP_OK | MAX_ITER | INFEASIBLE | NUMERICAL */
+        int*    iters_out,          /* [n_agents]  optional                                      */
+        double* kkt_out,            /* [n_agents][4] optional: stationarity, primal, guarded pivots, gap */
+        double* dual_out,           /* [n_agents][lscqp_dual_stride] optional                   */
+        void* stream);
+
+/* Same as lscqp_solve_batch with HOST buffers: copies inputs host->device, solves, copies
+ * ctrl/cost/status (and the optional outputs) back, and synchronises the stream. */
+int lscqp_solve_host(lscqp_handle* h, int n_agents,
+        const float* state, const float* goal, const double* limits, const float* sfc,
+        const int* obs_offsets, const double* normals, const double* rhs,
+        double* ctrl_out, double* cost_out, int* status_out, int* iters_out, double* kkt_out,
+        double* dual_out);
+
+/* Fused replan step with HOST buffers: copy trajectories in, assemble LSCs on the device,
+ * solve, copy the solutions back.  Obstacles are given as indices into the batch's own agents
+ * (what MultiSyncSimulator::broadcastMsgs builds, src/multi_sync_simulator.cpp:305-352). */
+int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents,
+        const float* state, const float* goal, const double* limits, const float* sfc,
+        const float* own_traj, const float* agent_meta,
+        const int* obs_offsets, const int* obs_index,      /* [sum K] neighbour agent ids */
+        double* ctrl_out, double* cost_out, int* status_out, int* iters_out);
+
+/* Device-side gather used by lscqp_replan_*: obs_traj[j] = own_traj[obs_index[j]] etc. */
+int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
+        const float* own_traj, const float* agent_meta, const float* agent_goal, const float* state,
+        float* obs_traj, float* obs_meta, float* obs_goal, float* obs_position, void* stream);
+
+/* Closed-loop glue on the device (AgentManager::doStep src/agent_manager.cpp:29-50 via
+ * Trajectory::getStateAt src/trajectory.cpp:156-170, and the previous-solution shift
+ * src/traj_planner.cpp:287-297, 402-411).  ctrl: [n][dim][M][6] doubles from the solve;
+ * writes the float trajectory [n][M][6][3] the reference stores (traj_optimizer.cpp:71-83),
+ * the next state [n][9] at time `step`, and the shifted trajectory for the next replan. */
+int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step,
+        float* traj_out, float* state_out, float* shifted_traj_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSCQP_H */

@@ -1,0 +1,831 @@
+// pdip_kernel.cuh -- batched primal-dual interior-point solve of the per-agent trajectory QP.
+//
+// One CTA per agent.  Replaces the CPLEX call of the reference
+// (src/traj_optimizer.cpp:18-156, model built by populatebyrow :216-514) for the whole batch the
+// serial loop src/multi_sync_simulator.cpp:354-362 walks.
+//
+// Formulation:
+//   * The equalities (initial state, C0..C2 continuity, LSC-mode terminal stop; :319-368, :504-511)
+//     are eliminated analytically.  Per dimension the free variables are the last three control
+//     points of each segment (one collapsed point for the last segment in LSC mode); the first three
+//     control points of segment m >= 1 follow from C0..C2 continuity,
+//         c[m][0] = y5,  c[m][1] = 2 y5 - y4,  c[m][2] = y3 - 4 y4 + 4 y5   (y = c[m-1][3..5]),
+//     and c[0][0..2] from the initial position / velocity / acceleration.  Reduced size
+//     NR = D(3M-2) (LSC mode) or 3DM; ordered by segment so the reduced KKT matrix is banded.
+//   * Inequalities are kept as rows q_r(c) >= 0 on the full control points: LSC half-spaces
+//     n.c - b >= 0 (:400-437), box bounds (world box, intersected with the SFC box when given;
+//     :238-270, :372-397), velocity / acceleration differences (:440-474, rescaled to unit
+//     coefficients).  Slack s and multiplier lam of every row live in registers of the owning thread.
+//   * Mehrotra predictor-corrector on (y, s, lam).  Per iteration the row weights are accumulated
+//     into the structured full-space Hessian (6x6 blocks per (dim, segment) + 3x3 blocks per control
+//     point), projected to the reduced space, factorised by a banded Cholesky in shared memory
+//     (warp 0) and used for the two triangular solve pairs.
+#pragma once
+#include <math.h>
+
+#ifdef LSCQP_CUDA_EMUL
+#define LSCQP_DYN_SMEM(name) double* name = emu_dyn_smem
+#else
+#define LSCQP_DYN_SMEM(name) extern __shared__ double name[]
+#endif
+
+namespace lscqp {
+
+struct SolveParams {
+    int n_agents;
+    int max_iter;
+    double mu_tol, rp_tol;
+    double dt, w_t;
+    double world_min[3], world_max[3];
+    int use_sfc;
+    const float*  state;        // [n][9]   position, velocity, acceleration
+    const float*  goal;         // [n][3]   current_goal_point
+    const double* limits;       // [n][8]   vmax[3], amax[3], radius, nominal_velocity
+    const float*  sfc;          // [n][M][6] box_min, box_max  (use_sfc)
+    const int*    obs_offsets;  // [n+1]
+    const double* normals;      // [sumK][M][3]
+    const double* rhs;          // [sumK][M][6]   b = n.p + d
+    double* ctrl_out;           // [n][D][M][6]
+    double* cost_out;           // [n]
+    int*    status_out;         // [n]
+    int*    iters_out;          // [n]     (may be null)
+    double* kkt_out;            // [n][4]  (may be null) stationarity, primal, dual, gap
+    double* dual_out;           // [n][dual_stride] (may be null)
+    int     dual_stride;
+    double  Q2[36];             // 2 * w_c * Q_base  (Hessian block of the jerk cost)
+    double  w_c;
+};
+
+enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3 };
+
+template <int M_, int D_, bool TERM_, int G_, int KPT_>
+struct Cfg {
+    static constexpr int M = M_, D = D_, G = G_, KPT = KPT_;
+    static constexpr bool TERM = TERM_;
+    static constexpr int NCP = 6 * M;                    // control points per dimension
+    static constexpr int CPW = ((NCP + 31) / 32) * 32;   // threads per obstacle group
+    static constexpr int NT = CPW * G;                   // threads per CTA
+    static constexpr int NW = NT / 32;
+    static constexpr int NV = D * NCP;                   // full-space variables
+    static constexpr int NZS = 3 * D;                    // reduced variables per stage
+    static constexpr int NR = TERM ? (M - 1) * NZS + D : M * NZS;
+    static constexpr int BW = 2 * NZS - 1;               // half bandwidth of the reduced matrix
+    static constexpr int LD = NR | 1;                    // odd leading dimension
+    static constexpr int NS = D * (D + 1) / 2;           // unique entries of a DxD symmetric block
+    static constexpr int KMAX = G * KPT;
+    static constexpr int NPAIR = BW * (BW + 1) / 2;      // trailing-update pairs per Cholesky column
+    static constexpr int NPR = (NPAIR + 31) / 32;
+    static constexpr int NRED = 4;
+    // shared memory layout (doubles)
+    static constexpr int O_Q2 = 0;
+    static constexpr int O_C = O_Q2 + 36;
+    static constexpr int O_DCA = O_C + NV;
+    static constexpr int O_DC = O_DCA + NV;
+    static constexpr int O_Y = O_DC + NV;
+    static constexpr int O_DY = O_Y + NR;
+    static constexpr int O_X0 = O_DY + NR;               // [D][3]
+    static constexpr int O_VLIM = O_X0 + 3 * D;          // [D]
+    static constexpr int O_ALIM = O_VLIM + D;            // [D]
+    static constexpr int O_GOAL = O_ALIM + D;            // [D]
+    static constexpr int O_LB = O_GOAL + D;              // [D][M]
+    static constexpr int O_UB = O_LB + D * M;            // [D][M]
+    static constexpr int O_TERMW = O_UB + D * M;         // [M]
+    static constexpr int O_NRM = O_TERMW + M;            // [KMAX][M][3]
+    static constexpr int O_SLABS = O_NRM + KMAX * M * 3; // [G][NCP][NS]
+    static constexpr int O_SLABT = O_SLABS + G * NCP * NS;   // [G][NCP][D]
+    static constexpr int O_WB = O_SLABT + G * NCP * D;   // [NV] x6: wB wV wA uB uV uA
+    static constexpr int O_WV = O_WB + NV;
+    static constexpr int O_WA = O_WV + NV;
+    static constexpr int O_UB_ = O_WA + NV;
+    static constexpr int O_UV = O_UB_ + NV;
+    static constexpr int O_UA = O_UV + NV;
+    static constexpr int O_BLK = O_UA + NV;              // [D][M][36]
+    static constexpr int O_RFULL = O_BLK + D * M * 36;   // [NV]
+    static constexpr int O_A = O_RFULL + NV;             // [NR][LD]
+    static constexpr int O_RHS = O_A + NR * LD;          // [NR]
+    static constexpr int O_DIAG0 = O_RHS + NR;           // [NR]
+    static constexpr int O_INVD = O_DIAG0 + NR;          // [NR]
+    static constexpr int O_RED = O_INVD + NR;            // [2][NW][NRED]
+    static constexpr int O_END = O_RED + 2 * NW * NRED;
+    static constexpr int SMEM_BYTES = O_END * 8;
+    // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
+    static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6;
+};
+
+// continuity map c[m][0..2] = T y[m-1][3..5]
+__device__ __forceinline__ double tmap(int a, double y3, double y4, double y5) {
+    return a == 0 ? y5 : (a == 1 ? 2.0 * y5 - y4 : y3 - 4.0 * y4 + 4.0 * y5);
+}
+__device__ __forceinline__ double tcoef(int a, int j) {   // T[a][j]
+    // a=0: (0,0,1)  a=1: (0,-1,2)  a=2: (1,-4,4)
+    return a == 0 ? (j == 2 ? 1.0 : 0.0) : (a == 1 ? (j == 0 ? 0.0 : (j == 1 ? -1.0 : 2.0))
+                                                    : (j == 0 ? 1.0 : (j == 1 ? -4.0 : 4.0)));
+}
+
+template <class C>
+__device__ __forceinline__ int ridx(int s, int k, int j) {
+    if (C::TERM && s == C::M - 1) return (C::M - 1) * C::NZS + k;
+    return s * C::NZS + k * 3 + j;
+}
+
+// full-space control point (k, m, i) from reduced vector yv and fixed initial points x0 (null for directions)
+template <class C>
+__device__ __forceinline__ double full_from_reduced(const double* yv, const double* x0, int k, int m, int i) {
+    if (i >= 3) return yv[ridx<C>(m, k, i - 3)];
+    if (m == 0) return x0 ? x0[k * 3 + i] : 0.0;
+    const double y3 = yv[ridx<C>(m - 1, k, 0)], y4 = yv[ridx<C>(m - 1, k, 1)], y5 = yv[ridx<C>(m - 1, k, 2)];
+    return tmap(i, y3, y4, y5);
+}
+
+// reduced component r of Z^T v for a full-space vector v [D][NCP]
+template <class C>
+__device__ __forceinline__ double reduce_from_full(const double* v, int r) {
+    if (C::TERM && r >= (C::M - 1) * C::NZS) {
+        const int k = r - (C::M - 1) * C::NZS;
+        const double* p = v + k * C::NCP + (C::M - 1) * 6;
+        return p[3] + p[4] + p[5];
+    }
+    const int s = r / C::NZS, k = (r % C::NZS) / 3, j = r % 3;
+    const double* p = v + k * C::NCP + s * 6;
+    double val = p[3 + j];
+    if (s + 1 < C::M) {
+        const double* q = p + 6;
+        val += tcoef(0, j) * q[0] + tcoef(1, j) * q[1] + tcoef(2, j) * q[2];
+    }
+    return val;
+}
+
+// support of reduced variable r in the full space (same dimension k): up to 4 (cp, coef) pairs
+template <class C>
+__device__ __forceinline__ int support(int r, int& k, int* cp, double* co) {
+    if (C::TERM && r >= (C::M - 1) * C::NZS) {
+        k = r - (C::M - 1) * C::NZS;
+        for (int a = 0; a < 3; a++) { cp[a] = (C::M - 1) * 6 + 3 + a; co[a] = 1.0; }
+        return 3;
+    }
+    const int s = r / C::NZS, j = r % 3;
+    k = (r % C::NZS) / 3;
+    cp[0] = s * 6 + 3 + j; co[0] = 1.0;
+    int n = 1;
+    if (s + 1 < C::M) {
+        for (int a = 0; a < 3; a++) {
+            const double t = tcoef(a, j);
+            if (t != 0.0) { cp[n] = (s + 1) * 6 + a; co[n] = t; n++; }
+        }
+    }
+    return n;
+}
+
+__device__ __forceinline__ int symidx3(int a, int b) {   // (0,0)(0,1)(0,2)(1,1)(1,2)(2,2)
+    if (a > b) { int t = a; a = b; b = t; }
+    return a == 0 ? b : (a == 1 ? 2 + b : 5);
+}
+__device__ __forceinline__ int symidx2(int a, int b) {   // (0,0)(0,1)(1,1)
+    return a + b;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// CTA-wide all-reduce of 4 values: v[0], v[1] summed, v[2] min, v[3] max.  One barrier (ping-pong scratch).
+template <class C>
+__device__ __forceinline__ void block_reduce4(double* v, double* red, int& phase) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a = warp_sum(v[0]), b = warp_sum(v[1]), c = warp_min(v[2]), d = warp_max(v[3]);
+    double* buf = red + phase * C::NW * C::NRED;
+    if (lane == 0) { buf[warp * 4 + 0] = a; buf[warp * 4 + 1] = b; buf[warp * 4 + 2] = c; buf[warp * 4 + 3] = d; }
+    __syncthreads();
+    a = 0; b = 0; c = INFINITY; d = -INFINITY;
+    for (int w = 0; w < C::NW; w++) {
+        a += buf[w * 4 + 0]; b += buf[w * 4 + 1]; c = fmin(c, buf[w * 4 + 2]); d = fmax(d, buf[w * 4 + 3]);
+    }
+    v[0] = a; v[1] = b; v[2] = c; v[3] = d;
+    phase ^= 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// banded Cholesky + triangular solves, executed by warp 0 only (callers bracket with __syncthreads)
+template <class C>
+__device__ __forceinline__ int chol_banded(double* A, const double* diag0, double* invd, const int* pr_i, const int* pr_k) {
+    const int lane = threadIdx.x & 31;
+    int bad = 0;
+    for (int j = 0; j < C::NR; j++) {
+        double d = A[j * C::LD + j];
+        if (!(d > 1e-13 * diag0[j])) { d = 1e300; bad++; }     // pivot guard: freeze that direction
+        const double inv = 1.0 / sqrt(d);
+        if (lane == 0) invd[j] = inv;
+        const int i = j + 1 + lane;
+        if (lane < C::BW && i < C::NR) A[i * C::LD + j] *= inv;
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < C::NPR; t++) {
+            const int ii = j + 1 + pr_i[t], kk = j + 1 + pr_k[t];
+            if (pr_i[t] >= 0 && ii < C::NR) A[ii * C::LD + kk] -= A[ii * C::LD + j] * A[kk * C::LD + j];
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+// solves (L L^T) x = b in place (b in shared memory), L strictly-lower entries in A, 1/L_jj in invd
+template <class C>
+__device__ __forceinline__ void chol_solve(const double* A, const double* invd, double* b) {
+    const int lane = threadIdx.x & 31;
+    for (int j = 0; j < C::NR; j++) {
+        const double z = b[j] * invd[j];
+        __syncwarp();
+        if (lane == 0) b[j] = z;
+        const int i = j + 1 + lane;
+        if (lane < C::BW && i < C::NR) b[i] -= A[i * C::LD + j] * z;
+        __syncwarp();
+    }
+    for (int j = C::NR - 1; j >= 0; j--) {
+        const double x = b[j] * invd[j];
+        __syncwarp();
+        if (lane == 0) b[j] = x;
+        const int i = j - 1 - lane;
+        if (lane < C::BW && i >= 0) b[i] -= A[j * C::LD + i] * x;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row algebra.  Row convention: q(c) >= 0, slack s > 0 with primal residual rp = s - q.
+struct RowAcc {
+    double sum_a, sum_b, vmin, vmax;
+};
+
+// predictor quantities for one row
+__device__ __forceinline__ void row_affine(double s, double lam, double q, double& W, double& u) {
+    const double rp = s - q;
+    W = lam / s;
+    u = W * rp;                       // lam + (lam*rp - s*lam)/s
+}
+__device__ __forceinline__ void row_affine_step(double s, double lam, double q, double dqa, double& dsa, double& dla) {
+    const double rp = s - q;
+    dsa = dqa - rp;
+    dla = -lam - (lam / s) * dsa;
+}
+__device__ __forceinline__ double ratio(double v, double dv) {
+    return dv < 0.0 ? -v / dv : INFINITY;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::NT)
+pdip_solve_kernel(const SolveParams p) {
+    constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, LD = C::LD, NS = C::NS;
+    constexpr int G = C::G, KPT = C::KPT, NT = C::NT;
+    LSCQP_DYN_SMEM(sm);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int agent = blockIdx.x;
+    if (agent >= p.n_agents) return;
+
+    double* sQ2 = sm + C::O_Q2;
+    double* s_c = sm + C::O_C;
+    double* s_dca = sm + C::O_DCA;
+    double* s_dc = sm + C::O_DC;
+    double* s_y = sm + C::O_Y;
+    double* s_dy = sm + C::O_DY;
+    double* s_x0 = sm + C::O_X0;
+    double* s_vlim = sm + C::O_VLIM;
+    double* s_alim = sm + C::O_ALIM;
+    double* s_goal = sm + C::O_GOAL;
+    double* s_lb = sm + C::O_LB;
+    double* s_ub = sm + C::O_UB;
+    double* s_termw = sm + C::O_TERMW;
+    double* s_nrm = sm + C::O_NRM;
+    double* slabS = sm + C::O_SLABS;
+    double* slabT = sm + C::O_SLABT;
+    double* s_wB = sm + C::O_WB;
+    double* s_wV = sm + C::O_WV;
+    double* s_wA = sm + C::O_WA;
+    double* s_uB = sm + C::O_UB_;
+    double* s_uV = sm + C::O_UV;
+    double* s_uA = sm + C::O_UA;
+    double* s_blk = sm + C::O_BLK;
+    double* s_rfull = sm + C::O_RFULL;
+    double* s_A = sm + C::O_A;
+    double* s_rhs = sm + C::O_RHS;
+    double* s_diag0 = sm + C::O_DIAG0;
+    double* s_invd = sm + C::O_INVD;
+    double* s_red = sm + C::O_RED;
+    int red_phase = 0;
+
+    // ---- thread roles
+    const int grp = tid / C::CPW, cp = tid % C::CPW;
+    const bool cp_valid = cp < NCP;
+    const int m_cp = cp / 6, i_cp = cp % 6;
+    const bool lsc_thread = cp_valid && !(m_cp == 0 && i_cp < 3);       // traj_optimizer.cpp:404
+    const bool var_thread = tid < NV;
+    const int k_v = tid / NCP, cp_v = tid % NCP, m_v = cp_v / 6, i_v = cp_v % 6;
+    // box rows owned by a variable thread: 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc-
+    const bool has_bnd = var_thread && !(m_v == 0 && i_v < 3);          // :260-265
+    const bool has_vel = var_thread && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
+    const bool has_acc = var_thread && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
+
+    const int obs0 = p.obs_offsets[agent];
+    int K = p.obs_offsets[agent + 1] - obs0;
+    if (K > C::KMAX) K = C::KMAX;
+
+    // ---- Cholesky trailing-update pair assignment (fixed per lane)
+    int pr_i[C::NPR], pr_k[C::NPR];
+#pragma unroll
+    for (int t = 0; t < C::NPR; t++) {
+        const int e = lane + 32 * t;
+        pr_i[t] = -1; pr_k[t] = 0;
+        if (e < C::NPAIR) {
+            // e -> (di, dk), dk <= di, row-major over the lower triangle
+            int di = (int) ((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((di + 1) * (di + 2) / 2 <= e) di++;
+            while (di * (di + 1) / 2 > e) di--;
+            pr_i[t] = di; pr_k[t] = e - di * (di + 1) / 2;
+        }
+    }
+
+    // ---- stage per-agent constants
+    if (tid < 36) sQ2[tid] = p.Q2[tid];
+    if (tid < D) {
+        const int k = tid;
+        const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
+                     acc = (double) p.state[agent * 9 + 6 + k];
+        // c0 = pos; 5/dt (c1 - c0) = vel; 20/dt^2 (c2 - 2 c1 + c0) = acc    (traj_optimizer.cpp:321-338)
+        const double c0 = pos, c1 = pos + vel * p.dt / 5.0, c2 = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - c0;
+        s_x0[k * 3 + 0] = c0; s_x0[k * 3 + 1] = c1; s_x0[k * 3 + 2] = c2;
+        s_vlim[k] = p.limits[agent * 8 + k] * p.dt / 5.0;                 // :448-453 scaled to unit coefficients
+        s_alim[k] = p.limits[agent * 8 + 3 + k] * p.dt * p.dt / 20.0;     // :462-471
+        s_goal[k] = (double) p.goal[agent * 3 + k];
+        for (int m = 0; m < M; m++) {
+            double lo = p.world_min[k], hi = p.world_max[k];              // :252-253
+            if (p.use_sfc) {                                               // :372-397, Box::convertToLSCs
+                lo = fmax(lo, (double) p.sfc[((size_t) agent * M + m) * 6 + k]);
+                hi = fmin(hi, (double) p.sfc[((size_t) agent * M + m) * 6 + 3 + k]);
+            }
+            s_lb[k * M + m] = lo; s_ub[k * M + m] = hi;
+        }
+    }
+    if (tid == 32) {
+        // getTerminalSegments_old, traj_optimizer.cpp:530-538 (float norm of the point3d difference)
+        const float dx = p.goal[agent * 3 + 0] - p.state[agent * 9 + 0], dy = p.goal[agent * 3 + 1] - p.state[agent * 9 + 1],
+                    dz = p.goal[agent * 3 + 2] - p.state[agent * 9 + 2];
+        const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const double flight = sqrt((double) nsq) / p.limits[agent * 8 + 7];
+        int ts = (int) ((M * p.dt - flight + 1e-9) / p.dt);
+        if (ts < 1) ts = 1;
+        for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
+    }
+    for (int e = tid; e < K * M * 3; e += NT) s_nrm[e] = p.normals[(size_t) obs0 * M * 3 + e];
+    __syncthreads();
+
+    // ---- per-thread row state (registers)
+    double ls[KPT], ll[KPT], lb_[KPT];     // LSC rows: slack, multiplier, rhs b
+    bool lact[KPT];
+    double bs[6], bl[6];                   // box rows
+#pragma unroll
+    for (int j = 0; j < KPT; j++) {
+        const int oi = grp + G * j;
+        lact[j] = false; ls[j] = 1.0; ll[j] = 0.0; lb_[j] = 0.0;
+        if (lsc_thread && oi < K) {
+            const double* n = s_nrm + (oi * M + m_cp) * 3;
+            // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped, traj_optimizer.cpp:409-411
+            const float fx = (float) n[0], fy = (float) n[1], fz = (float) n[2];
+            const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
+            lact[j] = !(sqrt((double) nsq) < 1e-5);
+            lb_[j] = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 6; e++) { bs[e] = 1.0; bl[e] = 0.0; }
+    const bool bact[6] = {has_bnd, has_bnd, has_vel, has_vel, has_acc, has_acc};
+
+    // number of rows
+    double red[4];
+    {
+        double cnt = 0;
+#pragma unroll
+        for (int j = 0; j < KPT; j++) cnt += lact[j] ? 1.0 : 0.0;
+#pragma unroll
+        for (int e = 0; e < 6; e++) cnt += bact[e] ? 1.0 : 0.0;
+        red[0] = cnt; red[1] = 0; red[2] = 0; red[3] = 0;
+        block_reduce4<C>(red, s_red, red_phase);
+    }
+    const double n_rows = red[0];
+
+    // ---- starting point: every free control point at the current position (hover)
+    if (tid < NR) {
+        int k;
+        if (C::TERM && tid >= (M - 1) * C::NZS) k = tid - (M - 1) * C::NZS; else k = (tid % C::NZS) / 3;
+        s_y[tid] = s_x0[k * 3];
+    }
+    __syncthreads();
+
+    // helpers -----------------------------------------------------------------------------------
+    // q for the box rows of this thread given a full-space vector (values) -- direction form has no constants
+    auto box_q = [&](const double* cv, bool direction, double* q) {
+        const double* cc = cv + k_v * NCP + cp_v;
+        const double c0 = cc[0];
+        const double lo = direction ? 0.0 : s_lb[k_v * M + m_v], hi = direction ? 0.0 : s_ub[k_v * M + m_v];
+        q[0] = c0 - lo; q[1] = hi - c0;
+        double dv = 0.0, da = 0.0;
+        if (has_vel) dv = cc[1] - c0;
+        if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
+        const double vl = direction ? 0.0 : s_vlim[k_v], al = direction ? 0.0 : s_alim[k_v];
+        q[2] = vl - dv; q[3] = vl + dv; q[4] = al - da; q[5] = al + da;
+    };
+    auto lsc_dot = [&](const double* cv, int oi) -> double {
+        const double* n = s_nrm + (oi * M + m_cp) * 3;
+        double r = n[0] * cv[cp] + n[1] * cv[NCP + cp];
+        if (D == 3) r += n[2] * cv[2 * NCP + cp];
+        return r;
+    };
+    auto compute_full = [&](const double* yv, const double* x0, double* out) {
+        if (var_thread) out[tid] = full_from_reduced<C>(yv, x0, k_v, m_v, i_v);
+    };
+
+    // write this thread's LSC accumulators to its group slab
+    auto store_slab = [&](const double* S, const double* T, bool withS) {
+        if (cp_valid) {
+            if (withS) {
+#pragma unroll
+                for (int e = 0; e < NS; e++) slabS[(grp * NCP + cp) * NS + e] = S[e];
+            }
+#pragma unroll
+            for (int e = 0; e < D; e++) slabT[(grp * NCP + cp) * D + e] = T[e];
+        }
+    };
+
+    // sum the group slabs into slab 0, build the 6x6 blocks (withS) and the full-space rhs, then project.
+    // rfull = -grad f + A^T u
+    auto assemble = [&](bool withS) {
+        __syncthreads();
+        // (1) reduce slabs over groups
+        for (int e = tid; e < NCP * D; e += NT) {
+            double a = slabT[e];
+            for (int g = 1; g < G; g++) a += slabT[g * NCP * D + e];
+            slabT[e] = a;
+        }
+        if (withS) {
+            for (int e = tid; e < NCP * NS; e += NT) {
+                double a = slabS[e];
+                for (int g = 1; g < G; g++) a += slabS[g * NCP * NS + e];
+                slabS[e] = a;
+            }
+        }
+        __syncthreads();
+        // (2) full-space blocks and rhs
+        if (withS) {
+            for (int e = tid; e < D * M * 36; e += NT) {
+                const int k = e / (M * 36), m = (e / 36) % M, a = (e % 36) / 6, b = e % 6;
+                const int v0 = k * NCP + m * 6;
+                double val = sQ2[a * 6 + b];
+                if (a == b) {
+                    const int dd = (D == 3) ? symidx3(k, k) : symidx2(k, k);
+                    val += s_wB[v0 + a] + slabS[(m * 6 + a) * NS + dd];
+                    if (a == 5) val += s_termw[m];
+                    if (a <= 4) val += s_wV[v0 + a];
+                    if (a >= 1) val += s_wV[v0 + a - 1];
+                }
+                if (a - b == 1 || b - a == 1) val -= s_wV[v0 + (a < b ? a : b)];
+                const int hi = a > b ? a : b, lo = a < b ? a : b;
+                for (int i = (hi - 2 > 0 ? hi - 2 : 0); i <= (lo < 3 ? lo : 3); i++) {
+                    const double da = (a - i == 1) ? -2.0 : 1.0, db = (b - i == 1) ? -2.0 : 1.0;
+                    val += s_wA[v0 + i] * da * db;
+                }
+                s_blk[e] = val;
+            }
+        }
+        if (var_thread) {
+            const int v0 = k_v * NCP + m_v * 6, a = i_v;
+            double gr = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; b++) gr += sQ2[a * 6 + b] * s_c[v0 + b];
+            if (a == 5) gr += s_termw[m_v] * (s_c[v0 + 5] - s_goal[k_v]);
+            double au = s_uB[tid] + slabT[cp_v * D + k_v];
+            if (a >= 1) au += s_uV[v0 + a - 1];
+            if (a <= 4) au -= s_uV[v0 + a];
+            for (int i = (a - 2 > 0 ? a - 2 : 0); i <= (a < 3 ? a : 3); i++) au += s_uA[v0 + i] * ((a - i == 1) ? -2.0 : 1.0);
+            s_rfull[tid] = au - gr;
+        }
+        __syncthreads();
+        // (3) project to the reduced space
+        if (withS) {
+            for (int e = tid; e < NR * (C::BW + 1); e += NT) {
+                const int r1 = e / (C::BW + 1), r2 = r1 - e % (C::BW + 1);
+                if (r2 < 0) continue;
+                int k1, k2, c1[4], c2[4];
+                double o1[4], o2[4];
+                const int n1 = support<C>(r1, k1, c1, o1), n2 = support<C>(r2, k2, c2, o2);
+                double val = 0.0;
+                for (int a = 0; a < n1; a++)
+                    for (int b = 0; b < n2; b++) {
+                        double f = 0.0;
+                        if (k1 == k2) {
+                            if (c1[a] / 6 == c2[b] / 6) f = s_blk[(k1 * M + c1[a] / 6) * 36 + (c1[a] % 6) * 6 + c2[b] % 6];
+                        } else if (c1[a] == c2[b]) {
+                            f = slabS[c1[a] * NS + ((D == 3) ? symidx3(k1, k2) : symidx2(k1, k2))];
+                        }
+                        val += o1[a] * o2[b] * f;
+                    }
+                s_A[r1 * LD + r2] = val;
+                if (r1 == r2) s_diag0[r1] = val;
+            }
+        }
+        if (tid < NR) s_rhs[tid] = reduce_from_full<C>(s_rfull, tid);
+        __syncthreads();
+    };
+
+    // one sweep over this thread's rows computing weights W (optional) and rhs multipliers u, then storing them.
+    // mode 0: initial least-squares point (W = 1, u = -q)
+    // mode 1: predictor (W = lam/s, u = W rp)
+    // mode 2: corrector (u = lam + (lam rp - rc)/s with rc = s lam + dsa dla - sigma mu)
+    auto row_sweep = [&](int mode, double sigmu) {
+        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+        const bool withS = mode != 2;
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            if (!lact[j]) continue;
+            const int oi = grp + G * j;
+            const double* n = s_nrm + (oi * M + m_cp) * 3;
+            const double q = lsc_dot(s_c, oi) - lb_[j];
+            double W = 1.0, u;
+            if (mode == 0) { u = -q; }
+            else if (mode == 1) { row_affine(ls[j], ll[j], q, W, u); }
+            else {
+                double dsa, dla;
+                row_affine_step(ls[j], ll[j], q, lsc_dot(s_dca, oi), dsa, dla);
+                const double rp = ls[j] - q, rc = ls[j] * ll[j] + dsa * dla - sigmu;
+                u = ll[j] + (ll[j] * rp - rc) / ls[j];
+            }
+            if (withS) {
+                if (D == 3) {
+                    S[0] += W * n[0] * n[0]; S[1] += W * n[0] * n[1]; S[2] += W * n[0] * n[2];
+                    S[3] += W * n[1] * n[1]; S[4] += W * n[1] * n[2]; S[5] += W * n[2] * n[2];
+                } else {
+                    S[0] += W * n[0] * n[0]; S[1] += W * n[0] * n[1]; S[2] += W * n[1] * n[1];
+                }
+            }
+            T[0] += u * n[0]; T[1] += u * n[1];
+            if (D == 3) T[2] += u * n[2];
+        }
+        store_slab(S, T, withS);
+        if (var_thread) {
+            double q[6], qa[6];
+            box_q(s_c, false, q);
+            if (mode == 2) box_q(s_dca, true, qa);
+            double W[6], u[6];
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                W[e] = 0.0; u[e] = 0.0;
+                if (!bact[e]) continue;
+                if (mode == 0) { W[e] = 1.0; u[e] = -q[e]; }
+                else if (mode == 1) { row_affine(bs[e], bl[e], q[e], W[e], u[e]); }
+                else {
+                    double dsa, dla;
+                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
+                    const double rp = bs[e] - q[e], rc = bs[e] * bl[e] + dsa * dla - sigmu;
+                    u[e] = bl[e] + (bl[e] * rp - rc) / bs[e];
+                }
+            }
+            // gradients: lb +e, ub -e, vel+ -(d), vel- +(d), acc+ -(d), acc- +(d)
+            if (withS) { s_wB[tid] = W[0] + W[1]; s_wV[tid] = W[2] + W[3]; s_wA[tid] = W[4] + W[5]; }
+            s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
+        }
+    };
+
+    // ---------------------------------------------------------------- initial point (least squares)
+    compute_full(s_y, s_x0, s_c);
+    __syncthreads();
+    row_sweep(0, 0.0);
+    assemble(true);
+    int bad_piv = 0;
+    if (tid < 32) {
+        bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
+        chol_solve<C>(s_A, s_invd, s_rhs);
+    }
+    __syncthreads();
+    if (tid < NR) s_y[tid] += s_rhs[tid];
+    __syncthreads();
+    compute_full(s_y, s_x0, s_c);
+    __syncthreads();
+    {
+        // s = q(y), lam = -s, then shift both into the positive orthant (Mehrotra / CVXOPT start)
+        double qmin = INFINITY, qmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            if (!lact[j]) continue;
+            ls[j] = lsc_dot(s_c, grp + G * j) - lb_[j];
+            qmin = fmin(qmin, ls[j]); qmax = fmax(qmax, ls[j]);
+        }
+        if (var_thread) {
+            double q[6];
+            box_q(s_c, false, q);
+#pragma unroll
+            for (int e = 0; e < 6; e++) if (bact[e]) { bs[e] = q[e]; qmin = fmin(qmin, q[e]); qmax = fmax(qmax, q[e]); }
+        }
+        red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
+        block_reduce4<C>(red, s_red, red_phase);
+        const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
+        const double shift_l = (red[3] >= 0.0) ? 1.0 + red[3] : 0.0;        // lam = -s; alpha_d = max(s) >= 0 -> lam += 1 + alpha_d
+#pragma unroll
+        for (int j = 0; j < KPT; j++) if (lact[j]) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
+#pragma unroll
+        for (int e = 0; e < 6; e++) if (bact[e]) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+    }
+
+    // ---------------------------------------------------------------- main loop
+    int status = ST_MAX_ITER, it = 0;
+    double mu = 0.0, rp_inf = 0.0;
+    for (it = 0; it < p.max_iter; it++) {
+        // (a) residual statistics
+        {
+            double sl = 0.0, rpm = 0.0;
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                if (!lact[j]) continue;
+                const double q = lsc_dot(s_c, grp + G * j) - lb_[j];
+                sl += ls[j] * ll[j]; rpm = fmax(rpm, fabs(ls[j] - q));
+            }
+            if (var_thread) {
+                double q[6];
+                box_q(s_c, false, q);
+#pragma unroll
+                for (int e = 0; e < 6; e++) if (bact[e]) { sl += bs[e] * bl[e]; rpm = fmax(rpm, fabs(bs[e] - q[e])); }
+            }
+            red[0] = sl; red[1] = 0; red[2] = 0; red[3] = rpm;
+            block_reduce4<C>(red, s_red, red_phase);
+            mu = red[0] / n_rows; rp_inf = red[3];
+        }
+        if (!(mu == mu) || !(rp_inf == rp_inf)) { status = ST_NUMERICAL; break; }
+        if (mu < p.mu_tol && rp_inf < p.rp_tol) { status = ST_OK; break; }
+
+        // (b) predictor
+        row_sweep(1, 0.0);
+        assemble(true);
+        if (tid < 32) {
+            bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
+            chol_solve<C>(s_A, s_invd, s_rhs);
+        }
+        __syncthreads();
+        if (tid < NR) s_dy[tid] = s_rhs[tid];
+        __syncthreads();
+        compute_full(s_dy, nullptr, s_dca);
+        __syncthreads();
+        double sigmu;
+        {
+            double amax = INFINITY, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                if (!lact[j]) continue;
+                const int oi = grp + G * j;
+                double dsa, dla;
+                row_affine_step(ls[j], ll[j], lsc_dot(s_c, oi) - lb_[j], lsc_dot(s_dca, oi), dsa, dla);
+                amax = fmin(amax, fmin(ratio(ls[j], dsa), ratio(ll[j], dla)));
+                s1 += ls[j] * dla + ll[j] * dsa; s2 += dsa * dla;
+            }
+            if (var_thread) {
+                double q[6], qa[6];
+                box_q(s_c, false, q); box_q(s_dca, true, qa);
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    if (!bact[e]) continue;
+                    double dsa, dla;
+                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
+                    amax = fmin(amax, fmin(ratio(bs[e], dsa), ratio(bl[e], dla)));
+                    s1 += bs[e] * dla + bl[e] * dsa; s2 += dsa * dla;
+                }
+            }
+            red[0] = s1; red[1] = s2; red[2] = amax; red[3] = 0;
+            block_reduce4<C>(red, s_red, red_phase);
+            const double a = fmin(1.0, red[2]);
+            const double mu_aff = (mu * n_rows + a * red[0] + a * a * red[1]) / n_rows;
+            double sg = mu_aff / mu;
+            sg = sg * sg * sg;
+            if (!(sg >= 0.0)) sg = 0.0;
+            if (sg > 1.0) sg = 1.0;
+            sigmu = sg * mu;
+        }
+
+        // (c) corrector
+        row_sweep(2, sigmu);
+        assemble(false);
+        if (tid < 32) chol_solve<C>(s_A, s_invd, s_rhs);
+        __syncthreads();
+        if (tid < NR) s_dy[tid] = s_rhs[tid];
+        __syncthreads();
+        compute_full(s_dy, nullptr, s_dc);
+        __syncthreads();
+
+        // (d) step length, (e) update
+        double lds[KPT], ldl[KPT], bds[6], bdl[6];
+        {
+            double amax = INFINITY;
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                lds[j] = 0; ldl[j] = 0;
+                if (!lact[j]) continue;
+                const int oi = grp + G * j;
+                const double q = lsc_dot(s_c, oi) - lb_[j];
+                double dsa, dla;
+                row_affine_step(ls[j], ll[j], q, lsc_dot(s_dca, oi), dsa, dla);
+                const double rp = ls[j] - q, rc = ls[j] * ll[j] + dsa * dla - sigmu;
+                lds[j] = lsc_dot(s_dc, oi) - rp;
+                ldl[j] = (-rc - ll[j] * lds[j]) / ls[j];
+                amax = fmin(amax, fmin(ratio(ls[j], lds[j]), ratio(ll[j], ldl[j])));
+            }
+            if (var_thread) {
+                double q[6], qa[6], qd[6];
+                box_q(s_c, false, q); box_q(s_dca, true, qa); box_q(s_dc, true, qd);
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    bds[e] = 0; bdl[e] = 0;
+                    if (!bact[e]) continue;
+                    double dsa, dla;
+                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
+                    const double rp = bs[e] - q[e], rc = bs[e] * bl[e] + dsa * dla - sigmu;
+                    bds[e] = qd[e] - rp;
+                    bdl[e] = (-rc - bl[e] * bds[e]) / bs[e];
+                    amax = fmin(amax, fmin(ratio(bs[e], bds[e]), ratio(bl[e], bdl[e])));
+                }
+            }
+            red[0] = 0; red[1] = 0; red[2] = amax; red[3] = 0;
+            block_reduce4<C>(red, s_red, red_phase);
+            const double a = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
+#pragma unroll
+            for (int j = 0; j < KPT; j++) if (lact[j]) { ls[j] += a * lds[j]; ll[j] += a * ldl[j]; }
+#pragma unroll
+            for (int e = 0; e < 6; e++) if (bact[e]) { bs[e] += a * bds[e]; bl[e] += a * bdl[e]; }
+            if (tid < NR) s_y[tid] += a * s_dy[tid];
+            __syncthreads();
+            compute_full(s_y, s_x0, s_c);
+            __syncthreads();
+        }
+    }
+
+    // ---------------------------------------------------------------- outputs
+    // stationarity: || Z^T (grad f - A^T lam) ||_inf  (reuse the sweep with u = lam)
+    {
+        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            if (!lact[j]) continue;
+            const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+            T[0] += ll[j] * n[0]; T[1] += ll[j] * n[1];
+            if (D == 3) T[2] += ll[j] * n[2];
+        }
+        store_slab(S, T, false);
+        if (var_thread) { s_uB[tid] = bl[0] - bl[1]; s_uV[tid] = bl[3] - bl[2]; s_uA[tid] = bl[5] - bl[4]; }
+        assemble(false);
+    }
+    double rd_inf = 0.0, cost = 0.0;
+    if (tid < NR) rd_inf = fabs(s_rhs[tid]);
+    if (var_thread) {
+        // objective x'Px + q'x + c0 with P = w_c Q (no 1/2, traj_optimizer.cpp:294) + terminal terms (:301-315)
+        const int v0 = k_v * NCP + m_v * 6;
+        double qc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) qc += sQ2[i_v * 6 + b] * s_c[v0 + b];
+        cost = 0.5 * s_c[tid] * qc;
+        if (i_v == 5) { const double e = s_c[tid] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
+        p.ctrl_out[(size_t) agent * NV + tid] = s_c[tid];
+    }
+    red[0] = cost; red[1] = 0; red[2] = 0; red[3] = rd_inf;
+    block_reduce4<C>(red, s_red, red_phase);
+    if (status == ST_MAX_ITER && rp_inf > 1e-6) status = ST_INFEASIBLE;
+    if (tid == 0) {
+        p.cost_out[agent] = red[0];
+        p.status_out[agent] = status;
+        if (p.iters_out) p.iters_out[agent] = it;
+        if (p.kkt_out) {
+            p.kkt_out[agent * 4 + 0] = red[3]; p.kkt_out[agent * 4 + 1] = rp_inf;
+            p.kkt_out[agent * 4 + 2] = (double) bad_piv; p.kkt_out[agent * 4 + 3] = mu;
+        }
+    }
+    if (p.dual_out) {
+        double* du = p.dual_out + (size_t) agent * p.dual_stride;
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            const int oi = grp + G * j;
+            if (cp_valid && oi < C::KMAX) du[(oi * M + m_cp) * 6 + i_cp] = lact[j] ? ll[j] : 0.0;
+        }
+        if (var_thread) {
+            // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2
+            const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
+            double* db = du + C::KMAX * M * 6 + tid * 6;
+            db[0] = bact[0] ? bl[0] : 0.0; db[1] = bact[1] ? bl[1] : 0.0;
+            db[2] = bact[2] ? bl[2] * sv : 0.0; db[3] = bact[3] ? bl[3] * sv : 0.0;
+            db[4] = bact[4] ? bl[4] * sa : 0.0; db[5] = bact[5] ? bl[5] * sa : 0.0;
+        }
+    }
+}
+
+}  // namespace lscqp

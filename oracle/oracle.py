@@ -1,0 +1,423 @@
+"""oracle/oracle.py -- Python face of the CPU checker.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; nothing under lsc_dr_planner_b200/ does.
+
+What it wraps
+  * oracle/lscqp_oracle.c  -- C restatement of the reference path
+    (src/traj_optimizer.cpp:163-538, src/traj_planner.cpp:611-736, include/geometry.hpp,
+    src/trajectory.cpp), built by oracle/Makefile into oracle/_build/liblscqp_oracle.so.
+  * oracle/_ref/libopengjk_ref.so -- the reference's own openGJK (when built here).
+  * HiGHS 1.12 (SciPy-bundled, private API scipy.optimize._highspy._core) standing in for
+    IBM CPLEX 20.1, which the reference calls at src/traj_optimizer.cpp:66 and which is
+    absent from this image.  QP-solution parity is therefore UNPINNED against CPLEX; it is
+    certified through KKT residuals on the restated model (unique minimiser).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liblscqp_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libopengjk_ref.so")
+INF = 1e30
+
+MODE_DLSC, MODE_LSC, MODE_BVC, MODE_ORCA, MODE_RECIPROCALRSFC = 0, 1, 2, 3, 4
+GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(
+            os.path.join(_HERE, "lscqp_oracle.c")):
+        subprocess.run(["make", "-C", _HERE, "_build/liblscqp_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/openGJK/openGJK.cpp") and (force or not os.path.exists(_REF)):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("M", C.c_int), ("n", C.c_int), ("phi", C.c_int), ("phi_n", C.c_int), ("dim", C.c_int),
+                ("dt", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
+                ("planner_mode", C.c_int), ("use_sfc", C.c_int), ("comm_range", C.c_double),
+                ("world_min", C.c_double * 3), ("world_max", C.c_double * 3), ("z_2d", C.c_double)]
+
+
+class _Agent(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("velocity", C.c_float * 3), ("acceleration", C.c_float * 3),
+                ("current_goal_point", C.c_float * 3), ("next_waypoint", C.c_float * 3),
+                ("max_vel", C.c_double * 3), ("max_acc", C.c_double * 3),
+                ("radius", C.c_double), ("nominal_velocity", C.c_double)]
+
+
+@dataclass
+class Config:
+    M: int = 5
+    n: int = 5
+    phi: int = 3
+    phi_n: int = 1
+    dim: int = 3
+    dt: float = 0.2
+    w_control: float = 0.01
+    w_terminal: float = 1.0
+    planner_mode: int = MODE_LSC
+    use_sfc: bool = False
+    comm_range: float = 0.0
+    world_min: tuple = (-10.0, -10.0, 0.0)
+    world_max: tuple = (10.0, 10.0, 2.5)
+    z_2d: float = 1.0
+
+    def c(self) -> _Cfg:
+        return _Cfg(self.M, self.n, self.phi, self.phi_n, self.dim, self.dt, self.w_control, self.w_terminal,
+                    self.planner_mode, int(self.use_sfc), self.comm_range,
+                    (C.c_double * 3)(*self.world_min), (C.c_double * 3)(*self.world_max), self.z_2d)
+
+
+@dataclass
+class Agent:
+    position: np.ndarray
+    velocity: np.ndarray
+    acceleration: np.ndarray
+    goal: np.ndarray
+    next_waypoint: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    max_vel: tuple = (1.0, 1.0, 1.0)
+    max_acc: tuple = (2.0, 2.0, 2.0)
+    radius: float = 0.15
+    nominal_velocity: float = 1.0
+    downwash: float = 2.0
+
+    def c(self) -> _Agent:
+        f3 = lambda a: (C.c_float * 3)(*np.asarray(a, np.float32).tolist())
+        return _Agent(f3(self.position), f3(self.velocity), f3(self.acceleration), f3(self.goal),
+                      f3(self.next_waypoint), (C.c_double * 3)(*self.max_vel), (C.c_double * 3)(*self.max_acc),
+                      self.radius, self.nominal_velocity)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_min_norm_hull.restype = C.c_double
+        _lib.orc_terminal_segments.restype = C.c_int
+        _lib.orc_qp_build.restype = C.c_int
+        _lib.orc_build_aeq_base.restype = C.c_int
+    return _lib
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF)
+        _ref.ref_gjk_hull_origin.restype = C.c_double
+    return _ref
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+# ---------------------------------------------------------------- constants
+def bernstein_basis(n: int) -> np.ndarray:
+    B = np.zeros((n + 1, n + 1))
+    lib().orc_bernstein_basis(n, _p(B, C.c_double))
+    return B
+
+
+def qbase(n=5, phi=3, phi_n=1, dt=0.2) -> np.ndarray:
+    Q = np.zeros((n + 1, n + 1))
+    lib().orc_build_qbase(n, phi, phi_n, C.c_double(dt), _p(Q, C.c_double))
+    return Q
+
+
+def aeq_base(M, n=5, phi=3, dt=0.2) -> np.ndarray:
+    A = np.zeros(((M - 2) * phi, M * (n + 1)))
+    rc = lib().orc_build_aeq_base(M, n, phi, C.c_double(dt), _p(A, C.c_double))
+    if rc != 0:
+        raise ValueError("[TrajOptimizer] Currently, only n=5, phi=3 is available")
+    return A
+
+
+def terminal_segments(cfg: Config, ag: Agent) -> int:
+    cc, ca = cfg.c(), ag.c()
+    return lib().orc_terminal_segments(C.byref(cc), C.byref(ca))
+
+
+# ---------------------------------------------------------------- QP model
+@dataclass
+class QP:
+    P: np.ndarray       # objective x'Px + q'x + c0 (no 1/2)
+    q: np.ndarray
+    c0: float
+    Aeq: np.ndarray
+    beq: np.ndarray
+    G: np.ndarray       # rlo <= Gx <= rhi
+    rlo: np.ndarray
+    rhi: np.ndarray
+    lb: np.ndarray
+    ub: np.ndarray
+
+
+def qp_build(cfg: Config, ag: Agent, lsc_point, lsc_normal, lsc_d, sfc=None) -> QP:
+    """Dense populatebyrow (src/traj_optimizer.cpp:216-514).  lsc_*: [K][M][n+1](,3)."""
+    lsc_point, lsc_normal, lsc_d = _f32(lsc_point), _f32(lsc_normal), _f64(lsc_d)
+    K = lsc_d.shape[0] if lsc_d.size else 0
+    nv, ne, ni = C.c_int(), C.c_int(), C.c_int()
+    cc, ca = cfg.c(), ag.c()
+    lib().orc_qp_sizes(C.byref(cc), K, _p(lsc_normal, C.c_float) if K else None,
+                       C.byref(nv), C.byref(ne), C.byref(ni))
+    nv, ne, ni = nv.value, ne.value, ni.value
+    P = np.zeros((nv, nv)); q = np.zeros(nv); c0 = C.c_double()
+    A = np.zeros((ne, nv)); b = np.zeros(ne)
+    G = np.zeros((ni, nv)); rlo = np.zeros(ni); rhi = np.zeros(ni)
+    lb = np.zeros(nv); ub = np.zeros(nv)
+    if sfc is None:
+        sfc = np.zeros((cfg.M, 6), np.float32)
+    sfc = _f32(sfc)
+    rc = lib().orc_qp_build(C.byref(cc), C.byref(ca), K, _p(lsc_point, C.c_float), _p(lsc_normal, C.c_float),
+                            _p(lsc_d, C.c_double), _p(sfc, C.c_float),
+                            _p(P, C.c_double), _p(q, C.c_double), C.byref(c0), _p(A, C.c_double), _p(b, C.c_double),
+                            _p(G, C.c_double), _p(rlo, C.c_double), _p(rhi, C.c_double),
+                            _p(lb, C.c_double), _p(ub, C.c_double))
+    if rc != 0:
+        raise ValueError(f"orc_qp_build failed rc={rc}")
+    return QP(P, q, c0.value, A, b, G, rlo, rhi, lb, ub)
+
+
+# ---------------------------------------------------------------- geometry / assembly
+def min_norm_hull(pts) -> tuple[np.ndarray, float]:
+    pts = _f64(pts)
+    v = np.zeros(3)
+    d = lib().orc_min_norm_hull(_p(pts, C.c_double), pts.shape[0], _p(v, C.c_double))
+    return v, d
+
+
+def ref_gjk(pts) -> tuple[np.ndarray, float]:
+    """The reference's own openGJK on (hull, origin) -- geometry.hpp:266-296."""
+    pts = _f64(pts)
+    v = np.zeros(3)
+    d = ref().ref_gjk_hull_origin(_p(pts, C.c_double), pts.shape[0], _p(v, C.c_double))
+    return v, d
+
+
+def closest_points_segments(l1s, l1e, l2s, l2e):
+    a, b, c, d = (_f32(x) for x in (l1s, l1e, l2s, l2e))
+    cp1 = np.zeros(3, np.float32); cp2 = np.zeros(3, np.float32); dist = C.c_double()
+    lib().orc_closest_points_segments(_p(a, C.c_float), _p(b, C.c_float), _p(c, C.c_float), _p(d, C.c_float),
+                                      _p(cp1, C.c_float), _p(cp2, C.c_float), C.byref(dist))
+    return cp1, cp2, dist.value
+
+
+def generate_lsc(cfg: Config, generator: int, ag: Agent, own_traj, obs_traj, obs_radius, obs_downwash,
+                 obs_goal=None, obs_position=None):
+    """generateLSC / generateCLSC / generateBVC (src/traj_planner.cpp:611-736).
+    Returns (point[K,M,6,3] f32, normal[K,M,6,3] f32, d[K,M,6] f64)."""
+    own_traj, obs_traj = _f32(own_traj), _f32(obs_traj)
+    K = obs_traj.shape[0]
+    N = cfg.n + 1
+    obs_radius, obs_downwash = _f32(obs_radius), _f32(obs_downwash)
+    obs_goal = _f32(np.zeros((K, 3)) if obs_goal is None else obs_goal)
+    obs_position = _f32(obs_traj[:, 0, 0, :] if obs_position is None else obs_position)
+    pt = np.zeros((K, cfg.M, N, 3), np.float32); nr = np.zeros((K, cfg.M, N, 3), np.float32)
+    d = np.zeros((K, cfg.M, N))
+    cc, ca = cfg.c(), ag.c()
+    lib().orc_generate_lsc(C.byref(cc), generator, C.byref(ca), C.c_double(ag.downwash), _p(own_traj, C.c_float), K,
+                           _p(obs_traj, C.c_float), _p(obs_radius, C.c_float), _p(obs_downwash, C.c_float),
+                           _p(obs_goal, C.c_float), _p(obs_position, C.c_float),
+                           _p(pt, C.c_float), _p(nr, C.c_float), _p(d, C.c_double))
+    return pt, nr, d
+
+
+def pack_planes(cfg: Config, lsc_point, lsc_normal, lsc_d):
+    """Packed form the kernels consume: normal[K,M,3] f64 and rhs b = n.p + d [K,M,6] f64
+    (the constant the reference's row n.(c - p) - d >= 0 carries, traj_optimizer.cpp:413-429).
+    Requires the normal to be shared by the n+1 records of one (oi, m), as every generator does."""
+    nr = np.asarray(lsc_normal, np.float64); pt = np.asarray(lsc_point, np.float64)
+    assert np.all(nr == nr[:, :, :1, :]), "normals differ inside one (obstacle, segment)"
+    normal = nr[:, :, 0, :].copy()
+    if cfg.dim == 2:
+        rhs = np.einsum("kmd,kmid->kmi", normal[..., :2], pt[..., :2]) + np.asarray(lsc_d)
+    else:
+        rhs = np.einsum("kmd,kmid->kmi", normal, pt) + np.asarray(lsc_d)
+    return normal, rhs
+
+
+# ---------------------------------------------------------------- closed-loop glue
+def get_state_at(cfg: Config, traj, time: float) -> np.ndarray:
+    traj = _f32(traj); out = np.zeros(9, np.float32)
+    lib().orc_get_state_at(cfg.M, cfg.n, C.c_double(cfg.dt), _p(traj, C.c_float), C.c_double(time), _p(out, C.c_float))
+    return out
+
+
+def shift_traj(cfg: Config, prev) -> np.ndarray:
+    prev = _f32(prev); out = np.zeros_like(prev)
+    lib().orc_shift_traj(cfg.M, cfg.n, _p(prev, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def const_vel_traj(cfg: Config, pos, vel) -> np.ndarray:
+    pos, vel = _f32(pos), _f32(vel); out = np.zeros((cfg.M, cfg.n + 1, 3), np.float32)
+    lib().orc_const_vel_traj(cfg.M, cfg.n, C.c_double(cfg.dt), _p(pos, C.c_float), _p(vel, C.c_float), _p(out, C.c_float))
+    return out
+
+
+# ---------------------------------------------------------------- HiGHS stand-in for CPLEX
+@dataclass
+class Solution:
+    status: str
+    x: np.ndarray
+    objective: float          # x'Px + q'x + c0  (== cplex.getObjValue(), traj_optimizer.cpp:100)
+    row_dual: np.ndarray      # [ne + ni]
+    col_dual: np.ndarray
+
+
+def solve_highs(qp: QP, tol: float = 1e-9) -> Solution:
+    """Solve the restated model with HiGHS's QP active-set solver."""
+    import scipy
+    import scipy.sparse as sp
+    from scipy.optimize._highspy import _core as hs
+    nv = qp.q.size
+    A = sp.csr_matrix(np.vstack([qp.Aeq, qp.G]))
+    lo = np.concatenate([qp.beq, qp.rlo]); hi = np.concatenate([qp.beq, qp.rhi])
+    lo = np.where(lo <= -INF, -hs.kHighsInf, lo); hi = np.where(hi >= INF, hs.kHighsInf, hi)
+    lb = np.where(qp.lb <= -INF, -hs.kHighsInf, qp.lb); ub = np.where(qp.ub >= INF, hs.kHighsInf, qp.ub)
+    h = hs._Highs()
+    h.setOptionValue("output_flag", False)
+    h.setOptionValue("primal_feasibility_tolerance", tol)
+    h.setOptionValue("dual_feasibility_tolerance", tol)
+    lp = hs.HighsLp()
+    lp.num_col_ = nv; lp.num_row_ = A.shape[0]
+    lp.col_cost_ = qp.q; lp.col_lower_ = lb; lp.col_upper_ = ub
+    lp.row_lower_ = lo; lp.row_upper_ = hi
+    lp.offset_ = qp.c0
+    lp.a_matrix_.format_ = hs.MatrixFormat.kRowwise
+    lp.a_matrix_.start_ = A.indptr; lp.a_matrix_.index_ = A.indices; lp.a_matrix_.value_ = A.data
+    h.passModel(lp)
+    Hl = sp.csc_matrix(np.tril(2.0 * qp.P))
+    hess = hs.HighsHessian()
+    hess.dim_ = nv; hess.format_ = hs.HessianFormat.kTriangular
+    hess.start_ = Hl.indptr; hess.index_ = Hl.indices; hess.value_ = Hl.data
+    h.passHessian(hess)
+    h.run()
+    sol = h.getSolution()
+    x = np.array(sol.col_value)
+    status = h.modelStatusToString(h.getModelStatus())
+    obj = float(x @ qp.P @ x + qp.q @ x + qp.c0)
+    return Solution(status, x, obj, np.array(sol.row_dual), np.array(sol.col_dual))
+
+
+def polish(qp: QP, sol: Solution, dual_tol: float = 1e-9, feas_tol: float = 1e-9):
+    """Refine a HiGHS solution to ~1e-12: take the rows/bounds HiGHS holds active (non-zero dual),
+    keep a linearly independent subset, and solve the equality-constrained KKT system exactly.
+    Returns (x, ok); ok is False (and x = sol.x) when the refined point is not primal feasible or
+    a multiplier has the wrong sign, i.e. when HiGHS's active set was not the optimal one."""
+    import scipy.linalg as sl
+    nv = qp.q.size
+    ne = qp.Aeq.shape[0]
+    rows, rhs, sign = [], [], []
+    rd = sol.row_dual[ne:]
+    ax = qp.G @ sol.x
+    for i in np.where(np.abs(rd) > dual_tol)[0]:
+        # pick the side the point sits on
+        if qp.rhi[i] < INF and (qp.rlo[i] <= -INF or abs(ax[i] - qp.rhi[i]) <= abs(ax[i] - qp.rlo[i])):
+            rows.append(qp.G[i]); rhs.append(qp.rhi[i]); sign.append(+1)
+        else:
+            rows.append(qp.G[i]); rhs.append(qp.rlo[i]); sign.append(-1)
+    for j in np.where(np.abs(sol.col_dual) > dual_tol)[0]:
+        e = np.zeros(nv); e[j] = 1
+        if abs(sol.x[j] - qp.ub[j]) <= abs(sol.x[j] - qp.lb[j]):
+            rows.append(e); rhs.append(qp.ub[j]); sign.append(+1)
+        else:
+            rows.append(e); rhs.append(qp.lb[j]); sign.append(-1)
+    Aall = np.vstack([qp.Aeq] + ([np.array(rows)] if rows else []))
+    ball = np.concatenate([qp.beq, np.array(rhs)])
+    _, R, piv = sl.qr(Aall.T, pivoting=True, mode="economic")
+    dg = np.abs(np.diag(R))
+    rk = int((dg > 1e-10 * dg[0]).sum())
+    keep = np.sort(piv[:rk])
+    Ak, bk = Aall[keep], ball[keep]
+    KKT = np.block([[2.0 * qp.P, Ak.T], [Ak, np.zeros((rk, rk))]])
+    try:
+        z = np.linalg.solve(KKT, np.concatenate([-qp.q, bk]))
+    except np.linalg.LinAlgError:
+        return sol.x, False
+    x = z[:nv]
+    gx = qp.G @ x
+    feas = (np.all(gx <= qp.rhi + feas_tol) and np.all(gx >= qp.rlo - feas_tol)
+            and np.all(x <= qp.ub + feas_tol) and np.all(x >= qp.lb - feas_tol))
+    mult = z[nv:]
+    ok_sign = True
+    for pos, r in enumerate(keep):
+        if r >= ne and mult[pos] * sign[r - ne] < -1e-7 * max(1.0, np.abs(mult).max()):
+            ok_sign = False
+    if feas and ok_sign and np.abs(x - sol.x).max() < 1e-3:
+        return x, True
+    return sol.x, False
+
+
+# ---------------------------------------------------------------- KKT certificate
+def kkt_certificate(qp: QP, x: np.ndarray) -> dict:
+    """Solver-independent optimality certificate for a primal point x of the restated model.
+
+    Every inequality (ranged rows and finite variable bounds) is written a.x <= h.  Multipliers
+    are recovered by non-negative least squares on the rows that are active within `act_tol`,
+    so the certificate needs no dual output from the solver under test:
+        stationarity  || 2Px + q + Aeq' y + Gact' z ||_inf   (z >= 0)
+        primal        max(|Aeq x - beq|, (a.x - h)+)
+    """
+    from scipy.optimize import nnls
+    nv = x.size
+    rows, rhs = [], []
+    for i in range(qp.G.shape[0]):
+        if qp.rhi[i] < INF:
+            rows.append(qp.G[i]); rhs.append(qp.rhi[i])
+        if qp.rlo[i] > -INF:
+            rows.append(-qp.G[i]); rhs.append(-qp.rlo[i])
+    for j in range(nv):
+        if qp.ub[j] < INF:
+            e = np.zeros(nv); e[j] = 1; rows.append(e); rhs.append(qp.ub[j])
+        if qp.lb[j] > -INF:
+            e = np.zeros(nv); e[j] = -1; rows.append(e); rhs.append(-qp.lb[j])
+    Gi = np.array(rows); hi = np.array(rhs)
+    norms = np.maximum(1.0, np.linalg.norm(Gi, axis=1))
+    slack = (hi - Gi @ x) / norms
+    prim_ineq = float(max(0.0, -slack.min())) if slack.size else 0.0
+    eqn = np.maximum(1.0, np.linalg.norm(qp.Aeq, axis=1))
+    prim_eq = float(np.abs((qp.Aeq @ x - qp.beq) / eqn).max())
+    grad = 2.0 * qp.P @ x + qp.q
+    act = np.where(slack <= 1e-6)[0]
+    # eliminate the free equality multipliers by projecting on null(Aeq)
+    U, S, Vt = np.linalg.svd(qp.Aeq, full_matrices=True)
+    rank = int((S > 1e-10 * S[0]).sum())
+    Z = Vt[rank:].T
+    gz = Z.T @ grad
+    if act.size:
+        Gz = (Gi[act] / norms[act, None]) @ Z
+        z, _ = nnls(Gz.T, -gz, maxiter=50 * Gz.shape[0] + 500)
+        res = gz + Gz.T @ z
+    else:
+        z = np.zeros(0); res = gz
+    return {"stationarity": float(np.abs(res).max()), "primal_eq": prim_eq, "primal_ineq": prim_ineq,
+            "n_active": int(act.size), "max_multiplier": float(z.max()) if z.size else 0.0,
+            "grad_scale": float(np.abs(grad).max())}

@@ -1,0 +1,37 @@
+// tests/cuda_emul/emul_pdip.cpp -- runs the unmodified PDIP kernel source on the CPU emulator.
+// TEST INFRASTRUCTURE ONLY (see cuda_emul.h).  Built by tests/cuda_emul/build.sh with g++.
+#define CUDA_EMUL_IMPL
+#define LSCQP_CUDA_EMUL
+#include "cuda_emul.h"
+#include "../../lsc_dr_planner_b200/csrc/host_common.hpp"
+
+using namespace lscqp;
+
+extern "C" int emul_dual_stride(int M, int D) { return 40 * M * 6 + D * M * 6 * 6; }
+
+extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
+                                const float* state, const float* goal, const double* limits, const float* sfc,
+                                const int* obs_offsets, const double* normals, const double* rhs,
+                                double* ctrl_out, double* cost_out, int* status_out, int* iters_out,
+                                double* kkt_out, double* dual_out) {
+    int rc = validate_config(*cfg);
+    if (rc) return rc;
+    SolveParams p;
+    fill_solve_params(*cfg, p);
+    p.n_agents = n_agents;
+    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
+    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
+    p.kkt_out = kkt_out; p.dual_out = dual_out;
+    const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
+#define X(M_, D_, T_)                                                                       \
+    if (cfg->M == M_ && cfg->dim == D_ && term == T_) {                                     \
+        using C = Cfg<M_, D_, T_, 4, 10>;                                                   \
+        p.dual_stride = C::DUAL_STRIDE;                                                     \
+        emu::launch(n_agents, C::NT, C::SMEM_BYTES, [&]() { pdip_solve_kernel<C>(p); });    \
+        return 0;                                                                           \
+    }
+    LSCQP_FOR_EACH_INSTANCE(X)
+#undef X
+    return LSCQP_E_INVALID;
+}
