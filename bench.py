@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- agent-QP solves/sec for one batched replan step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic agents: gather the neighbours'
+trajectories, assemble every LSC half-space (constructLSC), solve every agent's QP
+(trajOptimization).  Workload: random forest, 4096 agents per GPU, M=5 segments of degree 5, 3-D,
+K=40 neighbours (1080 LSC rows + 414 box/velocity/acceleration rows per QP), planes from the
+reference's real rule.  Agents are independent, so ranks hold disjoint batches (weak scaling) and
+there is no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent_qp_solves_per_sec"
+UNIT = "QP/s"
+
+
+def algorithmic_bytes(M: int, D: int, K: int) -> dict:
+    """packed fp64 layout, per agent-QP"""
+    b_solve = 8 * (K * M * 9 + 6 * M + 24) + 8 * (D * 6 * M + 2)
+    b_asm = 12 * 6 * M * (K + 1) + 16 * K + 8 * K * M * 9
+    return {"solve": b_solve, "assemble": b_asm, "unfused": b_solve + b_asm}
+
+
+def peaks() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """one agent through the reference's algorithm on one core: LSC generation + model build + QP solve"""
+    (cfg_kw, a_kw, own, obs_traj, obs_r, obs_dw, obs_goal, obs_pos) = args
+    from oracle import oracle as orc
+    cfg = orc.Config(**cfg_kw)
+    ag = orc.Agent(**a_kw)
+    t0 = time.perf_counter()
+    pt, nr, d = orc.generate_lsc(cfg, orc.GEN_LSC, ag, own, obs_traj, obs_r, obs_dw, obs_goal, obs_pos)
+    qp = orc.qp_build(cfg, ag, pt, nr, d)
+    sol = orc.solve_highs(qp)
+    return time.perf_counter() - t0, sol.status
+
+
+def cpu_reference_rate(batch, n_sample: int, cores: int, pool=None) -> tuple[float, float]:
+    """QP/s of the oracle port (restated populatebyrow + HiGHS standing in for CPLEX) on `cores` host processes"""
+    import multiprocessing as mp
+    cfg = batch.cfg
+    cfg_kw = dict(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, dt=cfg.dt, w_control=cfg.w_control, w_terminal=cfg.w_terminal,
+                  planner_mode=cfg.planner_mode, use_sfc=False, comm_range=0.0, world_min=cfg.world_min,
+                  world_max=cfg.world_max, z_2d=cfg.z_2d)
+    obs_traj, obs_meta, obs_goal, obs_pos = batch.obs_traj(), batch.obs_meta(), batch.obs_goal(), batch.obs_position()
+    jobs = []
+    for a in range(n_sample):
+        sl = slice(batch.obs_offsets[a], batch.obs_offsets[a + 1])
+        a_kw = dict(position=batch.state[a, :3], velocity=batch.state[a, 3:6], acceleration=batch.state[a, 6:9],
+                    goal=batch.goal[a], max_vel=tuple(batch.limits[a, :3]), max_acc=tuple(batch.limits[a, 3:6]),
+                    radius=float(batch.agent_meta[a, 0]), nominal_velocity=float(batch.limits[a, 7]),
+                    downwash=float(batch.agent_meta[a, 1]))
+        jobs.append((cfg_kw, a_kw, batch.own_traj[a], obs_traj[sl], obs_meta[sl, 0], obs_meta[sl, 1], obs_goal[sl], obs_pos[sl]))
+    own_pool = pool is None
+    if own_pool:
+        pool = mp.get_context("fork").Pool(cores)
+        pool.map(_cpu_worker, jobs[:cores])           # warm the workers (library load)
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, jobs, chunksize=max(1, n_sample // (4 * cores)))
+    wall = time.perf_counter() - t0
+    if own_pool:
+        pool.close()
+    per_qp = float(np.mean([r[0] for r in res]))
+    return n_sample / wall, per_qp
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; CPLEX itself is absent) on all host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from lsc_dr_planner_b200 import workloads as W
+    from oracle import oracle as orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    n_sample = args.ref_sample
+    batch = W.make_forest_batch(max(n_sample, 256), K=args.K, seed=20260001)
+    pool = mp.get_context("fork").Pool(cores)
+    cpu_reference_rate(batch, min(n_sample, 2 * cores), cores, pool)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(batch, n_sample, cores, pool)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, per_qp = cpu_reference_rate(batch, n_sample, cores, pool)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = args.steps * n_sample / wall
+    sample = f"{n_sample} agent-QPs per step of the same forest workload (K={args.K}, M=5, D=3)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.agents),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)", "ms_per_qp_one_core": 1e3 * per_qp},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_agents):
+    return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (gather + LSC assembly + PDIP solve)",
+            "agents_per_gpu": n_agents, "K": args.K, "M": 5, "degree": 5, "dim": 3, "rows_per_qp": 27 * args.K + 414,
+            "planner_mode": "lsc", "generator": "generateLSC", "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": f"agents sharded over {args.gpus} rank(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lsc_dr_planner_b200 import capi
+    from lsc_dr_planner_b200 import workloads as W
+    from lsc_dr_planner_b200.planner import BatchPlanner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the host baseline")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_agents = args.agents
+    batch = W.make_forest_batch(n_agents, K=args.K, seed=20260001 + rank)
+    planner = BatchPlanner(batch.cfg, device=local)
+    d = planner.upload(batch)
+    hb = planner.host_buffers(batch)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value): inputs in HBM, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        planner.replan_device(d, capi.GEN_LSC, stream)
+    torch.cuda.synchronize()
+    assert int((d.status != 0).sum().item()) == 0, "solver failed on the bench workload"
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    launches0 = planner.qp.launches
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev[s][0].record()
+        planner.assemble_device(d, capi.GEN_LSC, stream)
+        ev[s][1].record()
+        planner.solve_device(d, stream=stream)
+        ev[s][2].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = planner.qp.launches - launches0
+    t_asm = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    t_sol = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    t_step = t_asm + t_sol
+    iters_mean = float(d.iters.float().mean().item())
+
+    # ---- end-to-end through the host-buffer entry point (pinned host memory, copies inside)
+    for _ in range(max(1, args.warmup // 2)):
+        planner.replan_host_buffers(hb, n_agents)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        planner.replan_host_buffers(hb, n_agents)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop() if sampler else None
+    assert (hb["status"] == 0).all()
+
+    tt = torch.tensor([t_step.sum(), e2e_s, t_sol.mean(), t_asm.mean()], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, sol_ms, asm_ms = (float(x) for x in tt.tolist())
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * n_agents / (ms_per_step * 1e-3)
+        hbm, how = peaks()
+        ab = algorithmic_bytes(5, 3, args.K)
+        achieved = n_agents * ab["solve"] / (sol_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("pdip_solve_kernel_bytes_per_launch")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_agents),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "kernel_ms": {"assemble": asm_ms, "solve": sol_ms}, "pdip_iterations_mean": iters_mean,
+                "e2e": {"value": world * n_agents / e2e_s, "unit": UNIT, "h2d_bytes_per_step": planner.h2d_bytes(hb),
+                        "d2h_bytes_per_step": planner.d2h_bytes(hb), "ms_per_step": 1e3 * e2e_s,
+                        "api": "lscqp_replan_host (C ABI, pinned host buffers)"},
+                "roofline": {"kernel": "pdip_solve_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                             "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
+                             "algorithmic_bytes_per_qp": ab["solve"],
+                             "note": "latency/FP64-issue bound by design (SURVEY 8(d)): the HBM fraction is reported as required, "
+                                     "see DESIGN.md for the FP64 view",
+                             "assemble": {"achieved": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9,
+                                          "frac": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9 / hbm,
+                                          "algorithmic_bytes_per_qp": ab["assemble"]}},
+                "wall_s_timed_region": wall}
+        if not args.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+            cores = os.cpu_count() or 1
+            n_s = args.cpu_sample
+            rate, per_qp = cpu_reference_rate(batch, n_s, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {n_s} agent-QPs of the same batch, LSC generation + model build + solve",
+                                    "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)",
+                                    "ms_per_qp_one_core": 1e3 * per_qp}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=4096, help="agents per GPU")
+    ap.add_argument("--K", type=int, default=40)
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--ref-sample", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,7 +87,7 @@ int lscqp_max_obs_padded(const lscqp_handle* h);
  * All pointers are device pointers. */
 int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents,
         const float* own_traj,      /* [n_agents][M][6][3]  initial_traj                        */
-        const float* agent_meta,    /* [n_agents][4]        radius, downwash, -, -              */
+        const double* agent_meta,   /* [n_agents][2]        radius, downwash (doubles in Agent) */
         const float* agent_goal,    /* [n_agents][3]        current_goal_point (CLSC, LSC fallback) */
         const int*   obs_offsets,   /* [n_agents+1]                                              */
         const float* obs_traj,      /* [sum K][M][6][3]     obs_pred_trajs                      */
@@ -128,13 +128,13 @@ int lscqp_solve_host(lscqp_handle* h, int n_agents,
  * (what MultiSyncSimulator::broadcastMsgs builds, src/multi_sync_simulator.cpp:305-352). */
 int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents,
         const float* state, const float* goal, const double* limits, const float* sfc,
-        const float* own_traj, const float* agent_meta,
+        const float* own_traj, const double* agent_meta,
         const int* obs_offsets, const int* obs_index,      /* [sum K] neighbour agent ids */
         double* ctrl_out, double* cost_out, int* status_out, int* iters_out);
 
 /* Device-side gather used by lscqp_replan_*: obs_traj[j] = own_traj[obs_index[j]] etc. */
 int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
-        const float* own_traj, const float* agent_meta, const float* agent_goal, const float* state,
+        const float* own_traj, const double* agent_meta, const float* agent_goal, const float* state,
         float* obs_traj, float* obs_meta, float* obs_goal, float* obs_position, void* stream);
 
 /* Closed-loop glue on the device (AgentManager::doStep src/agent_manager.cpp:29-50 via

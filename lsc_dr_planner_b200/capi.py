@@ -1,0 +1,169 @@
+"""ctypes binding of liblscqp.so (include/lscqp.h).
+
+This is plumbing only: it loads the in-tree CUDA library and passes pointers through.  There is
+no CPU fallback -- if the library is missing or no CUDA device exists the calls raise.
+Device entry points take torch CUDA tensors (their data_ptr()), host entry points take numpy
+arrays (ideally backed by pinned memory, see `pinned`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblscqp.so")
+
+MODE_DLSC, MODE_LSC, MODE_BVC = 0, 1, 2
+GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
+STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL = 0, 1, 2, 3
+
+EXPORTS = ["lscqp_version", "lscqp_last_error", "lscqp_create", "lscqp_destroy", "lscqp_dual_stride",
+           "lscqp_max_obs_padded", "lscqp_assemble_lsc_batch", "lscqp_solve_batch", "lscqp_solve_host",
+           "lscqp_replan_host", "lscqp_gather_obstacles", "lscqp_step_batch"]
+
+
+class LscqpConfig(C.Structure):
+    _fields_ = [("M", C.c_int), ("n", C.c_int), ("phi", C.c_int), ("dim", C.c_int),
+                ("dt", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
+                ("planner_mode", C.c_int), ("use_sfc", C.c_int), ("comm_range", C.c_double),
+                ("world_min", C.c_double * 3), ("world_max", C.c_double * 3), ("z_2d", C.c_double),
+                ("max_obs", C.c_int), ("max_agents", C.c_int), ("max_iter", C.c_int), ("tol", C.c_double)]
+
+
+class LscqpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load liblscqp.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LscqpError(f"{LIB_PATH} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                             "there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.lscqp_version.restype = C.c_char_p
+        _lib.lscqp_last_error.restype = C.c_char_p
+        _lib.lscqp_launch_count.restype = C.c_ulonglong
+        _lib.lscqp_launch_count.argtypes = [C.c_void_p]
+        for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
+                     "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy"):
+            getattr(_lib, name).restype = C.c_int
+    return _lib
+
+
+def make_config(cfg, max_agents: int = 0) -> LscqpConfig:
+    """cfg: any object with the PlannerConfig fields (lsc_dr_planner_b200.workloads.PlannerConfig)."""
+    return LscqpConfig(cfg.M, cfg.n, cfg.phi, cfg.dim, cfg.dt, cfg.w_control, cfg.w_terminal, cfg.planner_mode,
+                       int(cfg.use_sfc), cfg.comm_range, (C.c_double * 3)(*cfg.world_min),
+                       (C.c_double * 3)(*cfg.world_max), cfg.z_2d, cfg.max_obs, max_agents,
+                       getattr(cfg, "max_iter", 0), getattr(cfg, "tol", 0.0))
+
+
+def _dp(t):
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "device entry points need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _hp(a, dtype):
+    if a is None:
+        return C.c_void_p(0)
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], (type(a), getattr(a, "dtype", None), dtype)
+    return C.c_void_p(a.ctypes.data)
+
+
+def pinned(shape, dtype):
+    """numpy array backed by pinned host memory (through torch's allocator)."""
+    import torch
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}[np.dtype(dtype).type]
+    t = torch.empty(shape, dtype=tdt, pin_memory=True)
+    a = t.numpy()
+    a._pin_owner = t if hasattr(a, "__dict__") else None
+    _PIN_KEEP.append(t)
+    return a
+
+
+_PIN_KEEP: list = []
+
+
+class LscQp:
+    """One handle = one (device, host thread).  Mirrors include/lscqp.h one to one."""
+
+    def __init__(self, cfg, device: int = 0, max_agents: int = 0):
+        self.lib = load()
+        self.cfg = cfg
+        self.ccfg = make_config(cfg, max_agents)
+        self.h = C.c_void_p()
+        rc = self.lib.lscqp_create(C.byref(self.ccfg), device, C.byref(self.h))
+        self._check(rc)
+        self.device = device
+        self.dual_stride = self.lib.lscqp_dual_stride(self.h)
+        self.kmax = self.lib.lscqp_max_obs_padded(self.h)
+        self.nv = cfg.dim * cfg.M * 6
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LscqpError(f"lscqp error {rc}: {self.lib.lscqp_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.lscqp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lscqp_launch_count(self.h))
+
+    # ------------------------------------------------------------------ device entry points
+    def solve_batch(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status,
+                    iters=None, kkt=None, dual=None, stream=0):
+        self._check(self.lib.lscqp_solve_batch(self.h, n, _dp(state), _dp(goal), _dp(limits), _dp(sfc), _dp(obs_offsets),
+                                               _dp(normals), _dp(rhs), _dp(ctrl), _dp(cost), _dp(status), _dp(iters),
+                                               _dp(kkt), _dp(dual), C.c_void_p(stream)))
+
+    def assemble_lsc_batch(self, generator, n, own_traj, agent_meta, agent_goal, obs_offsets, obs_traj, obs_meta,
+                           obs_goal, obs_position, normals, rhs, stream=0):
+        self._check(self.lib.lscqp_assemble_lsc_batch(self.h, generator, n, _dp(own_traj), _dp(agent_meta), _dp(agent_goal),
+                                                      _dp(obs_offsets), _dp(obs_traj), _dp(obs_meta), _dp(obs_goal),
+                                                      _dp(obs_position), _dp(normals), _dp(rhs), C.c_void_p(stream)))
+
+    def gather_obstacles(self, n_obs, obs_index, own_traj, agent_meta, agent_goal, state, obs_traj, obs_meta, obs_goal,
+                         obs_position, stream=0):
+        self._check(self.lib.lscqp_gather_obstacles(self.h, n_obs, _dp(obs_index), _dp(own_traj), _dp(agent_meta),
+                                                    _dp(agent_goal), _dp(state), _dp(obs_traj), _dp(obs_meta),
+                                                    _dp(obs_goal), _dp(obs_position), C.c_void_p(stream)))
+
+    def step_batch(self, n, ctrl, step, traj_out, state_out=None, shifted_out=None, stream=0):
+        self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),
+                                              _dp(shifted_out), C.c_void_p(stream)))
+
+    # ------------------------------------------------------------------ host entry points
+    def solve_host(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status, iters=None,
+                   kkt=None, dual=None):
+        self._check(self.lib.lscqp_solve_host(self.h, n, _hp(state, np.float32), _hp(goal, np.float32),
+                                              _hp(limits, np.float64), _hp(sfc, np.float32), _hp(obs_offsets, np.int32),
+                                              _hp(normals, np.float64), _hp(rhs, np.float64), _hp(ctrl, np.float64),
+                                              _hp(cost, np.float64), _hp(status, np.int32), _hp(iters, np.int32),
+                                              _hp(kkt, np.float64), _hp(dual, np.float64)))
+
+    def replan_host(self, generator, n, state, goal, limits, sfc, own_traj, agent_meta, obs_offsets, obs_index, ctrl,
+                    cost, status, iters=None):
+        self._check(self.lib.lscqp_replan_host(self.h, generator, n, _hp(state, np.float32), _hp(goal, np.float32),
+                                               _hp(limits, np.float64), _hp(sfc, np.float32), _hp(own_traj, np.float32),
+                                               _hp(agent_meta, np.float64), _hp(obs_offsets, np.int32),
+                                               _hp(obs_index, np.int32), _hp(ctrl, np.float64), _hp(cost, np.float64),
+                                               _hp(status, np.int32), _hp(iters, np.int32)))

@@ -1,0 +1,300 @@
+// lscqp.cu -- liblscqp.so: the C ABI of include/lscqp.h on top of the sm_100a kernels.
+// No CPU path exists here: every entry point launches CUDA kernels or fails with an error code.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_common.hpp"
+#include "lsc_assemble.cuh"
+#include "step_kernel.cuh"
+
+using namespace lscqp;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(LSCQP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+        bytes = n;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct lscqp_handle {
+    lscqp_config cfg;
+    int device;
+    SolveParams base;
+    int dual_stride, kmax, nv;
+    cudaStream_t stream;
+    // device staging for the *_host entry points
+    DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
+    DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
+    unsigned long long launches = 0;
+};
+
+extern "C" const char* lscqp_version(void) { return "lscqp-b200 0.1 (sm_100a)"; }
+extern "C" const char* lscqp_last_error(void) { return g_err.c_str(); }
+
+template <class C>
+static int set_smem_attr() {
+    return cudaFuncSetAttribute(pdip_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** out) {
+    if (!cfg || !out) return fail(LSCQP_E_INVALID, "null argument");
+    int rc = validate_config(*cfg);
+    if (rc) return fail(rc, "unsupported configuration (need n=5, phi=3, M in {5,10}, dim in {2,3}, "
+                            "mode in {DLSC,LSC,BVC}, comm_range<=0, max_obs<=40)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LSCQP_E_NODEVICE, "no CUDA device: liblscqp has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(LSCQP_E_NODEVICE, "device index out of range");
+    CK(cudaSetDevice(device));
+    lscqp_handle* h = new lscqp_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    fill_solve_params(*cfg, h->base);
+    const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
+    bool found = false;
+#define X(M_, D_, T_)                                                   \
+    if (cfg->M == M_ && cfg->dim == D_ && term == T_) {                 \
+        using C = Cfg<M_, D_, T_, 4, 10>;                               \
+        if (set_smem_attr<C>()) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); } \
+        h->dual_stride = C::DUAL_STRIDE; h->kmax = C::KMAX; h->nv = C::NV; found = true; \
+    }
+    LSCQP_FOR_EACH_INSTANCE(X)
+#undef X
+    if (!found) { delete h; return fail(LSCQP_E_INVALID, "no kernel instance"); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h; return fail(LSCQP_E_CUDA, "cudaStreamCreate failed");
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int lscqp_destroy(lscqp_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
+                      &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
+                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos};
+    for (DevBuf* b : bufs) b->release();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int lscqp_dual_stride(const lscqp_handle* h) { return h ? h->dual_stride : LSCQP_E_INVALID; }
+extern "C" int lscqp_max_obs_padded(const lscqp_handle* h) { return h ? h->kmax : LSCQP_E_INVALID; }
+extern "C" unsigned long long lscqp_launch_count(const lscqp_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* state, const float* goal,
+                                 const double* limits, const float* sfc, const int* obs_offsets,
+                                 const double* normals, const double* rhs, double* ctrl_out, double* cost_out,
+                                 int* status_out, int* iters_out, double* kkt_out, double* dual_out, void* stream) {
+    if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+    if (n_agents == 0) return 0;
+    SolveParams p = h->base;
+    p.n_agents = n_agents;
+    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
+    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
+    p.kkt_out = kkt_out; p.dual_out = dual_out; p.dual_stride = h->dual_stride;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool term = h->cfg.planner_mode == LSCQP_MODE_LSC;
+#define X(M_, D_, T_)                                                                   \
+    if (h->cfg.M == M_ && h->cfg.dim == D_ && term == T_) {                             \
+        using C = Cfg<M_, D_, T_, 4, 10>;                                               \
+        pdip_solve_kernel<C><<<n_agents, C::NT, C::SMEM_BYTES, st>>>(p);                \
+    }
+    LSCQP_FOR_EACH_INSTANCE(X)
+#undef X
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents, const float* own_traj,
+                                        const double* agent_meta, const float* agent_goal, const int* obs_offsets,
+                                        const float* obs_traj, const float* obs_meta, const float* obs_goal,
+                                        const float* obs_position, double* normals_out, double* rhs_out, void* stream) {
+    if (!h || n_agents < 0 || !own_traj || !agent_meta || !obs_offsets || !obs_traj || !obs_meta || !normals_out || !rhs_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (generator < 0 || generator > 2) return fail(LSCQP_E_INVALID, "unknown generator");
+    if ((generator == LSCQP_GEN_CLSC && (!obs_goal || !agent_goal)) || (generator == LSCQP_GEN_LSC && (!obs_position || !agent_goal)))
+        return fail(LSCQP_E_INVALID, "generator needs goal / position arrays");
+    if (n_agents == 0) return 0;
+    AssembleParams p;
+    p.n_agents = n_agents; p.generator = generator; p.dim = h->cfg.dim;
+    p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
+    p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;
+    p.normals = normals_out; p.rhs = rhs_out;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
+    else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index, const float* own_traj,
+                                      const double* agent_meta, const float* agent_goal, const float* state,
+                                      float* obs_traj, float* obs_meta, float* obs_goal, float* obs_position, void* stream) {
+    if (!h || n_obs < 0 || !obs_index || !own_traj || !agent_meta || !agent_goal || !state || !obs_traj || !obs_meta ||
+        !obs_goal || !obs_position)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (n_obs == 0) return 0;
+    GatherParams p;
+    p.n_obs = n_obs; p.M = h->cfg.M; p.obs_index = obs_index; p.own_traj = own_traj; p.agent_meta = agent_meta;
+    p.agent_goal = agent_goal; p.state = state; p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal;
+    p.obs_position = obs_position;
+    const size_t total = (size_t) n_obs * h->cfg.M * 18;
+    int blocks = (int) ((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gather_obstacles_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step, float* traj_out,
+                                float* state_out, float* shifted_traj_out, void* stream) {
+    if (!h || n_agents < 0 || !ctrl || !traj_out) return fail(LSCQP_E_INVALID, "null argument");
+    if (n_agents == 0) return 0;
+    StepParams p;
+    p.n_agents = n_agents; p.dim = h->cfg.dim; p.dt = h->cfg.dt; p.step = step; p.z_2d = h->cfg.z_2d;
+    p.ctrl = ctrl; p.traj_out = traj_out; p.state_out = state_out; p.shifted_out = shifted_traj_out;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int blocks = (n_agents + 127) / 128;
+    if (h->cfg.M == 5) step_kernel<5><<<blocks, 128, 0, st>>>(p);
+    else step_kernel<10><<<blocks, 128, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOST-buffer entry points: what a TrajOptimizer / simulator running on the CPU calls.
+#define RESERVE(buf, n) do { if ((buf).reserve(n)) return fail(LSCQP_E_CUDA, "cudaMalloc failed"); } while (0)
+
+extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* state, const float* goal,
+                                const double* limits, const float* sfc, const int* obs_offsets,
+                                const double* normals, const double* rhs, double* ctrl_out, double* cost_out,
+                                int* status_out, int* iters_out, double* kkt_out, double* dual_out) {
+    if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (n_agents == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const int M = h->cfg.M;
+    const size_t sumK = (size_t) obs_offsets[n_agents];
+    if (sumK > 0 && (!normals || !rhs)) return fail(LSCQP_E_INVALID, "null planes");
+    cudaStream_t st = h->stream;
+    RESERVE(h->d_state, n_agents * 9 * sizeof(float)); RESERVE(h->d_goal, n_agents * 3 * sizeof(float));
+    RESERVE(h->d_limits, n_agents * 8 * sizeof(double)); RESERVE(h->d_off, (n_agents + 1) * sizeof(int));
+    RESERVE(h->d_normals, (sumK * M * 3 + 1) * sizeof(double)); RESERVE(h->d_rhs, (sumK * M * 6 + 1) * sizeof(double));
+    RESERVE(h->d_ctrl, (size_t) n_agents * h->nv * sizeof(double)); RESERVE(h->d_cost, n_agents * sizeof(double));
+    RESERVE(h->d_status, n_agents * sizeof(int)); RESERVE(h->d_iters, n_agents * sizeof(int));
+    RESERVE(h->d_kkt, n_agents * 4 * sizeof(double));
+    if (dual_out) RESERVE(h->d_dual, (size_t) n_agents * h->dual_stride * sizeof(double));
+    if (h->cfg.use_sfc) {
+        if (!sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+        RESERVE(h->d_sfc, (size_t) n_agents * M * 6 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_sfc.p, sfc, (size_t) n_agents * M * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->d_state.p, state, n_agents * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_goal.p, goal, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_limits.p, limits, n_agents * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (sumK) {
+        CK(cudaMemcpyAsync(h->d_normals.p, normals, sumK * M * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_rhs.p, rhs, sumK * M * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    int rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
+                               h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(),
+                               h->d_normals.as<double>(), h->d_rhs.as<double>(), h->d_ctrl.as<double>(),
+                               h->d_cost.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), h->d_kkt.as<double>(),
+                               dual_out ? h->d_dual.as<double>() : nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctrl_out, h->d_ctrl.p, (size_t) n_agents * h->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cost_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status_out, h->d_status.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters_out) CK(cudaMemcpyAsync(iters_out, h->d_iters.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (kkt_out) CK(cudaMemcpyAsync(kkt_out, h->d_kkt.p, n_agents * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dual_out) CK(cudaMemcpyAsync(dual_out, h->d_dual.p, (size_t) n_agents * h->dual_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, const float* state, const float* goal,
+                                 const double* limits, const float* sfc, const float* own_traj, const double* agent_meta,
+                                 const int* obs_offsets, const int* obs_index, double* ctrl_out, double* cost_out,
+                                 int* status_out, int* iters_out) {
+    if (!h || n_agents < 0 || !state || !goal || !limits || !own_traj || !agent_meta || !obs_offsets || !ctrl_out ||
+        !cost_out || !status_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (n_agents == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const int M = h->cfg.M;
+    const size_t sumK = (size_t) obs_offsets[n_agents];
+    if (sumK > 0 && !obs_index) return fail(LSCQP_E_INVALID, "null obs_index");
+    cudaStream_t st = h->stream;
+    RESERVE(h->d_state, n_agents * 9 * sizeof(float)); RESERVE(h->d_goal, n_agents * 3 * sizeof(float));
+    RESERVE(h->d_limits, n_agents * 8 * sizeof(double)); RESERVE(h->d_off, (n_agents + 1) * sizeof(int));
+    RESERVE(h->d_own, (size_t) n_agents * M * 18 * sizeof(float)); RESERVE(h->d_ameta, n_agents * 2 * sizeof(double));
+    RESERVE(h->d_index, (sumK + 1) * sizeof(int));
+    RESERVE(h->d_otraj, (sumK * M * 18 + 1) * sizeof(float)); RESERVE(h->d_ometa, (sumK * 4 + 1) * sizeof(float));
+    RESERVE(h->d_ogoal, (sumK * 3 + 1) * sizeof(float)); RESERVE(h->d_opos, (sumK * 3 + 1) * sizeof(float));
+    RESERVE(h->d_normals, (sumK * M * 3 + 1) * sizeof(double)); RESERVE(h->d_rhs, (sumK * M * 6 + 1) * sizeof(double));
+    RESERVE(h->d_ctrl, (size_t) n_agents * h->nv * sizeof(double)); RESERVE(h->d_cost, n_agents * sizeof(double));
+    RESERVE(h->d_status, n_agents * sizeof(int)); RESERVE(h->d_iters, n_agents * sizeof(int));
+    if (h->cfg.use_sfc) {
+        if (!sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+        RESERVE(h->d_sfc, (size_t) n_agents * M * 6 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_sfc.p, sfc, (size_t) n_agents * M * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->d_state.p, state, n_agents * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_goal.p, goal, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_limits.p, limits, n_agents * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_own.p, own_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_ameta.p, agent_meta, n_agents * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (sumK) CK(cudaMemcpyAsync(h->d_index.p, obs_index, sumK * sizeof(int), cudaMemcpyHostToDevice, st));
+    int rc = lscqp_gather_obstacles(h, (int) sumK, h->d_index.as<int>(), h->d_own.as<float>(), h->d_ameta.as<double>(),
+                                    h->d_goal.as<float>(), h->d_state.as<float>(), h->d_otraj.as<float>(),
+                                    h->d_ometa.as<float>(), h->d_ogoal.as<float>(), h->d_opos.as<float>(), st);
+    if (rc) return rc;
+    rc = lscqp_assemble_lsc_batch(h, generator, n_agents, h->d_own.as<float>(), h->d_ameta.as<double>(), h->d_goal.as<float>(),
+                                  h->d_off.as<int>(), h->d_otraj.as<float>(), h->d_ometa.as<float>(), h->d_ogoal.as<float>(),
+                                  h->d_opos.as<float>(), h->d_normals.as<double>(), h->d_rhs.as<double>(), st);
+    if (rc) return rc;
+    rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
+                           h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(), h->d_normals.as<double>(),
+                           h->d_rhs.as<double>(), h->d_ctrl.as<double>(), h->d_cost.as<double>(), h->d_status.as<int>(),
+                           h->d_iters.as<int>(), nullptr, nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctrl_out, h->d_ctrl.p, (size_t) n_agents * h->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cost_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status_out, h->d_status.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters_out) CK(cudaMemcpyAsync(iters_out, h->d_iters.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}

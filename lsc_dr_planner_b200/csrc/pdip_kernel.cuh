@@ -725,50 +725,50 @@ pdip_solve_kernel(const SolveParams p) {
         compute_full(s_dy, nullptr, s_dc);
         __syncthreads();
 
-        // (d) step length, (e) update
-        double lds[KPT], ldl[KPT], bds[6], bdl[6];
-        {
+        // (d) step length, (e) update.  The row directions are recomputed in the update sweep instead of
+        // being kept in registers across the CTA reduction.
+        double alpha = 1.0;
+        for (int pass = 0; pass < 2; pass++) {
             double amax = INFINITY;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                lds[j] = 0; ldl[j] = 0;
                 if (!lact[j]) continue;
                 const int oi = grp + G * j;
                 const double q = lsc_dot(s_c, oi) - lb_[j];
                 double dsa, dla;
                 row_affine_step(ls[j], ll[j], q, lsc_dot(s_dca, oi), dsa, dla);
                 const double rp = ls[j] - q, rc = ls[j] * ll[j] + dsa * dla - sigmu;
-                lds[j] = lsc_dot(s_dc, oi) - rp;
-                ldl[j] = (-rc - ll[j] * lds[j]) / ls[j];
-                amax = fmin(amax, fmin(ratio(ls[j], lds[j]), ratio(ll[j], ldl[j])));
+                const double ds = lsc_dot(s_dc, oi) - rp;
+                const double dl = (-rc - ll[j] * ds) / ls[j];
+                if (pass == 0) amax = fmin(amax, fmin(ratio(ls[j], ds), ratio(ll[j], dl)));
+                else { ls[j] += alpha * ds; ll[j] += alpha * dl; }
             }
             if (var_thread) {
                 double q[6], qa[6], qd[6];
                 box_q(s_c, false, q); box_q(s_dca, true, qa); box_q(s_dc, true, qd);
 #pragma unroll
                 for (int e = 0; e < 6; e++) {
-                    bds[e] = 0; bdl[e] = 0;
                     if (!bact[e]) continue;
                     double dsa, dla;
                     row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
                     const double rp = bs[e] - q[e], rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                    bds[e] = qd[e] - rp;
-                    bdl[e] = (-rc - bl[e] * bds[e]) / bs[e];
-                    amax = fmin(amax, fmin(ratio(bs[e], bds[e]), ratio(bl[e], bdl[e])));
+                    const double ds = qd[e] - rp;
+                    const double dl = (-rc - bl[e] * ds) / bs[e];
+                    if (pass == 0) amax = fmin(amax, fmin(ratio(bs[e], ds), ratio(bl[e], dl)));
+                    else { bs[e] += alpha * ds; bl[e] += alpha * dl; }
                 }
             }
-            red[0] = 0; red[1] = 0; red[2] = amax; red[3] = 0;
-            block_reduce4<C>(red, s_red, red_phase);
-            const double a = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
-#pragma unroll
-            for (int j = 0; j < KPT; j++) if (lact[j]) { ls[j] += a * lds[j]; ll[j] += a * ldl[j]; }
-#pragma unroll
-            for (int e = 0; e < 6; e++) if (bact[e]) { bs[e] += a * bds[e]; bl[e] += a * bdl[e]; }
-            if (tid < NR) s_y[tid] += a * s_dy[tid];
-            __syncthreads();
-            compute_full(s_y, s_x0, s_c);
-            __syncthreads();
+            if (pass == 0) {
+                red[0] = 0; red[1] = 0; red[2] = amax; red[3] = 0;
+                block_reduce4<C>(red, s_red, red_phase);
+                alpha = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
+            }
         }
+        __syncthreads();          // every thread is done reading s_c / s_dc
+        if (tid < NR) s_y[tid] += alpha * s_dy[tid];
+        __syncthreads();
+        compute_full(s_y, s_x0, s_c);
+        __syncthreads();
     }
 
     // ---------------------------------------------------------------- outputs

@@ -96,7 +96,7 @@ class Batch:
     goal: np.ndarray           # [N,3]  f32
     limits: np.ndarray         # [N,8]  f64  vmax[3], amax[3], radius, nominal_velocity
     next_waypoint: np.ndarray  # [N,3]  f32
-    agent_meta: np.ndarray     # [N,4]  f32  radius, downwash, 0, 0
+    agent_meta: np.ndarray     # [N,2]  f64  radius, downwash
     own_traj: np.ndarray       # [N,M,6,3] f32 initial_traj
     obs_offsets: np.ndarray    # [N+1] i32
     obs_index: np.ndarray      # [sumK] i32 neighbour agent ids
@@ -119,25 +119,19 @@ class Batch:
     def obs_goal(self) -> np.ndarray:
         return np.ascontiguousarray(self.goal[self.obs_index])
 
+    def obs_position(self) -> np.ndarray:
+        return np.ascontiguousarray(self.state[self.obs_index, :3])
 
-def _sample_positions(rng, n, half, zlo, zhi, min_sep, dim):
-    pos = np.zeros((0, 3))
-    from scipy.spatial import cKDTree
-    scale = np.array([1.0, 1.0, 0.5])          # downwash 2: vertical separation counts half
-    while pos.shape[0] < n:
-        cand = np.column_stack([rng.uniform(-half, half, 2 * n), rng.uniform(-half, half, 2 * n),
-                                rng.uniform(zlo, zhi, 2 * n) if dim == 3 else np.full(2 * n, 1.0)])
-        for c in cand:
-            if pos.shape[0] == 0:
-                pos = c[None]
-                continue
-            if pos.shape[0] >= n:
-                break
-            # cheap incremental check (n is modest; the tree is rebuilt in blocks)
-            d = np.abs((pos - c) * scale)
-            if (np.sqrt((d * d).sum(1)).min()) >= min_sep:
-                pos = np.vstack([pos, c])
-    return pos[:n]
+
+def _sample_positions(rng, n, cell, jitter, zlo, zhi, dim):
+    """jittered square grid (cell size `cell`, xy jitter +-`jitter`): minimum horizontal separation
+    cell - 2*jitter by construction, O(n)."""
+    side = int(np.ceil(np.sqrt(n)))
+    ij = np.stack(np.meshgrid(np.arange(side), np.arange(side), indexing="ij"), -1).reshape(-1, 2)
+    ij = ij[rng.permutation(side * side)[:n]]
+    xy = (ij - (side - 1) / 2.0) * cell + rng.uniform(-jitter, jitter, (n, 2))
+    z = rng.uniform(zlo, zhi, n) if dim == 3 else np.full(n, 1.0)
+    return np.column_stack([xy, z]), side * cell / 2.0
 
 
 def make_forest_batch(n_agents: int, K: int = 40, seed: int = 20260001,
@@ -148,11 +142,10 @@ def make_forest_batch(n_agents: int, K: int = 40, seed: int = 20260001,
     rng = np.random.default_rng(seed)
     M, dt = cfg.M, cfg.dt
     radius, downwash, vmax, amax = 0.15, 2.0, 1.0, 2.0
-    half = max(8.0, 0.7 * np.sqrt(n_agents))
+    # horizontal separation >= 1.3 m: the braking trajectories' hulls stay >= 2r apart
+    pos, half = _sample_positions(rng, n_agents, 2.0, 0.35, 0.5, 2.0, cfg.dim)
     cfg.world_min = (-half - 2.0, -half - 2.0, 0.0)
     cfg.world_max = (half + 2.0, half + 2.0, 2.5)
-    # separation large enough that the braking trajectories' hulls stay >= 2r apart
-    pos = _sample_positions(rng, n_agents, half, 0.5, 2.0, 2 * radius * 1.2 + 0.9 * moving, cfg.dim)
     vel = np.zeros((n_agents, 3)); acc = np.zeros((n_agents, 3))
     if moving:
         vel = rng.uniform(-0.45, 0.45, (n_agents, 3)); acc = rng.uniform(-0.5, 0.5, (n_agents, 3))
@@ -176,7 +169,7 @@ def make_forest_batch(n_agents: int, K: int = 40, seed: int = 20260001,
                             (20.0 / dt ** 2) * (traj[:, 0, 2, :] - 2 * traj[:, 0, 1, :] + traj[:, 0, 0, :])],
                            axis=1).astype(np.float32)
     limits = np.tile(np.array([vmax] * 3 + [amax] * 3 + [radius, 1.0]), (n_agents, 1))
-    meta = np.zeros((n_agents, 4), np.float32); meta[:, 0] = radius; meta[:, 1] = downwash
+    meta = np.zeros((n_agents, 2), np.float64); meta[:, 0] = radius; meta[:, 1] = downwash
     return Batch(cfg, state, goal.astype(np.float32), limits, goal.astype(np.float32), meta,
                  traj, (np.arange(n_agents + 1) * k).astype(np.int32), idx.reshape(-1))
 

@@ -4,6 +4,8 @@
 #define LSCQP_CUDA_EMUL
 #include "cuda_emul.h"
 #include "../../lsc_dr_planner_b200/csrc/host_common.hpp"
+#include "../../lsc_dr_planner_b200/csrc/lsc_assemble.cuh"
+#include "../../lsc_dr_planner_b200/csrc/step_kernel.cuh"
 
 using namespace lscqp;
 
@@ -34,4 +36,31 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     LSCQP_FOR_EACH_INSTANCE(X)
 #undef X
     return LSCQP_E_INVALID;
+}
+
+extern "C" int emul_assemble_lsc_batch(const lscqp_config* cfg, int generator, int n_agents, const float* own_traj,
+                                       const double* agent_meta, const float* agent_goal, const int* obs_offsets,
+                                       const float* obs_traj, const float* obs_meta, const float* obs_goal,
+                                       const float* obs_position, double* normals_out, double* rhs_out) {
+    AssembleParams p;
+    p.n_agents = n_agents; p.generator = generator; p.dim = cfg->dim;
+    p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
+    p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;
+    p.normals = normals_out; p.rhs = rhs_out;
+    if (cfg->M == 5) emu::launch(n_agents, 128, 5 * 18 * 4 + 64, [&]() { lsc_assemble_kernel<5>(p); });
+    else if (cfg->M == 10) emu::launch(n_agents, 128, 10 * 18 * 4 + 64, [&]() { lsc_assemble_kernel<10>(p); });
+    else return LSCQP_E_INVALID;
+    return 0;
+}
+
+extern "C" int emul_step_batch(const lscqp_config* cfg, int n_agents, const double* ctrl, double step, float* traj_out,
+                               float* state_out, float* shifted_out) {
+    StepParams p;
+    p.n_agents = n_agents; p.dim = cfg->dim; p.dt = cfg->dt; p.step = step; p.z_2d = cfg->z_2d;
+    p.ctrl = ctrl; p.traj_out = traj_out; p.state_out = state_out; p.shifted_out = shifted_out;
+    const int blocks = (n_agents + 127) / 128;
+    if (cfg->M == 5) emu::launch(blocks, 128, 64, [&]() { step_kernel<5>(p); });
+    else if (cfg->M == 10) emu::launch(blocks, 128, 64, [&]() { step_kernel<10>(p); });
+    else return LSCQP_E_INVALID;
+    return 0;
 }

@@ -1,0 +1,61 @@
+"""ctypes face of tests/cuda_emul/_build/libemul.so: the kernel sources run on the CPU thread emulator.
+TEST INFRASTRUCTURE ONLY -- never imported by the package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from lsc_dr_planner_b200 import capi
+
+_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emul", "_build", "libemul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a, dt):
+    if a is None:
+        return C.c_void_p(0)
+    assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def solve_batch(cfg, n, state, goal, limits, sfc, off, normals, rhs, want_dual=False):
+    cc = capi.make_config(cfg)
+    nv = cfg.dim * cfg.M * 6
+    ctrl = np.zeros((n, nv)); cost = np.zeros(n); status = np.zeros(n, np.int32); iters = np.zeros(n, np.int32)
+    kkt = np.zeros((n, 4))
+    ds = lib().emul_dual_stride(cfg.M, cfg.dim)
+    dual = np.zeros((n, ds)) if want_dual else None
+    rc = lib().emul_solve_batch(C.byref(cc), n, _p(state, np.float32), _p(goal, np.float32), _p(limits, np.float64),
+                                _p(sfc, np.float32), _p(off, np.int32), _p(normals, np.float64), _p(rhs, np.float64),
+                                _p(ctrl, np.float64), _p(cost, np.float64), _p(status, np.int32), _p(iters, np.int32),
+                                _p(kkt, np.float64), _p(dual, np.float64))
+    assert rc == 0, rc
+    return ctrl, cost, status, iters, kkt, dual
+
+
+def assemble(cfg, generator, n, own_traj, agent_meta, agent_goal, off, obs_traj, obs_meta, obs_goal, obs_position):
+    cc = capi.make_config(cfg)
+    sk = int(off[n])
+    normals = np.zeros((sk, cfg.M, 3)); rhs = np.zeros((sk, cfg.M, 6))
+    rc = lib().emul_assemble_lsc_batch(C.byref(cc), generator, n, _p(own_traj, np.float32), _p(agent_meta, np.float64),
+                                       _p(agent_goal, np.float32), _p(off, np.int32), _p(obs_traj, np.float32),
+                                       _p(obs_meta, np.float32), _p(obs_goal, np.float32), _p(obs_position, np.float32),
+                                       _p(normals, np.float64), _p(rhs, np.float64))
+    assert rc == 0, rc
+    return normals, rhs
+
+
+def step(cfg, n, ctrl, t):
+    cc = capi.make_config(cfg)
+    traj = np.zeros((n, cfg.M, 6, 3), np.float32); state = np.zeros((n, 9), np.float32); shifted = np.zeros_like(traj)
+    rc = lib().emul_step_batch(C.byref(cc), n, _p(ctrl, np.float64), C.c_double(t), _p(traj, np.float32),
+                               _p(state, np.float32), _p(shifted, np.float32))
+    assert rc == 0, rc
+    return traj, state, shifted

@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs."""
+import numpy as np
+import pytest
+
+from common import (near_goals, oracle_config, oracle_lsc, oracle_planes, oracle_qp_from_planes, oracle_solution)
+from lsc_dr_planner_b200 import capi
+from lsc_dr_planner_b200 import workloads as W
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CTRL_TOL = 1e-5        # metres, SURVEY.md 8(c): control points vs the oracle's polished optimum
+OBJ_RTOL = 1e-6        # relative objective difference
+PRIMAL_TOL = 1e-8      # scaled primal infeasibility of the returned point
+
+
+def _planner(cfg):
+    from lsc_dr_planner_b200.planner import BatchPlanner
+    return BatchPlanner(cfg, device=0)
+
+
+def _solve_host(planner, batch, agents, off, normals, rhs, sfc=None, want_dual=False):
+    n = len(agents)
+    cfg = batch.cfg
+    state = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents])
+    limits = np.ascontiguousarray(batch.limits[agents])
+    ctrl = np.zeros((n, cfg.dim * cfg.M * 6)); cost = np.zeros(n); status = np.zeros(n, np.int32)
+    iters = np.zeros(n, np.int32); kkt = np.zeros((n, 4))
+    dual = np.zeros((n, planner.qp.dual_stride)) if want_dual else None
+    planner.qp.solve_host(n, state, goal, limits, sfc, off, normals, rhs, ctrl, cost, status, iters, kkt, dual)
+    return ctrl, cost, status, iters, kkt, dual
+
+
+def _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, sfc=None, min_checked=1):
+    checked = 0
+    errs = []
+    for i, a in enumerate(agents):
+        sl = slice(off[i], off[i + 1])
+        qp = oracle_qp_from_planes(batch, a, normals[sl], rhs[sl], None if sfc is None else sfc[i])
+        cert = orc.kkt_certificate(qp, ctrl[i])
+        assert cert["primal_eq"] < PRIMAL_TOL, (a, cert)
+        assert cert["primal_ineq"] < PRIMAL_TOL, (a, cert)
+        xe, ok = oracle_solution(qp)
+        if not ok:
+            continue
+        checked += 1
+        assert status[i] == capi.STATUS_OK, (a, status[i])
+        err = np.abs(ctrl[i] - xe).max()
+        errs.append(err)
+        assert err < CTRL_TOL, (a, err)
+        obj = xe @ qp.P @ xe + qp.q @ xe + qp.c0
+        assert abs(cost[i] - obj) <= OBJ_RTOL * max(1.0, abs(obj)), (a, cost[i], obj)
+    assert checked >= min_checked
+    return np.array(errs)
+
+
+@pytest.mark.parametrize("M,dim,mode,K", [(5, 3, capi.MODE_LSC, 40), (5, 3, capi.MODE_DLSC, 40), (10, 2, capi.MODE_LSC, 9),
+                                          (5, 2, capi.MODE_LSC, 12), (10, 3, capi.MODE_DLSC, 40), (5, 3, capi.MODE_BVC, 7)])
+def test_solve_parity_real_rule(M, dim, mode, K):
+    """config 2 shape (and the launch-file shape M=10/D=2): oracle-generated planes, GPU solve vs oracle optimum"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode)
+    batch = W.make_forest_batch(64, K=K, cfg=cfg)
+    agents = list(range(0, 64, 4))
+    gen = orc.GEN_BVC if mode == capi.MODE_BVC else orc.GEN_LSC
+    off, normals, rhs = oracle_planes(batch, agents, gen)
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
+    errs = _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=12)
+    assert np.median(errs) < 1e-7
+    assert iters.max() < 40
+
+
+def test_solve_parity_synthetic_planes():
+    """config 4 shape: random half-spaces with a strictly feasible point"""
+    batch = W.make_forest_batch(256, K=40, seed=20260004)
+    off, normals, rhs = W.make_synthetic_planes(batch, K=40)
+    agents = list(range(0, 256, 16))
+    sel_off = np.array([0] + list(np.cumsum([off[a + 1] - off[a] for a in agents])), np.int32)
+    sel_n = np.concatenate([normals[off[a]:off[a + 1]] for a in agents]); sel_r = np.concatenate([rhs[off[a]:off[a + 1]] for a in agents])
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, sel_off, sel_n, sel_r)
+    _check_against_oracle(batch, agents, sel_off, sel_n, sel_r, ctrl, cost, status, min_checked=12)
+
+
+def test_solve_with_sfc_boxes():
+    """SFC rows (world_use_octomap): per-segment boxes around the previous solution"""
+    cfg = W.PlannerConfig(use_sfc=True)
+    batch = W.make_forest_batch(64, K=16, cfg=cfg)
+    lo = batch.own_traj.min(axis=2) - 0.6; hi = batch.own_traj.max(axis=2) + 0.6
+    batch.sfc = np.ascontiguousarray(np.concatenate([lo, hi], axis=-1).astype(np.float32))
+    agents = list(range(0, 64, 8))
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    planner = _planner(batch.cfg)
+    sfc = np.ascontiguousarray(batch.sfc[agents])
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs, sfc=sfc)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, sfc=sfc, min_checked=6)
+
+
+def test_empty_and_ragged_obstacle_lists():
+    """K = 0 for some agents, different K per agent, zero agents"""
+    batch = W.make_forest_batch(64, K=40)
+    agents = [0, 1, 2, 3, 4, 5]
+    ks = [0, 1, 40, 7, 0, 23]
+    cfgo = oracle_config(batch.cfg)
+    normals, rhs, off = [], [], [0]
+    for a, k in zip(agents, ks):
+        pt, nr, d = oracle_lsc(batch, a, orc.GEN_LSC)
+        n_, r_ = orc.pack_planes(cfgo, pt[:k], nr[:k], d[:k]) if k else (np.zeros((0, 5, 3)), np.zeros((0, 5, 6)))
+        normals.append(n_); rhs.append(r_); off.append(off[-1] + k)
+    normals = np.ascontiguousarray(np.concatenate(normals)); rhs = np.ascontiguousarray(np.concatenate(rhs)); off = np.array(off, np.int32)
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=5)
+    # zero agents: a no-op that must not fail
+    planner.qp.solve_host(0, batch.state[:0].copy(), batch.goal[:0].copy(), batch.limits[:0].copy(), None,
+                          np.zeros(1, np.int32), None, None, np.zeros((0, 90)), np.zeros(0), np.zeros(0, np.int32))
+
+
+def test_zero_normal_rows_are_skipped():
+    """rows whose normal is shorter than SP_EPSILON_FLOAT are dropped (traj_optimizer.cpp:409-411)"""
+    batch = W.make_forest_batch(64, K=8)
+    agents = [3, 9]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    normals[1] = 0.0; rhs[1] = 5.0            # would be infeasible if it were not skipped
+    normals[off[1] + 2, 3] = 1e-7
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=2)
+
+
+def test_infeasible_is_reported_not_nan():
+    """contradictory half-spaces: status != OK, finite outputs (caller falls back to initial_traj, traj_planner.cpp:767-797)"""
+    batch = W.make_forest_batch(64, K=2)
+    agents = [0, 1]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    normals[0, :, :] = [1.0, 0.0, 0.0]; rhs[0] = 100.0        # x >= 100
+    normals[1, :, :] = [-1.0, 0.0, 0.0]; rhs[1] = 100.0       # -x >= 100
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
+    assert status[0] != capi.STATUS_OK
+    assert status[1] == capi.STATUS_OK
+    assert np.isfinite(ctrl[1]).all()
+
+
+@pytest.mark.parametrize("generator,M,dim", [(capi.GEN_LSC, 5, 3), (capi.GEN_CLSC, 10, 2), (capi.GEN_CLSC, 5, 3), (capi.GEN_BVC, 5, 3)])
+def test_assembly_parity(generator, M, dim):
+    """device LSC assembly vs the oracle's restatement of generateLSC / generateCLSC / generateBVC"""
+    import torch
+    cfg = W.PlannerConfig(M=M, dim=dim)
+    batch = W.make_forest_batch(96, K=24, cfg=cfg)
+    if generator == capi.GEN_CLSC:
+        near_goals(batch)
+    planner = _planner(batch.cfg)
+    d = planner.upload(batch)
+    planner.assemble_device(d, generator)
+    torch.cuda.synchronize()
+    normals = d.normals.cpu().numpy(); rhs = d.rhs.cpu().numpy()
+    agents = list(range(0, 96, 6))
+    off, n_ref, r_ref = oracle_planes(batch, agents, generator)
+    exact = 0; total = 0
+    for i, a in enumerate(agents):
+        sl = slice(batch.obs_offsets[a], batch.obs_offsets[a + 1])
+        got_n, got_r = normals[sl], rhs[sl]
+        want_n, want_r = n_ref[off[i]:off[i + 1]], r_ref[off[i]:off[i + 1]]
+        # normals are float32 values: equal up to one float ulp of a unit vector
+        assert np.abs(got_n - want_n).max() <= 2.4e-7, (a, np.abs(got_n - want_n).max())
+        assert np.abs(got_r - want_r).max() <= 2e-6, (a, np.abs(got_r - want_r).max())
+        exact += int((got_n == want_n).sum()); total += got_n.size
+    assert exact / total > 0.99
+
+
+def test_replan_host_matches_device_path_and_oracle():
+    """fused host entry point: trajectories in, solutions out"""
+    import torch
+    batch = W.make_forest_batch(128, K=40)
+    planner = _planner(batch.cfg)
+    out = planner.replan_host(batch, capi.GEN_LSC)
+    d = planner.upload(batch)
+    planner.replan_device(d, capi.GEN_LSC)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["ctrl"], d.ctrl.cpu().numpy())
+    assert (out["status"] == 0).all()
+    agents = [0, 17, 99]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    _check_against_oracle(batch, agents, off, normals, rhs, out["ctrl"][agents], out["cost"][agents], out["status"][agents], min_checked=2)
+
+
+def test_step_kernel_parity():
+    """closed-loop glue: float narrowing, getStateAt, previous-solution shift"""
+    import torch
+    for M, dim in ((5, 3), (10, 2)):
+        cfg = W.PlannerConfig(M=M, dim=dim)
+        batch = W.make_forest_batch(64, K=4, cfg=cfg)
+        planner = _planner(batch.cfg)
+        cfgo = oracle_config(batch.cfg)
+        rng = np.random.default_rng(1)
+        traj = batch.own_traj.astype(np.float64) + rng.normal(0, 1e-3, batch.own_traj.shape)
+        ctrl = np.ascontiguousarray(np.transpose(traj, (0, 3, 1, 2))[:, :dim].reshape(64, -1))
+        dev = torch.device("cuda", 0)
+        t_ctrl = torch.from_numpy(ctrl).to(dev)
+        t_traj = torch.empty((64, M, 6, 3), dtype=torch.float32, device=dev)
+        t_state = torch.empty((64, 9), dtype=torch.float32, device=dev)
+        t_shift = torch.empty((64, M, 6, 3), dtype=torch.float32, device=dev)
+        for step in (0.1, 0.2):
+            planner.qp.step_batch(64, t_ctrl, step, t_traj, t_state, t_shift)
+            torch.cuda.synchronize()
+            got_traj, got_state, got_shift = t_traj.cpu().numpy(), t_state.cpu().numpy(), t_shift.cpu().numpy()
+            for a in range(0, 64, 7):
+                want = traj[a].astype(np.float32)
+                if dim == 2:
+                    want[..., 2] = np.float32(cfg.z_2d)
+                assert np.array_equal(got_traj[a], want)
+                st = orc.get_state_at(cfgo, want, step)
+                if dim == 2:
+                    st[2] = np.float32(cfg.z_2d)
+                assert np.allclose(got_state[a], st, rtol=2e-6, atol=2e-6), (a, got_state[a], st)
+                assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
+
+
+def test_full_size_properties():
+    """BASELINE size (4096 agents, K=40): size-independent properties of the solutions"""
+    import torch
+    batch = W.make_forest_batch(4096, K=40)
+    planner = _planner(batch.cfg)
+    d = planner.upload(batch)
+    planner.assemble_device(d, capi.GEN_LSC)
+    planner.solve_device(d, want_kkt=True)
+    torch.cuda.synchronize()
+    status = d.status.cpu().numpy(); ctrl = d.ctrl.cpu().numpy().reshape(4096, 3, 5, 6); kkt = d.kkt.cpu().numpy()
+    assert (status == 0).all(), np.bincount(status)
+    # equalities: initial state, C0/C1/C2 continuity, terminal stop
+    st = batch.state.astype(np.float64); dt = batch.cfg.dt
+    assert np.abs(ctrl[:, :, 0, 0] - st[:, 0:3]).max() < 1e-12
+    assert np.abs(5 / dt * (ctrl[:, :, 0, 1] - ctrl[:, :, 0, 0]) - st[:, 3:6]).max() < 1e-9
+    assert np.abs(20 / dt ** 2 * (ctrl[:, :, 0, 2] - 2 * ctrl[:, :, 0, 1] + ctrl[:, :, 0, 0]) - st[:, 6:9]).max() < 1e-7
+    assert np.abs(ctrl[:, :, 1:, 0] - ctrl[:, :, :-1, 5]).max() < 1e-12
+    assert np.abs((ctrl[:, :, 1:, 1] - ctrl[:, :, 1:, 0]) - (ctrl[:, :, :-1, 5] - ctrl[:, :, :-1, 4])).max() < 1e-12
+    assert np.abs(ctrl[:, :, -1, 5] - ctrl[:, :, -1, 3]).max() == 0
+    # inequalities: LSC rows, velocity / acceleration limits
+    normals = d.normals.cpu().numpy().reshape(4096, 40, 5, 3); rhs = d.rhs.cpu().numpy().reshape(4096, 40, 5, 6)
+    lhs = np.einsum("akmd,admi->akmi", normals, ctrl)
+    viol = (rhs - lhs); viol[:, :, 0, :3] = -1
+    assert viol.max() < 1e-8, viol.max()
+    vel = 5 / dt * np.diff(ctrl, axis=3); acc = 20 / dt ** 2 * np.diff(ctrl, n=2, axis=3)
+    assert np.abs(vel[:, :, 1:]).max() < 1 + 1e-7 and np.abs(acc[:, :, 1:]).max() < 2 + 1e-6
+    # interior-point certificate from the kernel itself
+    assert kkt[:, 1].max() < 1e-9 and kkt[:, 3].max() < 1e-10
+    # idempotence: solving the same batch again is bit-identical (no atomics / order dependence)
+    c1 = d.ctrl.clone()
+    planner.solve_device(d)
+    torch.cuda.synchronize()
+    assert torch.equal(c1, d.ctrl)
