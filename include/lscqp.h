@@ -58,7 +58,7 @@ typedef struct lscqp_config {
     int max_obs;                   /* capacity: obstacles per agent (<= 40)                    */
     int max_agents;                /* capacity of the staging buffers for the *_host calls     */
     int max_iter;                  /* interior-point iteration cap (0 = default 60)            */
-    double tol;                    /* complementarity / primal tolerance (0 = default 1e-10)   */
+    double tol;                    /* complementarity / primal tolerance (0 = default 1e-11)   */
 } lscqp_config;
 
 typedef struct lscqp_handle lscqp_handle;

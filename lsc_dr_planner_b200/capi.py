@@ -86,7 +86,6 @@ def pinned(shape, dtype):
     tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32}[np.dtype(dtype).type]
     t = torch.empty(shape, dtype=tdt, pin_memory=True)
     a = t.numpy()
-    a._pin_owner = t if hasattr(a, "__dict__") else None
     _PIN_KEEP.append(t)
     return a
 

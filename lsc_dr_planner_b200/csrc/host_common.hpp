@@ -63,7 +63,7 @@ inline int validate_config(const lscqp_config& c) {
 inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     std::memset(&p, 0, sizeof(p));
     p.max_iter = c.max_iter > 0 ? c.max_iter : 60;
-    p.mu_tol = c.tol > 0 ? c.tol : 1e-10;
+    p.mu_tol = c.tol > 0 ? c.tol : 1e-11;
     p.rp_tol = 1e-9;
     p.dt = c.dt; p.w_t = c.w_terminal; p.w_c = c.w_control;
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }

@@ -76,6 +76,7 @@ struct Cfg {
     static constexpr int NPAIR = BW * (BW + 1) / 2;      // trailing-update pairs per Cholesky column
     static constexpr int NPR = (NPAIR + 31) / 32;
     static constexpr int NRED = 4;
+    static constexpr int MIN_CTAS = NT > 128 ? 2 : 3;    // register budget: 65536 / (MIN_CTAS * NT) per thread
     // shared memory layout (doubles)
     static constexpr int O_Q2 = 0;
     static constexpr int O_C = O_Q2 + 36;
@@ -106,7 +107,9 @@ struct Cfg {
     static constexpr int O_DIAG0 = O_RHS + NR;           // [NR]
     static constexpr int O_INVD = O_DIAG0 + NR;          // [NR]
     static constexpr int O_RED = O_INVD + NR;            // [2][NW][NRED]
-    static constexpr int O_END = O_RED + 2 * NW * NRED;
+    static constexpr int O_TT = O_RED + 2 * NW * NRED;   // T[3][3] then TT[3][3][3]
+    static constexpr int O_RTAB = O_TT + 36;             // int[3*NR]: stage, dim, j (-1 = collapsed terminal point)
+    static constexpr int O_END = O_RTAB + (3 * NR + 1) / 2;
     static constexpr int SMEM_BYTES = O_END * 8;
     // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
     static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6;
@@ -222,7 +225,7 @@ __device__ __forceinline__ int chol_banded(double* A, const double* diag0, doubl
     for (int j = 0; j < C::NR; j++) {
         double d = A[j * C::LD + j];
         if (!(d > 1e-13 * diag0[j])) { d = 1e300; bad++; }     // pivot guard: freeze that direction
-        const double inv = 1.0 / sqrt(d);
+        const double inv = rsqrt(d);
         if (lane == 0) invd[j] = inv;
         const int i = j + 1 + lane;
         if (lane < C::BW && i < C::NR) A[i * C::LD + j] *= inv;
@@ -260,29 +263,21 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* invd, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-row algebra.  Row convention: q(c) >= 0, slack s > 0 with primal residual rp = s - q.
-struct RowAcc {
-    double sum_a, sum_b, vmin, vmax;
+// Row algebra.  Row convention: q(c) >= 0, slack s > 0, multiplier lam > 0.  Every row starts with
+// the same primal residual rp = s - q (the start-up shift) and every step scales it by (1 - alpha),
+// so rp is one scalar for the whole QP and neither q nor the row constants are needed after start-up.
+struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a fraction (no division per row)
+    double num, den;
+    __device__ __forceinline__ void init() { num = 1.0; den = 0.0; }
+    __device__ __forceinline__ void add(double v, double dv) {
+        if (dv < 0.0 && v * den < num * (-dv)) { num = v; den = -dv; }
+    }
+    __device__ __forceinline__ double value() const { return den > 0.0 ? num / den : INFINITY; }
 };
-
-// predictor quantities for one row
-__device__ __forceinline__ void row_affine(double s, double lam, double q, double& W, double& u) {
-    const double rp = s - q;
-    W = lam / s;
-    u = W * rp;                       // lam + (lam*rp - s*lam)/s
-}
-__device__ __forceinline__ void row_affine_step(double s, double lam, double q, double dqa, double& dsa, double& dla) {
-    const double rp = s - q;
-    dsa = dqa - rp;
-    dla = -lam - (lam / s) * dsa;
-}
-__device__ __forceinline__ double ratio(double v, double dv) {
-    return dv < 0.0 ? -v / dv : INFINITY;
-}
 
 // ---------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT)
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS)
 pdip_solve_kernel(const SolveParams p) {
     constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, LD = C::LD, NS = C::NS;
     constexpr int G = C::G, KPT = C::KPT, NT = C::NT;
@@ -320,6 +315,9 @@ pdip_solve_kernel(const SolveParams p) {
     double* s_diag0 = sm + C::O_DIAG0;
     double* s_invd = sm + C::O_INVD;
     double* s_red = sm + C::O_RED;
+    double* s_T = sm + C::O_TT;            // T[a][j]
+    double* s_TT = sm + C::O_TT + 9;       // TT[a][j1][j2] = T[a][j1] T[a][j2]
+    int* s_rtab = reinterpret_cast<int*>(sm + C::O_RTAB);
     int red_phase = 0;
 
     // ---- thread roles
@@ -333,6 +331,7 @@ pdip_solve_kernel(const SolveParams p) {
     const bool has_bnd = var_thread && !(m_v == 0 && i_v < 3);          // :260-265
     const bool has_vel = var_thread && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
     const bool has_acc = var_thread && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
+    const unsigned bmask = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u);
 
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
@@ -345,7 +344,6 @@ pdip_solve_kernel(const SolveParams p) {
         const int e = lane + 32 * t;
         pr_i[t] = -1; pr_k[t] = 0;
         if (e < C::NPAIR) {
-            // e -> (di, dk), dk <= di, row-major over the lower triangle
             int di = (int) ((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
             while ((di + 1) * (di + 2) / 2 <= e) di++;
             while (di * (di + 1) / 2 > e) di--;
@@ -355,6 +353,14 @@ pdip_solve_kernel(const SolveParams p) {
 
     // ---- stage per-agent constants
     if (tid < 36) sQ2[tid] = p.Q2[tid];
+    if (tid >= 64 && tid < 64 + 9) { const int e = tid - 64; s_T[e] = tcoef(e / 3, e % 3); }
+    if (tid >= 96 && tid < 96 + 27) { const int e = tid - 96; s_TT[e] = tcoef(e / 9, (e / 3) % 3) * tcoef(e / 9, e % 3); }
+    for (int r = tid; r < NR; r += NT) {
+        int st, k, j;
+        if (C::TERM && r >= (M - 1) * C::NZS) { st = M - 1; k = r - (M - 1) * C::NZS; j = -1; }
+        else { st = r / C::NZS; k = (r % C::NZS) / 3; j = r % 3; }
+        s_rtab[3 * r] = st; s_rtab[3 * r + 1] = k; s_rtab[3 * r + 2] = j;
+    }
     if (tid < D) {
         const int k = tid;
         const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
@@ -385,74 +391,54 @@ pdip_solve_kernel(const SolveParams p) {
         for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
     }
     for (int e = tid; e < K * M * 3; e += NT) s_nrm[e] = p.normals[(size_t) obs0 * M * 3 + e];
+    // starting point: every free control point at the current position (hover)
+    if (tid < NR) {
+        int k;
+        if (C::TERM && tid >= (M - 1) * C::NZS) k = tid - (M - 1) * C::NZS; else k = (tid % C::NZS) / 3;
+        s_y[tid] = (double) p.state[agent * 9 + k];
+    }
     __syncthreads();
+    if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
 
-    // ---- per-thread row state (registers)
-    double ls[KPT], ll[KPT], lb_[KPT];     // LSC rows: slack, multiplier, rhs b
-    bool lact[KPT];
-    double bs[6], bl[6];                   // box rows
+    // ---- per-thread row state (registers): slack and multiplier of every owned row
+    double ls[KPT], ll[KPT];
+    double bs[6], bl[6];
+    unsigned lmask = 0;
 #pragma unroll
     for (int j = 0; j < KPT; j++) {
         const int oi = grp + G * j;
-        lact[j] = false; ls[j] = 1.0; ll[j] = 0.0; lb_[j] = 0.0;
+        ls[j] = 1.0; ll[j] = 0.0;
         if (lsc_thread && oi < K) {
             const double* n = s_nrm + (oi * M + m_cp) * 3;
             // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped, traj_optimizer.cpp:409-411
             const float fx = (float) n[0], fy = (float) n[1], fz = (float) n[2];
             const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
-            lact[j] = !(sqrt((double) nsq) < 1e-5);
-            lb_[j] = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            if (!(sqrt((double) nsq) < 1e-5)) lmask |= 1u << j;
         }
     }
 #pragma unroll
     for (int e = 0; e < 6; e++) { bs[e] = 1.0; bl[e] = 0.0; }
-    const bool bact[6] = {has_bnd, has_bnd, has_vel, has_vel, has_acc, has_acc};
 
-    // number of rows
     double red[4];
     {
-        double cnt = 0;
-#pragma unroll
-        for (int j = 0; j < KPT; j++) cnt += lact[j] ? 1.0 : 0.0;
-#pragma unroll
-        for (int e = 0; e < 6; e++) cnt += bact[e] ? 1.0 : 0.0;
-        red[0] = cnt; red[1] = 0; red[2] = 0; red[3] = 0;
-        block_reduce4<C>(red, s_red, red_phase);
+        red[0] = (double) (__popc(lmask) + __popc(bmask)); red[1] = 0; red[2] = 0; red[3] = 0;
+        block_reduce4<C>(red, s_red, red_phase);       // (barrier: s_c is complete after this)
     }
     const double n_rows = red[0];
 
-    // ---- starting point: every free control point at the current position (hover)
-    if (tid < NR) {
-        int k;
-        if (C::TERM && tid >= (M - 1) * C::NZS) k = tid - (M - 1) * C::NZS; else k = (tid % C::NZS) / 3;
-        s_y[tid] = s_x0[k * 3];
-    }
-    __syncthreads();
-
     // helpers -----------------------------------------------------------------------------------
-    // q for the box rows of this thread given a full-space vector (values) -- direction form has no constants
-    auto box_q = [&](const double* cv, bool direction, double* q) {
-        const double* cc = cv + k_v * NCP + cp_v;
-        const double c0 = cc[0];
-        const double lo = direction ? 0.0 : s_lb[k_v * M + m_v], hi = direction ? 0.0 : s_ub[k_v * M + m_v];
-        q[0] = c0 - lo; q[1] = hi - c0;
-        double dv = 0.0, da = 0.0;
-        if (has_vel) dv = cc[1] - c0;
-        if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
-        const double vl = direction ? 0.0 : s_vlim[k_v], al = direction ? 0.0 : s_alim[k_v];
-        q[2] = vl - dv; q[3] = vl + dv; q[4] = al - da; q[5] = al + da;
+    // directional change of the six box rows of this thread for a full-space direction dv
+    auto box_dq = [&](const double* dv, double* dq) {
+        const double* d = dv + k_v * NCP + cp_v;
+        const double d0 = d[0];
+        double dvv = 0.0, daa = 0.0;
+        if (has_vel) dvv = d[1] - d0;
+        if (has_acc) daa = d[2] - 2.0 * d[1] + d0;
+        dq[0] = d0; dq[1] = -d0; dq[2] = -dvv; dq[3] = dvv; dq[4] = -daa; dq[5] = daa;
     };
-    auto lsc_dot = [&](const double* cv, int oi) -> double {
-        const double* n = s_nrm + (oi * M + m_cp) * 3;
-        double r = n[0] * cv[cp] + n[1] * cv[NCP + cp];
-        if (D == 3) r += n[2] * cv[2 * NCP + cp];
-        return r;
+    auto load_cp = [&](const double* v, double& x, double& y, double& z) {
+        x = v[cp]; y = v[NCP + cp]; z = (D == 3) ? v[2 * NCP + cp] : 0.0;
     };
-    auto compute_full = [&](const double* yv, const double* x0, double* out) {
-        if (var_thread) out[tid] = full_from_reduced<C>(yv, x0, k_v, m_v, i_v);
-    };
-
-    // write this thread's LSC accumulators to its group slab
     auto store_slab = [&](const double* S, const double* T, bool withS) {
         if (cp_valid) {
             if (withS) {
@@ -463,26 +449,93 @@ pdip_solve_kernel(const SolveParams p) {
             for (int e = 0; e < D; e++) slabT[(grp * NCP + cp) * D + e] = T[e];
         }
     };
+    auto accum = [&](double* S, double* T, const double* n, double W, double u, bool withS) {
+        if (withS) {
+            if (D == 3) {
+                const double wx = W * n[0], wy = W * n[1], wz = W * n[2];
+                S[0] += wx * n[0]; S[1] += wx * n[1]; S[2] += wx * n[2];
+                S[3] += wy * n[1]; S[4] += wy * n[2]; S[5] += wz * n[2];
+            } else {
+                const double wx = W * n[0], wy = W * n[1];
+                S[0] += wx * n[0]; S[1] += wx * n[1]; S[2] += wy * n[1];
+            }
+        }
+        T[0] += u * n[0]; T[1] += u * n[1];
+        if (D == 3) T[2] += u * n[2];
+    };
+    auto store_box = [&](const double* W, const double* u, bool withS) {
+        // gradients of the rows: lb +e, ub -e, vel+ -(d), vel- +(d), acc+ -(d), acc- +(d)
+        if (withS) { s_wB[tid] = W[0] + W[1]; s_wV[tid] = W[2] + W[3]; s_wA[tid] = W[4] + W[5]; }
+        s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
+    };
 
-    // sum the group slabs into slab 0, build the 6x6 blocks (withS) and the full-space rhs, then project.
-    // rfull = -grad f + A^T u
+    // reduced-matrix entry (r1 >= r2) from the full-space blocks ("projection")
+    auto red_entry = [&](int r1, int r2) -> double {
+        const int s1 = s_rtab[3 * r1], k1 = s_rtab[3 * r1 + 1], j1 = s_rtab[3 * r1 + 2];
+        const int s2 = s_rtab[3 * r2], k2 = s_rtab[3 * r2 + 1], j2 = s_rtab[3 * r2 + 2];
+        double val = 0.0;
+        if (s1 == s2) {
+            const int st = s1;
+            if (k1 == k2) {
+                const double* B = s_blk + (k1 * M + st) * 36;
+                if (j1 < 0) {
+                    for (int a = 3; a < 6; a++) for (int b = 3; b < 6; b++) val += B[a * 6 + b];
+                } else {
+                    val = B[(3 + j1) * 6 + 3 + j2];
+                    if (st + 1 < M) {
+                        const double* Bn = B + 36;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const double ta = s_T[a * 3 + j1];
+#pragma unroll
+                            for (int b = 0; b < 3; b++) val += ta * s_T[b * 3 + j2] * Bn[a * 6 + b];
+                        }
+                    }
+                }
+            } else {
+                const int si = (D == 3) ? symidx3(k1, k2) : symidx2(k1, k2);
+                if (j1 < 0) {
+                    for (int a = 3; a < 6; a++) val += slabS[(st * 6 + a) * NS + si];
+                } else {
+                    if (j1 == j2) val = slabS[(st * 6 + 3 + j1) * NS + si];
+                    if (st + 1 < M) {
+#pragma unroll
+                        for (int a = 0; a < 3; a++) val += s_TT[a * 9 + j1 * 3 + j2] * slabS[((st + 1) * 6 + a) * NS + si];
+                    }
+                }
+            }
+        } else if (s1 == s2 + 1 && k1 == k2) {
+            const double* B = s_blk + (k1 * M + s1) * 36;
+            if (j1 < 0) {
+                for (int a = 3; a < 6; a++)
+#pragma unroll
+                    for (int b = 0; b < 3; b++) val += B[a * 6 + b] * s_T[b * 3 + j2];
+            } else {
+#pragma unroll
+                for (int b = 0; b < 3; b++) val += B[(3 + j1) * 6 + b] * s_T[b * 3 + j2];
+            }
+        }
+        return val;
+    };
+
+    // sum the group slabs, build the 6x6 blocks (withS) and the full-space rhs  -grad f + A^T u, then project.
     auto assemble = [&](bool withS) {
         __syncthreads();
-        // (1) reduce slabs over groups
         for (int e = tid; e < NCP * D; e += NT) {
             double a = slabT[e];
+#pragma unroll
             for (int g = 1; g < G; g++) a += slabT[g * NCP * D + e];
             slabT[e] = a;
         }
         if (withS) {
             for (int e = tid; e < NCP * NS; e += NT) {
                 double a = slabS[e];
+#pragma unroll
                 for (int g = 1; g < G; g++) a += slabS[g * NCP * NS + e];
                 slabS[e] = a;
             }
         }
         __syncthreads();
-        // (2) full-space blocks and rhs
         if (withS) {
             for (int e = tid; e < D * M * 36; e += NT) {
                 const int k = e / (M * 36), m = (e / 36) % M, a = (e % 36) / 6, b = e % 6;
@@ -517,25 +570,11 @@ pdip_solve_kernel(const SolveParams p) {
             s_rfull[tid] = au - gr;
         }
         __syncthreads();
-        // (3) project to the reduced space
         if (withS) {
             for (int e = tid; e < NR * (C::BW + 1); e += NT) {
                 const int r1 = e / (C::BW + 1), r2 = r1 - e % (C::BW + 1);
                 if (r2 < 0) continue;
-                int k1, k2, c1[4], c2[4];
-                double o1[4], o2[4];
-                const int n1 = support<C>(r1, k1, c1, o1), n2 = support<C>(r2, k2, c2, o2);
-                double val = 0.0;
-                for (int a = 0; a < n1; a++)
-                    for (int b = 0; b < n2; b++) {
-                        double f = 0.0;
-                        if (k1 == k2) {
-                            if (c1[a] / 6 == c2[b] / 6) f = s_blk[(k1 * M + c1[a] / 6) * 36 + (c1[a] % 6) * 6 + c2[b] % 6];
-                        } else if (c1[a] == c2[b]) {
-                            f = slabS[c1[a] * NS + ((D == 3) ? symidx3(k1, k2) : symidx2(k1, k2))];
-                        }
-                        val += o1[a] * o2[b] * f;
-                    }
+                const double val = red_entry(r1, r2);
                 s_A[r1 * LD + r2] = val;
                 if (r1 == r2) s_diag0[r1] = val;
             }
@@ -544,167 +583,183 @@ pdip_solve_kernel(const SolveParams p) {
         __syncthreads();
     };
 
-    // one sweep over this thread's rows computing weights W (optional) and rhs multipliers u, then storing them.
-    // mode 0: initial least-squares point (W = 1, u = -q)
-    // mode 1: predictor (W = lam/s, u = W rp)
-    // mode 2: corrector (u = lam + (lam rp - rc)/s with rc = s lam + dsa dla - sigma mu)
-    auto row_sweep = [&](int mode, double sigmu) {
-        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
-        const bool withS = mode != 2;
-#pragma unroll
-        for (int j = 0; j < KPT; j++) {
-            if (!lact[j]) continue;
-            const int oi = grp + G * j;
-            const double* n = s_nrm + (oi * M + m_cp) * 3;
-            const double q = lsc_dot(s_c, oi) - lb_[j];
-            double W = 1.0, u;
-            if (mode == 0) { u = -q; }
-            else if (mode == 1) { row_affine(ls[j], ll[j], q, W, u); }
-            else {
-                double dsa, dla;
-                row_affine_step(ls[j], ll[j], q, lsc_dot(s_dca, oi), dsa, dla);
-                const double rp = ls[j] - q, rc = ls[j] * ll[j] + dsa * dla - sigmu;
-                u = ll[j] + (ll[j] * rp - rc) / ls[j];
-            }
-            if (withS) {
-                if (D == 3) {
-                    S[0] += W * n[0] * n[0]; S[1] += W * n[0] * n[1]; S[2] += W * n[0] * n[2];
-                    S[3] += W * n[1] * n[1]; S[4] += W * n[1] * n[2]; S[5] += W * n[2] * n[2];
-                } else {
-                    S[0] += W * n[0] * n[0]; S[1] += W * n[0] * n[1]; S[2] += W * n[1] * n[1];
-                }
-            }
-            T[0] += u * n[0]; T[1] += u * n[1];
-            if (D == 3) T[2] += u * n[2];
+    int bad_piv = 0;
+    auto factor_solve = [&](bool factor) {
+        if (tid < 32) {
+            if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
+            chol_solve<C>(s_A, s_invd, s_rhs);
         }
-        store_slab(S, T, withS);
-        if (var_thread) {
-            double q[6], qa[6];
-            box_q(s_c, false, q);
-            if (mode == 2) box_q(s_dca, true, qa);
-            double W[6], u[6];
-#pragma unroll
-            for (int e = 0; e < 6; e++) {
-                W[e] = 0.0; u[e] = 0.0;
-                if (!bact[e]) continue;
-                if (mode == 0) { W[e] = 1.0; u[e] = -q[e]; }
-                else if (mode == 1) { row_affine(bs[e], bl[e], q[e], W[e], u[e]); }
-                else {
-                    double dsa, dla;
-                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
-                    const double rp = bs[e] - q[e], rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                    u[e] = bl[e] + (bl[e] * rp - rc) / bs[e];
-                }
-            }
-            // gradients: lb +e, ub -e, vel+ -(d), vel- +(d), acc+ -(d), acc- +(d)
-            if (withS) { s_wB[tid] = W[0] + W[1]; s_wV[tid] = W[2] + W[3]; s_wA[tid] = W[4] + W[5]; }
-            s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
-        }
+        __syncthreads();
     };
 
     // ---------------------------------------------------------------- initial point (least squares)
-    compute_full(s_y, s_x0, s_c);
-    __syncthreads();
-    row_sweep(0, 0.0);
+    // minimise f(y) + 1/2 |q(y)|^2 : W = 1, u = -q at the hover point; then s = q, lam = -q, both shifted
+    // into the positive orthant (Mehrotra / CVXOPT start).  q of every row is kept in ls[] / bs[] meanwhile.
+    {
+        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+        double cx, cy, cz;
+        if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            if (!(lmask >> j & 1u)) continue;
+            const int oi = grp + G * j;
+            const double* n = s_nrm + (oi * M + m_cp) * 3;
+            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            if (D == 3) q += n[2] * cz;
+            ls[j] = q;
+            accum(S, T, n, 1.0, -q, true);
+        }
+        store_slab(S, T, true);
+        if (var_thread) {
+            const double* cc = s_c + k_v * NCP + cp_v;
+            const double c0 = cc[0];
+            double dv = 0.0, da = 0.0;
+            if (has_vel) dv = cc[1] - c0;
+            if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
+            bs[0] = c0 - s_lb[k_v * M + m_v]; bs[1] = s_ub[k_v * M + m_v] - c0;
+            bs[2] = s_vlim[k_v] - dv; bs[3] = s_vlim[k_v] + dv; bs[4] = s_alim[k_v] - da; bs[5] = s_alim[k_v] + da;
+            double W[6], u[6];
+#pragma unroll
+            for (int e = 0; e < 6; e++) { const bool on = bmask >> e & 1u; W[e] = on ? 1.0 : 0.0; u[e] = on ? -bs[e] : 0.0; }
+            store_box(W, u, true);
+        }
+    }
     assemble(true);
-    int bad_piv = 0;
-    if (tid < 32) {
-        bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
-        chol_solve<C>(s_A, s_invd, s_rhs);
+    factor_solve(true);
+    if (tid < NR) { s_dy[tid] = s_rhs[tid]; s_y[tid] += s_rhs[tid]; }
+    __syncthreads();
+    if (var_thread) {
+        s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
+        s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
     }
     __syncthreads();
-    if (tid < NR) s_y[tid] += s_rhs[tid];
-    __syncthreads();
-    compute_full(s_y, s_x0, s_c);
-    __syncthreads();
+    double rp;      // the common primal residual s - q
     {
-        // s = q(y), lam = -s, then shift both into the positive orthant (Mehrotra / CVXOPT start)
+        double dx, dy, dz;
+        if (cp_valid) load_cp(s_dc, dx, dy, dz); else { dx = dy = dz = 0; }
         double qmin = INFINITY, qmax = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            if (!lact[j]) continue;
-            ls[j] = lsc_dot(s_c, grp + G * j) - lb_[j];
+            if (!(lmask >> j & 1u)) continue;
+            const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+            double dq = n[0] * dx + n[1] * dy;
+            if (D == 3) dq += n[2] * dz;
+            ls[j] += dq;
             qmin = fmin(qmin, ls[j]); qmax = fmax(qmax, ls[j]);
         }
         if (var_thread) {
-            double q[6];
-            box_q(s_c, false, q);
+            double dq[6];
+            box_dq(s_dc, dq);
 #pragma unroll
-            for (int e = 0; e < 6; e++) if (bact[e]) { bs[e] = q[e]; qmin = fmin(qmin, q[e]); qmax = fmax(qmax, q[e]); }
+            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += dq[e]; qmin = fmin(qmin, bs[e]); qmax = fmax(qmax, bs[e]); }
         }
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
         block_reduce4<C>(red, s_red, red_phase);
         const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
         const double shift_l = (red[3] >= 0.0) ? 1.0 + red[3] : 0.0;        // lam = -s; alpha_d = max(s) >= 0 -> lam += 1 + alpha_d
 #pragma unroll
-        for (int j = 0; j < KPT; j++) if (lact[j]) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
+        for (int j = 0; j < KPT; j++) if (lmask >> j & 1u) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
 #pragma unroll
-        for (int e = 0; e < 6; e++) if (bact[e]) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+        for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+        rp = shift_s;
     }
 
     // ---------------------------------------------------------------- main loop
     int status = ST_MAX_ITER, it = 0;
-    double mu = 0.0, rp_inf = 0.0;
-    for (it = 0; it < p.max_iter; it++) {
-        // (a) residual statistics
+    double mu = 0.0, sigmu = 0.0, alpha = 0.0;
+    bool have_step = false;       // a (dca, dc, sigmu, alpha) step is pending and is applied by the next sweep A
+    for (it = 0; it <= p.max_iter; it++) {
+        // ---- sweep A: apply the pending step, then predictor weights of the new point
         {
-            double sl = 0.0, rpm = 0.0;
+            double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+            double ax, ay, az, dx, dy, dz;
+            if (have_step && cp_valid) { load_cp(s_dca, ax, ay, az); load_cp(s_dc, dx, dy, dz); }
+            else { ax = ay = az = dx = dy = dz = 0; }
+            const double rp_new = have_step ? (1.0 - alpha) * rp : rp;
+            double sl = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!lact[j]) continue;
-                const double q = lsc_dot(s_c, grp + G * j) - lb_[j];
-                sl += ls[j] * ll[j]; rpm = fmax(rpm, fabs(ls[j] - q));
+                if (!(lmask >> j & 1u)) continue;
+                const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+                if (have_step) {
+                    double dqa = n[0] * ax + n[1] * ay, dq = n[0] * dx + n[1] * dy;
+                    if (D == 3) { dqa += n[2] * az; dq += n[2] * dz; }
+                    const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                    const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
+                    const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
+                    const double ds = dq - rp, dl = -(rc + ll[j] * ds) * rs;
+                    ls[j] += alpha * ds; ll[j] += alpha * dl;
+                }
+                const double W = ll[j] / ls[j];
+                sl += ls[j] * ll[j];
+                accum(S, T, n, W, W * rp_new, true);
             }
+            store_slab(S, T, true);
             if (var_thread) {
-                double q[6];
-                box_q(s_c, false, q);
+                double W[6], u[6], dqa[6], dq[6];
+                if (have_step) { box_dq(s_dca, dqa); box_dq(s_dc, dq); }
 #pragma unroll
-                for (int e = 0; e < 6; e++) if (bact[e]) { sl += bs[e] * bl[e]; rpm = fmax(rpm, fabs(bs[e] - q[e])); }
+                for (int e = 0; e < 6; e++) {
+                    W[e] = 0.0; u[e] = 0.0;
+                    if (!(bmask >> e & 1u)) continue;
+                    if (have_step) {
+                        const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                        const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
+                        const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
+                        const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
+                        bs[e] += alpha * ds; bl[e] += alpha * dl;
+                    }
+                    W[e] = bl[e] / bs[e]; u[e] = W[e] * rp_new;
+                    sl += bs[e] * bl[e];
+                }
+                store_box(W, u, true);
             }
-            red[0] = sl; red[1] = 0; red[2] = 0; red[3] = rpm;
+            rp = rp_new;
+            red[0] = sl; red[1] = 0; red[2] = 0; red[3] = 0;
             block_reduce4<C>(red, s_red, red_phase);
-            mu = red[0] / n_rows; rp_inf = red[3];
+            mu = red[0] / n_rows;
         }
-        if (!(mu == mu) || !(rp_inf == rp_inf)) { status = ST_NUMERICAL; break; }
-        if (mu < p.mu_tol && rp_inf < p.rp_tol) { status = ST_OK; break; }
+        if (!(mu == mu)) { status = ST_NUMERICAL; break; }
+        if (mu < p.mu_tol && fabs(rp) < p.rp_tol) { status = ST_OK; break; }
+        if (it == p.max_iter) break;
 
-        // (b) predictor
-        row_sweep(1, 0.0);
+        // ---- predictor
         assemble(true);
-        if (tid < 32) {
-            bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
-            chol_solve<C>(s_A, s_invd, s_rhs);
-        }
-        __syncthreads();
+        factor_solve(true);
         if (tid < NR) s_dy[tid] = s_rhs[tid];
         __syncthreads();
-        compute_full(s_dy, nullptr, s_dca);
+        if (var_thread) s_dca[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
         __syncthreads();
-        double sigmu;
+        // ---- sweep B: affine step length and centering parameter
         {
-            double amax = INFINITY, s1 = 0.0, s2 = 0.0;
+            double ax, ay, az;
+            if (cp_valid) load_cp(s_dca, ax, ay, az); else { ax = ay = az = 0; }
+            MinRatio mr; mr.init();
+            double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!lact[j]) continue;
-                const int oi = grp + G * j;
-                double dsa, dla;
-                row_affine_step(ls[j], ll[j], lsc_dot(s_c, oi) - lb_[j], lsc_dot(s_dca, oi), dsa, dla);
-                amax = fmin(amax, fmin(ratio(ls[j], dsa), ratio(ll[j], dla)));
+                if (!(lmask >> j & 1u)) continue;
+                const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+                double dqa = n[0] * ax + n[1] * ay;
+                if (D == 3) dqa += n[2] * az;
+                const double W = ll[j] / ls[j];
+                const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
+                mr.add(ls[j], dsa); mr.add(ll[j], dla);
                 s1 += ls[j] * dla + ll[j] * dsa; s2 += dsa * dla;
             }
             if (var_thread) {
-                double q[6], qa[6];
-                box_q(s_c, false, q); box_q(s_dca, true, qa);
+                double dqa[6];
+                box_dq(s_dca, dqa);
 #pragma unroll
                 for (int e = 0; e < 6; e++) {
-                    if (!bact[e]) continue;
-                    double dsa, dla;
-                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
-                    amax = fmin(amax, fmin(ratio(bs[e], dsa), ratio(bl[e], dla)));
+                    if (!(bmask >> e & 1u)) continue;
+                    const double W = bl[e] / bs[e];
+                    const double dsa = dqa[e] - rp, dla = -bl[e] - W * dsa;
+                    mr.add(bs[e], dsa); mr.add(bl[e], dla);
                     s1 += bs[e] * dla + bl[e] * dsa; s2 += dsa * dla;
                 }
             }
-            red[0] = s1; red[1] = s2; red[2] = amax; red[3] = 0;
+            red[0] = s1; red[1] = s2; red[2] = mr.value(); red[3] = 0;
             block_reduce4<C>(red, s_red, red_phase);
             const double a = fmin(1.0, red[2]);
             const double mu_aff = (mu * n_rows + a * red[0] + a * a * red[1]) / n_rows;
@@ -714,76 +769,123 @@ pdip_solve_kernel(const SolveParams p) {
             if (sg > 1.0) sg = 1.0;
             sigmu = sg * mu;
         }
-
-        // (c) corrector
-        row_sweep(2, sigmu);
-        assemble(false);
-        if (tid < 32) chol_solve<C>(s_A, s_invd, s_rhs);
-        __syncthreads();
-        if (tid < NR) s_dy[tid] = s_rhs[tid];
-        __syncthreads();
-        compute_full(s_dy, nullptr, s_dc);
-        __syncthreads();
-
-        // (d) step length, (e) update.  The row directions are recomputed in the update sweep instead of
-        // being kept in registers across the CTA reduction.
-        double alpha = 1.0;
-        for (int pass = 0; pass < 2; pass++) {
-            double amax = INFINITY;
+        // ---- sweep C: corrector right-hand side
+        {
+            double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+            double ax, ay, az;
+            if (cp_valid) load_cp(s_dca, ax, ay, az); else { ax = ay = az = 0; }
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!lact[j]) continue;
-                const int oi = grp + G * j;
-                const double q = lsc_dot(s_c, oi) - lb_[j];
-                double dsa, dla;
-                row_affine_step(ls[j], ll[j], q, lsc_dot(s_dca, oi), dsa, dla);
-                const double rp = ls[j] - q, rc = ls[j] * ll[j] + dsa * dla - sigmu;
-                const double ds = lsc_dot(s_dc, oi) - rp;
-                const double dl = (-rc - ll[j] * ds) / ls[j];
-                if (pass == 0) amax = fmin(amax, fmin(ratio(ls[j], ds), ratio(ll[j], dl)));
-                else { ls[j] += alpha * ds; ll[j] += alpha * dl; }
+                if (!(lmask >> j & 1u)) continue;
+                const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+                double dqa = n[0] * ax + n[1] * ay;
+                if (D == 3) dqa += n[2] * az;
+                const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
+                const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
+                accum(S, T, n, 0.0, ll[j] + (ll[j] * rp - rc) * rs, false);
             }
+            store_slab(S, T, false);
             if (var_thread) {
-                double q[6], qa[6], qd[6];
-                box_q(s_c, false, q); box_q(s_dca, true, qa); box_q(s_dc, true, qd);
+                double W[6], u[6], dqa[6];
+                box_dq(s_dca, dqa);
 #pragma unroll
                 for (int e = 0; e < 6; e++) {
-                    if (!bact[e]) continue;
-                    double dsa, dla;
-                    row_affine_step(bs[e], bl[e], q[e], qa[e], dsa, dla);
-                    const double rp = bs[e] - q[e], rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                    const double ds = qd[e] - rp;
-                    const double dl = (-rc - bl[e] * ds) / bs[e];
-                    if (pass == 0) amax = fmin(amax, fmin(ratio(bs[e], ds), ratio(bl[e], dl)));
-                    else { bs[e] += alpha * ds; bl[e] += alpha * dl; }
+                    W[e] = 0.0; u[e] = 0.0;
+                    if (!(bmask >> e & 1u)) continue;
+                    const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                    const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
+                    const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
+                    u[e] = bl[e] + (bl[e] * rp - rc) * rs;
                 }
-            }
-            if (pass == 0) {
-                red[0] = 0; red[1] = 0; red[2] = amax; red[3] = 0;
-                block_reduce4<C>(red, s_red, red_phase);
-                alpha = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
+                store_box(W, u, false);
             }
         }
-        __syncthreads();          // every thread is done reading s_c / s_dc
+        assemble(false);
+        factor_solve(false);
+        if (tid < NR) s_dy[tid] = s_rhs[tid];
+        __syncthreads();
+        if (var_thread) s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
+        __syncthreads();
+        // ---- sweep D: step length of the combined direction
+        {
+            double ax, ay, az, dx, dy, dz;
+            if (cp_valid) { load_cp(s_dca, ax, ay, az); load_cp(s_dc, dx, dy, dz); } else { ax = ay = az = dx = dy = dz = 0; }
+            MinRatio mr; mr.init();
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                if (!(lmask >> j & 1u)) continue;
+                const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+                double dqa = n[0] * ax + n[1] * ay, dq = n[0] * dx + n[1] * dy;
+                if (D == 3) { dqa += n[2] * az; dq += n[2] * dz; }
+                const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
+                const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
+                const double ds = dq - rp, dl = -(rc + ll[j] * ds) * rs;
+                mr.add(ls[j], ds); mr.add(ll[j], dl);
+            }
+            if (var_thread) {
+                double dqa[6], dq[6];
+                box_dq(s_dca, dqa); box_dq(s_dc, dq);
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    if (!(bmask >> e & 1u)) continue;
+                    const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                    const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
+                    const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
+                    const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
+                    mr.add(bs[e], ds); mr.add(bl[e], dl);
+                }
+            }
+            red[0] = 0; red[1] = 0; red[2] = mr.value(); red[3] = 0;
+            block_reduce4<C>(red, s_red, red_phase);
+            alpha = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
+            have_step = true;
+        }
+        // the reduced iterate moves now; the rows follow in the next sweep A (s_dca / s_dc stay valid until then)
         if (tid < NR) s_y[tid] += alpha * s_dy[tid];
         __syncthreads();
-        compute_full(s_y, s_x0, s_c);
-        __syncthreads();
+        if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+        // (assemble() starts with a barrier before anything reads s_c)
     }
 
     // ---------------------------------------------------------------- outputs
-    // stationarity: || Z^T (grad f - A^T lam) ||_inf  (reuse the sweep with u = lam)
+    // true primal residual of the returned point, recomputed from the row constants
+    double rp_true = 0.0;
+    __syncthreads();
     {
+        double cx, cy, cz;
+        if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
         double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            if (!lact[j]) continue;
-            const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
-            T[0] += ll[j] * n[0]; T[1] += ll[j] * n[1];
-            if (D == 3) T[2] += ll[j] * n[2];
+            if (!(lmask >> j & 1u)) continue;
+            const int oi = grp + G * j;
+            const double* n = s_nrm + (oi * M + m_cp) * 3;
+            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            if (D == 3) q += n[2] * cz;
+            rp_true = fmax(rp_true, fabs(ls[j] - q));
+            accum(S, T, n, 0.0, ll[j], false);
         }
         store_slab(S, T, false);
-        if (var_thread) { s_uB[tid] = bl[0] - bl[1]; s_uV[tid] = bl[3] - bl[2]; s_uA[tid] = bl[5] - bl[4]; }
+        if (var_thread) {
+            const double* cc = s_c + k_v * NCP + cp_v;
+            const double c0 = cc[0];
+            double dv = 0.0, da = 0.0, q[6];
+            if (has_vel) dv = cc[1] - c0;
+            if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
+            q[0] = c0 - s_lb[k_v * M + m_v]; q[1] = s_ub[k_v * M + m_v] - c0;
+            q[2] = s_vlim[k_v] - dv; q[3] = s_vlim[k_v] + dv; q[4] = s_alim[k_v] - da; q[5] = s_alim[k_v] + da;
+            double W[6] = {0, 0, 0, 0, 0, 0}, u[6];
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                const bool on = bmask >> e & 1u;
+                u[e] = on ? bl[e] : 0.0;
+                if (on) rp_true = fmax(rp_true, fabs(bs[e] - q[e]));
+            }
+            store_box(W, u, false);
+        }
+        // stationarity || Z^T (grad f - A^T lam) ||_inf through the same projection (u = lam)
         assemble(false);
     }
     double rd_inf = 0.0, cost = 0.0;
@@ -798,15 +900,16 @@ pdip_solve_kernel(const SolveParams p) {
         if (i_v == 5) { const double e = s_c[tid] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
         p.ctrl_out[(size_t) agent * NV + tid] = s_c[tid];
     }
-    red[0] = cost; red[1] = 0; red[2] = 0; red[3] = rd_inf;
+    red[0] = cost; red[1] = 0; red[2] = -rp_true; red[3] = rd_inf;
     block_reduce4<C>(red, s_red, red_phase);
-    if (status == ST_MAX_ITER && rp_inf > 1e-6) status = ST_INFEASIBLE;
+    rp_true = -red[2];
+    if (status == ST_MAX_ITER && rp_true > 1e-6) status = ST_INFEASIBLE;
     if (tid == 0) {
         p.cost_out[agent] = red[0];
         p.status_out[agent] = status;
         if (p.iters_out) p.iters_out[agent] = it;
         if (p.kkt_out) {
-            p.kkt_out[agent * 4 + 0] = red[3]; p.kkt_out[agent * 4 + 1] = rp_inf;
+            p.kkt_out[agent * 4 + 0] = red[3]; p.kkt_out[agent * 4 + 1] = rp_true;
             p.kkt_out[agent * 4 + 2] = (double) bad_piv; p.kkt_out[agent * 4 + 3] = mu;
         }
     }
@@ -815,15 +918,15 @@ pdip_solve_kernel(const SolveParams p) {
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
             const int oi = grp + G * j;
-            if (cp_valid && oi < C::KMAX) du[(oi * M + m_cp) * 6 + i_cp] = lact[j] ? ll[j] : 0.0;
+            if (cp_valid && oi < C::KMAX) du[(oi * M + m_cp) * 6 + i_cp] = (lmask >> j & 1u) ? ll[j] : 0.0;
         }
         if (var_thread) {
             // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2
             const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
             double* db = du + C::KMAX * M * 6 + tid * 6;
-            db[0] = bact[0] ? bl[0] : 0.0; db[1] = bact[1] ? bl[1] : 0.0;
-            db[2] = bact[2] ? bl[2] * sv : 0.0; db[3] = bact[3] ? bl[3] * sv : 0.0;
-            db[4] = bact[4] ? bl[4] * sa : 0.0; db[5] = bact[5] ? bl[5] * sa : 0.0;
+            db[0] = (bmask & 1u) ? bl[0] : 0.0; db[1] = (bmask & 2u) ? bl[1] : 0.0;
+            db[2] = (bmask & 4u) ? bl[2] * sv : 0.0; db[3] = (bmask & 8u) ? bl[3] * sv : 0.0;
+            db[4] = (bmask & 16u) ? bl[4] * sa : 0.0; db[5] = (bmask & 32u) ? bl[5] * sa : 0.0;
         }
     }
 }

@@ -32,8 +32,8 @@ class PlannerConfig:
     world_max: tuple = (10.0, 10.0, 2.5)
     z_2d: float = 1.0
     max_obs: int = 40
-    max_iter: int = 60
-    tol: float = 1e-8
+    max_iter: int = 0            # 0 = library default (60)
+    tol: float = 0.0             # 0 = library default (1e-11 on the mean complementarity gap)
 
 
 def bernstein_from_poly(coef: np.ndarray, t0: float, t1: float) -> np.ndarray:

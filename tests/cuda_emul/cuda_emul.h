@@ -80,6 +80,10 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) {
     __syncwarp();
     return r;
 }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+#undef __launch_bounds__
+#define __launch_bounds__(...)
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
