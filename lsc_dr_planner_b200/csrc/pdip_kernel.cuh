@@ -29,7 +29,7 @@
 #define LSCQP_DYN_SMEM(name) extern __shared__ double name[]
 #endif
 
-namespace lscqp {
+namespace lscqp {   // @phase helpers
 
 struct SolveParams {
     int n_agents;
@@ -70,7 +70,10 @@ struct Cfg {
     static constexpr int NZS = 3 * D;                    // reduced variables per stage
     static constexpr int NR = TERM ? (M - 1) * NZS + D : M * NZS;
     static constexpr int BW = 2 * NZS - 1;               // half bandwidth of the reduced matrix
-    static constexpr int LD = NR | 1;                    // odd leading dimension
+    static constexpr int NRP = ((NR + 2) / 3) * 3;       // padded to whole 3x3 panels (identity rows)
+    static constexpr int NB = NRP / 3;                   // panels
+    static constexpr int BWS = BW + 2;                   // stored / assembled half bandwidth (panel overhang)
+    static constexpr int LD = NRP | 1;                   // odd leading dimension
     static constexpr int NS = D * (D + 1) / 2;           // unique entries of a DxD symmetric block
     static constexpr int KMAX = G * KPT;
     static constexpr int NPAIR = BW * (BW + 1) / 2;      // trailing-update pairs per Cholesky column
@@ -103,10 +106,10 @@ struct Cfg {
     static constexpr int O_BLK = O_UA + NV;              // [D][M][36]
     static constexpr int O_RFULL = O_BLK + D * M * 36;   // [NV]
     static constexpr int O_A = O_RFULL + NV;             // [NR][LD]
-    static constexpr int O_RHS = O_A + NR * LD;          // [NR]
-    static constexpr int O_DIAG0 = O_RHS + NR;           // [NR]
-    static constexpr int O_INVD = O_DIAG0 + NR;          // [NR]
-    static constexpr int O_RED = O_INVD + NR;            // [2][NW][NRED]
+    static constexpr int O_RHS = O_A + NRP * LD;         // [NRP]
+    static constexpr int O_DIAG0 = O_RHS + NRP;          // [NRP]
+    static constexpr int O_INVD = O_DIAG0 + NRP;         // [NRP]
+    static constexpr int O_RED = O_INVD + NRP;           // [2][NW][NRED]
     static constexpr int O_TT = O_RED + 2 * NW * NRED;   // T[3][3] then TT[3][3][3]
     static constexpr int O_RTAB = O_TT + 36;             // int[3*NR]: stage, dim, j (-1 = collapsed terminal point)
     static constexpr int O_END = O_RTAB + (3 * NR + 1) / 2;
@@ -200,7 +203,7 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// CTA-wide all-reduce of 4 values: v[0], v[1] summed, v[2] min, v[3] max.  One barrier (ping-pong scratch).
+// CTA-wide all-reduce of 4 values: v[0], v[1] summed, v[2] min, v[3] max.  One barrier (ping-pong scratch).   // @phase reduce4
 template <class C>
 __device__ __forceinline__ void block_reduce4(double* v, double* red, int& phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -217,47 +220,103 @@ __device__ __forceinline__ void block_reduce4(double* v, double* red, int& phase
 }
 
 // ---------------------------------------------------------------------------------------------
-// banded Cholesky + triangular solves, executed by warp 0 only (callers bracket with __syncthreads)
+// Banded Cholesky and triangular solves in shared memory, executed by warp 0 only (callers bracket
+// with __syncthreads).  Right-looking with 3-column panels: the 3x3 diagonal block is factorised in
+// closed form by every lane (broadcast loads, no communication), each lane then finishes the three
+// L entries of one row below the panel in registers, and the trailing window is updated with
+// 3-term dot products -- 3 warp barriers per panel instead of 6.
+struct Panel3 {                 // L3 = [l11 0 0; l21 l22 0; l31 l32 l33], i* = 1/l**   // @phase chol
+    double l21, l31, l32, i1, i2, i3;
+};
+
+template <class C>
+__device__ __forceinline__ Panel3 factor_diag3(const double* A, const double* diag0, int c0, int& bad) {
+    Panel3 P;
+    const double p11 = A[c0 * C::LD + c0], p21 = A[(c0 + 1) * C::LD + c0], p31 = A[(c0 + 2) * C::LD + c0];
+    const double p22 = A[(c0 + 1) * C::LD + c0 + 1], p32 = A[(c0 + 2) * C::LD + c0 + 1], p33 = A[(c0 + 2) * C::LD + c0 + 2];
+    double d = p11;
+    if (!(d > 1e-13 * diag0[c0])) { d = 1e300; bad++; }         // pivot guard: freeze that direction
+    P.i1 = rsqrt(d);
+    P.l21 = p21 * P.i1; P.l31 = p31 * P.i1;
+    d = p22 - P.l21 * P.l21;
+    if (!(d > 1e-13 * diag0[c0 + 1])) { d = 1e300; bad++; }
+    P.i2 = rsqrt(d);
+    P.l32 = (p32 - P.l31 * P.l21) * P.i2;
+    d = p33 - P.l31 * P.l31 - P.l32 * P.l32;
+    if (!(d > 1e-13 * diag0[c0 + 2])) { d = 1e300; bad++; }
+    P.i3 = rsqrt(d);
+    return P;
+}
+
 template <class C>
 __device__ __forceinline__ int chol_banded(double* A, const double* diag0, double* invd, const int* pr_i, const int* pr_k) {
     const int lane = threadIdx.x & 31;
     int bad = 0;
-    for (int j = 0; j < C::NR; j++) {
-        double d = A[j * C::LD + j];
-        if (!(d > 1e-13 * diag0[j])) { d = 1e300; bad++; }     // pivot guard: freeze that direction
-        const double inv = rsqrt(d);
-        if (lane == 0) invd[j] = inv;
-        const int i = j + 1 + lane;
-        if (lane < C::BW && i < C::NR) A[i * C::LD + j] *= inv;
+    for (int J = 0; J < C::NB; J++) {
+        const int c0 = 3 * J;
+        const Panel3 P = factor_diag3<C>(A, diag0, c0, bad);
+        const int i = c0 + 3 + lane;
+        double a0 = 0, a1 = 0, a2 = 0;
+        const bool row = lane < C::BW && i < C::NRP;
+        if (row) { a0 = A[i * C::LD + c0]; a1 = A[i * C::LD + c0 + 1]; a2 = A[i * C::LD + c0 + 2]; }
+        __syncwarp();                                           // every lane has read the diagonal block
+        if (lane == 0) {
+            invd[c0] = P.i1; invd[c0 + 1] = P.i2; invd[c0 + 2] = P.i3;
+            A[(c0 + 1) * C::LD + c0] = P.l21; A[(c0 + 2) * C::LD + c0] = P.l31; A[(c0 + 2) * C::LD + c0 + 1] = P.l32;
+        }
+        if (row) {
+            const double l0 = a0 * P.i1;
+            const double l1 = (a1 - l0 * P.l21) * P.i2;
+            const double l2 = (a2 - l0 * P.l31 - l1 * P.l32) * P.i3;
+            A[i * C::LD + c0] = l0; A[i * C::LD + c0 + 1] = l1; A[i * C::LD + c0 + 2] = l2;
+        }
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < C::NPR; t++) {
-            const int ii = j + 1 + pr_i[t], kk = j + 1 + pr_k[t];
-            if (pr_i[t] >= 0 && ii < C::NR) A[ii * C::LD + kk] -= A[ii * C::LD + j] * A[kk * C::LD + j];
+            const int ii = c0 + 3 + pr_i[t], kk = c0 + 3 + pr_k[t];
+            if (pr_i[t] >= 0 && ii < C::NRP) {
+                const double* li = A + ii * C::LD + c0;
+                const double* lk = A + kk * C::LD + c0;
+                A[ii * C::LD + kk] -= li[0] * lk[0] + li[1] * lk[1] + li[2] * lk[2];
+            }
         }
         __syncwarp();
     }
     return bad;
 }
 
-// solves (L L^T) x = b in place (b in shared memory), L strictly-lower entries in A, 1/L_jj in invd
+// solves (L L^T) x = b in place (b in shared memory)   // @phase trisolve
 template <class C>
 __device__ __forceinline__ void chol_solve(const double* A, const double* invd, double* b) {
     const int lane = threadIdx.x & 31;
-    for (int j = 0; j < C::NR; j++) {
-        const double z = b[j] * invd[j];
+    for (int J = 0; J < C::NB; J++) {
+        const int c0 = 3 * J;
+        const double l21 = A[(c0 + 1) * C::LD + c0], l31 = A[(c0 + 2) * C::LD + c0], l32 = A[(c0 + 2) * C::LD + c0 + 1];
+        const double z0 = b[c0] * invd[c0];
+        const double z1 = (b[c0 + 1] - l21 * z0) * invd[c0 + 1];
+        const double z2 = (b[c0 + 2] - l31 * z0 - l32 * z1) * invd[c0 + 2];
+        const int i = c0 + 3 + lane;
+        double bi = 0;
+        const bool row = lane < C::BW && i < C::NRP;
+        if (row) bi = b[i] - A[i * C::LD + c0] * z0 - A[i * C::LD + c0 + 1] * z1 - A[i * C::LD + c0 + 2] * z2;
         __syncwarp();
-        if (lane == 0) b[j] = z;
-        const int i = j + 1 + lane;
-        if (lane < C::BW && i < C::NR) b[i] -= A[i * C::LD + j] * z;
+        if (lane == 0) { b[c0] = z0; b[c0 + 1] = z1; b[c0 + 2] = z2; }
+        if (row) b[i] = bi;
         __syncwarp();
     }
-    for (int j = C::NR - 1; j >= 0; j--) {
-        const double x = b[j] * invd[j];
+    for (int J = C::NB - 1; J >= 0; J--) {
+        const int c0 = 3 * J;
+        const double l21 = A[(c0 + 1) * C::LD + c0], l31 = A[(c0 + 2) * C::LD + c0], l32 = A[(c0 + 2) * C::LD + c0 + 1];
+        const double x2 = b[c0 + 2] * invd[c0 + 2];
+        const double x1 = (b[c0 + 1] - l32 * x2) * invd[c0 + 1];
+        const double x0 = (b[c0] - l21 * x1 - l31 * x2) * invd[c0];
+        const int i = c0 - 1 - lane;                            // rows above the panel that couple to it
+        double bi = 0;
+        const bool row = lane < C::BW && i >= 0;
+        if (row) bi = b[i] - A[c0 * C::LD + i] * x0 - A[(c0 + 1) * C::LD + i] * x1 - A[(c0 + 2) * C::LD + i] * x2;
         __syncwarp();
-        if (lane == 0) b[j] = x;
-        const int i = j - 1 - lane;
-        if (lane < C::BW && i >= 0) b[i] -= A[j * C::LD + i] * x;
+        if (lane == 0) { b[c0] = x0; b[c0 + 1] = x1; b[c0 + 2] = x2; }
+        if (row) b[i] = bi;
         __syncwarp();
     }
 }
@@ -266,7 +325,7 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* invd, 
 // Row algebra.  Row convention: q(c) >= 0, slack s > 0, multiplier lam > 0.  Every row starts with
 // the same primal residual rp = s - q (the start-up shift) and every step scales it by (1 - alpha),
 // so rp is one scalar for the whole QP and neither q nor the row constants are needed after start-up.
-struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a fraction (no division per row)
+struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a fraction (no division per row)   // @phase minratio
     double num, den;
     __device__ __forceinline__ void init() { num = 1.0; den = 0.0; }
     __device__ __forceinline__ void add(double v, double dv) {
@@ -278,7 +337,7 @@ struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a 
 // ---------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS)
-pdip_solve_kernel(const SolveParams p) {
+pdip_solve_kernel(const SolveParams p) {   // @phase setup
     constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, LD = C::LD, NS = C::NS;
     constexpr int G = C::G, KPT = C::KPT, NT = C::NT;
     LSCQP_DYN_SMEM(sm);
@@ -428,7 +487,7 @@ pdip_solve_kernel(const SolveParams p) {
 
     // helpers -----------------------------------------------------------------------------------
     // directional change of the six box rows of this thread for a full-space direction dv
-    auto box_dq = [&](const double* dv, double* dq) {
+    auto box_dq = [&](const double* dv, double* dq) {   // @phase row_helpers
         const double* d = dv + k_v * NCP + cp_v;
         const double d0 = d[0];
         double dvv = 0.0, daa = 0.0;
@@ -470,7 +529,7 @@ pdip_solve_kernel(const SolveParams p) {
     };
 
     // reduced-matrix entry (r1 >= r2) from the full-space blocks ("projection")
-    auto red_entry = [&](int r1, int r2) -> double {
+    auto red_entry = [&](int r1, int r2) -> double {   // @phase red_entry
         const int s1 = s_rtab[3 * r1], k1 = s_rtab[3 * r1 + 1], j1 = s_rtab[3 * r1 + 2];
         const int s2 = s_rtab[3 * r2], k2 = s_rtab[3 * r2 + 1], j2 = s_rtab[3 * r2 + 2];
         double val = 0.0;
@@ -519,7 +578,7 @@ pdip_solve_kernel(const SolveParams p) {
     };
 
     // sum the group slabs, build the 6x6 blocks (withS) and the full-space rhs  -grad f + A^T u, then project.
-    auto assemble = [&](bool withS) {
+    auto assemble = [&](bool withS) {   // @phase assemble
         __syncthreads();
         for (int e = tid; e < NCP * D; e += NT) {
             double a = slabT[e];
@@ -571,20 +630,20 @@ pdip_solve_kernel(const SolveParams p) {
         }
         __syncthreads();
         if (withS) {
-            for (int e = tid; e < NR * (C::BW + 1); e += NT) {
-                const int r1 = e / (C::BW + 1), r2 = r1 - e % (C::BW + 1);
+            for (int e = tid; e < C::NRP * (C::BWS + 1); e += NT) {
+                const int r1 = e / (C::BWS + 1), r2 = r1 - e % (C::BWS + 1);
                 if (r2 < 0) continue;
-                const double val = red_entry(r1, r2);
+                const double val = r1 < NR ? red_entry(r1, r2) : (r1 == r2 ? 1.0 : 0.0);    // identity padding rows
                 s_A[r1 * LD + r2] = val;
                 if (r1 == r2) s_diag0[r1] = val;
             }
         }
-        if (tid < NR) s_rhs[tid] = reduce_from_full<C>(s_rfull, tid);
+        if (tid < C::NRP) s_rhs[tid] = tid < NR ? reduce_from_full<C>(s_rfull, tid) : 0.0;
         __syncthreads();
     };
 
     int bad_piv = 0;
-    auto factor_solve = [&](bool factor) {
+    auto factor_solve = [&](bool factor) {   // @phase factor_solve_call
         if (tid < 32) {
             if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
             chol_solve<C>(s_A, s_invd, s_rhs);
@@ -592,7 +651,7 @@ pdip_solve_kernel(const SolveParams p) {
         __syncthreads();
     };
 
-    // ---------------------------------------------------------------- initial point (least squares)
+    // ---------------------------------------------------------------- initial point (least squares)   // @phase init_point
     // minimise f(y) + 1/2 |q(y)|^2 : W = 1, u = -q at the hover point; then s = q, lam = -q, both shifted
     // into the positive orthant (Mehrotra / CVXOPT start).  q of every row is kept in ls[] / bs[] meanwhile.
     {
@@ -664,7 +723,7 @@ pdip_solve_kernel(const SolveParams p) {
         rp = shift_s;
     }
 
-    // ---------------------------------------------------------------- main loop
+    // ---------------------------------------------------------------- main loop   // @phase sweepA
     int status = ST_MAX_ITER, it = 0;
     double mu = 0.0, sigmu = 0.0, alpha = 0.0;
     bool have_step = false;       // a (dca, dc, sigmu, alpha) step is pending and is applied by the next sweep A
@@ -723,14 +782,14 @@ pdip_solve_kernel(const SolveParams p) {
         if (mu < p.mu_tol && fabs(rp) < p.rp_tol) { status = ST_OK; break; }
         if (it == p.max_iter) break;
 
-        // ---- predictor
+        // ---- predictor   // @phase predictor_glue
         assemble(true);
         factor_solve(true);
         if (tid < NR) s_dy[tid] = s_rhs[tid];
         __syncthreads();
         if (var_thread) s_dca[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
         __syncthreads();
-        // ---- sweep B: affine step length and centering parameter
+        // ---- sweep B: affine step length and centering parameter   // @phase sweepB
         {
             double ax, ay, az;
             if (cp_valid) load_cp(s_dca, ax, ay, az); else { ax = ay = az = 0; }
@@ -769,7 +828,7 @@ pdip_solve_kernel(const SolveParams p) {
             if (sg > 1.0) sg = 1.0;
             sigmu = sg * mu;
         }
-        // ---- sweep C: corrector right-hand side
+        // ---- sweep C: corrector right-hand side   // @phase sweepC
         {
             double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
             double ax, ay, az;
@@ -807,7 +866,7 @@ pdip_solve_kernel(const SolveParams p) {
         __syncthreads();
         if (var_thread) s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
         __syncthreads();
-        // ---- sweep D: step length of the combined direction
+        // ---- sweep D: step length of the combined direction   // @phase sweepD
         {
             double ax, ay, az, dx, dy, dz;
             if (cp_valid) { load_cp(s_dca, ax, ay, az); load_cp(s_dc, dx, dy, dz); } else { ax = ay = az = dx = dy = dz = 0; }
@@ -849,7 +908,7 @@ pdip_solve_kernel(const SolveParams p) {
         // (assemble() starts with a barrier before anything reads s_c)
     }
 
-    // ---------------------------------------------------------------- outputs
+    // ---------------------------------------------------------------- outputs   // @phase outputs
     // true primal residual of the returned point, recomputed from the row constants
     double rp_true = 0.0;
     __syncthreads();
