@@ -325,11 +325,29 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* invd, 
 // Row algebra.  Row convention: q(c) >= 0, slack s > 0, multiplier lam > 0.  Every row starts with
 // the same primal residual rp = s - q (the start-up shift) and every step scales it by (1 - alpha),
 // so rp is one scalar for the whole QP and neither q nor the row constants are needed after start-up.
+// 1/x for normal positive x: hardware seed (2^-20) + three Newton steps, no special-case branch
+__device__ __forceinline__ double fast_rcp(double x) {
+#ifdef LSCQP_CUDA_EMUL
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#endif
+}
+
 struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a fraction (no division per row)   // @phase minratio
     double num, den;
     __device__ __forceinline__ void init() { num = 1.0; den = 0.0; }
     __device__ __forceinline__ void add(double v, double dv) {
-        if (dv < 0.0 && v * den < num * (-dv)) { num = v; den = -dv; }
+        const bool t = dv < 0.0 && v * den < num * (-dv);
+        num = t ? v : num; den = t ? -dv : den;
     }
     __device__ __forceinline__ double value() const { return den > 0.0 ? num / den : INFINITY; }
 };
@@ -449,7 +467,16 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (ts < 1) ts = 1;
         for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
     }
-    for (int e = tid; e < K * M * 3; e += NT) s_nrm[e] = p.normals[(size_t) obs0 * M * 3 + e];
+    for (int e = tid; e < K * M; e += NT) {
+        // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference
+        // (traj_optimizer.cpp:409-411): here they become the constant row 0.c >= -1, which never binds
+        const double* g = p.normals + ((size_t) obs0 * M + e) * 3;
+        double nx = g[0], ny = g[1], nz = g[2];
+        const float fx = (float) nx, fy = (float) ny, fz = (float) nz;
+        const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
+        if (sqrt((double) nsq) < 1e-5) { nx = 0.0; ny = 0.0; nz = 0.0; }
+        s_nrm[e * 3] = nx; s_nrm[e * 3 + 1] = ny; s_nrm[e * 3 + 2] = nz;
+    }
     // starting point: every free control point at the current position (hover)
     if (tid < NR) {
         int k;
@@ -462,25 +489,16 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     // ---- per-thread row state (registers): slack and multiplier of every owned row
     double ls[KPT], ll[KPT];
     double bs[6], bl[6];
-    unsigned lmask = 0;
+    // rows of this thread: obstacles grp, grp + G, ... < K on its control point (none for the fixed points)
+    const int nrow = (lsc_thread && K > grp) ? (K - grp + G - 1) / G : 0;
 #pragma unroll
-    for (int j = 0; j < KPT; j++) {
-        const int oi = grp + G * j;
-        ls[j] = 1.0; ll[j] = 0.0;
-        if (lsc_thread && oi < K) {
-            const double* n = s_nrm + (oi * M + m_cp) * 3;
-            // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped, traj_optimizer.cpp:409-411
-            const float fx = (float) n[0], fy = (float) n[1], fz = (float) n[2];
-            const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
-            if (!(sqrt((double) nsq) < 1e-5)) lmask |= 1u << j;
-        }
-    }
+    for (int j = 0; j < KPT; j++) { ls[j] = 1.0; ll[j] = 0.0; }
 #pragma unroll
     for (int e = 0; e < 6; e++) { bs[e] = 1.0; bl[e] = 0.0; }
 
     double red[4];
     {
-        red[0] = (double) (__popc(lmask) + __popc(bmask)); red[1] = 0; red[2] = 0; red[3] = 0;
+        red[0] = (double) (nrow + __popc(bmask)); red[1] = 0; red[2] = 0; red[3] = 0;
         block_reduce4<C>(red, s_red, red_phase);       // (barrier: s_c is complete after this)
     }
     const double n_rows = red[0];
@@ -660,11 +678,12 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            if (!(lmask >> j & 1u)) continue;
+            if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
             double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
             if (D == 3) q += n[2] * cz;
+            if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             ls[j] = q;
             accum(S, T, n, 1.0, -q, true);
         }
@@ -699,7 +718,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         double qmin = INFINITY, qmax = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            if (!(lmask >> j & 1u)) continue;
+            if (j >= nrow) break;
             const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
             double dq = n[0] * dx + n[1] * dy;
             if (D == 3) dq += n[2] * dz;
@@ -717,7 +736,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
         const double shift_l = (red[3] >= 0.0) ? 1.0 + red[3] : 0.0;        // lam = -s; alpha_d = max(s) >= 0 -> lam += 1 + alpha_d
 #pragma unroll
-        for (int j = 0; j < KPT; j++) if (lmask >> j & 1u) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
+        for (int j = 0; j < KPT; j++) if (j < nrow) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
 #pragma unroll
         for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
         rp = shift_s;
@@ -738,18 +757,18 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             double sl = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!(lmask >> j & 1u)) continue;
+                if (j >= nrow) break;
                 const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
                 if (have_step) {
                     double dqa = n[0] * ax + n[1] * ay, dq = n[0] * dx + n[1] * dy;
                     if (D == 3) { dqa += n[2] * az; dq += n[2] * dz; }
-                    const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                    const double rs = fast_rcp(ls[j]), W = ll[j] * rs;
                     const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
                     const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
                     const double ds = dq - rp, dl = -(rc + ll[j] * ds) * rs;
                     ls[j] += alpha * ds; ll[j] += alpha * dl;
                 }
-                const double W = ll[j] / ls[j];
+                const double W = ll[j] * fast_rcp(ls[j]);
                 sl += ls[j] * ll[j];
                 accum(S, T, n, W, W * rp_new, true);
             }
@@ -762,13 +781,13 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                     W[e] = 0.0; u[e] = 0.0;
                     if (!(bmask >> e & 1u)) continue;
                     if (have_step) {
-                        const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                        const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
                         const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
                         const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
                         const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
                         bs[e] += alpha * ds; bl[e] += alpha * dl;
                     }
-                    W[e] = bl[e] / bs[e]; u[e] = W[e] * rp_new;
+                    W[e] = bl[e] * fast_rcp(bs[e]); u[e] = W[e] * rp_new;
                     sl += bs[e] * bl[e];
                 }
                 store_box(W, u, true);
@@ -797,11 +816,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!(lmask >> j & 1u)) continue;
+                if (j >= nrow) break;
                 const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
                 double dqa = n[0] * ax + n[1] * ay;
                 if (D == 3) dqa += n[2] * az;
-                const double W = ll[j] / ls[j];
+                const double W = ll[j] * fast_rcp(ls[j]);
                 const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
                 mr.add(ls[j], dsa); mr.add(ll[j], dla);
                 s1 += ls[j] * dla + ll[j] * dsa; s2 += dsa * dla;
@@ -812,7 +831,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
                 for (int e = 0; e < 6; e++) {
                     if (!(bmask >> e & 1u)) continue;
-                    const double W = bl[e] / bs[e];
+                    const double W = bl[e] * fast_rcp(bs[e]);
                     const double dsa = dqa[e] - rp, dla = -bl[e] - W * dsa;
                     mr.add(bs[e], dsa); mr.add(bl[e], dla);
                     s1 += bs[e] * dla + bl[e] * dsa; s2 += dsa * dla;
@@ -835,11 +854,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (cp_valid) load_cp(s_dca, ax, ay, az); else { ax = ay = az = 0; }
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!(lmask >> j & 1u)) continue;
+                if (j >= nrow) break;
                 const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
                 double dqa = n[0] * ax + n[1] * ay;
                 if (D == 3) dqa += n[2] * az;
-                const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                const double rs = fast_rcp(ls[j]), W = ll[j] * rs;
                 const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
                 const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
                 accum(S, T, n, 0.0, ll[j] + (ll[j] * rp - rc) * rs, false);
@@ -852,7 +871,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 for (int e = 0; e < 6; e++) {
                     W[e] = 0.0; u[e] = 0.0;
                     if (!(bmask >> e & 1u)) continue;
-                    const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                    const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
                     const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
                     u[e] = bl[e] + (bl[e] * rp - rc) * rs;
@@ -873,11 +892,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             MinRatio mr; mr.init();
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
-                if (!(lmask >> j & 1u)) continue;
+                if (j >= nrow) break;
                 const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
                 double dqa = n[0] * ax + n[1] * ay, dq = n[0] * dx + n[1] * dy;
                 if (D == 3) { dqa += n[2] * az; dq += n[2] * dz; }
-                const double rs = 1.0 / ls[j], W = ll[j] * rs;
+                const double rs = fast_rcp(ls[j]), W = ll[j] * rs;
                 const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
                 const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
                 const double ds = dq - rp, dl = -(rc + ll[j] * ds) * rs;
@@ -889,7 +908,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
                 for (int e = 0; e < 6; e++) {
                     if (!(bmask >> e & 1u)) continue;
-                    const double rs = 1.0 / bs[e], Wo = bl[e] * rs;
+                    const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
                     const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
                     const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
@@ -918,11 +937,12 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            if (!(lmask >> j & 1u)) continue;
+            if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
             double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
             if (D == 3) q += n[2] * cz;
+            if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             rp_true = fmax(rp_true, fabs(ls[j] - q));
             accum(S, T, n, 0.0, ll[j], false);
         }
@@ -977,7 +997,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
             const int oi = grp + G * j;
-            if (cp_valid && oi < C::KMAX) du[(oi * M + m_cp) * 6 + i_cp] = (lmask >> j & 1u) ? ll[j] : 0.0;
+            if (cp_valid && oi < C::KMAX) {
+                const double* n = s_nrm + (oi * M + m_cp) * 3;
+                const bool real_row = j < nrow && !(n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0);
+                du[(oi * M + m_cp) * 6 + i_cp] = real_row ? ll[j] : 0.0;
+            }
         }
         if (var_thread) {
             // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2
