@@ -107,6 +107,9 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
         const int*    obs_offsets,  /* [n_agents+1]                                              */
         const double* normals,      /* [sum K][M][3]                                             */
         const double* rhs,          /* [sum K][M][6]                                             */
+        const float*  initial_traj, /* [n_agents][M][6][3] optional (NULL = cold start): the initial_traj the
+                                       reference passes to TrajOptimizer::solve; used only as the solver's
+                                       starting point, never in the model (traj_optimizer.cpp:216-218)  */
         double* ctrl_out,           /* [n_agents][dim][M][6]  index order of traj_optimizer.cpp:241 */
         double* cost_out,           /* [n_agents]  objective incl. constant (cplex.getObjValue) */
         int*    status_out,         /* [n_agents]  LSCQP_OK | MAX_ITER | INFEASIBLE | NUMERICAL */
@@ -119,7 +122,7 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
  * ctrl/cost/status (and the optional outputs) back, and synchronises the stream. */
 int lscqp_solve_host(lscqp_handle* h, int n_agents,
         const float* state, const float* goal, const double* limits, const float* sfc,
-        const int* obs_offsets, const double* normals, const double* rhs,
+        const int* obs_offsets, const double* normals, const double* rhs, const float* initial_traj,
         double* ctrl_out, double* cost_out, int* status_out, int* iters_out, double* kkt_out,
         double* dual_out);
 

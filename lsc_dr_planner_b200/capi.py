@@ -129,9 +129,9 @@ class LscQp:
 
     # ------------------------------------------------------------------ device entry points
     def solve_batch(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status,
-                    iters=None, kkt=None, dual=None, stream=0):
+                    iters=None, kkt=None, dual=None, stream=0, initial_traj=None):
         self._check(self.lib.lscqp_solve_batch(self.h, n, _dp(state), _dp(goal), _dp(limits), _dp(sfc), _dp(obs_offsets),
-                                               _dp(normals), _dp(rhs), _dp(ctrl), _dp(cost), _dp(status), _dp(iters),
+                                               _dp(normals), _dp(rhs), _dp(initial_traj), _dp(ctrl), _dp(cost), _dp(status), _dp(iters),
                                                _dp(kkt), _dp(dual), C.c_void_p(stream)))
 
     def assemble_lsc_batch(self, generator, n, own_traj, agent_meta, agent_goal, obs_offsets, obs_traj, obs_meta,
@@ -152,10 +152,11 @@ class LscQp:
 
     # ------------------------------------------------------------------ host entry points
     def solve_host(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status, iters=None,
-                   kkt=None, dual=None):
+                   kkt=None, dual=None, initial_traj=None):
         self._check(self.lib.lscqp_solve_host(self.h, n, _hp(state, np.float32), _hp(goal, np.float32),
                                               _hp(limits, np.float64), _hp(sfc, np.float32), _hp(obs_offsets, np.int32),
-                                              _hp(normals, np.float64), _hp(rhs, np.float64), _hp(ctrl, np.float64),
+                                              _hp(normals, np.float64), _hp(rhs, np.float64), _hp(initial_traj, np.float32),
+                                              _hp(ctrl, np.float64),
                                               _hp(cost, np.float64), _hp(status, np.int32), _hp(iters, np.int32),
                                               _hp(kkt, np.float64), _hp(dual, np.float64)))
 

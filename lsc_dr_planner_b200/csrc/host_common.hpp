@@ -65,6 +65,9 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     p.max_iter = c.max_iter > 0 ? c.max_iter : 60;
     p.mu_tol = c.tol > 0 ? c.tol : 1e-11;
     p.rp_tol = 1e-9;
+    p.mu0 = 0.1 * (c.w_terminal > 0 ? c.w_terminal : 1.0);   // warm start: initial complementarity target
+    p.warm_delta = 1e-3;                                      // warm start: minimum initial slack
+    p.warm_reject = 0.02;                                     // warm start: largest row violation still accepted
     p.dt = c.dt; p.w_t = c.w_terminal; p.w_c = c.w_control;
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }
     p.use_sfc = c.use_sfc;

@@ -107,8 +107,9 @@ extern "C" unsigned long long lscqp_launch_count(const lscqp_handle* h) { return
 
 extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* state, const float* goal,
                                  const double* limits, const float* sfc, const int* obs_offsets,
-                                 const double* normals, const double* rhs, double* ctrl_out, double* cost_out,
-                                 int* status_out, int* iters_out, double* kkt_out, double* dual_out, void* stream) {
+                                 const double* normals, const double* rhs, const float* initial_traj, double* ctrl_out,
+                                 double* cost_out, int* status_out, int* iters_out, double* kkt_out, double* dual_out,
+                                 void* stream) {
     if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
@@ -116,7 +117,7 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     SolveParams p = h->base;
     p.n_agents = n_agents;
     p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
-    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs; p.warm_traj = initial_traj;
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out; p.dual_stride = h->dual_stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -198,8 +199,8 @@ extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctr
 
 extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* state, const float* goal,
                                 const double* limits, const float* sfc, const int* obs_offsets,
-                                const double* normals, const double* rhs, double* ctrl_out, double* cost_out,
-                                int* status_out, int* iters_out, double* kkt_out, double* dual_out) {
+                                const double* normals, const double* rhs, const float* initial_traj, double* ctrl_out,
+                                double* cost_out, int* status_out, int* iters_out, double* kkt_out, double* dual_out) {
     if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
@@ -228,9 +229,14 @@ extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* stat
         CK(cudaMemcpyAsync(h->d_normals.p, normals, sumK * M * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->d_rhs.p, rhs, sumK * M * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    if (initial_traj) {
+        RESERVE(h->d_own, (size_t) n_agents * M * 18 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_own.p, initial_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     int rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
                                h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(),
-                               h->d_normals.as<double>(), h->d_rhs.as<double>(), h->d_ctrl.as<double>(),
+                               h->d_normals.as<double>(), h->d_rhs.as<double>(), initial_traj ? h->d_own.as<float>() : nullptr,
+                               h->d_ctrl.as<double>(),
                                h->d_cost.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), h->d_kkt.as<double>(),
                                dual_out ? h->d_dual.as<double>() : nullptr, st);
     if (rc) return rc;
@@ -288,8 +294,8 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     if (rc) return rc;
     rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
                            h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(), h->d_normals.as<double>(),
-                           h->d_rhs.as<double>(), h->d_ctrl.as<double>(), h->d_cost.as<double>(), h->d_status.as<int>(),
-                           h->d_iters.as<int>(), nullptr, nullptr, st);
+                           h->d_rhs.as<double>(), h->d_own.as<float>(), h->d_ctrl.as<double>(), h->d_cost.as<double>(),
+                           h->d_status.as<int>(), h->d_iters.as<int>(), nullptr, nullptr, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctrl_out, h->d_ctrl.p, (size_t) n_agents * h->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(cost_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -45,6 +45,8 @@ struct SolveParams {
     const int*    obs_offsets;  // [n+1]
     const double* normals;      // [sumK][M][3]
     const double* rhs;          // [sumK][M][6]   b = n.p + d
+    const float*  warm_traj;    // [n][M][6][3] initial_traj used as the starting point (may be null: cold start)
+    double mu0, warm_delta, warm_reject;   // warm start: complementarity target, minimum slack, rejection threshold
     double* ctrl_out;           // [n][D][M][6]
     double* cost_out;           // [n]
     int*    status_out;         // [n]
@@ -477,14 +479,22 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (sqrt((double) nsq) < 1e-5) { nx = 0.0; ny = 0.0; nz = 0.0; }
         s_nrm[e * 3] = nx; s_nrm[e * 3 + 1] = ny; s_nrm[e * 3 + 2] = nz;
     }
-    // starting point: every free control point at the current position (hover)
-    if (tid < NR) {
-        int k;
-        if (C::TERM && tid >= (M - 1) * C::NZS) k = tid - (M - 1) * C::NZS; else k = (tid % C::NZS) / 3;
-        s_y[tid] = (double) p.state[agent * 9 + k];
-    }
-    __syncthreads();
-    if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+    // starting point: the free control points of initial_traj when given (the reference hands it to
+    // TrajOptimizer::solve, traj_optimizer.cpp:18-21), else every free control point at the current position
+    bool warm = p.warm_traj != nullptr;
+    auto set_start = [&](bool from_traj) {
+        if (tid < NR) {
+            int st, k, j;
+            if (C::TERM && tid >= (M - 1) * C::NZS) { st = M - 1; k = tid - (M - 1) * C::NZS; j = 2; }
+            else { st = tid / C::NZS; k = (tid % C::NZS) / 3; j = tid % 3; }
+            s_y[tid] = from_traj ? (double) p.warm_traj[(((size_t) agent * M + st) * 6 + 3 + j) * 3 + k]
+                                 : (double) p.state[agent * 9 + k];
+        }
+        __syncthreads();
+        if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+        __syncthreads();
+    };
+    set_start(warm);
 
     // ---- per-thread row state (registers): slack and multiplier of every owned row
     double ls[KPT], ll[KPT];
@@ -669,11 +679,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         __syncthreads();
     };
 
-    // ---------------------------------------------------------------- initial point (least squares)   // @phase init_point
-    // minimise f(y) + 1/2 |q(y)|^2 : W = 1, u = -q at the hover point; then s = q, lam = -q, both shifted
-    // into the positive orthant (Mehrotra / CVXOPT start).  q of every row is kept in ls[] / bs[] meanwhile.
-    {
-        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+    // ---------------------------------------------------------------- initial point   // @phase init_point
+    // q of every row at the starting point is kept in ls[] / bs[] until s and lam are set.
+    auto rows_q = [&]() {
         double cx, cy, cz;
         if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
 #pragma unroll
@@ -685,9 +693,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (D == 3) q += n[2] * cz;
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             ls[j] = q;
-            accum(S, T, n, 1.0, -q, true);
         }
-        store_slab(S, T, true);
         if (var_thread) {
             const double* cc = s_c + k_v * NCP + cp_v;
             const double c0 = cc[0];
@@ -696,25 +702,58 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
             bs[0] = c0 - s_lb[k_v * M + m_v]; bs[1] = s_ub[k_v * M + m_v] - c0;
             bs[2] = s_vlim[k_v] - dv; bs[3] = s_vlim[k_v] + dv; bs[4] = s_alim[k_v] - da; bs[5] = s_alim[k_v] + da;
+        }
+    };
+    rows_q();
+    if (warm) {
+        // an initial_traj that violates rows by more than warm_reject is not used (cold start instead)
+        double qmin = INFINITY;
+#pragma unroll
+        for (int j = 0; j < KPT; j++) if (j < nrow) qmin = fmin(qmin, ls[j]);
+#pragma unroll
+        for (int e = 0; e < 6; e++) if (bmask >> e & 1u) qmin = fmin(qmin, bs[e]);
+        red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = 0;
+        block_reduce4<C>(red, s_red, red_phase);
+        if (red[2] < -p.warm_reject) {
+            warm = false;
+            __syncthreads();
+            set_start(false);
+            rows_q();
+        }
+    }
+    if (!warm) {
+        // cold start: minimise f(y) + 1/2 |q(y)|^2 (W = 1, u = -q at the hover point); then s = q, lam = -q,
+        // both shifted into the positive orthant (Mehrotra / CVXOPT start)
+        double S[6] = {0, 0, 0, 0, 0, 0}, T[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            if (j >= nrow) break;
+            const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
+            accum(S, T, n, 1.0, -ls[j], true);
+        }
+        store_slab(S, T, true);
+        if (var_thread) {
             double W[6], u[6];
 #pragma unroll
             for (int e = 0; e < 6; e++) { const bool on = bmask >> e & 1u; W[e] = on ? 1.0 : 0.0; u[e] = on ? -bs[e] : 0.0; }
             store_box(W, u, true);
         }
     }
-    assemble(true);
-    factor_solve(true);
-    if (tid < NR) { s_dy[tid] = s_rhs[tid]; s_y[tid] += s_rhs[tid]; }
-    __syncthreads();
-    if (var_thread) {
-        s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
-        s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+    if (!warm) {
+        assemble(true);
+        factor_solve(true);
+        if (tid < NR) { s_dy[tid] = s_rhs[tid]; s_y[tid] += s_rhs[tid]; }
+        __syncthreads();
+        if (var_thread) {
+            s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
+            s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double rp;      // the common primal residual s - q
     {
         double dx, dy, dz;
-        if (cp_valid) load_cp(s_dc, dx, dy, dz); else { dx = dy = dz = 0; }
+        if (!warm && cp_valid) load_cp(s_dc, dx, dy, dz); else { dx = dy = dz = 0; }
         double qmin = INFINITY, qmax = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
@@ -726,20 +765,30 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             qmin = fmin(qmin, ls[j]); qmax = fmax(qmax, ls[j]);
         }
         if (var_thread) {
-            double dq[6];
-            box_dq(s_dc, dq);
+            double dq[6] = {0, 0, 0, 0, 0, 0};
+            if (!warm) box_dq(s_dc, dq);
 #pragma unroll
             for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += dq[e]; qmin = fmin(qmin, bs[e]); qmax = fmax(qmax, bs[e]); }
         }
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
         block_reduce4<C>(red, s_red, red_phase);
-        const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
-        const double shift_l = (red[3] >= 0.0) ? 1.0 + red[3] : 0.0;        // lam = -s; alpha_d = max(s) >= 0 -> lam += 1 + alpha_d
+        if (warm) {
+            // warm start: s = q + shift (shift = 0 when initial_traj is strictly inside by warm_delta), s lam = mu0
+            const double shift_s = fmax(0.0, p.warm_delta - red[2]);
 #pragma unroll
-        for (int j = 0; j < KPT; j++) if (j < nrow) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
+            for (int j = 0; j < KPT; j++) if (j < nrow) { ls[j] += shift_s; ll[j] = p.mu0 / ls[j]; }
 #pragma unroll
-        for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
-        rp = shift_s;
+            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = p.mu0 / bs[e]; }
+            rp = shift_s;
+        } else {
+            const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
+            const double shift_l = (red[3] >= 0.0) ? 1.0 + red[3] : 0.0;        // lam = -s; alpha_d = max(s) >= 0 -> lam += 1 + alpha_d
+#pragma unroll
+            for (int j = 0; j < KPT; j++) if (j < nrow) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
+#pragma unroll
+            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+            rp = shift_s;
+        }
     }
 
     // ---------------------------------------------------------------- main loop   // @phase sweepA

@@ -67,10 +67,11 @@ class BatchPlanner:
         self.qp.assemble_lsc_batch(generator, d.n, d.own_traj, d.agent_meta, d.goal, d.obs_offsets, d.obs_traj,
                                    d.obs_meta, d.obs_goal, d.obs_position, d.normals, d.rhs, stream)
 
-    def solve_device(self, d: DeviceBatch, want_kkt: bool = False, dual=None, stream: int = 0):
-        """trajOptimization for every agent"""
+    def solve_device(self, d: DeviceBatch, want_kkt: bool = False, dual=None, stream: int = 0, warm: bool = True):
+        """trajOptimization for every agent (initial_traj = the batch's own_traj as the solver's starting point)"""
         self.qp.solve_batch(d.n, d.state, d.goal, d.limits, d.sfc, d.obs_offsets, d.normals, d.rhs,
-                            d.ctrl, d.cost, d.status, d.iters, d.kkt if want_kkt else None, dual, stream)
+                            d.ctrl, d.cost, d.status, d.iters, d.kkt if want_kkt else None, dual, stream,
+                            initial_traj=d.own_traj if warm else None)
 
     def replan_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0):
         self.assemble_device(d, generator, stream)

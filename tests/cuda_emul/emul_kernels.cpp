@@ -14,7 +14,7 @@ extern "C" int emul_dual_stride(int M, int D) { return 40 * M * 6 + D * M * 6 * 
 extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
                                 const float* state, const float* goal, const double* limits, const float* sfc,
                                 const int* obs_offsets, const double* normals, const double* rhs,
-                                double* ctrl_out, double* cost_out, int* status_out, int* iters_out,
+                                const float* initial_traj, double* ctrl_out, double* cost_out, int* status_out, int* iters_out,
                                 double* kkt_out, double* dual_out) {
     int rc = validate_config(*cfg);
     if (rc) return rc;
@@ -22,7 +22,7 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     fill_solve_params(*cfg, p);
     p.n_agents = n_agents;
     p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
-    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs; p.warm_traj = initial_traj;
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out;
     const bool term = cfg->planner_mode == LSCQP_MODE_LSC;

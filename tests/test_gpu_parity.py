@@ -19,7 +19,7 @@ def _planner(cfg):
     return BatchPlanner(cfg, device=0)
 
 
-def _solve_host(planner, batch, agents, off, normals, rhs, sfc=None, want_dual=False):
+def _solve_host(planner, batch, agents, off, normals, rhs, sfc=None, want_dual=False, warm=False):
     n = len(agents)
     cfg = batch.cfg
     state = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents])
@@ -27,7 +27,9 @@ def _solve_host(planner, batch, agents, off, normals, rhs, sfc=None, want_dual=F
     ctrl = np.zeros((n, cfg.dim * cfg.M * 6)); cost = np.zeros(n); status = np.zeros(n, np.int32)
     iters = np.zeros(n, np.int32); kkt = np.zeros((n, 4))
     dual = np.zeros((n, planner.qp.dual_stride)) if want_dual else None
-    planner.qp.solve_host(n, state, goal, limits, sfc, off, normals, rhs, ctrl, cost, status, iters, kkt, dual)
+    initial_traj = np.ascontiguousarray(batch.own_traj[agents]) if warm else None
+    planner.qp.solve_host(n, state, goal, limits, sfc, off, normals, rhs, ctrl, cost, status, iters, kkt, dual,
+                          initial_traj=initial_traj)
     return ctrl, cost, status, iters, kkt, dual
 
 
@@ -68,6 +70,33 @@ def test_solve_parity_real_rule(M, dim, mode, K):
     errs = _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=8)
     assert np.median(errs) < 1e-7
     assert iters.max() < 40
+
+
+@pytest.mark.parametrize("M,dim,mode,K", [(5, 3, capi.MODE_LSC, 40), (10, 2, capi.MODE_LSC, 9), (5, 3, capi.MODE_DLSC, 24)])
+def test_warm_start_parity(M, dim, mode, K):
+    """initial_traj as the solver's starting point: same optimum, fewer iterations than the cold start"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode)
+    batch = W.make_forest_batch(64, K=K, cfg=cfg)
+    agents = list(range(1, 64, 4))
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    planner = _planner(batch.cfg)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs, warm=True)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=8)
+    ctrl_c, cost_c, status_c, iters_c, _, _ = _solve_host(planner, batch, agents, off, normals, rhs, warm=False)
+    assert np.abs(ctrl - ctrl_c).max() < CTRL_TOL
+    assert iters.mean() < iters_c.mean()
+
+
+def test_warm_start_from_infeasible_trajectory():
+    """a starting trajectory that violates rows (and the model's equalities) is only a hint: same optimum"""
+    batch = W.make_forest_batch(64, K=40)
+    agents = list(range(0, 64, 8))
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    planner = _planner(batch.cfg)
+    rng = np.random.default_rng(3)
+    batch.own_traj = (batch.own_traj + rng.normal(0, 0.5, batch.own_traj.shape)).astype(np.float32)
+    ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs, warm=True)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=6)
 
 
 def test_solve_parity_synthetic_planes():
