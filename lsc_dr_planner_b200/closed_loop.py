@@ -1,0 +1,130 @@
+"""Closed-loop batched simulation (BASELINE config 5): N agents x T replans, agents sharded over ranks.
+
+Per step, for the agents a rank owns (what MultiSyncSimulator::run does serially,
+src/multi_sync_simulator.cpp:81-129):
+    broadcastMsgs  -> neighbour lists from the all-gathered positions (K nearest within comm range)
+    constructLSC   -> lscqp_gather_obstacles + lscqp_assemble_lsc_batch   (device)
+    trajOptimization -> lscqp_solve_batch, started from the shifted previous solution (device)
+    failsafe       -> agents whose QP failed keep initial_traj (src/traj_planner.cpp:767-797)
+    doStep         -> lscqp_step_batch: float trajectory, state at t = dt, shifted trajectory (device)
+    exchange       -> one all-gather of trajectories / states per step (NCCL over NVLink on GPUs)
+Neighbour search uses torch (cdist + topk): it is simulator harness, not the hot path."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+from .sharding import allgather_rows, shard_range
+from .workloads import Batch
+
+
+class ClosedLoopSim:
+    def __init__(self, batch: Batch, device: int = 0, rank: int = 0, world: int = 1, K: int = 40,
+                 comm_range: float = 0.0, generator: int = capi.GEN_LSC):
+        import torch
+        from .planner import BatchPlanner
+        self.torch = torch
+        self.cfg = batch.cfg
+        self.N = batch.n_agents
+        self.K = min(K, self.N - 1, self.cfg.max_obs)
+        self.comm_range = comm_range
+        self.generator = generator
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_range(self.N, rank, world)
+        self.n_local = self.hi - self.lo
+        self.planner = BatchPlanner(batch.cfg, device)
+        dev = torch.device("cuda", device)
+        self.dev = dev
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        M = self.cfg.M
+        # global (replicated) per-agent data
+        self.state = t(batch.state)                      # [N,9]
+        self.goal = t(batch.goal)                        # [N,3]
+        self.agent_meta = t(batch.agent_meta)            # [N,2]
+        self.limits = t(batch.limits)
+        # first replan: constant-velocity trajectories from the current state (traj_planner.cpp:276-279, 400-401)
+        self.traj = self._const_vel(self.state)          # [N,M,6,3] initial_traj / obs_pred_trajs of this step
+        # local scratch
+        n, sk = max(self.n_local, 1), max(self.n_local * self.K, 1)
+        self.obs_offsets = (torch.arange(self.n_local + 1, device=dev, dtype=torch.int32) * self.K).contiguous()
+        self.obs_traj = torch.empty((sk, M, 6, 3), dtype=torch.float32, device=dev)
+        self.obs_meta = torch.empty((sk, 4), dtype=torch.float32, device=dev)
+        self.obs_goal = torch.empty((sk, 3), dtype=torch.float32, device=dev)
+        self.obs_position = torch.empty((sk, 3), dtype=torch.float32, device=dev)
+        self.normals = torch.empty((sk, M, 3), dtype=torch.float64, device=dev)
+        self.rhs = torch.empty((sk, M, 6), dtype=torch.float64, device=dev)
+        self.ctrl = torch.empty((n, self.cfg.dim * M * 6), dtype=torch.float64, device=dev)
+        self.cost = torch.empty((n,), dtype=torch.float64, device=dev)
+        self.status = torch.empty((n,), dtype=torch.int32, device=dev)
+        self.iters = torch.empty((n,), dtype=torch.int32, device=dev)
+        self.traj_out = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev)
+        self.state_out = torch.empty((n, 9), dtype=torch.float32, device=dev)
+        self.shifted = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev)
+        self.failed_total = 0
+        self.steps = 0
+
+    def _const_vel(self, state):
+        torch = self.torch
+        M, dt = self.cfg.M, self.cfg.dt
+        tt = (torch.arange(M * 6, device=self.dev, dtype=torch.float32) * np.float32(dt / 5.0)).view(1, M, 6, 1)
+        # Trajectory::planConstVelTraj (src/trajectory.cpp:77-89): time advances by dt/n per control point
+        return (state[:, None, None, 0:3] + state[:, None, None, 3:6] * tt).contiguous()
+
+    def neighbours(self):
+        """K nearest agents of every local agent (optionally within the L-inf communication range,
+        src/multi_sync_simulator.cpp:319-328); padded with the farthest ones when fewer are in range."""
+        torch = self.torch
+        pos = self.state[:, 0:3]
+        d = torch.cdist(pos[self.lo:self.hi], pos)
+        idx_self = torch.arange(self.lo, self.hi, device=self.dev)
+        d[torch.arange(self.n_local, device=self.dev), idx_self] = float("inf")
+        if self.comm_range > 0:
+            linf = (pos[self.lo:self.hi, None, :] - pos[None, :, :]).abs().amax(dim=-1)
+            d = torch.where(linf > self.comm_range, d + 1e6, d)
+        return torch.topk(d, self.K, dim=1, largest=False).indices.to(torch.int32).contiguous().view(-1)
+
+    def step(self):
+        """one replan + one simulation step of length dt for the local shard, then the exchange"""
+        torch = self.torch
+        qp = self.planner.qp
+        n, lo, hi = self.n_local, self.lo, self.hi
+        if n > 0:
+            obs_index = self.neighbours()
+            own = self.traj[lo:hi].contiguous()
+            st, goal, lim, meta = (self.state[lo:hi].contiguous(), self.goal[lo:hi].contiguous(),
+                                   self.limits[lo:hi].contiguous(), self.agent_meta[lo:hi].contiguous())
+            qp.gather_obstacles(n * self.K, obs_index, self.traj, self.agent_meta, self.goal, self.state,
+                                self.obs_traj, self.obs_meta, self.obs_goal, self.obs_position)
+            qp.assemble_lsc_batch(self.generator, n, own, meta, goal, self.obs_offsets, self.obs_traj, self.obs_meta,
+                                  self.obs_goal, self.obs_position, self.normals, self.rhs)
+            qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
+                           self.status, self.iters, initial_traj=own)
+            # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797)
+            bad = self.status != 0
+            if bool(bad.any()):
+                D, M = self.cfg.dim, self.cfg.M
+                fallback = own.permute(0, 3, 1, 2)[:, :D].reshape(n, -1).to(torch.float64)
+                self.ctrl[bad] = fallback[bad]
+                self.failed_total += int(bad.sum())
+            qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted)
+            new_traj, new_state = self.shifted, self.state_out
+        else:
+            new_traj = self.shifted[:0]; new_state = self.state_out[:0]
+        self.traj = allgather_rows(new_traj[:n], self.N)
+        self.state = allgather_rows(new_state[:n], self.N)
+        if self.world == 1:
+            self.traj = self.traj.clone(); self.state = self.state.clone()
+        self.steps += 1
+
+    def min_separation_ratio(self) -> float:
+        """min over pairs of (downwash-scaled distance) / (r_i + r_j) at the current positions (>= 1 is safe)"""
+        torch = self.torch
+        pos = self.state[:, 0:3].to(torch.float64).clone()
+        r = self.agent_meta[:, 0]; dw = self.agent_meta[:, 1]
+        pos[:, 2] = pos[:, 2] / dw
+        d = torch.cdist(pos, pos) / (r[:, None] + r[None, :])
+        d.fill_diagonal_(float("inf"))
+        return float(d.min())
+
+    def max_goal_distance(self) -> float:
+        return float((self.state[:, 0:3] - self.goal).norm(dim=1).max())

@@ -64,3 +64,5 @@ extern "C" int emul_step_batch(const lscqp_config* cfg, int n_agents, const doub
     else return LSCQP_E_INVALID;
     return 0;
 }
+
+extern "C" void emul_jerk_gram(int n, int phi, double dt, double* Q) { jerk_gram(n, phi, dt, Q); }

@@ -1,0 +1,124 @@
+"""CPU tests that step the *unmodified* CUDA kernel sources on the cooperative thread emulator
+(tests/cuda_emul) and compare them with the oracle -- the same assertions the GPU parity tests make,
+at sizes the emulator finishes in seconds."""
+import os
+
+import numpy as np
+import pytest
+
+import emul
+from common import near_goals, oracle_config, oracle_planes, oracle_qp_from_planes, oracle_solution
+from lsc_dr_planner_b200 import workloads as W
+from oracle import oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,cfg,K", [("m5d3lsc", W.PlannerConfig(M=5, dim=3, planner_mode=1), 40),
+                                        ("m10d2lsc", W.PlannerConfig(M=10, dim=2, planner_mode=1), 9),
+                                        ("m5d3dlsc", W.PlannerConfig(M=5, dim=3, planner_mode=0), 16)])
+def test_solve_kernel_matches_golden_solutions(name, cfg, K):
+    g = np.load(os.path.join(GOLDEN, "qp_golden.npz"))
+    batch = W.make_forest_batch(64, K=K, cfg=cfg)
+    off, normals, rhs = g[name + "_off"], g[name + "_normals"], g[name + "_rhs"]
+    agents = [0, 5, 11, 17, 23, 42]
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    sel = [int(i) for i in g[name + "_keep"][:3]]
+    for warm in (False, True):
+        it = np.ascontiguousarray(batch.own_traj[agents]) if warm else None
+        ctrl, cost, status, iters, kkt, _ = emul.solve_batch(batch.cfg, len(agents), st, goal, lim, None,
+                                                             np.ascontiguousarray(off), np.ascontiguousarray(normals),
+                                                             np.ascontiguousarray(rhs), initial_traj=it)
+        assert (status == 0).all()
+        for x, i in zip(g[name + "_x"][:3], sel):
+            assert np.abs(ctrl[i] - x).max() < 1e-5, (name, warm, i, np.abs(ctrl[i] - x).max())
+        assert kkt[:, 1].max() < 1e-9 and kkt[:, 3].max() < 1e-10
+
+
+def test_solve_kernel_duals_give_a_kkt_certificate():
+    """the multipliers returned in dual_out (reference row scaling) certify stationarity of the restated model"""
+    cfg = W.PlannerConfig()
+    batch = W.make_forest_batch(64, K=40, cfg=cfg)
+    agents = [3, 20]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    ctrl, cost, status, iters, kkt, dual = emul.solve_batch(batch.cfg, 2, st, goal, lim, None, off, normals, rhs, want_dual=True)
+    M, D = cfg.M, cfg.dim
+    for i, a in enumerate(agents):
+        qp = oracle_qp_from_planes(batch, a, normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]])
+        x = ctrl[i]
+        grad = 2 * qp.P @ x + qp.q
+        K = off[i + 1] - off[i]
+        lsc = dual[i, :40 * M * 6].reshape(40, M, 6)
+        box = dual[i, 40 * M * 6:].reshape(D * M * 6, 6)
+        # rebuild sum_r lam_r a_r in the reference's row order / scaling
+        r = 0
+        acc = np.zeros_like(grad)
+        for oi in range(K):
+            for m in range(M):
+                for j in range(6):
+                    if m == 0 and j < 3:
+                        continue
+                    acc += lsc[oi, m, j] * qp.G[r]          # rows n.x >= b
+                    r += 1
+        for k in range(D):
+            for m in range(M):
+                for j in range(5):
+                    if m == 0 and j < 2:
+                        continue
+                    v = k * M * 6 + m * 6 + j
+                    acc -= box[v, 2] * qp.G[r]; acc -= box[v, 3] * qp.G[r + 1]     # rows a.x <= vmax
+                    r += 2
+                for j in range(4):
+                    if m == 0 and j < 1:
+                        continue
+                    v = k * M * 6 + m * 6 + j
+                    acc -= box[v, 4] * qp.G[r]; acc -= box[v, 5] * qp.G[r + 1]
+                    r += 2
+        assert r == qp.G.shape[0]
+        acc += box[:, 0] - box[:, 1]                         # variable bounds lb <= x <= ub
+        # project on the null space of the equalities (their multipliers are free)
+        _, S, Vt = np.linalg.svd(qp.Aeq, full_matrices=True)
+        Z = Vt[int((S > 1e-10 * S[0]).sum()):].T
+        res = Z.T @ (grad - acc)
+        assert np.abs(res).max() < 1e-6 * max(1.0, np.abs(grad).max()), np.abs(res).max()
+        assert dual[i].min() >= 0
+        assert abs(cost[i] - (x @ qp.P @ x + qp.q @ x + qp.c0)) < 1e-8 * max(1.0, abs(cost[i]))
+
+
+@pytest.mark.parametrize("generator,M,dim", [(0, 5, 3), (1, 10, 2), (1, 5, 3), (2, 5, 3)])
+def test_assembly_kernel_matches_oracle(generator, M, dim):
+    cfg = W.PlannerConfig(M=M, dim=dim)
+    b = W.make_forest_batch(32, K=12, cfg=cfg)
+    if generator == 1:
+        near_goals(b)
+    n = 6
+    off = np.ascontiguousarray(b.obs_offsets[:n + 1])
+    sk = off[n]
+    normals, rhs = emul.assemble(b.cfg, generator, n, b.own_traj[:n].copy(), b.agent_meta[:n].copy(), b.goal[:n].copy(), off,
+                                 b.obs_traj()[:sk].copy(), b.obs_meta()[:sk].copy(), b.obs_goal()[:sk].copy(),
+                                 b.obs_position()[:sk].copy())
+    _, n_ref, r_ref = oracle_planes(b, list(range(n)), generator)
+    assert np.abs(normals - n_ref).max() <= 2.4e-7
+    assert np.abs(rhs - r_ref).max() <= 2e-6
+    assert (normals == n_ref).mean() > 0.99
+
+
+def test_step_kernel_matches_oracle():
+    for M, dim in ((5, 3), (10, 2)):
+        cfg = W.PlannerConfig(M=M, dim=dim)
+        batch = W.make_forest_batch(64, K=4, cfg=cfg)
+        cfgo = oracle_config(cfg)
+        traj = batch.own_traj[:8].astype(np.float64) + np.random.default_rng(2).normal(0, 1e-3, batch.own_traj[:8].shape)
+        ctrl = np.ascontiguousarray(np.transpose(traj, (0, 3, 1, 2))[:, :dim].reshape(8, -1))
+        got_traj, got_state, got_shift = emul.step(batch.cfg, 8, ctrl, 0.1)
+        for a in range(8):
+            want = traj[a].astype(np.float32)
+            if dim == 2:
+                want[..., 2] = np.float32(cfg.z_2d)
+            assert np.array_equal(got_traj[a], want)
+            st = orc.get_state_at(cfgo, want, 0.1)
+            if dim == 2:
+                st[2] = np.float32(cfg.z_2d)
+            assert np.allclose(got_state[a], st, rtol=2e-6, atol=2e-6)
+            assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))

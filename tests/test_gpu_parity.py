@@ -279,3 +279,54 @@ def test_full_size_properties():
     planner.solve_device(d)
     torch.cuda.synchronize()
     assert torch.equal(c1, d.ctrl)
+
+
+def test_closed_loop_circle_swap_is_collision_free():
+    """16 agents on a circle swapping positions (missions/*: antipodal goals), 60 replans of 0.2 s:
+    no collision (safety ratio >= 1, what the reference's summary CSV reports) and progress towards the goals"""
+    from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
+    n = 16
+    cfg = W.PlannerConfig()
+    batch = W.make_forest_batch(n, K=15, cfg=cfg, moving=False)
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    pos = np.stack([4 * np.cos(ang), 4 * np.sin(ang), np.full(n, 1.0)], 1).astype(np.float32)
+    batch.state[:] = 0; batch.state[:, :3] = pos
+    batch.goal = (-pos * [1, 1, -1]).astype(np.float32)
+    batch.cfg.world_min = (-6.0, -6.0, 0.0); batch.cfg.world_max = (6.0, 6.0, 2.5)
+    sim = ClosedLoopSim(batch, device=0, K=15)
+    d0 = sim.max_goal_distance()
+    worst = np.inf
+    for _ in range(60):
+        sim.step()
+        worst = min(worst, sim.min_separation_ratio())
+    assert worst >= 1.0 - 1e-3, worst
+    assert sim.failed_total == 0
+    assert sim.max_goal_distance() < 0.75 * d0
+
+
+def test_cpp_shim_end_to_end():
+    """the C++ class surfaces (include/lscqp_shim.hpp) driven like traj_planner.cpp drives the reference's classes"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "shim", "shim_smoke")
+    libdir = os.path.join(root, "lsc_dr_planner_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "shim", "shim_smoke.cpp"), "-o", exe,
+                    "-L" + libdir, "-l:liblscqp.so", "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines()
+    cps = np.array([[float(v) for v in l.split()[3:]] for l in out if l.startswith("cp ")]).reshape(5, 6, 3)
+    assert "qpfailed 1" in out
+    # the same QP through the oracle
+    cfgo = orc.Config(world_min=(-5, -5, 0), world_max=(5, 5, 2.5))
+    ag = orc.Agent(np.array([0, 0, 1]), np.zeros(3), np.zeros(3), np.array([3, 0, 1]))
+    pt = np.tile(np.array([1, 0, 1], np.float32), (1, 5, 6, 1)); nr = np.tile(np.array([-1, 0, 0], np.float32), (1, 5, 6, 1))
+    qp = orc.qp_build(cfgo, ag, pt, nr, np.full((1, 5, 6), 0.4))
+    xe, ok = oracle_solution(qp)
+    assert ok
+    want = xe.reshape(3, 5, 6).transpose(1, 2, 0)
+    assert np.abs(cps - want).max() < 1e-5
+    assert cps[..., 0].max() <= 0.6 + 1e-6
+    cost = float([l for l in out if l.startswith("cost")][0].split()[1])
+    assert abs(cost - (xe @ qp.P @ xe + qp.q @ xe + qp.c0)) < 1e-6 * max(1.0, cost)
+    b = [l for l in out if l.startswith("batch")][0].split()
+    assert b[1] == "0" and b[2] == "0" and float(b[3]) > 0.3 and float(b[4]) < 2.7
