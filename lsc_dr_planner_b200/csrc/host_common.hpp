@@ -1,7 +1,9 @@
 // host_common.hpp -- host-side constants shared by the CUDA library and the CPU emulation harness.
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstring>
+#include <vector>
 #include "../../include/lscqp.h"
 #include "pdip_kernel.cuh"
 
@@ -74,6 +76,73 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     double Q[36];
     jerk_gram(c.n, c.phi, c.dt, Q);
     for (int e = 0; e < 36; e++) p.Q2[e] = 2.0 * c.w_control * Q[e];
+}
+
+// Projection table of one kernel instance: every entry (r1 >= r2, inside the stored band) of the reduced matrix
+// Z^T Phi Z as a linear combination of the full-space sources the kernel keeps in shared memory
+// (6x6 blocks per (dimension, segment), then the per-control-point cross-dimension blocks).  Z is the continuity
+// map of pdip_kernel.cuh: reduced variable (stage s, dim k, j) is control point (s, 3+j) and, through
+// T = [[0,0,1],[0,-1,2],[1,-4,4]], the first three control points of segment s+1; the collapsed terminal variable
+// is the sum of the last three control points.
+struct ProjTable {
+    std::vector<int4> ent;        // dest, first term, term count (-1: identity padding), diagonal index or -1
+    std::vector<double2> term;    // coef, source index
+};
+
+template <class C>
+inline ProjTable build_projection() {
+    constexpr int M = C::M, D = C::D, NR = C::NR, NS = C::NS;
+    static const double T[3][3] = {{0, 0, 1}, {0, -1, 2}, {1, -4, 4}};
+    auto symidx = [](int a, int b) { if (a > b) std::swap(a, b); return D == 3 ? (a == 0 ? b : (a == 1 ? 2 + b : 5)) : a + b; };
+    auto blk = [](int k, int m, int a, int b) { return (k * M + m) * 36 + a * 6 + b; };
+    auto sidx = [&](int cp, int k1, int k2) { return D * M * 36 + cp * NS + symidx(k1, k2); };
+    struct Var { int s, k, j; };
+    auto decode = [](int r) {
+        Var v;
+        if (C::TERM && r >= (M - 1) * C::NZS) { v.s = M - 1; v.k = r - (M - 1) * C::NZS; v.j = -1; }
+        else { v.s = r / C::NZS; v.k = (r % C::NZS) / 3; v.j = r % 3; }
+        return v;
+    };
+    struct Ent { int dest, diag, count; std::vector<std::pair<double, int>> t; };
+    std::vector<Ent> ents;
+    for (int r1 = 0; r1 < C::NRP; r1++)
+        for (int off = 0; off <= C::BWS; off++) {
+            const int r2 = r1 - off;
+            if (r2 < 0) continue;
+            Ent e; e.dest = r1 * C::LD + r2; e.diag = (r1 == r2) ? r1 : -1; e.count = 0;
+            if (r1 >= NR) { e.count = (r1 == r2) ? -1 : 0; ents.push_back(e); continue; }
+            const Var a = decode(r1), b = decode(r2);
+            auto add = [&](double c, int idx) { if (c != 0.0) e.t.push_back({c, idx}); };
+            if (a.s == b.s) {
+                const int st = a.s;
+                if (a.k == b.k) {
+                    if (a.j < 0) { for (int x = 3; x < 6; x++) for (int y = 3; y < 6; y++) add(1.0, blk(a.k, st, x, y)); }
+                    else {
+                        add(1.0, blk(a.k, st, 3 + a.j, 3 + b.j));
+                        if (st + 1 < M) for (int x = 0; x < 3; x++) for (int y = 0; y < 3; y++) add(T[x][a.j] * T[y][b.j], blk(a.k, st + 1, x, y));
+                    }
+                } else {
+                    if (a.j < 0) { for (int x = 3; x < 6; x++) add(1.0, sidx(st * 6 + x, a.k, b.k)); }
+                    else {
+                        if (a.j == b.j) add(1.0, sidx(st * 6 + 3 + a.j, a.k, b.k));
+                        if (st + 1 < M) for (int x = 0; x < 3; x++) add(T[x][a.j] * T[x][b.j], sidx((st + 1) * 6 + x, a.k, b.k));
+                    }
+                }
+            } else if (a.s == b.s + 1 && a.k == b.k) {
+                if (a.j < 0) { for (int x = 3; x < 6; x++) for (int y = 0; y < 3; y++) add(T[y][b.j], blk(a.k, a.s, x, y)); }
+                else for (int y = 0; y < 3; y++) add(T[y][b.j], blk(a.k, a.s, 3 + a.j, y));
+            }
+            e.count = (int) e.t.size();
+            ents.push_back(e);
+        }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) { return x.count > y.count; });
+    ProjTable out;
+    for (const Ent& e : ents) {
+        int4 h; h.x = e.dest; h.y = (int) out.term.size(); h.z = e.count; h.w = e.diag;
+        out.ent.push_back(h);
+        for (auto& t : e.t) { double2 d; d.x = t.first; d.y = (double) t.second; out.term.push_back(d); }
+    }
+    return out;
 }
 
 // kernel instances: (M, D, TERM) with 4 obstacle groups x 10 rows per thread (K <= 40)

@@ -46,6 +46,7 @@ struct lscqp_handle {
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
+    DevBuf d_proj_ent, d_proj_term;
     unsigned long long launches = 0;
 };
 
@@ -78,6 +79,13 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
         using C = Cfg<M_, D_, T_, 4, 10>;                               \
         if (set_smem_attr<C>()) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); } \
         h->dual_stride = C::DUAL_STRIDE; h->kmax = C::KMAX; h->nv = C::NV; found = true; \
+        const ProjTable tab = build_projection<C>();                    \
+        if (h->d_proj_ent.reserve(tab.ent.size() * sizeof(int4)) || h->d_proj_term.reserve(tab.term.size() * sizeof(double2)) || \
+            cudaMemcpy(h->d_proj_ent.p, tab.ent.data(), tab.ent.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess || \
+            cudaMemcpy(h->d_proj_term.p, tab.term.data(), tab.term.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) { \
+            delete h; return fail(LSCQP_E_CUDA, "projection table upload failed"); }           \
+        h->base.proj_ent = h->d_proj_ent.as<int4>(); h->base.proj_term = h->d_proj_term.as<double2>(); \
+        h->base.n_proj_ent = (int) tab.ent.size();                      \
     }
     LSCQP_FOR_EACH_INSTANCE(X)
 #undef X
@@ -94,7 +102,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
-                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos};
+                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;

@@ -55,6 +55,11 @@ struct SolveParams {
     double* dual_out;           // [n][dual_stride] (may be null)
     int     dual_stride;
     double  Q2[36];             // 2 * w_c * Q_base  (Hessian block of the jerk cost)
+    // projection table (host-built, see host_common.hpp:build_projection): reduced-matrix entry e is
+    //   A[dest_e] = sum_t coef_t * src[idx_t],   src = [6x6 blocks | per-control-point cross blocks]
+    const int4*   proj_ent;     // [n_ent]  dest offset, first term, term count, diagonal index (or -1)
+    const double2* proj_term;   // [n_term] coef, idx (as a double-encoded integer)
+    int n_proj_ent;
     double  w_c;
 };
 
@@ -95,26 +100,24 @@ struct Cfg {
     static constexpr int O_GOAL = O_ALIM + D;            // [D]
     static constexpr int O_LB = O_GOAL + D;              // [D][M]
     static constexpr int O_UB = O_LB + D * M;            // [D][M]
-    static constexpr int O_TERMW = O_UB + D * M;         // [M]
-    static constexpr int O_NRM = O_TERMW + M;            // [KMAX][M][3]
-    static constexpr int O_SLABS = O_NRM + KMAX * M * 3; // [G][NCP][NS]
-    static constexpr int O_SLABT = O_SLABS + G * NCP * NS;   // [G][NCP][D]
+    static constexpr int O_TERMW = O_UB + D * M;         // [M] terminal weights, then the distance to the goal
+    static constexpr int O_NRM = O_TERMW + M + 1;        // [KMAX][M][3]
+    static constexpr int O_SLABT = O_NRM + KMAX * M * 3; // [G][NCP][D]
     static constexpr int O_WB = O_SLABT + G * NCP * D;   // [NV] x6: wB wV wA uB uV uA
     static constexpr int O_WV = O_WB + NV;
     static constexpr int O_WA = O_WV + NV;
     static constexpr int O_UB_ = O_WA + NV;
     static constexpr int O_UV = O_UB_ + NV;
     static constexpr int O_UA = O_UV + NV;
-    static constexpr int O_BLK = O_UA + NV;              // [D][M][36]
-    static constexpr int O_RFULL = O_BLK + D * M * 36;   // [NV]
+    static constexpr int O_BLK = O_UA + NV;              // [D][M][36]   projection sources: blocks, then slab 0 of S
+    static constexpr int O_SLABS = O_BLK + D * M * 36;   // [G][NCP][NS]
+    static constexpr int O_RFULL = O_SLABS + G * NCP * NS;   // [NV]
     static constexpr int O_A = O_RFULL + NV;             // [NR][LD]
     static constexpr int O_RHS = O_A + NRP * LD;         // [NRP]
     static constexpr int O_DIAG0 = O_RHS + NRP;          // [NRP]
     static constexpr int O_INVD = O_DIAG0 + NRP;         // [NRP]
     static constexpr int O_RED = O_INVD + NRP;           // [2][NW][NRED]
-    static constexpr int O_TT = O_RED + 2 * NW * NRED;   // T[3][3] then TT[3][3][3]
-    static constexpr int O_RTAB = O_TT + 36;             // int[3*NR]: stage, dim, j (-1 = collapsed terminal point)
-    static constexpr int O_END = O_RTAB + (3 * NR + 1) / 2;
+    static constexpr int O_END = O_RED + 2 * NW * NRED;
     static constexpr int SMEM_BYTES = O_END * 8;
     // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
     static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6;
@@ -394,9 +397,6 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     double* s_diag0 = sm + C::O_DIAG0;
     double* s_invd = sm + C::O_INVD;
     double* s_red = sm + C::O_RED;
-    double* s_T = sm + C::O_TT;            // T[a][j]
-    double* s_TT = sm + C::O_TT + 9;       // TT[a][j1][j2] = T[a][j1] T[a][j2]
-    int* s_rtab = reinterpret_cast<int*>(sm + C::O_RTAB);
     int red_phase = 0;
 
     // ---- thread roles
@@ -432,14 +432,6 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     // ---- stage per-agent constants
     if (tid < 36) sQ2[tid] = p.Q2[tid];
-    if (tid >= 64 && tid < 64 + 9) { const int e = tid - 64; s_T[e] = tcoef(e / 3, e % 3); }
-    if (tid >= 96 && tid < 96 + 27) { const int e = tid - 96; s_TT[e] = tcoef(e / 9, (e / 3) % 3) * tcoef(e / 9, e % 3); }
-    for (int r = tid; r < NR; r += NT) {
-        int st, k, j;
-        if (C::TERM && r >= (M - 1) * C::NZS) { st = M - 1; k = r - (M - 1) * C::NZS; j = -1; }
-        else { st = r / C::NZS; k = (r % C::NZS) / 3; j = r % 3; }
-        s_rtab[3 * r] = st; s_rtab[3 * r + 1] = k; s_rtab[3 * r + 2] = j;
-    }
     if (tid < D) {
         const int k = tid;
         const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
@@ -468,6 +460,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         int ts = (int) ((M * p.dt - flight + 1e-9) / p.dt);
         if (ts < 1) ts = 1;
         for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
+        s_termw[M] = sqrt((double) nsq);
     }
     for (int e = tid; e < K * M; e += NT) {
         // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference
@@ -556,55 +549,6 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
     };
 
-    // reduced-matrix entry (r1 >= r2) from the full-space blocks ("projection")
-    auto red_entry = [&](int r1, int r2) -> double {   // @phase red_entry
-        const int s1 = s_rtab[3 * r1], k1 = s_rtab[3 * r1 + 1], j1 = s_rtab[3 * r1 + 2];
-        const int s2 = s_rtab[3 * r2], k2 = s_rtab[3 * r2 + 1], j2 = s_rtab[3 * r2 + 2];
-        double val = 0.0;
-        if (s1 == s2) {
-            const int st = s1;
-            if (k1 == k2) {
-                const double* B = s_blk + (k1 * M + st) * 36;
-                if (j1 < 0) {
-                    for (int a = 3; a < 6; a++) for (int b = 3; b < 6; b++) val += B[a * 6 + b];
-                } else {
-                    val = B[(3 + j1) * 6 + 3 + j2];
-                    if (st + 1 < M) {
-                        const double* Bn = B + 36;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const double ta = s_T[a * 3 + j1];
-#pragma unroll
-                            for (int b = 0; b < 3; b++) val += ta * s_T[b * 3 + j2] * Bn[a * 6 + b];
-                        }
-                    }
-                }
-            } else {
-                const int si = (D == 3) ? symidx3(k1, k2) : symidx2(k1, k2);
-                if (j1 < 0) {
-                    for (int a = 3; a < 6; a++) val += slabS[(st * 6 + a) * NS + si];
-                } else {
-                    if (j1 == j2) val = slabS[(st * 6 + 3 + j1) * NS + si];
-                    if (st + 1 < M) {
-#pragma unroll
-                        for (int a = 0; a < 3; a++) val += s_TT[a * 9 + j1 * 3 + j2] * slabS[((st + 1) * 6 + a) * NS + si];
-                    }
-                }
-            }
-        } else if (s1 == s2 + 1 && k1 == k2) {
-            const double* B = s_blk + (k1 * M + s1) * 36;
-            if (j1 < 0) {
-                for (int a = 3; a < 6; a++)
-#pragma unroll
-                    for (int b = 0; b < 3; b++) val += B[a * 6 + b] * s_T[b * 3 + j2];
-            } else {
-#pragma unroll
-                for (int b = 0; b < 3; b++) val += B[(3 + j1) * 6 + b] * s_T[b * 3 + j2];
-            }
-        }
-        return val;
-    };
-
     // sum the group slabs, build the 6x6 blocks (withS) and the full-space rhs  -grad f + A^T u, then project.
     auto assemble = [&](bool withS) {   // @phase assemble
         __syncthreads();
@@ -623,25 +567,31 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             }
         }
         __syncthreads();
-        if (withS) {
-            for (int e = tid; e < D * M * 36; e += NT) {
-                const int k = e / (M * 36), m = (e / 36) % M, a = (e % 36) / 6, b = e % 6;
-                const int v0 = k * NCP + m * 6;
-                double val = sQ2[a * 6 + b];
-                if (a == b) {
-                    const int dd = (D == 3) ? symidx3(k, k) : symidx2(k, k);
-                    val += s_wB[v0 + a] + slabS[(m * 6 + a) * NS + dd];
-                    if (a == 5) val += s_termw[m];
-                    if (a <= 4) val += s_wV[v0 + a];
-                    if (a >= 1) val += s_wV[v0 + a - 1];
-                }
-                if (a - b == 1 || b - a == 1) val -= s_wV[v0 + (a < b ? a : b)];
-                const int hi = a > b ? a : b, lo = a < b ? a : b;
-                for (int i = (hi - 2 > 0 ? hi - 2 : 0); i <= (lo < 3 ? lo : 3); i++) {
-                    const double da = (a - i == 1) ? -2.0 : 1.0, db = (b - i == 1) ? -2.0 : 1.0;
-                    val += s_wA[v0 + i] * da * db;
-                }
-                s_blk[e] = val;
+        if (withS && var_thread) {
+            // row a of the 6x6 block of (dimension k_v, segment m_v): jerk Gram + terminal + bounds on the diagonal,
+            // tri-diagonal velocity stencils (1,-1), penta-diagonal acceleration stencils (1,-2,1), LSC diagonal block
+            const int v0 = k_v * NCP + m_v * 6, a = i_v;
+            const double wv0 = a <= 4 ? s_wV[v0 + a] : 0.0, wvm = a >= 1 ? s_wV[v0 + a - 1] : 0.0;
+            const double wa0 = a <= 3 ? s_wA[v0 + a] : 0.0, wa1 = (a >= 1 && a <= 4) ? s_wA[v0 + a - 1] : 0.0,
+                         wa2 = a >= 2 ? s_wA[v0 + a - 2] : 0.0;
+            const int dd = (D == 3) ? symidx3(k_v, k_v) : symidx2(k_v, k_v);
+            double row[6];
+#pragma unroll
+            for (int b = 0; b < 6; b++) row[b] = sQ2[a * 6 + b];
+            // diagonal
+            double dg = s_wB[tid] + slabS[cp_v * NS + dd] + wv0 + wvm + wa0 + 4.0 * wa1 + wa2;
+            if (a == 5) dg += s_termw[m_v];
+            // neighbours: (a, a+1): -wV[a] - 2 wA[a] - 2 wA[a-1];  (a, a+2): wA[a];  mirrored for a-1, a-2
+            const double up1 = -wv0 - 2.0 * wa0 - 2.0 * wa1, dn1 = -wvm - 2.0 * wa1 - 2.0 * wa2;
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                double add = 0.0;
+                if (b == a) add = dg;
+                else if (b == a + 1) add = up1;
+                else if (b == a - 1) add = dn1;
+                else if (b == a + 2) add = wa0;
+                else if (b == a - 2) add = wa2;
+                s_blk[(k_v * M + m_v) * 36 + a * 6 + b] = row[b] + add;
             }
         }
         if (var_thread) {
@@ -658,12 +608,16 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         }
         __syncthreads();
         if (withS) {
-            for (int e = tid; e < C::NRP * (C::BWS + 1); e += NT) {
-                const int r1 = e / (C::BWS + 1), r2 = r1 - e % (C::BWS + 1);
-                if (r2 < 0) continue;
-                const double val = r1 < NR ? red_entry(r1, r2) : (r1 == r2 ? 1.0 : 0.0);    // identity padding rows
-                s_A[r1 * LD + r2] = val;
-                if (r1 == r2) s_diag0[r1] = val;
+            for (int e = tid; e < p.n_proj_ent; e += NT) {
+                const int4 h = p.proj_ent[e];
+                double val = 0.0;
+                for (int t = 0; t < h.z; t++) {
+                    const double2 ct = p.proj_term[h.y + t];
+                    val += ct.x * s_blk[(int) ct.y];
+                }
+                if (h.z < 0) val = 1.0;                                     // identity padding rows
+                s_A[h.x] = val;
+                if (h.w >= 0) s_diag0[h.w] = val;
             }
         }
         if (tid < C::NRP) s_rhs[tid] = tid < NR ? reduce_from_full<C>(s_rfull, tid) : 0.0;
@@ -773,12 +727,14 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
         block_reduce4<C>(red, s_red, red_phase);
         if (warm) {
-            // warm start: s = q + shift (shift = 0 when initial_traj is strictly inside by warm_delta), s lam = mu0
+            // warm start: s = q + shift (shift = 0 when initial_traj is strictly inside by warm_delta), s lam = mu0;
+            // the multiplier scale follows the terminal-cost gradient (~ distance to the goal)
             const double shift_s = fmax(0.0, p.warm_delta - red[2]);
+            const double mu0 = p.mu0 * fmax(1.0, 0.1 * s_termw[M]);
 #pragma unroll
-            for (int j = 0; j < KPT; j++) if (j < nrow) { ls[j] += shift_s; ll[j] = p.mu0 / ls[j]; }
+            for (int j = 0; j < KPT; j++) if (j < nrow) { ls[j] += shift_s; ll[j] = mu0 / ls[j]; }
 #pragma unroll
-            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = p.mu0 / bs[e]; }
+            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = mu0 / bs[e]; }
             rp = shift_s;
         } else {
             const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p

@@ -23,6 +23,8 @@
 #define __restrict__
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
 namespace emu {
 struct Thread {
     ucontext_t ctx;

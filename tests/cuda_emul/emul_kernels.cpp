@@ -30,6 +30,8 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     if (cfg->M == M_ && cfg->dim == D_ && term == T_) {                                     \
         using C = Cfg<M_, D_, T_, 4, 10>;                                                   \
         p.dual_stride = C::DUAL_STRIDE;                                                     \
+        static const ProjTable tab = build_projection<C>();                                 \
+        p.proj_ent = tab.ent.data(); p.proj_term = tab.term.data(); p.n_proj_ent = (int) tab.ent.size(); \
         emu::launch(n_agents, C::NT, C::SMEM_BYTES, [&]() { pdip_solve_kernel<C>(p); });    \
         return 0;                                                                           \
     }
