@@ -115,8 +115,9 @@ struct Cfg {
     static constexpr int O_A = O_RFULL + NV;             // [NR][LD]
     static constexpr int O_RHS = O_A + NRP * LD;         // [NRP]
     static constexpr int O_DIAG0 = O_RHS + NRP;          // [NRP]
-    static constexpr int O_INVD = O_DIAG0 + NRP;         // [NRP]
-    static constexpr int O_RED = O_INVD + NRP;           // [2][NW][NRED]
+    static constexpr int O_INVD = O_DIAG0 + NRP;         // [NB][6] inverse diagonal blocks
+    static constexpr int O_SBUF = O_INVD + 2 * NRP;      // [32][3] scaled panel rows of the running factorisation
+    static constexpr int O_RED = O_SBUF + 96;            // [2][NW][NRED]
     static constexpr int O_END = O_RED + 2 * NW * NRED;
     static constexpr int SMEM_BYTES = O_END * 8;
     // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
@@ -225,103 +226,120 @@ __device__ __forceinline__ void block_reduce4(double* v, double* red, int& phase
 }
 
 // ---------------------------------------------------------------------------------------------
-// Banded Cholesky and triangular solves in shared memory, executed by warp 0 only (callers bracket
-// with __syncthreads).  Right-looking with 3-column panels: the 3x3 diagonal block is factorised in
-// closed form by every lane (broadcast loads, no communication), each lane then finishes the three
-// L entries of one row below the panel in registers, and the trailing window is updated with
-// 3-term dot products -- 3 warp barriers per panel instead of 6.
-struct Panel3 {                 // L3 = [l11 0 0; l21 l22 0; l31 l32 l33], i* = 1/l**   // @phase chol
-    double l21, l31, l32, i1, i2, i3;
-};
-
-template <class C>
-__device__ __forceinline__ Panel3 factor_diag3(const double* A, const double* diag0, int c0, int& bad) {
-    Panel3 P;
-    const double p11 = A[c0 * C::LD + c0], p21 = A[(c0 + 1) * C::LD + c0], p31 = A[(c0 + 2) * C::LD + c0];
-    const double p22 = A[(c0 + 1) * C::LD + c0 + 1], p32 = A[(c0 + 2) * C::LD + c0 + 1], p33 = A[(c0 + 2) * C::LD + c0 + 2];
-    double d = p11;
-    if (!(d > 1e-13 * diag0[c0])) { d = 1e300; bad++; }         // pivot guard: freeze that direction
-    P.i1 = rsqrt(d);
-    P.l21 = p21 * P.i1; P.l31 = p31 * P.i1;
-    d = p22 - P.l21 * P.l21;
-    if (!(d > 1e-13 * diag0[c0 + 1])) { d = 1e300; bad++; }
-    P.i2 = rsqrt(d);
-    P.l32 = (p32 - P.l31 * P.l21) * P.i2;
-    d = p33 - P.l31 * P.l31 - P.l32 * P.l32;
-    if (!(d > 1e-13 * diag0[c0 + 2])) { d = 1e300; bad++; }
-    P.i3 = rsqrt(d);
-    return P;
+// Banded block-LDL^T factorisation and solves in shared memory, executed by warp 0 only (callers bracket
+// with __syncthreads).  Phi = Lb Db Lb^T with 3x3 diagonal blocks Db_J (the running Schur complements P_J) and a
+// unit-block-diagonal Lb.  Right-looking over 3-column panels:
+//   * every lane factorises P_J = L D L^T (3x3, closed form, reciprocals by rcp + Newton) from broadcast loads;
+//   * lane l finishes row i = c0 + 3 + l of the panel in registers: t = a L^-T, s = t D^-1, abar = s L^-1 (= a P_J^-1);
+//   * the trailing window is updated with 3-term products  A_ik -= s_i . t_k ;
+//   * abar replaces the panel entries (that is Lb), P_J^-1 is kept for the solves.
+// The solves then need no per-panel triangular solve on their dependency chain:
+//   forward  w_J = b_J - sum_{I<J} Lb_JI w_I ;  middle  v_J = P_J^-1 w_J ;  backward  x_J = v_J - sum_{I>J} Lb_IJ^T x_I.
+// 1/x on the factorisation's critical path: hardware seed + two Newton steps (1e-12 relative; the interior-point
+// iteration is self-correcting, the residuals never go through the factor)
+__device__ __forceinline__ double pivot_rcp(double x) {
+#ifdef LSCQP_CUDA_EMUL
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#endif
 }
 
 template <class C>
-__device__ __forceinline__ int chol_banded(double* A, const double* diag0, double* invd, const int* pr_i, const int* pr_k) {
+__device__ __forceinline__ int chol_banded(double* A, const double* diag0, double* pinv, double* sbuf,
+                                           const int* pr_i, const int* pr_k) {   // @phase chol
     const int lane = threadIdx.x & 31;
     int bad = 0;
     for (int J = 0; J < C::NB; J++) {
         const int c0 = 3 * J;
-        const Panel3 P = factor_diag3<C>(A, diag0, c0, bad);
+        const double p11 = A[c0 * C::LD + c0], p21 = A[(c0 + 1) * C::LD + c0], p31 = A[(c0 + 2) * C::LD + c0];
+        const double p22 = A[(c0 + 1) * C::LD + c0 + 1], p32 = A[(c0 + 2) * C::LD + c0 + 1], p33 = A[(c0 + 2) * C::LD + c0 + 2];
         const int i = c0 + 3 + lane;
-        double a0 = 0, a1 = 0, a2 = 0;
         const bool row = lane < C::BW && i < C::NRP;
+        double a0 = 0, a1 = 0, a2 = 0;
         if (row) { a0 = A[i * C::LD + c0]; a1 = A[i * C::LD + c0 + 1]; a2 = A[i * C::LD + c0 + 2]; }
-        __syncwarp();                                           // every lane has read the diagonal block
-        if (lane == 0) {
-            invd[c0] = P.i1; invd[c0 + 1] = P.i2; invd[c0 + 2] = P.i3;
-            A[(c0 + 1) * C::LD + c0] = P.l21; A[(c0 + 2) * C::LD + c0] = P.l31; A[(c0 + 2) * C::LD + c0 + 1] = P.l32;
-        }
+        // 3x3 LDL^T with pivot guard (a non-positive pivot freezes that direction)
+        double d1 = p11;
+        if (!(d1 > 1e-13 * diag0[c0])) { d1 = 1e300; bad++; }
+        const double r1 = pivot_rcp(d1);
+        const double l21 = p21 * r1, l31 = p31 * r1;
+        double d2 = p22 - l21 * p21;
+        if (!(d2 > 1e-13 * diag0[c0 + 1])) { d2 = 1e300; bad++; }
+        const double r2 = pivot_rcp(d2);
+        const double u32 = p32 - l31 * p21, l32 = u32 * r2;
+        double d3 = p33 - l31 * p31 - l32 * u32;
+        if (!(d3 > 1e-13 * diag0[c0 + 2])) { d3 = 1e300; bad++; }
+        const double r3 = pivot_rcp(d3);
+        // L^-1 = [1 0 0; m21 1 0; m31 m32 1]
+        const double m21 = -l21, m32 = -l32, m31 = l21 * l32 - l31;
+        // row of the panel: t = a L^-T, s = t D^-1, abar = s L^-1
+        const double t0 = a0, t1 = a1 + m21 * a0, t2 = a2 + m31 * a0 + m32 * a1;
+        const double s0 = t0 * r1, s1 = t1 * r2, s2 = t2 * r3;
+        const double ab0 = s0 + m21 * s1 + m31 * s2, ab1 = s1 + m32 * s2, ab2 = s2;
+        __syncwarp();                                           // every lane has read the panel
         if (row) {
-            const double l0 = a0 * P.i1;
-            const double l1 = (a1 - l0 * P.l21) * P.i2;
-            const double l2 = (a2 - l0 * P.l31 - l1 * P.l32) * P.i3;
-            A[i * C::LD + c0] = l0; A[i * C::LD + c0 + 1] = l1; A[i * C::LD + c0 + 2] = l2;
+            A[i * C::LD + c0] = t0; A[i * C::LD + c0 + 1] = t1; A[i * C::LD + c0 + 2] = t2;
+            sbuf[lane * 3] = s0; sbuf[lane * 3 + 1] = s1; sbuf[lane * 3 + 2] = s2;
+        }
+        if (lane == 0) {
+            // P^-1 = L^-T D^-1 L^-1 (symmetric): 11 12 13 22 23 33
+            double* q = pinv + 6 * J;
+            q[0] = r1 + m21 * m21 * r2 + m31 * m31 * r3; q[1] = m21 * r2 + m31 * m32 * r3; q[2] = m31 * r3;
+            q[3] = r2 + m32 * m32 * r3; q[4] = m32 * r3; q[5] = r3;
         }
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < C::NPR; t++) {
             const int ii = c0 + 3 + pr_i[t], kk = c0 + 3 + pr_k[t];
             if (pr_i[t] >= 0 && ii < C::NRP) {
-                const double* li = A + ii * C::LD + c0;
-                const double* lk = A + kk * C::LD + c0;
-                A[ii * C::LD + kk] -= li[0] * lk[0] + li[1] * lk[1] + li[2] * lk[2];
+                const double* si = sbuf + pr_i[t] * 3;
+                const double* tk = A + kk * C::LD + c0;
+                A[ii * C::LD + kk] -= si[0] * tk[0] + si[1] * tk[1] + si[2] * tk[2];
             }
         }
         __syncwarp();
+        if (row) { A[i * C::LD + c0] = ab0; A[i * C::LD + c0 + 1] = ab1; A[i * C::LD + c0 + 2] = ab2; }
+        // (the next panel reads its diagonal block and rows from columns >= c0 + 3 only; the writes above are ordered
+        //  before any later read of these columns by the barriers of the next iterations / the caller)
     }
+    __syncwarp();
     return bad;
 }
 
-// solves (L L^T) x = b in place (b in shared memory)   // @phase trisolve
+// solves Phi x = b in place (b in shared memory) with the factors left by chol_banded
 template <class C>
-__device__ __forceinline__ void chol_solve(const double* A, const double* invd, double* b) {
+__device__ __forceinline__ void chol_solve(const double* A, const double* pinv, double* b) {   // @phase trisolve
     const int lane = threadIdx.x & 31;
     for (int J = 0; J < C::NB; J++) {
         const int c0 = 3 * J;
-        const double l21 = A[(c0 + 1) * C::LD + c0], l31 = A[(c0 + 2) * C::LD + c0], l32 = A[(c0 + 2) * C::LD + c0 + 1];
-        const double z0 = b[c0] * invd[c0];
-        const double z1 = (b[c0 + 1] - l21 * z0) * invd[c0 + 1];
-        const double z2 = (b[c0 + 2] - l31 * z0 - l32 * z1) * invd[c0 + 2];
+        const double w0 = b[c0], w1 = b[c0 + 1], w2 = b[c0 + 2];
         const int i = c0 + 3 + lane;
-        double bi = 0;
-        const bool row = lane < C::BW && i < C::NRP;
-        if (row) bi = b[i] - A[i * C::LD + c0] * z0 - A[i * C::LD + c0 + 1] * z1 - A[i * C::LD + c0 + 2] * z2;
-        __syncwarp();
-        if (lane == 0) { b[c0] = z0; b[c0 + 1] = z1; b[c0 + 2] = z2; }
-        if (row) b[i] = bi;
+        if (lane < C::BW && i < C::NRP) {
+            const double* ab = A + i * C::LD + c0;
+            b[i] = (b[i] - ab[0] * w0) - (ab[1] * w1 + ab[2] * w2);
+        }
         __syncwarp();
     }
+    if (lane < C::NB) {
+        const double* q = pinv + 6 * lane;
+        const double w0 = b[3 * lane], w1 = b[3 * lane + 1], w2 = b[3 * lane + 2];
+        b[3 * lane] = q[0] * w0 + q[1] * w1 + q[2] * w2;
+        b[3 * lane + 1] = q[1] * w0 + q[3] * w1 + q[4] * w2;
+        b[3 * lane + 2] = q[2] * w0 + q[4] * w1 + q[5] * w2;
+    }
+    __syncwarp();
     for (int J = C::NB - 1; J >= 0; J--) {
         const int c0 = 3 * J;
-        const double l21 = A[(c0 + 1) * C::LD + c0], l31 = A[(c0 + 2) * C::LD + c0], l32 = A[(c0 + 2) * C::LD + c0 + 1];
-        const double x2 = b[c0 + 2] * invd[c0 + 2];
-        const double x1 = (b[c0 + 1] - l32 * x2) * invd[c0 + 1];
-        const double x0 = (b[c0] - l21 * x1 - l31 * x2) * invd[c0];
+        const double x0 = b[c0], x1 = b[c0 + 1], x2 = b[c0 + 2];
         const int i = c0 - 1 - lane;                            // rows above the panel that couple to it
-        double bi = 0;
-        const bool row = lane < C::BW && i >= 0;
-        if (row) bi = b[i] - A[c0 * C::LD + i] * x0 - A[(c0 + 1) * C::LD + i] * x1 - A[(c0 + 2) * C::LD + i] * x2;
-        __syncwarp();
-        if (lane == 0) { b[c0] = x0; b[c0 + 1] = x1; b[c0 + 2] = x2; }
-        if (row) b[i] = bi;
+        if (lane < C::BW && i >= 0)
+            b[i] = (b[i] - A[c0 * C::LD + i] * x0) - (A[(c0 + 1) * C::LD + i] * x1 + A[(c0 + 2) * C::LD + i] * x2);
         __syncwarp();
     }
 }
@@ -627,7 +645,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     int bad_piv = 0;
     auto factor_solve = [&](bool factor) {   // @phase factor_solve_call
         if (tid < 32) {
-            if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, pr_i, pr_k);
+            if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, sm + C::O_SBUF, pr_i, pr_k);
             chol_solve<C>(s_A, s_invd, s_rhs);
         }
         __syncthreads();
