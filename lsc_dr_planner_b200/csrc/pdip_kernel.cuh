@@ -348,7 +348,8 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* pinv, 
 // Row algebra.  Row convention: q(c) >= 0, slack s > 0, multiplier lam > 0.  Every row starts with
 // the same primal residual rp = s - q (the start-up shift) and every step scales it by (1 - alpha),
 // so rp is one scalar for the whole QP and neither q nor the row constants are needed after start-up.
-// 1/x for normal positive x: hardware seed (2^-20) + three Newton steps, no special-case branch
+// 1/x for normal positive x: hardware seed (2^-20) + two Newton steps (1e-12 relative), no special-case branch.
+// It only scales Newton directions and multiplier updates; residuals never pass through it.
 __device__ __forceinline__ double fast_rcp(double x) {
 #ifdef LSCQP_CUDA_EMUL
     return 1.0 / x;
@@ -359,20 +360,21 @@ __device__ __forceinline__ double fast_rcp(double x) {
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
     return r;
 #endif
 }
 
-struct MinRatio {            // running min of v / (-dv) over dv < 0, kept as a fraction (no division per row)   // @phase minratio
-    double num, den;
-    __device__ __forceinline__ void init() { num = 1.0; den = 0.0; }
+// Step-to-boundary ratio test min_r v_r / (-dv_r) over dv_r < 0.  Kept in fp32: the step is multiplied by 0.99
+// afterwards, so the 1e-7 relative error of the float quotient cannot push an iterate through its bound, and the
+// value only gates "full step or not" otherwise.
+struct MinRatio {   // @phase minratio
+    float best;
+    __device__ __forceinline__ void init() { best = 3.0e38f; }
     __device__ __forceinline__ void add(double v, double dv) {
-        const bool t = dv < 0.0 && v * den < num * (-dv);
-        num = t ? v : num; den = t ? -dv : den;
+        const float r = __fdividef((float) v, -(float) dv);
+        best = (dv < 0.0) ? fminf(best, r) : best;
     }
-    __device__ __forceinline__ double value() const { return den > 0.0 ? num / den : INFINITY; }
+    __device__ __forceinline__ double value() const { return (double) best; }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) {
     __syncwarp();
     return r;
 }
+inline float __fdividef(float a, float b) { return a / b; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 #undef __launch_bounds__
