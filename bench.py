@@ -163,6 +163,7 @@ def workload_config(args, n_agents):
     return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (gather + LSC assembly + PDIP solve)",
             "agents_per_gpu": n_agents, "K": args.K, "M": 5, "degree": 5, "dim": 3, "rows_per_qp": 27 * args.K + 414,
             "planner_mode": "lsc", "generator": "generateLSC", "l2": "flushed between timed steps (256 MiB write)",
+            "solver": "warm start from initial_traj, exact presolve (velocity-bound row pruning) on; see `variants` for off",
             "parallelism": f"agents sharded over {args.gpus} rank(s), no data-path collective"}
 
 
@@ -265,6 +266,35 @@ def run_ours(args):
                                           "frac": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9 / hbm,
                                           "algorithmic_bytes_per_qp": ab["assemble"]}},
                 "wall_s_timed_region": wall}
+        # secondary numbers (same timing method, 5 steps each): presolve off, and config-4 style synthetic planes
+        variants = {}
+        try:
+            import copy
+            def timed(fn, reps=5):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                tot = 0.0
+                for s_ in range(reps):
+                    flush.fill_(s_ & 0xFF)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b.record(); torch.cuda.synchronize()
+                    tot += a.elapsed_time(b)
+                return tot / reps
+            cfg2 = copy.copy(batch.cfg); cfg2.presolve = False
+            planner2 = BatchPlanner(cfg2, device=local)
+            ms = timed(lambda: planner2.solve_device(d, stream=stream))
+            variants["solve_no_presolve"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
+            ms = timed(lambda: planner2.solve_device(d, stream=stream, warm=False))
+            variants["solve_no_presolve_cold_start"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
+            off, nrm, rhs_ = W.make_synthetic_planes(batch, K=args.K)
+            d.normals.copy_(torch.from_numpy(nrm).to(d.normals.device)); d.rhs.copy_(torch.from_numpy(rhs_).to(d.rhs.device))
+            ms = timed(lambda: planner.solve_device(d, stream=stream))
+            ok = int((d.status != 0).sum().item()) == 0
+            variants["solve_synthetic_planes_config4"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item()), "all_ok": ok}
+        except Exception as exc:  # secondary numbers must never break the contract line
+            variants["error"] = repr(exc)
+        line["variants"] = variants
         if not args.no_cpu:
             from oracle import oracle as orc
             orc.build()

@@ -59,6 +59,8 @@ typedef struct lscqp_config {
     int max_agents;                /* capacity of the staging buffers for the *_host calls     */
     int max_iter;                  /* interior-point iteration cap (0 = default 60)            */
     double tol;                    /* complementarity / primal tolerance (0 = default 1e-11)   */
+    int presolve;                  /* 1: drop obstacles whose rows are all proven inactive by
+                                      bound propagation through the velocity rows (exact)      */
 } lscqp_config;
 
 typedef struct lscqp_handle lscqp_handle;

@@ -159,7 +159,7 @@ inline lscqp_config make_lscqp_config(const Param& p, const Mission& m, int max_
     c.planner_mode = (int) p.planner_mode; c.use_sfc = p.world_use_octomap ? 1 : 0;
     c.comm_range = 0.0;     // communication-range rows (traj_optimizer.cpp:478-500) are not built yet: see DESIGN.md
     for (int k = 0; k < 3; k++) { c.world_min[k] = (double) m.world_min(k); c.world_max[k] = (double) m.world_max(k); }
-    c.z_2d = p.world_z_2d; c.max_obs = max_obs; c.max_agents = 1; c.max_iter = 0; c.tol = 0;
+    c.z_2d = p.world_z_2d; c.max_obs = max_obs; c.max_agents = 1; c.max_iter = 0; c.tol = 0; c.presolve = 1;
     return c;
 }
 

@@ -29,7 +29,8 @@ class LscqpConfig(C.Structure):
                 ("dt", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
                 ("planner_mode", C.c_int), ("use_sfc", C.c_int), ("comm_range", C.c_double),
                 ("world_min", C.c_double * 3), ("world_max", C.c_double * 3), ("z_2d", C.c_double),
-                ("max_obs", C.c_int), ("max_agents", C.c_int), ("max_iter", C.c_int), ("tol", C.c_double)]
+                ("max_obs", C.c_int), ("max_agents", C.c_int), ("max_iter", C.c_int), ("tol", C.c_double),
+                ("presolve", C.c_int)]
 
 
 class LscqpError(RuntimeError):
@@ -62,7 +63,7 @@ def make_config(cfg, max_agents: int = 0) -> LscqpConfig:
     return LscqpConfig(cfg.M, cfg.n, cfg.phi, cfg.dim, cfg.dt, cfg.w_control, cfg.w_terminal, cfg.planner_mode,
                        int(cfg.use_sfc), cfg.comm_range, (C.c_double * 3)(*cfg.world_min),
                        (C.c_double * 3)(*cfg.world_max), cfg.z_2d, cfg.max_obs, max_agents,
-                       getattr(cfg, "max_iter", 0), getattr(cfg, "tol", 0.0))
+                       getattr(cfg, "max_iter", 0), getattr(cfg, "tol", 0.0), int(getattr(cfg, "presolve", True)))
 
 
 def _dp(t):

@@ -73,6 +73,7 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     p.dt = c.dt; p.w_t = c.w_terminal; p.w_c = c.w_control;
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }
     p.use_sfc = c.use_sfc;
+    p.presolve = c.presolve;
     double Q[36];
     jerk_gram(c.n, c.phi, c.dt, Q);
     for (int e = 0; e < 36; e++) p.Q2[e] = 2.0 * c.w_control * Q[e];

@@ -38,6 +38,7 @@ struct SolveParams {
     double dt, w_t;
     double world_min[3], world_max[3];
     int use_sfc;
+    int presolve;               // drop obstacles whose rows are all proven inactive by velocity-bound propagation (exact)
     const float*  state;        // [n][9]   position, velocity, acceleration
     const float*  goal;         // [n][3]   current_goal_point
     const double* limits;       // [n][8]   vmax[3], amax[3], radius, nominal_velocity
@@ -118,7 +119,8 @@ struct Cfg {
     static constexpr int O_INVD = O_DIAG0 + NRP;         // [NB][6] inverse diagonal blocks
     static constexpr int O_SBUF = O_INVD + 2 * NRP;      // [32][3] scaled panel rows of the running factorisation
     static constexpr int O_RED = O_SBUF + 96;            // [2][NW][NRED]
-    static constexpr int O_END = O_RED + 2 * NW * NRED;
+    static constexpr int O_ACT = O_RED + 2 * NW * NRED;  // int[KMAX]: original obstacle index of each kept slot, int keep[KMAX], int n_act
+    static constexpr int O_END = O_ACT + KMAX + 2;
     static constexpr int SMEM_BYTES = O_END * 8;
     // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
     static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6;
@@ -482,10 +484,43 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
         s_termw[M] = sqrt((double) nsq);
     }
+    // ---- presolve: an obstacle is dropped when every one of its rows is strictly satisfied by *any* point that
+    // obeys the velocity rows (traj_optimizer.cpp:443-454): chaining |c[j+1] - c[j]| <= vmax dt/5 from the fixed
+    // control point c[0][2] bounds control point (m, i) to a box of half-width (5m + i - 2) vmax_k dt / 5 around it.
+    // Such rows are redundant for the feasible set, so the minimiser (and its multipliers: zero) is unchanged.
+    int* s_act = reinterpret_cast<int*>(sm + C::O_ACT);
+    int* s_keep = s_act + C::KMAX;
+    for (int e = tid; e < C::KMAX; e += NT) s_keep[e] = (e < K && !p.presolve) ? 1 : 0;
+    __syncthreads();
+    if (p.presolve && lsc_thread) {
+        const double steps = (double) (5 * m_cp + i_cp - 2);
+        for (int oi = grp; oi < K; oi += G) {
+            const double* g = p.normals + ((size_t) (obs0 + oi) * M + m_cp) * 3;
+            const double nx = g[0], ny = g[1], nz = (D == 3) ? g[2] : 0.0;
+            const double b = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            double lo = nx * s_x0[2] + ny * s_x0[5] - steps * (fabs(nx) * s_vlim[0] + fabs(ny) * s_vlim[1]);
+            if (D == 3) lo += nz * s_x0[8] - steps * fabs(nz) * s_vlim[2];
+            const bool zero_normal = (float) nx == 0.0f && (float) ny == 0.0f && (D == 2 || (float) nz == 0.0f);
+            if (!(lo - b > 1e-6) && !zero_normal) s_keep[oi] = 1;      // benign race: every writer stores 1
+        }
+    }
+    __syncthreads();
+    if (tid < K && s_keep[tid]) {
+        int pos = 0;
+        for (int u = 0; u < tid; u++) pos += s_keep[u];
+        s_act[pos] = tid;
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int u = 0; u < K; u++) n += s_keep[u];
+        s_keep[C::KMAX] = n;
+    }
+    __syncthreads();
+    K = s_keep[C::KMAX];                                               // kept obstacles, compacted into slots 0..K-1
     for (int e = tid; e < K * M; e += NT) {
         // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference
         // (traj_optimizer.cpp:409-411): here they become the constant row 0.c >= -1, which never binds
-        const double* g = p.normals + ((size_t) obs0 * M + e) * 3;
+        const double* g = p.normals + ((size_t) (obs0 + s_act[e / M]) * M + e % M) * 3;
         double nx = g[0], ny = g[1], nz = g[2];
         const float fx = (float) nx, fy = (float) ny, fz = (float) nz;
         const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
@@ -663,7 +698,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
-            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
             if (D == 3) q += n[2] * cz;
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             ls[j] = q;
@@ -965,7 +1000,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
-            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
             if (D == 3) q += n[2] * cz;
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             rp_true = fmax(rp_true, fabs(ls[j] - q));
@@ -1019,14 +1054,14 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     }
     if (p.dual_out) {
         double* du = p.dual_out + (size_t) agent * p.dual_stride;
+        for (int e = tid; e < C::KMAX * M * 6; e += NT) du[e] = 0.0;       // dropped / skipped rows: multiplier 0
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            const int oi = grp + G * j;
-            if (cp_valid && oi < C::KMAX) {
-                const double* n = s_nrm + (oi * M + m_cp) * 3;
-                const bool real_row = j < nrow && !(n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0);
-                du[(oi * M + m_cp) * 6 + i_cp] = real_row ? ll[j] : 0.0;
-            }
+            if (j >= nrow) break;
+            const int slot = grp + G * j;
+            const double* n = s_nrm + (slot * M + m_cp) * 3;
+            if (!(n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0)) du[(s_act[slot] * M + m_cp) * 6 + i_cp] = ll[j];
         }
         if (var_thread) {
             // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2

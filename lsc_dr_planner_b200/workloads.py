@@ -34,6 +34,7 @@ class PlannerConfig:
     max_obs: int = 40
     max_iter: int = 0            # 0 = library default (60)
     tol: float = 0.0             # 0 = library default (1e-11 on the mean complementarity gap)
+    presolve: bool = True        # exact row pruning by bound propagation (lscqp_config.presolve)
 
 
 def bernstein_from_poly(coef: np.ndarray, t0: float, t1: float) -> np.ndarray:

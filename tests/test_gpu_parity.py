@@ -99,6 +99,28 @@ def test_warm_start_from_infeasible_trajectory():
     _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=6)
 
 
+def test_presolve_is_exact():
+    """dropping obstacles proven inactive by bound propagation does not move the optimum"""
+    import copy
+    batch = W.make_forest_batch(256, K=40)
+    agents = list(range(0, 256, 8))
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    cfg_off = copy.copy(batch.cfg); cfg_off.presolve = False
+    p_on, p_off = _planner(batch.cfg), _planner(cfg_off)
+    c_on, cost_on, st_on, it_on, _, dual_on = _solve_host(p_on, batch, agents, off, normals, rhs, want_dual=True)
+    c_off, cost_off, st_off, it_off, _, dual_off = _solve_host(p_off, batch, agents, off, normals, rhs, want_dual=True)
+    assert (st_on == 0).all() and (st_off == 0).all()
+    assert np.abs(c_on - c_off).max() < CTRL_TOL
+    assert np.abs(cost_on - cost_off).max() <= OBJ_RTOL * np.abs(cost_off).max()
+    # multipliers of dropped rows are exactly zero with presolve and negligible without (the others need not be
+    # unique at degenerate vertices, so they are not compared entry by entry)
+    dropped = (np.abs(dual_on[:, :40 * 5 * 6]).reshape(len(agents), 40, 30).sum(axis=2) == 0)
+    assert dropped.mean() > 0.5
+    lsc_off = np.abs(dual_off[:, :40 * 5 * 6]).reshape(len(agents), 40, 30)
+    assert lsc_off[dropped].max() < 1e-6
+    _check_against_oracle(batch, agents[:8], off, normals, rhs, c_on, cost_on, st_on, min_checked=5)
+
+
 def test_solve_parity_synthetic_planes():
     """config 4 shape: random half-spaces with a strictly feasible point"""
     batch = W.make_forest_batch(256, K=40, seed=20260004)
