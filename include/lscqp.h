@@ -53,7 +53,8 @@ typedef struct lscqp_config {
     double dt, w_control, w_terminal;   /* param.dt, control_input_weight, terminal_weight    */
     int planner_mode;              /* LSCQP_MODE_*; LSC adds the terminal-stop equalities      */
     int use_sfc;                   /* param.world_use_octomap: box constraints from `sfc`      */
-    double comm_range;             /* param.communication_range; must be <= 0 in this release  */
+    double comm_range;             /* param.communication_range; > 0 adds the rows of
+                                      traj_optimizer.cpp:477-500 (LSC mode only), <= 0 disables  */
     double world_min[3], world_max[3], z_2d;   /* mission.world_min/max, param.world_z_2d      */
     int max_obs;                   /* capacity: obstacles per agent (<= 40)                    */
     int max_agents;                /* capacity of the staging buffers for the *_host calls     */
@@ -80,7 +81,8 @@ int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** out);
 int lscqp_destroy(lscqp_handle* h);
 
 /* Number of doubles per agent in dual_out (layout: [max_obs_padded][M][6] LSC rows, then
- * [dim*M*6][6] box rows = lb, ub, vel+, vel-, acc+, acc- of the variable's stencil). */
+ * [dim*M*6][6] box rows = lb, ub, vel+, vel-, acc+, acc- of the variable's stencil, then with
+ * comm_range > 0 [dim][M + M(M-1)/2][2] communication pairs = upper-side, lower-side). */
 int lscqp_dual_stride(const lscqp_handle* h);
 int lscqp_max_obs_padded(const lscqp_handle* h);
 
@@ -106,6 +108,7 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
         const float*  goal,         /* [n_agents][3]  current_goal_point                        */
         const double* limits,       /* [n_agents][8]  max_vel[3], max_acc[3], radius, nominal_velocity */
         const float*  sfc,          /* [n_agents][M][6] box_min, box_max (use_sfc) or NULL      */
+        const float*  next_waypoint,/* [n_agents][3] agent.next_waypoint (comm_range > 0) or NULL */
         const int*    obs_offsets,  /* [n_agents+1]                                              */
         const double* normals,      /* [sum K][M][3]                                             */
         const double* rhs,          /* [sum K][M][6]                                             */
@@ -123,7 +126,7 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
 /* Same as lscqp_solve_batch with HOST buffers: copies inputs host->device, solves, copies
  * ctrl/cost/status (and the optional outputs) back, and synchronises the stream. */
 int lscqp_solve_host(lscqp_handle* h, int n_agents,
-        const float* state, const float* goal, const double* limits, const float* sfc,
+        const float* state, const float* goal, const double* limits, const float* sfc, const float* next_waypoint,
         const int* obs_offsets, const double* normals, const double* rhs, const float* initial_traj,
         double* ctrl_out, double* cost_out, int* status_out, int* iters_out, double* kkt_out,
         double* dual_out);
@@ -132,7 +135,7 @@ int lscqp_solve_host(lscqp_handle* h, int n_agents,
  * solve, copy the solutions back.  Obstacles are given as indices into the batch's own agents
  * (what MultiSyncSimulator::broadcastMsgs builds, src/multi_sync_simulator.cpp:305-352). */
 int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents,
-        const float* state, const float* goal, const double* limits, const float* sfc,
+        const float* state, const float* goal, const double* limits, const float* sfc, const float* next_waypoint,
         const float* own_traj, const double* agent_meta,
         const int* obs_offsets, const int* obs_index,      /* [sum K] neighbour agent ids */
         double* ctrl_out, double* cost_out, int* status_out, int* iters_out);

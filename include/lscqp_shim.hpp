@@ -157,7 +157,8 @@ inline lscqp_config make_lscqp_config(const Param& p, const Mission& m, int max_
     c.M = p.M; c.n = p.n; c.phi = p.phi; c.dim = p.world_dimension;
     c.dt = p.dt; c.w_control = p.control_input_weight; c.w_terminal = p.terminal_weight;
     c.planner_mode = (int) p.planner_mode; c.use_sfc = p.world_use_octomap ? 1 : 0;
-    c.comm_range = 0.0;     // communication-range rows (traj_optimizer.cpp:478-500) are not built yet: see DESIGN.md
+    // communication-range rows (traj_optimizer.cpp:477-500) exist in LSC mode only on the device side
+    c.comm_range = (p.planner_mode == PlannerMode::LSC) ? p.communication_range : 0.0;
     for (int k = 0; k < 3; k++) { c.world_min[k] = (double) m.world_min(k); c.world_max[k] = (double) m.world_max(k); }
     c.z_2d = p.world_z_2d; c.max_obs = max_obs; c.max_agents = 1; c.max_iter = 0; c.tol = 0; c.presolve = 1;
     return c;
@@ -178,10 +179,11 @@ public:
     TrajOptResult solve(const Agent& agent, const CollisionConstraints& constraints, const traj_t& initial_traj,
                         bool /*use_primal_algorithm*/) {
         const int M = param.M, N = param.n + 1, D = param.world_dimension;
-        float state[9], goal[3];
+        float state[9], goal[3], wp[3];
         for (int k = 0; k < 3; k++) {
             state[k] = agent.current_state.position(k); state[3 + k] = agent.current_state.velocity(k);
             state[6 + k] = agent.current_state.acceleration(k); goal[k] = agent.current_goal_point(k);
+            wp[k] = agent.next_waypoint(k);
         }
         double limits[8] = {agent.max_vel[0], agent.max_vel[1], agent.max_vel[2], agent.max_acc[0], agent.max_acc[1],
                             agent.max_acc[2], agent.radius, agent.nominal_velocity};
@@ -196,7 +198,7 @@ public:
         int offsets[2] = {0, (int) constraints.getObsSize()};
         std::vector<double> ctrl(D * M * N);
         double cost = 0; int status = 0;
-        int rc = lscqp_solve_host(handle, 1, state, goal, limits, param.world_use_octomap ? sfc.data() : nullptr, offsets,
+        int rc = lscqp_solve_host(handle, 1, state, goal, limits, param.world_use_octomap ? sfc.data() : nullptr, wp, offsets,
                                   normals.data(), rhs.data(), have_warm ? warm.data() : nullptr, ctrl.data(), &cost, &status,
                                   nullptr, nullptr, nullptr);
         if (rc != 0 || status != LSCQP_OK) throw PlanningReport::QPFAILED;
@@ -238,7 +240,7 @@ public:
     void plan(int generator, const std::vector<Agent>& agents, const std::vector<traj_t>& initial_trajs,
               const std::vector<std::vector<int>>& neighbours, std::vector<traj_t>& desired, std::vector<int>& status) {
         const int n = (int) agents.size(), M = param.M, N = param.n + 1, D = param.world_dimension;
-        std::vector<float> state(n * 9), goal(n * 3), own(n * M * N * 3);
+        std::vector<float> state(n * 9), goal(n * 3), wp(n * 3), own(n * M * N * 3);
         std::vector<double> limits(n * 8), meta(n * 2), ctrl((size_t) n * D * M * N), cost(n);
         std::vector<int> off(n + 1, 0), index, iters(n);
         for (int a = 0; a < n; a++) {
@@ -246,6 +248,7 @@ public:
             for (int k = 0; k < 3; k++) {
                 state[a * 9 + k] = g.current_state.position(k); state[a * 9 + 3 + k] = g.current_state.velocity(k);
                 state[a * 9 + 6 + k] = g.current_state.acceleration(k); goal[a * 3 + k] = g.current_goal_point(k);
+                wp[a * 3 + k] = g.next_waypoint(k);
                 limits[a * 8 + k] = g.max_vel[k]; limits[a * 8 + 3 + k] = g.max_acc[k];
             }
             limits[a * 8 + 6] = g.radius; limits[a * 8 + 7] = g.nominal_velocity; meta[a * 2] = g.radius; meta[a * 2 + 1] = g.downwash;
@@ -254,7 +257,7 @@ public:
             off[a + 1] = (int) index.size();
         }
         status.assign(n, 0);
-        int rc = lscqp_replan_host(handle, generator, n, state.data(), goal.data(), limits.data(), nullptr, own.data(), meta.data(),
+        int rc = lscqp_replan_host(handle, generator, n, state.data(), goal.data(), limits.data(), nullptr, wp.data(), own.data(), meta.data(),
                                    off.data(), index.data(), ctrl.data(), cost.data(), status.data(), iters.data());
         if (rc != 0) throw std::runtime_error(std::string("[BatchTrajOptimizer] ") + lscqp_last_error());
         desired.assign(n, traj_t(M, param.n, param.dt));

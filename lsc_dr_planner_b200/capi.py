@@ -130,8 +130,9 @@ class LscQp:
 
     # ------------------------------------------------------------------ device entry points
     def solve_batch(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status,
-                    iters=None, kkt=None, dual=None, stream=0, initial_traj=None):
-        self._check(self.lib.lscqp_solve_batch(self.h, n, _dp(state), _dp(goal), _dp(limits), _dp(sfc), _dp(obs_offsets),
+                    iters=None, kkt=None, dual=None, stream=0, initial_traj=None, next_waypoint=None):
+        self._check(self.lib.lscqp_solve_batch(self.h, n, _dp(state), _dp(goal), _dp(limits), _dp(sfc), _dp(next_waypoint),
+                                               _dp(obs_offsets),
                                                _dp(normals), _dp(rhs), _dp(initial_traj), _dp(ctrl), _dp(cost), _dp(status), _dp(iters),
                                                _dp(kkt), _dp(dual), C.c_void_p(stream)))
 
@@ -153,18 +154,20 @@ class LscQp:
 
     # ------------------------------------------------------------------ host entry points
     def solve_host(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status, iters=None,
-                   kkt=None, dual=None, initial_traj=None):
+                   kkt=None, dual=None, initial_traj=None, next_waypoint=None):
         self._check(self.lib.lscqp_solve_host(self.h, n, _hp(state, np.float32), _hp(goal, np.float32),
-                                              _hp(limits, np.float64), _hp(sfc, np.float32), _hp(obs_offsets, np.int32),
+                                              _hp(limits, np.float64), _hp(sfc, np.float32),
+                                              _hp(next_waypoint, np.float32), _hp(obs_offsets, np.int32),
                                               _hp(normals, np.float64), _hp(rhs, np.float64), _hp(initial_traj, np.float32),
                                               _hp(ctrl, np.float64),
                                               _hp(cost, np.float64), _hp(status, np.int32), _hp(iters, np.int32),
                                               _hp(kkt, np.float64), _hp(dual, np.float64)))
 
     def replan_host(self, generator, n, state, goal, limits, sfc, own_traj, agent_meta, obs_offsets, obs_index, ctrl,
-                    cost, status, iters=None):
+                    cost, status, iters=None, next_waypoint=None):
         self._check(self.lib.lscqp_replan_host(self.h, generator, n, _hp(state, np.float32), _hp(goal, np.float32),
-                                               _hp(limits, np.float64), _hp(sfc, np.float32), _hp(own_traj, np.float32),
+                                               _hp(limits, np.float64), _hp(sfc, np.float32),
+                                               _hp(next_waypoint, np.float32), _hp(own_traj, np.float32),
                                                _hp(agent_meta, np.float64), _hp(obs_offsets, np.int32),
                                                _hp(obs_index, np.int32), _hp(ctrl, np.float64), _hp(cost, np.float64),
                                                _hp(status, np.int32), _hp(iters, np.int32)))

@@ -56,7 +56,7 @@ inline int validate_config(const lscqp_config& c) {
     if (!(c.dim == 2 || c.dim == 3)) return LSCQP_E_INVALID;
     if (!(c.planner_mode == LSCQP_MODE_DLSC || c.planner_mode == LSCQP_MODE_LSC || c.planner_mode == LSCQP_MODE_BVC))
         return LSCQP_E_INVALID;
-    if (c.comm_range > 0) return LSCQP_E_INVALID;
+    if (c.comm_range > 0 && c.planner_mode != LSCQP_MODE_LSC) return LSCQP_E_INVALID;   // comm rows are built for LSC mode
     if (c.max_obs < 0 || c.max_obs > 40) return LSCQP_E_INVALID;
     if (!(c.dt > 0) || !(c.w_control > 0) || !(c.w_terminal >= 0)) return LSCQP_E_INVALID;
     return 0;
@@ -74,6 +74,7 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }
     p.use_sfc = c.use_sfc;
     p.presolve = c.presolve;
+    p.comm_range = c.comm_range;
     double Q[36];
     jerk_gram(c.n, c.phi, c.dt, Q);
     for (int e = 0; e < 36; e++) p.Q2[e] = 2.0 * c.w_control * Q[e];
@@ -133,6 +134,21 @@ inline ProjTable build_projection() {
                 if (a.j < 0) { for (int x = 3; x < 6; x++) for (int y = 0; y < 3; y++) add(T[y][b.j], blk(a.k, a.s, x, y)); }
                 else for (int y = 0; y < 3; y++) add(T[y][b.j], blk(a.k, a.s, 3 + a.j, y));
             }
+            if (C::COMM) {
+                // communication-range pairs act on the end-point variables E(k, a) directly
+                auto endpoint = [](int k, int a) { return (C::TERM && a == M - 1) ? (M - 1) * C::NZS + k : a * C::NZS + k * 3 + 2; };
+                const int src0 = C::O_WC - C::O_BLK;
+                for (int k = 0; k < D; k++)
+                    for (int x = 0; x < M; x++) {
+                        const int Ea = endpoint(k, x);
+                        if (r1 == Ea && r2 == Ea) add(1.0, src0 + k * C::PP + x);                    // box pair of E_x
+                        for (int y = 0; y < x; y++) {
+                            const int Eb = endpoint(k, y), pe = src0 + k * C::PP + M + x * (x - 1) / 2 + y;
+                            if ((r1 == Ea && r2 == Ea) || (r1 == Eb && r2 == Eb)) add(1.0, pe);
+                            if (r1 == std::max(Ea, Eb) && r2 == std::min(Ea, Eb)) add(-1.0, pe);
+                        }
+                    }
+            }
             e.count = (int) e.t.size();
             ents.push_back(e);
         }
@@ -146,9 +162,10 @@ inline ProjTable build_projection() {
     return out;
 }
 
-// kernel instances: (M, D, TERM) with 4 obstacle groups x 10 rows per thread (K <= 40)
+// kernel instances: (M, D, TERM, COMM) with 4 obstacle groups x 10 rows per thread (K <= 40)
 #define LSCQP_FOR_EACH_INSTANCE(X) \
-    X(5, 3, true) X(5, 3, false) X(5, 2, true) X(5, 2, false) \
-    X(10, 3, true) X(10, 3, false) X(10, 2, true) X(10, 2, false)
+    X(5, 3, true, false) X(5, 3, false, false) X(5, 2, true, false) X(5, 2, false, false) \
+    X(10, 3, true, false) X(10, 3, false, false) X(10, 2, true, false) X(10, 2, false, false) \
+    X(5, 3, true, true) X(5, 2, true, true) X(10, 3, true, true) X(10, 2, true, true)
 
 }  // namespace lscqp

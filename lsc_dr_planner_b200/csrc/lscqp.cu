@@ -46,7 +46,7 @@ struct lscqp_handle {
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
-    DevBuf d_proj_ent, d_proj_term;
+    DevBuf d_proj_ent, d_proj_term, d_wp;
     unsigned long long launches = 0;
 };
 
@@ -62,7 +62,7 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     if (!cfg || !out) return fail(LSCQP_E_INVALID, "null argument");
     int rc = validate_config(*cfg);
     if (rc) return fail(rc, "unsupported configuration (need n=5, phi=3, M in {5,10}, dim in {2,3}, "
-                            "mode in {DLSC,LSC,BVC}, comm_range<=0, max_obs<=40)");
+                            "mode in {DLSC,LSC,BVC}, comm_range>0 only in LSC mode, max_obs<=40)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(LSCQP_E_NODEVICE, "no CUDA device: liblscqp has no CPU fallback");
@@ -74,9 +74,10 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     fill_solve_params(*cfg, h->base);
     const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
     bool found = false;
-#define X(M_, D_, T_)                                                   \
-    if (cfg->M == M_ && cfg->dim == D_ && term == T_) {                 \
-        using C = Cfg<M_, D_, T_, 4, 10>;                               \
+    const bool comm = cfg->comm_range > 0;
+#define X(M_, D_, T_, C_)                                               \
+    if (cfg->M == M_ && cfg->dim == D_ && term == T_ && comm == C_) {   \
+        using C = Cfg<M_, D_, T_, 4, 10, C_>;                           \
         if (set_smem_attr<C>()) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); } \
         h->dual_stride = C::DUAL_STRIDE; h->kmax = C::KMAX; h->nv = C::NV; found = true; \
         const ProjTable tab = build_projection<C>();                    \
@@ -102,7 +103,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
-                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term};
+                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term, &h->d_wp};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -114,25 +115,27 @@ extern "C" int lscqp_max_obs_padded(const lscqp_handle* h) { return h ? h->kmax 
 extern "C" unsigned long long lscqp_launch_count(const lscqp_handle* h) { return h ? h->launches : 0; }
 
 extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* state, const float* goal,
-                                 const double* limits, const float* sfc, const int* obs_offsets,
+                                 const double* limits, const float* sfc, const float* next_waypoint, const int* obs_offsets,
                                  const double* normals, const double* rhs, const float* initial_traj, double* ctrl_out,
                                  double* cost_out, int* status_out, int* iters_out, double* kkt_out, double* dual_out,
                                  void* stream) {
     if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+    if (h->cfg.comm_range > 0 && !next_waypoint) return fail(LSCQP_E_INVALID, "comm_range set but next_waypoint is null");
     if (n_agents == 0) return 0;
     SolveParams p = h->base;
     p.n_agents = n_agents;
-    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
+    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc; p.next_waypoint = next_waypoint;
     p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs; p.warm_traj = initial_traj;
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out; p.dual_stride = h->dual_stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool term = h->cfg.planner_mode == LSCQP_MODE_LSC;
-#define X(M_, D_, T_)                                                                   \
-    if (h->cfg.M == M_ && h->cfg.dim == D_ && term == T_) {                             \
-        using C = Cfg<M_, D_, T_, 4, 10>;                                               \
+    const bool comm = h->cfg.comm_range > 0;
+#define X(M_, D_, T_, C_)                                                               \
+    if (h->cfg.M == M_ && h->cfg.dim == D_ && term == T_ && comm == C_) {               \
+        using C = Cfg<M_, D_, T_, 4, 10, C_>;                                           \
         pdip_solve_kernel<C><<<n_agents, C::NT, C::SMEM_BYTES, st>>>(p);                \
     }
     LSCQP_FOR_EACH_INSTANCE(X)
@@ -206,7 +209,7 @@ extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctr
 #define RESERVE(buf, n) do { if ((buf).reserve(n)) return fail(LSCQP_E_CUDA, "cudaMalloc failed"); } while (0)
 
 extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* state, const float* goal,
-                                const double* limits, const float* sfc, const int* obs_offsets,
+                                const double* limits, const float* sfc, const float* next_waypoint, const int* obs_offsets,
                                 const double* normals, const double* rhs, const float* initial_traj, double* ctrl_out,
                                 double* cost_out, int* status_out, int* iters_out, double* kkt_out, double* dual_out) {
     if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
@@ -237,12 +240,18 @@ extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* stat
         CK(cudaMemcpyAsync(h->d_normals.p, normals, sumK * M * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->d_rhs.p, rhs, sumK * M * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    if (h->cfg.comm_range > 0) {
+        if (!next_waypoint) return fail(LSCQP_E_INVALID, "comm_range set but next_waypoint is null");
+        RESERVE(h->d_wp, n_agents * 3 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_wp.p, next_waypoint, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     if (initial_traj) {
         RESERVE(h->d_own, (size_t) n_agents * M * 18 * sizeof(float));
         CK(cudaMemcpyAsync(h->d_own.p, initial_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     int rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
-                               h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(),
+                               h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr,
+                               h->cfg.comm_range > 0 ? h->d_wp.as<float>() : nullptr, h->d_off.as<int>(),
                                h->d_normals.as<double>(), h->d_rhs.as<double>(), initial_traj ? h->d_own.as<float>() : nullptr,
                                h->d_ctrl.as<double>(),
                                h->d_cost.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), h->d_kkt.as<double>(),
@@ -259,7 +268,8 @@ extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* stat
 }
 
 extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, const float* state, const float* goal,
-                                 const double* limits, const float* sfc, const float* own_traj, const double* agent_meta,
+                                 const double* limits, const float* sfc, const float* next_waypoint, const float* own_traj,
+                                 const double* agent_meta,
                                  const int* obs_offsets, const int* obs_index, double* ctrl_out, double* cost_out,
                                  int* status_out, int* iters_out) {
     if (!h || n_agents < 0 || !state || !goal || !limits || !own_traj || !agent_meta || !obs_offsets || !ctrl_out ||
@@ -290,6 +300,11 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     CK(cudaMemcpyAsync(h->d_limits.p, limits, n_agents * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_own.p, own_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (h->cfg.comm_range > 0) {
+        if (!next_waypoint) return fail(LSCQP_E_INVALID, "comm_range set but next_waypoint is null");
+        RESERVE(h->d_wp, n_agents * 3 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_wp.p, next_waypoint, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     CK(cudaMemcpyAsync(h->d_ameta.p, agent_meta, n_agents * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (sumK) CK(cudaMemcpyAsync(h->d_index.p, obs_index, sumK * sizeof(int), cudaMemcpyHostToDevice, st));
     int rc = lscqp_gather_obstacles(h, (int) sumK, h->d_index.as<int>(), h->d_own.as<float>(), h->d_ameta.as<double>(),
@@ -301,7 +316,8 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
                                   h->d_opos.as<float>(), h->d_normals.as<double>(), h->d_rhs.as<double>(), st);
     if (rc) return rc;
     rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
-                           h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->d_off.as<int>(), h->d_normals.as<double>(),
+                           h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->cfg.comm_range > 0 ? h->d_wp.as<float>() : nullptr,
+                           h->d_off.as<int>(), h->d_normals.as<double>(),
                            h->d_rhs.as<double>(), h->d_own.as<float>(), h->d_ctrl.as<double>(), h->d_cost.as<double>(),
                            h->d_status.as<int>(), h->d_iters.as<int>(), nullptr, nullptr, st);
     if (rc) return rc;

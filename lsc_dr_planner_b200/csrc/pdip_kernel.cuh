@@ -43,6 +43,8 @@ struct SolveParams {
     const float*  goal;         // [n][3]   current_goal_point
     const double* limits;       // [n][8]   vmax[3], amax[3], radius, nominal_velocity
     const float*  sfc;          // [n][M][6] box_min, box_max  (use_sfc)
+    const float*  next_waypoint;   // [n][3]  (communication-range rows)
+    double comm_range;
     const int*    obs_offsets;  // [n+1]
     const double* normals;      // [sumK][M][3]
     const double* rhs;          // [sumK][M][6]   b = n.p + d
@@ -66,10 +68,11 @@ struct SolveParams {
 
 enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3 };
 
-template <int M_, int D_, bool TERM_, int G_, int KPT_>
+template <int M_, int D_, bool TERM_, int G_, int KPT_, bool COMM_ = false>
 struct Cfg {
     static constexpr int M = M_, D = D_, G = G_, KPT = KPT_;
     static constexpr bool TERM = TERM_;
+    static constexpr bool COMM = COMM_;                  // communication-range rows (traj_optimizer.cpp:477-500): dense reduced matrix
     static constexpr int NCP = 6 * M;                    // control points per dimension
     static constexpr int CPW = ((NCP + 31) / 32) * 32;   // threads per obstacle group
     static constexpr int NT = CPW * G;                   // threads per CTA
@@ -77,15 +80,19 @@ struct Cfg {
     static constexpr int NV = D * NCP;                   // full-space variables
     static constexpr int NZS = 3 * D;                    // reduced variables per stage
     static constexpr int NR = TERM ? (M - 1) * NZS + D : M * NZS;
-    static constexpr int BW = 2 * NZS - 1;               // half bandwidth of the reduced matrix
+    static constexpr int NRP0 = ((NR + 2) / 3) * 3;
+    static constexpr int BW = COMM ? NRP0 - 1 : 2 * NZS - 1;   // half bandwidth of the reduced matrix (dense with comm rows)
     static constexpr int NRP = ((NR + 2) / 3) * 3;       // padded to whole 3x3 panels (identity rows)
     static constexpr int NB = NRP / 3;                   // panels
-    static constexpr int BWS = BW + 2;                   // stored / assembled half bandwidth (panel overhang)
+    static constexpr int BWS = COMM ? NRP0 - 1 : BW + 2;  // stored / assembled half bandwidth (panel overhang)
     static constexpr int LD = NRP | 1;                   // odd leading dimension
     static constexpr int NS = D * (D + 1) / 2;           // unique entries of a DxD symmetric block
     static constexpr int KMAX = G * KPT;
-    static constexpr int NPAIR = BW * (BW + 1) / 2;      // trailing-update pairs per Cholesky column
-    static constexpr int NPR = (NPAIR + 31) / 32;
+    static constexpr int NPAIR = COMM ? 0 : BW * (BW + 1) / 2;   // trailing-update pairs per panel (banded instances)
+    static constexpr int PP = M * (M - 1) / 2 + M;       // comm pairs per dimension: end-point differences + end-point boxes
+    static constexpr int PC = COMM ? D * PP : 0;         // comm (+/-) row pairs, one per thread t < PC
+    static constexpr int NBX = COMM ? 8 : 6;             // box-type rows per variable thread
+    static constexpr int NPR = NPAIR ? (NPAIR + 31) / 32 : 1;
     static constexpr int NRED = 4;
     static constexpr int MIN_CTAS = NT > 128 ? 2 : 3;    // register budget: 65536 / (MIN_CTAS * NT) per thread
     // shared memory layout (doubles)
@@ -117,13 +124,14 @@ struct Cfg {
     static constexpr int O_RHS = O_A + NRP * LD;         // [NRP]
     static constexpr int O_DIAG0 = O_RHS + NRP;          // [NRP]
     static constexpr int O_INVD = O_DIAG0 + NRP;         // [NB][6] inverse diagonal blocks
-    static constexpr int O_SBUF = O_INVD + 2 * NRP;      // [32][3] scaled panel rows of the running factorisation
-    static constexpr int O_RED = O_SBUF + 96;            // [2][NW][NRED]
+    static constexpr int O_SBUF = O_INVD + 2 * NRP;      // [rows][3] scaled panel rows of the running factorisation
+    static constexpr int O_WC = O_SBUF + (COMM ? 3 * NRP : 96);   // [PC] comm pair weights (projection source), then [PC] rhs multipliers
+    static constexpr int O_RED = O_WC + 2 * PC;          // [2][NW][NRED]
     static constexpr int O_ACT = O_RED + 2 * NW * NRED;  // int[KMAX]: original obstacle index of each kept slot, int keep[KMAX], int n_act
     static constexpr int O_END = O_ACT + KMAX + 2;
     static constexpr int SMEM_BYTES = O_END * 8;
     // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
-    static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6;
+    static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6 + 2 * PC;   // (+ comm pairs: upper-side, lower-side multiplier)
 };
 
 // continuity map c[m][0..2] = T y[m-1][3..5]
@@ -347,6 +355,113 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* pinv, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense variant for the instances with communication-range rows (their end-point couplings fill the band).
+// Same block-LDL^T recurrences; the panel rows are looped in chunks of 32 by warp 0 and the trailing update is
+// spread over the whole CTA (two CTA barriers per panel).  These instances serve the small reference missions
+// (10 agents, launch/simulation.launch), not the throughput benchmark.
+template <class C>
+__device__ __forceinline__ int chol_dense_cta(double* A, const double* diag0, double* pinv, double* sbuf) {
+    constexpr int CH = (C::NRP + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int bad = 0;
+    for (int J = 0; J < C::NB; J++) {
+        const int c0 = 3 * J;
+        double ab[CH][3];
+        if (tid < 32) {
+            const double p11 = A[c0 * C::LD + c0], p21 = A[(c0 + 1) * C::LD + c0], p31 = A[(c0 + 2) * C::LD + c0];
+            const double p22 = A[(c0 + 1) * C::LD + c0 + 1], p32 = A[(c0 + 2) * C::LD + c0 + 1], p33 = A[(c0 + 2) * C::LD + c0 + 2];
+            double d1 = p11;
+            if (!(d1 > 1e-13 * diag0[c0])) { d1 = 1e300; bad++; }
+            const double r1 = pivot_rcp(d1);
+            const double l21 = p21 * r1, l31 = p31 * r1;
+            double d2 = p22 - l21 * p21;
+            if (!(d2 > 1e-13 * diag0[c0 + 1])) { d2 = 1e300; bad++; }
+            const double r2 = pivot_rcp(d2);
+            const double u32 = p32 - l31 * p21, l32 = u32 * r2;
+            double d3 = p33 - l31 * p31 - l32 * u32;
+            if (!(d3 > 1e-13 * diag0[c0 + 2])) { d3 = 1e300; bad++; }
+            const double r3 = pivot_rcp(d3);
+            const double m21 = -l21, m32 = -l32, m31 = l21 * l32 - l31;
+            double tt[CH][3];
+#pragma unroll
+            for (int ch = 0; ch < CH; ch++) {
+                const int i = c0 + 3 + lane + 32 * ch;
+                double a0 = 0, a1 = 0, a2 = 0;
+                if (i < C::NRP) { a0 = A[i * C::LD + c0]; a1 = A[i * C::LD + c0 + 1]; a2 = A[i * C::LD + c0 + 2]; }
+                tt[ch][0] = a0; tt[ch][1] = a1 + m21 * a0; tt[ch][2] = a2 + m31 * a0 + m32 * a1;
+                const double s0 = tt[ch][0] * r1, s1 = tt[ch][1] * r2, s2 = tt[ch][2] * r3;
+                ab[ch][0] = s0 + m21 * s1 + m31 * s2; ab[ch][1] = s1 + m32 * s2; ab[ch][2] = s2;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < CH; ch++) {
+                const int i = c0 + 3 + lane + 32 * ch;
+                if (i < C::NRP) {
+                    A[i * C::LD + c0] = tt[ch][0]; A[i * C::LD + c0 + 1] = tt[ch][1]; A[i * C::LD + c0 + 2] = tt[ch][2];
+                    double* sb = sbuf + (i - c0 - 3) * 3;
+                    sb[0] = tt[ch][0] * r1; sb[1] = tt[ch][1] * r2; sb[2] = tt[ch][2] * r3;
+                }
+            }
+            if (lane == 0) {
+                double* q = pinv + 6 * J;
+                q[0] = r1 + m21 * m21 * r2 + m31 * m31 * r3; q[1] = m21 * r2 + m31 * m32 * r3; q[2] = m31 * r3;
+                q[3] = r2 + m32 * m32 * r3; q[4] = m32 * r3; q[5] = r3;
+            }
+        }
+        __syncthreads();
+        const int w = C::NRP - c0 - 3;
+        for (int e = tid; e < w * (w + 1) / 2; e += C::NT) {
+            int di = (int) ((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((di + 1) * (di + 2) / 2 <= e) di++;
+            while (di * (di + 1) / 2 > e) di--;
+            const int dk = e - di * (di + 1) / 2;
+            const double* si = sbuf + di * 3;
+            const double* tk = A + (c0 + 3 + dk) * C::LD + c0;
+            A[(c0 + 3 + di) * C::LD + c0 + 3 + dk] -= si[0] * tk[0] + si[1] * tk[1] + si[2] * tk[2];
+        }
+        __syncthreads();
+        if (tid < 32) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ch++) {
+                const int i = c0 + 3 + lane + 32 * ch;
+                if (i < C::NRP) { A[i * C::LD + c0] = ab[ch][0]; A[i * C::LD + c0 + 1] = ab[ch][1]; A[i * C::LD + c0 + 2] = ab[ch][2]; }
+            }
+        }
+    }
+    __syncthreads();
+    return bad;
+}
+
+template <class C>
+__device__ __forceinline__ void solve_dense_warp(const double* A, const double* pinv, double* b) {
+    const int lane = threadIdx.x & 31;
+    for (int J = 0; J < C::NB; J++) {
+        const int c0 = 3 * J;
+        const double w0 = b[c0], w1 = b[c0 + 1], w2 = b[c0 + 2];
+        for (int i = c0 + 3 + lane; i < C::NRP; i += 32) {
+            const double* ab = A + i * C::LD + c0;
+            b[i] = (b[i] - ab[0] * w0) - (ab[1] * w1 + ab[2] * w2);
+        }
+        __syncwarp();
+    }
+    if (lane < C::NB) {
+        const double* q = pinv + 6 * lane;
+        const double w0 = b[3 * lane], w1 = b[3 * lane + 1], w2 = b[3 * lane + 2];
+        b[3 * lane] = q[0] * w0 + q[1] * w1 + q[2] * w2;
+        b[3 * lane + 1] = q[1] * w0 + q[3] * w1 + q[4] * w2;
+        b[3 * lane + 2] = q[2] * w0 + q[4] * w1 + q[5] * w2;
+    }
+    __syncwarp();
+    for (int J = C::NB - 1; J >= 0; J--) {
+        const int c0 = 3 * J;
+        const double x0 = b[c0], x1 = b[c0 + 1], x2 = b[c0 + 2];
+        for (int i = c0 - 1 - lane; i >= 0; i -= 32)
+            b[i] = (b[i] - A[c0 * C::LD + i] * x0) - (A[(c0 + 1) * C::LD + i] * x1 + A[(c0 + 2) * C::LD + i] * x2);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row algebra.  Row convention: q(c) >= 0, slack s > 0, multiplier lam > 0.  Every row starts with
 // the same primal residual rp = s - q (the start-up shift) and every step scales it by (1 - alpha),
 // so rp is one scalar for the whole QP and neither q nor the row constants are needed after start-up.
@@ -419,6 +534,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     double* s_diag0 = sm + C::O_DIAG0;
     double* s_invd = sm + C::O_INVD;
     double* s_red = sm + C::O_RED;
+    double* s_wC = sm + C::O_WC;           // comm pair weights [PC], then rhs multipliers [PC]
     int red_phase = 0;
 
     // ---- thread roles
@@ -432,7 +548,28 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     const bool has_bnd = var_thread && !(m_v == 0 && i_v < 3);          // :260-265
     const bool has_vel = var_thread && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
     const bool has_acc = var_thread && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
-    const unsigned bmask = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u);
+    // communication-range pair of this thread (traj_optimizer.cpp:477-500), on the segment end points E_a = c[a][5]:
+    //   |E_a - E_b| <= range/2 - radius  for b < a  (c[mi][0] = E_{mi-1});  E_a within range/2 - radius of the
+    //   current position (mi = 0) and within range/2 - 1e-5 of next_waypoint (merged into one interval)
+    const bool has_comm = C::COMM && tid < C::PC;
+    int ca_idx = 0, cb_idx = -1;
+    double c_hp = 0.0, c_hm = 0.0;
+    if (has_comm) {
+        const int kc = tid / C::PP, r = tid % C::PP;
+        const double r1 = 0.5 * p.comm_range - p.limits[agent * 8 + 6], r2 = 0.5 * p.comm_range - 1e-5;
+        if (r < M) {
+            const double pos = (double) p.state[agent * 9 + kc], wp = (double) p.next_waypoint[agent * 3 + kc];
+            ca_idx = kc * NCP + r * 6 + 5;
+            c_hp = fmin(pos + r1, wp + r2); c_hm = fmax(pos - r1, wp - r2);
+        } else {
+            int e = r - M, a = 1;
+            while (a * (a + 1) / 2 <= e) a++;                     // pair e -> (a, b), 0 <= b < a <= M-1
+            const int b = e - a * (a - 1) / 2;
+            ca_idx = kc * NCP + a * 6 + 5; cb_idx = kc * NCP + b * 6 + 5;
+            c_hp = r1; c_hm = -r1;
+        }
+    }
+    const unsigned bmask = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u) | (has_comm ? 192u : 0u);
 
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
@@ -546,13 +683,13 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     // ---- per-thread row state (registers): slack and multiplier of every owned row
     double ls[KPT], ll[KPT];
-    double bs[6], bl[6];
+    double bs[C::NBX], bl[C::NBX];
     // rows of this thread: obstacles grp, grp + G, ... < K on its control point (none for the fixed points)
     const int nrow = (lsc_thread && K > grp) ? (K - grp + G - 1) / G : 0;
 #pragma unroll
     for (int j = 0; j < KPT; j++) { ls[j] = 1.0; ll[j] = 0.0; }
 #pragma unroll
-    for (int e = 0; e < 6; e++) { bs[e] = 1.0; bl[e] = 0.0; }
+    for (int e = 0; e < C::NBX; e++) { bs[e] = 1.0; bl[e] = 0.0; }
 
     double red[4];
     {
@@ -570,6 +707,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (has_vel) dvv = d[1] - d0;
         if (has_acc) daa = d[2] - 2.0 * d[1] + d0;
         dq[0] = d0; dq[1] = -d0; dq[2] = -dvv; dq[3] = dvv; dq[4] = -daa; dq[5] = daa;
+        if (C::COMM) {
+            double dvc = 0.0;
+            if (has_comm) dvc = dv[ca_idx] - (cb_idx >= 0 ? dv[cb_idx] : 0.0);
+            dq[C::NBX - 2] = -dvc; dq[C::NBX - 1] = dvc;
+        }
     };
     auto load_cp = [&](const double* v, double& x, double& y, double& z) {
         x = v[cp]; y = v[NCP + cp]; z = (D == 3) ? v[2 * NCP + cp] : 0.0;
@@ -602,6 +744,11 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         // gradients of the rows: lb +e, ub -e, vel+ -(d), vel- +(d), acc+ -(d), acc- +(d)
         if (withS) { s_wB[tid] = W[0] + W[1]; s_wV[tid] = W[2] + W[3]; s_wA[tid] = W[4] + W[5]; }
         s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
+        if (C::COMM && has_comm) {
+            // rows hp - v >= 0 (gradient -g) and v - hm >= 0 (gradient +g), g = e_a - e_b
+            if (withS) s_wC[tid] = W[C::NBX - 2] + W[C::NBX - 1];
+            s_wC[C::PC + tid] = u[C::NBX - 1] - u[C::NBX - 2];
+        }
     };
 
     // sum the group slabs, build the 6x6 blocks (withS) and the full-space rhs  -grad f + A^T u, then project.
@@ -675,13 +822,31 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 if (h.w >= 0) s_diag0[h.w] = val;
             }
         }
-        if (tid < C::NRP) s_rhs[tid] = tid < NR ? reduce_from_full<C>(s_rfull, tid) : 0.0;
+        if (tid < C::NRP) {
+            double r = tid < NR ? reduce_from_full<C>(s_rfull, tid) : 0.0;
+            if (C::COMM && tid < NR) {
+                // end-point variables also collect A^T u of the comm pairs they appear in
+                int st = -1, k = 0;
+                if (C::TERM && tid >= (M - 1) * C::NZS) { st = M - 1; k = tid - (M - 1) * C::NZS; }
+                else if (tid % 3 == 2) { st = tid / C::NZS; k = (tid % C::NZS) / 3; }
+                if (st >= 0) {
+                    const double* uc = s_wC + C::PC + k * C::PP;
+                    r += uc[st];                                                      // box pair of E_st
+                    for (int b = 0; b < st; b++) r += uc[M + st * (st - 1) / 2 + b];           // pairs (st, b): +g
+                    for (int a = st + 1; a < M; a++) r -= uc[M + a * (a - 1) / 2 + st];        // pairs (a, st): -g
+                }
+            }
+            s_rhs[tid] = r;
+        }
         __syncthreads();
     };
 
     int bad_piv = 0;
     auto factor_solve = [&](bool factor) {   // @phase factor_solve_call
-        if (tid < 32) {
+        if (C::COMM) {
+            if (factor) bad_piv += chol_dense_cta<C>(s_A, s_diag0, s_invd, sm + C::O_SBUF);
+            if (tid < 32) solve_dense_warp<C>(s_A, s_invd, s_rhs);
+        } else if (tid < 32) {
             if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, sm + C::O_SBUF, pr_i, pr_k);
             chol_solve<C>(s_A, s_invd, s_rhs);
         }
@@ -711,6 +876,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
             bs[0] = c0 - s_lb[k_v * M + m_v]; bs[1] = s_ub[k_v * M + m_v] - c0;
             bs[2] = s_vlim[k_v] - dv; bs[3] = s_vlim[k_v] + dv; bs[4] = s_alim[k_v] - da; bs[5] = s_alim[k_v] + da;
+            if (C::COMM) {
+                const double v = has_comm ? s_c[ca_idx] - (cb_idx >= 0 ? s_c[cb_idx] : 0.0) : 0.0;
+                bs[C::NBX - 2] = c_hp - v; bs[C::NBX - 1] = v - c_hm;
+            }
         }
     };
     rows_q();
@@ -720,7 +889,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
         for (int j = 0; j < KPT; j++) if (j < nrow) qmin = fmin(qmin, ls[j]);
 #pragma unroll
-        for (int e = 0; e < 6; e++) if (bmask >> e & 1u) qmin = fmin(qmin, bs[e]);
+        for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) qmin = fmin(qmin, bs[e]);
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = 0;
         block_reduce4<C>(red, s_red, red_phase);
         if (red[2] < -p.warm_reject) {
@@ -742,9 +911,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         }
         store_slab(S, T, true);
         if (var_thread) {
-            double W[6], u[6];
+            double W[C::NBX], u[C::NBX];
 #pragma unroll
-            for (int e = 0; e < 6; e++) { const bool on = bmask >> e & 1u; W[e] = on ? 1.0 : 0.0; u[e] = on ? -bs[e] : 0.0; }
+            for (int e = 0; e < C::NBX; e++) { const bool on = bmask >> e & 1u; W[e] = on ? 1.0 : 0.0; u[e] = on ? -bs[e] : 0.0; }
             store_box(W, u, true);
         }
     }
@@ -774,10 +943,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             qmin = fmin(qmin, ls[j]); qmax = fmax(qmax, ls[j]);
         }
         if (var_thread) {
-            double dq[6] = {0, 0, 0, 0, 0, 0};
+            double dq[C::NBX] = {};
             if (!warm) box_dq(s_dc, dq);
 #pragma unroll
-            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += dq[e]; qmin = fmin(qmin, bs[e]); qmax = fmax(qmax, bs[e]); }
+            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bs[e] += dq[e]; qmin = fmin(qmin, bs[e]); qmax = fmax(qmax, bs[e]); }
         }
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
         block_reduce4<C>(red, s_red, red_phase);
@@ -789,7 +958,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
             for (int j = 0; j < KPT; j++) if (j < nrow) { ls[j] += shift_s; ll[j] = mu0 / ls[j]; }
 #pragma unroll
-            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = mu0 / bs[e]; }
+            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = mu0 / bs[e]; }
             rp = shift_s;
         } else {
             const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
@@ -797,7 +966,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
             for (int j = 0; j < KPT; j++) if (j < nrow) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
 #pragma unroll
-            for (int e = 0; e < 6; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
             rp = shift_s;
         }
     }
@@ -834,10 +1003,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             }
             store_slab(S, T, true);
             if (var_thread) {
-                double W[6], u[6], dqa[6], dq[6];
+                double W[C::NBX], u[C::NBX], dqa[C::NBX], dq[C::NBX];
                 if (have_step) { box_dq(s_dca, dqa); box_dq(s_dc, dq); }
 #pragma unroll
-                for (int e = 0; e < 6; e++) {
+                for (int e = 0; e < C::NBX; e++) {
                     W[e] = 0.0; u[e] = 0.0;
                     if (!(bmask >> e & 1u)) continue;
                     if (have_step) {
@@ -886,10 +1055,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 s1 += ls[j] * dla + ll[j] * dsa; s2 += dsa * dla;
             }
             if (var_thread) {
-                double dqa[6];
+                double dqa[C::NBX];
                 box_dq(s_dca, dqa);
 #pragma unroll
-                for (int e = 0; e < 6; e++) {
+                for (int e = 0; e < C::NBX; e++) {
                     if (!(bmask >> e & 1u)) continue;
                     const double W = bl[e] * fast_rcp(bs[e]);
                     const double dsa = dqa[e] - rp, dla = -bl[e] - W * dsa;
@@ -925,10 +1094,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             }
             store_slab(S, T, false);
             if (var_thread) {
-                double W[6], u[6], dqa[6];
+                double W[C::NBX], u[C::NBX], dqa[C::NBX];
                 box_dq(s_dca, dqa);
 #pragma unroll
-                for (int e = 0; e < 6; e++) {
+                for (int e = 0; e < C::NBX; e++) {
                     W[e] = 0.0; u[e] = 0.0;
                     if (!(bmask >> e & 1u)) continue;
                     const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
@@ -963,10 +1132,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 mr.add(ls[j], ds); mr.add(ll[j], dl);
             }
             if (var_thread) {
-                double dqa[6], dq[6];
+                double dqa[C::NBX], dq[C::NBX];
                 box_dq(s_dca, dqa); box_dq(s_dc, dq);
 #pragma unroll
-                for (int e = 0; e < 6; e++) {
+                for (int e = 0; e < C::NBX; e++) {
                     if (!(bmask >> e & 1u)) continue;
                     const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
@@ -977,7 +1146,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             }
             red[0] = 0; red[1] = 0; red[2] = mr.value(); red[3] = 0;
             block_reduce4<C>(red, s_red, red_phase);
-            alpha = red[2] >= 1.0 ? 1.0 : 0.99 * red[2];
+            // (the ratio is a float quotient: a full step needs a margin above 1, otherwise stay 1% inside)
+            alpha = red[2] >= 1.0001 ? 1.0 : 0.99 * fmin(red[2], 1.0);
             have_step = true;
         }
         // the reduced iterate moves now; the rows follow in the next sweep A (s_dca / s_dc stay valid until then)
@@ -1010,14 +1180,18 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (var_thread) {
             const double* cc = s_c + k_v * NCP + cp_v;
             const double c0 = cc[0];
-            double dv = 0.0, da = 0.0, q[6];
+            double dv = 0.0, da = 0.0, q[C::NBX];
             if (has_vel) dv = cc[1] - c0;
             if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
             q[0] = c0 - s_lb[k_v * M + m_v]; q[1] = s_ub[k_v * M + m_v] - c0;
             q[2] = s_vlim[k_v] - dv; q[3] = s_vlim[k_v] + dv; q[4] = s_alim[k_v] - da; q[5] = s_alim[k_v] + da;
-            double W[6] = {0, 0, 0, 0, 0, 0}, u[6];
+            if (C::COMM) {
+                const double v = has_comm ? s_c[ca_idx] - (cb_idx >= 0 ? s_c[cb_idx] : 0.0) : 0.0;
+                q[C::NBX - 2] = c_hp - v; q[C::NBX - 1] = v - c_hm;
+            }
+            double W[C::NBX] = {}, u[C::NBX];
 #pragma unroll
-            for (int e = 0; e < 6; e++) {
+            for (int e = 0; e < C::NBX; e++) {
                 const bool on = bmask >> e & 1u;
                 u[e] = on ? bl[e] : 0.0;
                 if (on) rp_true = fmax(rp_true, fabs(bs[e] - q[e]));
@@ -1070,6 +1244,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             db[0] = (bmask & 1u) ? bl[0] : 0.0; db[1] = (bmask & 2u) ? bl[1] : 0.0;
             db[2] = (bmask & 4u) ? bl[2] * sv : 0.0; db[3] = (bmask & 8u) ? bl[3] * sv : 0.0;
             db[4] = (bmask & 16u) ? bl[4] * sa : 0.0; db[5] = (bmask & 32u) ? bl[5] * sa : 0.0;
+            if (C::COMM && has_comm) { double* dc = du + C::KMAX * M * 6 + NV * 6 + tid * 2; dc[0] = bl[C::NBX - 2]; dc[1] = bl[C::NBX - 1]; }
         }
     }
 }

@@ -32,6 +32,7 @@ class DeviceBatch:
         self.obs_offsets = t(batch.obs_offsets.astype(np.int32))
         self.obs_index = t(batch.obs_index.astype(np.int32))
         self.sfc = t(batch.sfc) if batch.sfc is not None else None
+        self.next_waypoint = t(batch.next_waypoint) if cfg.comm_range > 0 else None
         sk = max(self.sum_k, 1)
         self.obs_traj = torch.empty((sk, M, 6, 3), dtype=torch.float32, device=dev)
         self.obs_meta = torch.empty((sk, 4), dtype=torch.float32, device=dev)
@@ -71,7 +72,7 @@ class BatchPlanner:
         """trajOptimization for every agent (initial_traj = the batch's own_traj as the solver's starting point)"""
         self.qp.solve_batch(d.n, d.state, d.goal, d.limits, d.sfc, d.obs_offsets, d.normals, d.rhs,
                             d.ctrl, d.cost, d.status, d.iters, d.kkt if want_kkt else None, dual, stream,
-                            initial_traj=d.own_traj if warm else None)
+                            initial_traj=d.own_traj if warm else None, next_waypoint=d.next_waypoint)
 
     def replan_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0):
         self.assemble_device(d, generator, stream)
@@ -84,7 +85,7 @@ class BatchPlanner:
         b = {}
         for name, arr, dt in (("state", batch.state, np.float32), ("goal", batch.goal, np.float32),
                               ("limits", batch.limits, np.float64), ("own_traj", batch.own_traj, np.float32),
-                              ("agent_meta", batch.agent_meta, np.float64),
+                              ("agent_meta", batch.agent_meta, np.float64), ("next_waypoint", batch.next_waypoint, np.float32),
                               ("obs_offsets", batch.obs_offsets, np.int32), ("obs_index", batch.obs_index, np.int32)):
             p = capi.pinned(arr.shape, dt)
             p[...] = arr
@@ -101,7 +102,8 @@ class BatchPlanner:
 
     def replan_host_buffers(self, b: dict, n: int, generator: int = capi.GEN_LSC):
         self.qp.replan_host(generator, n, b["state"], b["goal"], b["limits"], b["sfc"], b["own_traj"], b["agent_meta"],
-                            b["obs_offsets"], b["obs_index"], b["ctrl"], b["cost"], b["status"], b["iters"])
+                            b["obs_offsets"], b["obs_index"], b["ctrl"], b["cost"], b["status"], b["iters"],
+                            next_waypoint=b["next_waypoint"] if self.cfg.comm_range > 0 else None)
 
     def replan_host(self, batch: Batch, generator: int = capi.GEN_LSC) -> dict:
         b = self.host_buffers(batch)

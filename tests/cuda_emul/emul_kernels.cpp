@@ -9,11 +9,11 @@
 
 using namespace lscqp;
 
-extern "C" int emul_dual_stride(int M, int D) { return 40 * M * 6 + D * M * 6 * 6; }
+extern "C" int emul_dual_stride(int M, int D, int comm) { return 40 * M * 6 + D * M * 6 * 6 + (comm ? 2 * D * (M * (M - 1) / 2 + M) : 0); }
 
 extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
                                 const float* state, const float* goal, const double* limits, const float* sfc,
-                                const int* obs_offsets, const double* normals, const double* rhs,
+                                const float* next_waypoint, const int* obs_offsets, const double* normals, const double* rhs,
                                 const float* initial_traj, double* ctrl_out, double* cost_out, int* status_out, int* iters_out,
                                 double* kkt_out, double* dual_out) {
     int rc = validate_config(*cfg);
@@ -21,14 +21,15 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     SolveParams p;
     fill_solve_params(*cfg, p);
     p.n_agents = n_agents;
-    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc;
+    p.state = state; p.goal = goal; p.limits = limits; p.sfc = sfc; p.next_waypoint = next_waypoint;
     p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs; p.warm_traj = initial_traj;
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out;
     const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
-#define X(M_, D_, T_)                                                                       \
-    if (cfg->M == M_ && cfg->dim == D_ && term == T_) {                                     \
-        using C = Cfg<M_, D_, T_, 4, 10>;                                                   \
+    const bool comm = cfg->comm_range > 0;
+#define X(M_, D_, T_, C_)                                                                   \
+    if (cfg->M == M_ && cfg->dim == D_ && term == T_ && comm == C_) {                       \
+        using C = Cfg<M_, D_, T_, 4, 10, C_>;                                               \
         p.dual_stride = C::DUAL_STRIDE;                                                     \
         static const ProjTable tab = build_projection<C>();                                 \
         p.proj_ent = tab.ent.data(); p.proj_term = tab.term.data(); p.n_proj_ent = (int) tab.ent.size(); \

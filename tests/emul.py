@@ -25,15 +25,15 @@ def _p(a, dt):
     return C.c_void_p(a.ctypes.data)
 
 
-def solve_batch(cfg, n, state, goal, limits, sfc, off, normals, rhs, want_dual=False, initial_traj=None):
+def solve_batch(cfg, n, state, goal, limits, sfc, off, normals, rhs, want_dual=False, initial_traj=None, next_waypoint=None):
     cc = capi.make_config(cfg)
     nv = cfg.dim * cfg.M * 6
     ctrl = np.zeros((n, nv)); cost = np.zeros(n); status = np.zeros(n, np.int32); iters = np.zeros(n, np.int32)
     kkt = np.zeros((n, 4))
-    ds = lib().emul_dual_stride(cfg.M, cfg.dim)
+    ds = lib().emul_dual_stride(cfg.M, cfg.dim, int(cfg.comm_range > 0))
     dual = np.zeros((n, ds)) if want_dual else None
     rc = lib().emul_solve_batch(C.byref(cc), n, _p(state, np.float32), _p(goal, np.float32), _p(limits, np.float64),
-                                _p(sfc, np.float32), _p(off, np.int32), _p(normals, np.float64), _p(rhs, np.float64),
+                                _p(sfc, np.float32), _p(next_waypoint, np.float32), _p(off, np.int32), _p(normals, np.float64), _p(rhs, np.float64),
                                 _p(initial_traj, np.float32),
                                 _p(ctrl, np.float64), _p(cost, np.float64), _p(status, np.int32), _p(iters, np.int32),
                                 _p(kkt, np.float64), _p(dual, np.float64))

@@ -9,6 +9,7 @@ using namespace DynamicPlanning;
 int main(int argc, char** argv) {
     Param param; Mission mission;
     param.control_input_weight = 0.01; param.terminal_weight = 1.0; param.planner_mode = PlannerMode::LSC;
+    param.communication_range = 0.0;     // (the comm-range variant is covered by the Python parity tests)
     Agent agent;
     agent.current_state.position = point3d(0, 0, 1);
     agent.current_goal_point = point3d(3, 0, 1);

@@ -122,3 +122,36 @@ def test_step_kernel_matches_oracle():
                 st[2] = np.float32(cfg.z_2d)
             assert np.allclose(got_state[a], st, rtol=2e-6, atol=2e-6)
             assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
+
+
+@pytest.mark.parametrize("M,dim,K", [(5, 3, 10), (10, 2, 9)])
+def test_solve_kernel_with_communication_range_rows(M, dim, K):
+    """communication-range rows (traj_optimizer.cpp:477-500; launch/simulation.launch sets range 3): dense instance"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=1, comm_range=0.7)       # tight enough to bind within the 1 s horizon
+    batch = W.make_forest_batch(64, K=K, cfg=cfg)
+    rng = np.random.default_rng(11)
+    d = rng.normal(size=(64, 3)); d[:, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    batch.goal = (batch.state[:, :3] + 5.0 * d).astype(np.float32)            # far goals: the agent wants to leave the range
+    batch.next_waypoint = (batch.state[:, :3] + rng.uniform(-0.05, 0.05, (64, 3))).astype(np.float32)
+    if dim == 2:
+        batch.next_waypoint[:, 2] = cfg.z_2d
+    agents = [0, 9, 30]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    wp = np.ascontiguousarray(batch.next_waypoint[agents])
+    ctrl, cost, status, iters, kkt, dual = emul.solve_batch(batch.cfg, len(agents), st, goal, lim, None, off, normals, rhs,
+                                                            want_dual=True, next_waypoint=wp)
+    assert (status == 0).all(), status
+    checked = 0
+    for i, a in enumerate(agents):
+        qp = oracle_qp_from_planes(batch, a, normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]])
+        assert qp.G.shape[0] == (off[i + 1] - off[i]) * (6 * M - 3) + 2 * dim * (5 * M - 2) + 2 * dim * (4 * M - 1) + dim * M * (M + 3)
+        cert = orc.kkt_certificate(qp, ctrl[i])
+        assert cert["primal_eq"] < 1e-8 and cert["primal_ineq"] < 1e-8, cert
+        xe, ok = oracle_solution(qp)
+        if ok:
+            checked += 1
+            assert np.abs(ctrl[i] - xe).max() < 1e-5, (a, np.abs(ctrl[i] - xe).max())
+    assert checked >= 2
+    # the comm rows must matter for at least one of these agents (otherwise the test proves nothing)
+    assert np.abs(dual[:, -2 * dim * (M * (M - 1) // 2 + M):]).max() > 1e-6

@@ -351,3 +351,31 @@ def test_cpp_shim_end_to_end():
     assert abs(cost - (xe @ qp.P @ xe + qp.q @ xe + qp.c0)) < 1e-6 * max(1.0, cost)
     b = [l for l in out if l.startswith("batch")][0].split()
     assert b[1] == "0" and b[2] == "0" and float(b[3]) > 0.3 and float(b[4]) < 2.7
+
+
+@pytest.mark.parametrize("M,dim,K,rng_", [(10, 2, 9, 0.7), (5, 3, 12, 0.7), (10, 2, 9, 3.0)])
+def test_communication_range_rows(M, dim, K, rng_):
+    """the launch-file shape (M=10, 2-D, communication_range 3, generateCLSC) and a binding range: rows of
+    traj_optimizer.cpp:477-500 through the dense instance, assembly on the device"""
+    import torch
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=capi.MODE_LSC, comm_range=rng_)
+    batch = W.make_forest_batch(64, K=K, cfg=cfg)
+    r = np.random.default_rng(11)
+    d = r.normal(size=(64, 3)); d[:, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    batch.goal = (batch.state[:, :3] + (5.0 if rng_ < 1 else 0.6) * d).astype(np.float32)
+    batch.next_waypoint = (batch.state[:, :3] + r.uniform(-0.05, 0.05, (64, 3))).astype(np.float32)
+    if dim == 2:
+        batch.next_waypoint[:, 2] = cfg.z_2d; batch.goal[:, 2] = cfg.z_2d
+    planner = _planner(batch.cfg)
+    dev = planner.upload(batch)
+    planner.replan_device(dev, capi.GEN_CLSC)
+    torch.cuda.synchronize()
+    status = dev.status.cpu().numpy(); ctrl = dev.ctrl.cpu().numpy(); cost = dev.cost.cpu().numpy()
+    assert (status == 0).all(), status
+    agents = [0, 9, 30, 41]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_CLSC)
+    _check_against_oracle(batch, agents, off, normals, rhs, ctrl[agents], cost[agents], status[agents], min_checked=2)
+    if rng_ < 1:      # the range must actually bind: end points stay within range/2 - radius of the start
+        end = ctrl.reshape(64, dim, M, 6)[:, :, :, 5]
+        dist = np.abs(end - batch.state[:, None, :dim].transpose(0, 2, 1)).max(axis=(1, 2))
+        assert dist.max() <= 0.5 * rng_ - 0.15 + 1e-7 and dist.max() > 0.5 * rng_ - 0.15 - 1e-4
