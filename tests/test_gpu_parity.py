@@ -371,11 +371,16 @@ def test_communication_range_rows(M, dim, K, rng_):
     planner.replan_device(dev, capi.GEN_CLSC)
     torch.cuda.synchronize()
     status = dev.status.cpu().numpy(); ctrl = dev.ctrl.cpu().numpy(); cost = dev.cost.cpu().numpy()
-    assert (status == 0).all(), status
-    agents = [0, 9, 30, 41]
+    # a 0.2 m leash can be infeasible for agents that cannot brake in time: those must be *reported*, the rest solved
+    ok_agents = np.where(status == 0)[0]
+    assert len(ok_agents) >= (64 if rng_ > 1 else 8), np.bincount(status)
+    agents = [int(a) for a in ok_agents[:4]]
     off, normals, rhs = oracle_planes(batch, agents, orc.GEN_CLSC)
     _check_against_oracle(batch, agents, off, normals, rhs, ctrl[agents], cost[agents], status[agents], min_checked=2)
+    for a in np.where(status != 0)[0][:2]:         # the oracle agrees that the reported ones have no solution
+        o2, n2, r2 = oracle_planes(batch, [int(a)], orc.GEN_CLSC)
+        assert orc.solve_highs(oracle_qp_from_planes(batch, int(a), n2, r2)).status != "Optimal"
     if rng_ < 1:      # the range must actually bind: end points stay within range/2 - radius of the start
-        end = ctrl.reshape(64, dim, M, 6)[:, :, :, 5]
-        dist = np.abs(end - batch.state[:, None, :dim].transpose(0, 2, 1)).max(axis=(1, 2))
+        end = ctrl.reshape(64, dim, M, 6)[ok_agents][:, :, :, 5]
+        dist = np.abs(end - batch.state[ok_agents][:, :dim, None]).max(axis=(1, 2))
         assert dist.max() <= 0.5 * rng_ - 0.15 + 1e-7 and dist.max() > 0.5 * rng_ - 0.15 - 1e-4
