@@ -281,6 +281,10 @@ def run_ours(args):
                     a.record(); fn(); b.record(); torch.cuda.synchronize()
                     tot += a.elapsed_time(b)
                 return tot / reps
+            cfg3 = copy.copy(batch.cfg); cfg3.presolve = 3        # presolve on, light instances off (one pass, 128-thread CTAs)
+            planner3 = BatchPlanner(cfg3, device=local)
+            ms = timed(lambda: planner3.solve_device(d, stream=stream))
+            variants["solve_full_instance_only"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
             cfg2 = copy.copy(batch.cfg); cfg2.presolve = False
             planner2 = BatchPlanner(cfg2, device=local)
             ms = timed(lambda: planner2.solve_device(d, stream=stream))

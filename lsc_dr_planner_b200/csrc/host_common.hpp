@@ -73,7 +73,8 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     p.dt = c.dt; p.w_t = c.w_terminal; p.w_c = c.w_control;
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }
     p.use_sfc = c.use_sfc;
-    p.presolve = c.presolve;
+    p.presolve = c.presolve & 1;
+    p.klass = nullptr; p.klass_mode = 0;
     p.comm_range = c.comm_range;
     double Q[36];
     jerk_gram(c.n, c.phi, c.dt, Q);
@@ -86,13 +87,16 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
 // map of pdip_kernel.cuh: reduced variable (stage s, dim k, j) is control point (s, 3+j) and, through
 // T = [[0,0,1],[0,-1,2],[1,-4,4]], the first three control points of segment s+1; the collapsed terminal variable
 // is the sum of the last three control points.
+// The table is laid out as one term stream per thread (ProjTerm, pdip_kernel.cuh): the entries are dealt to the
+// threads so that every thread walks the same number of terms (longest-processing-time first), term i of thread t
+// sits at [i * NT + t] (coalesced, address independent of the data, so the loads pipeline).
 struct ProjTable {
-    std::vector<int4> ent;        // dest, first term, term count (-1: identity padding), diagonal index or -1
-    std::vector<double2> term;    // coef, source index
+    std::vector<ProjTerm> term;   // [len][nt]
+    int len = 0, nt = 0;
 };
 
 template <class C>
-inline ProjTable build_projection() {
+inline ProjTable build_projection(int nt = C::NT) {
     constexpr int M = C::M, D = C::D, NR = C::NR, NS = C::NS;
     static const double T[3][3] = {{0, 0, 1}, {0, -1, 2}, {1, -4, 4}};
     auto symidx = [](int a, int b) { if (a > b) std::swap(a, b); return D == 3 ? (a == 0 ? b : (a == 1 ? 2 + b : 5)) : a + b; };
@@ -153,14 +157,41 @@ inline ProjTable build_projection() {
             ents.push_back(e);
         }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) { return x.count > y.count; });
-    ProjTable out;
+    std::vector<std::vector<ProjTerm>> lane(nt);
     for (const Ent& e : ents) {
-        int4 h; h.x = e.dest; h.y = (int) out.term.size(); h.z = e.count; h.w = e.diag;
-        out.ent.push_back(h);
-        for (auto& t : e.t) { double2 d; d.x = t.first; d.y = (double) t.second; out.term.push_back(d); }
+        int best = 0;
+        for (int t = 1; t < nt; t++) if (lane[t].size() < lane[best].size()) best = t;
+        int dest = e.dest;
+        if (e.diag >= 0) dest |= PROJ_DIAG;
+        if (e.count < 0) dest |= PROJ_ONE;
+        if (e.count <= 0) { lane[best].push_back(ProjTerm{0.0, 0, dest}); continue; }
+        for (int i = 0; i < e.count; i++)
+            lane[best].push_back(ProjTerm{e.t[i].first, e.t[i].second, i + 1 == e.count ? dest : -1});
     }
+    ProjTable out;
+    out.nt = nt;
+    for (int t = 0; t < nt; t++) out.len = std::max(out.len, (int) lane[t].size());
+    out.term.assign((size_t) out.len * nt, ProjTerm{0.0, 0, -1});
+    for (int t = 0; t < nt; t++)
+        for (size_t i = 0; i < lane[t].size(); i++) out.term[i * nt + t] = lane[t][i];
     return out;
 }
+
+// Light instances (two-pass dispatch, SolveParams::klass_mode): one obstacle group, LSCQP_LIGHT_KPT kept obstacles at
+// most, a quarter of the threads -- so the serial factorisation of one QP overlaps the row sweeps of many others on the
+// same SM.  Agents whose presolve keeps more obstacles fall through to the full-capacity instance.
+#ifndef LSCQP_LIGHT_G
+#define LSCQP_LIGHT_G 1
+#endif
+#ifndef LSCQP_LIGHT_KPT
+#define LSCQP_LIGHT_KPT 8
+#endif
+template <int M_, int D_, bool T_, bool COMM_>
+struct Instance {
+    using Full = Cfg<M_, D_, T_, 4, 10, COMM_>;
+    using Light = Cfg<M_, D_, T_, LSCQP_LIGHT_G, LSCQP_LIGHT_KPT, false>;
+    static constexpr bool HAS_LIGHT = !COMM_;
+};
 
 // kernel instances: (M, D, TERM, COMM) with 4 obstacle groups x 10 rows per thread (K <= 40)
 #define LSCQP_FOR_EACH_INSTANCE(X) \

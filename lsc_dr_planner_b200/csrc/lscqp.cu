@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "host_common.hpp"
+#include "solve_instances.hpp"
 #include "lsc_assemble.cuh"
 #include "step_kernel.cuh"
 
@@ -46,17 +47,13 @@ struct lscqp_handle {
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
-    DevBuf d_proj_ent, d_proj_term, d_wp;
+    DevBuf d_proj_ent, d_proj_term, d_wp, d_klass;
+    bool two_pass = false;
     unsigned long long launches = 0;
 };
 
 extern "C" const char* lscqp_version(void) { return "lscqp-b200 0.1 (sm_100a)"; }
 extern "C" const char* lscqp_last_error(void) { return g_err.c_str(); }
-
-template <class C>
-static int set_smem_attr() {
-    return cudaFuncSetAttribute(pdip_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess ? 0 : -1;
-}
 
 extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** out) {
     if (!cfg || !out) return fail(LSCQP_E_INVALID, "null argument");
@@ -72,25 +69,24 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     h->cfg = *cfg;
     h->device = device;
     fill_solve_params(*cfg, h->base);
-    const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
-    bool found = false;
-    const bool comm = cfg->comm_range > 0;
-#define X(M_, D_, T_, C_)                                               \
-    if (cfg->M == M_ && cfg->dim == D_ && term == T_ && comm == C_) {   \
-        using C = Cfg<M_, D_, T_, 4, 10, C_>;                           \
-        if (set_smem_attr<C>()) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); } \
-        h->dual_stride = C::DUAL_STRIDE; h->kmax = C::KMAX; h->nv = C::NV; found = true; \
-        const ProjTable tab = build_projection<C>();                    \
-        if (h->d_proj_ent.reserve(tab.ent.size() * sizeof(int4)) || h->d_proj_term.reserve(tab.term.size() * sizeof(double2)) || \
-            cudaMemcpy(h->d_proj_ent.p, tab.ent.data(), tab.ent.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess || \
-            cudaMemcpy(h->d_proj_term.p, tab.term.data(), tab.term.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) { \
-            delete h; return fail(LSCQP_E_CUDA, "projection table upload failed"); }           \
-        h->base.proj_ent = h->d_proj_ent.as<int4>(); h->base.proj_term = h->d_proj_term.as<double2>(); \
-        h->base.n_proj_ent = (int) tab.ent.size();                      \
-    }
-    LSCQP_FOR_EACH_INSTANCE(X)
-#undef X
+    InstanceInfo info;
+    int found = inst_query_0(*cfg, &info);
+    if (!found) found = inst_query_1(*cfg, &info);
+    if (!found) found = inst_query_2(*cfg, &info);
+    if (!found) found = inst_query_3(*cfg, &info);
+    if (found < 0) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); }
     if (!found) { delete h; return fail(LSCQP_E_INVALID, "no kernel instance"); }
+    h->dual_stride = info.dual_stride; h->kmax = info.kmax; h->nv = info.nv;
+    h->two_pass = info.has_light && (cfg->presolve & 1) && !(cfg->presolve & 2);
+    const ProjTable& tab = info.tab;
+    const ProjTable& tabl = info.tab_light;
+    if (h->d_proj_ent.reserve(tab.term.size() * sizeof(ProjTerm)) || h->d_proj_term.reserve((tabl.term.size() + 1) * sizeof(ProjTerm)) ||
+        cudaMemcpy(h->d_proj_ent.p, tab.term.data(), tab.term.size() * sizeof(ProjTerm), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_proj_term.p, tabl.term.data(), tabl.term.size() * sizeof(ProjTerm), cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete h; return fail(LSCQP_E_CUDA, "projection table upload failed");
+    }
+    h->base.proj = h->d_proj_ent.as<ProjTerm>(); h->base.proj_len = tab.len;
+    h->base.proj_light = h->d_proj_term.as<ProjTerm>(); h->base.proj_len_light = tabl.len;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h; return fail(LSCQP_E_CUDA, "cudaStreamCreate failed");
     }
@@ -103,7 +99,8 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
-                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term, &h->d_wp};
+                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
+                      &h->d_klass};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -131,16 +128,15 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out; p.dual_stride = h->dual_stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool term = h->cfg.planner_mode == LSCQP_MODE_LSC;
-    const bool comm = h->cfg.comm_range > 0;
-#define X(M_, D_, T_, C_)                                                               \
-    if (h->cfg.M == M_ && h->cfg.dim == D_ && term == T_ && comm == C_) {               \
-        using C = Cfg<M_, D_, T_, 4, 10, C_>;                                           \
-        pdip_solve_kernel<C><<<n_agents, C::NT, C::SMEM_BYTES, st>>>(p);                \
+    if (h->two_pass) {
+        if (h->d_klass.reserve((size_t) n_agents * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
+        p.klass = h->d_klass.as<int>();
     }
-    LSCQP_FOR_EACH_INSTANCE(X)
-#undef X
-    h->launches++;
+    int launched = inst_launch_0(h->cfg, p, n_agents, h->two_pass, st);
+    if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, h->two_pass, st);
+    if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, h->two_pass, st);
+    if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, h->two_pass, st);
+    h->launches += launched;
     CK(cudaGetLastError());
     return 0;
 }

@@ -29,7 +29,17 @@
 #define LSCQP_DYN_SMEM(name) extern __shared__ double name[]
 #endif
 
+#ifndef LSCQP_LIGHT_MINCTAS
+#define LSCQP_LIGHT_MINCTAS 10
+#endif
+
 namespace lscqp {   // @phase helpers
+
+// one term of the projection stream (host_common.hpp:build_projection): val += coef * src[src]; a term with
+// dest >= 0 closes an entry of the reduced matrix: A[dest & PROJ_MASK] = val (PROJ_ONE: 1.0, the identity padding;
+// PROJ_DIAG: also kept as the unregularised diagonal for the pivot guard)
+struct alignas(16) ProjTerm { double coef; int src; int dest; };
+enum { PROJ_MASK = 0xFFFFF, PROJ_ONE = 1 << 29, PROJ_DIAG = 1 << 30 };
 
 struct SolveParams {
     int n_agents;
@@ -60,10 +70,15 @@ struct SolveParams {
     double  Q2[36];             // 2 * w_c * Q_base  (Hessian block of the jerk cost)
     // projection table (host-built, see host_common.hpp:build_projection): reduced-matrix entry e is
     //   A[dest_e] = sum_t coef_t * src[idx_t],   src = [6x6 blocks | per-control-point cross blocks]
-    const int4*   proj_ent;     // [n_ent]  dest offset, first term, term count, diagonal index (or -1)
-    const double2* proj_term;   // [n_term] coef, idx (as a double-encoded integer)
-    int n_proj_ent;
+    const ProjTerm* proj;       // [proj_len][NT] term streams of the full-capacity instance
+    const ProjTerm* proj_light; // [proj_len_light][NT_light] of the light instance (klass_mode 1)
+    int proj_len, proj_len_light;
     double  w_c;
+    // two-pass dispatch (lscqp.cu): the light instance (few kept obstacles per thread, many resident QPs per SM)
+    // runs first with klass_mode 1 and flags the agents whose kept obstacles exceed its capacity; the full-capacity
+    // instance then runs with klass_mode 2 and solves only the flagged agents.  0: solve every agent.
+    int*    klass;              // [n]
+    int     klass_mode;
 };
 
 enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3 };
@@ -85,7 +100,11 @@ struct Cfg {
     static constexpr int NRP = ((NR + 2) / 3) * 3;       // padded to whole 3x3 panels (identity rows)
     static constexpr int NB = NRP / 3;                   // panels
     static constexpr int BWS = COMM ? NRP0 - 1 : BW + 2;  // stored / assembled half bandwidth (panel overhang)
-    static constexpr int LD = NRP | 1;                   // odd leading dimension
+    // leading dimension of the reduced matrix.  Banded instances store only the band: with LD >= BWS the address
+    // i LD + j of an entry with 0 <= i - j <= BWS is unique (row i occupies i (LD + 1) - BWS .. i (LD + 1)), so
+    // the dense indexing works unchanged on a skewed band of (NRP - 1)(LD + 1) + 1 doubles.
+    static constexpr int LD = COMM ? (NRP | 1) : (BWS | 1);
+    static constexpr int A_SIZE = COMM ? NRP * LD : (NRP - 1) * (LD + 1) + 1;
     static constexpr int NS = D * (D + 1) / 2;           // unique entries of a DxD symmetric block
     static constexpr int KMAX = G * KPT;
     static constexpr int NPAIR = COMM ? 0 : BW * (BW + 1) / 2;   // trailing-update pairs per panel (banded instances)
@@ -94,13 +113,20 @@ struct Cfg {
     static constexpr int NBX = COMM ? 8 : 6;             // box-type rows per variable thread
     static constexpr int NPR = NPAIR ? (NPAIR + 31) / 32 : 1;
     static constexpr int NRED = 4;
-    static constexpr int MIN_CTAS = NT > 128 ? 2 : 3;    // register budget: 65536 / (MIN_CTAS * NT) per thread
-    // shared memory layout (doubles)
+    static constexpr int VPT = (NV + NT - 1) / NT;       // variables (box-row owners) per thread
+    static constexpr int KRAW = 40;                      // obstacle capacity of the ABI (lscqp_config.max_obs <= 40)
+    // register budget: 65536 / (MIN_CTAS * NT) per thread (the light instances are shared-memory bound)
+    static constexpr int MIN_CTAS = NT > 128 ? 2 : (NT == 128 ? 3 : LSCQP_LIGHT_MINCTAS);
+    static_assert(!COMM || VPT == 1, "communication-range instances keep one variable per thread");
+    static_assert(KMAX <= KRAW, "KMAX beyond the ABI capacity");
+    // shared memory layout (doubles).  Two regions are shared by buffers whose lifetimes do not overlap:
+    //   * the 6x6 blocks (projection source, live from the block build to the end of the projection) start on top of
+    //     the two full-space directions dca / dc (dead between sweep A and the back-substitution of the predictor);
+    //   * the row weights wB / wV / wA (live from sweep A to the block build) sit in the reduced matrix A
+    //     (written by the projection, dead again once the corrector is solved).
     static constexpr int O_Q2 = 0;
     static constexpr int O_C = O_Q2 + 36;
-    static constexpr int O_DCA = O_C + NV;
-    static constexpr int O_DC = O_DCA + NV;
-    static constexpr int O_Y = O_DC + NV;
+    static constexpr int O_Y = O_C + NV;
     static constexpr int O_DY = O_Y + NR;
     static constexpr int O_X0 = O_DY + NR;               // [D][3]
     static constexpr int O_VLIM = O_X0 + 3 * D;          // [D]
@@ -111,27 +137,31 @@ struct Cfg {
     static constexpr int O_TERMW = O_UB + D * M;         // [M] terminal weights, then the distance to the goal
     static constexpr int O_NRM = O_TERMW + M + 1;        // [KMAX][M][3]
     static constexpr int O_SLABT = O_NRM + KMAX * M * 3; // [G][NCP][D]
-    static constexpr int O_WB = O_SLABT + G * NCP * D;   // [NV] x6: wB wV wA uB uV uA
-    static constexpr int O_WV = O_WB + NV;
-    static constexpr int O_WA = O_WV + NV;
-    static constexpr int O_UB_ = O_WA + NV;
+    static constexpr int O_UB_ = O_SLABT + G * NCP * D;  // [NV] x3: uB uV uA
     static constexpr int O_UV = O_UB_ + NV;
     static constexpr int O_UA = O_UV + NV;
-    static constexpr int O_BLK = O_UA + NV;              // [D][M][36]   projection sources: blocks, then slab 0 of S
+    static constexpr int O_DCA = O_UA + NV;              // [NV] affine direction, [NV] combined direction ...
+    static constexpr int O_DC = O_DCA + NV;
+    static constexpr int O_BLK = O_DCA;                  // ... under [D][M][36] projection sources: blocks, then slab 0 of S
     static constexpr int O_SLABS = O_BLK + D * M * 36;   // [G][NCP][NS]
     static constexpr int O_RFULL = O_SLABS + G * NCP * NS;   // [NV]
-    static constexpr int O_A = O_RFULL + NV;             // [NR][LD]
-    static constexpr int O_RHS = O_A + NRP * LD;         // [NRP]
+    static constexpr int O_A = O_RFULL + NV;             // reduced matrix (A_SIZE) ...
+    static constexpr int O_WB = O_A;                     // ... over [NV] x3: wB wV wA
+    static constexpr int O_WV = O_WB + NV;
+    static constexpr int O_WA = O_WV + NV;
+    static constexpr int O_RHS = O_A + A_SIZE;           // [NRP]
     static constexpr int O_DIAG0 = O_RHS + NRP;          // [NRP]
     static constexpr int O_INVD = O_DIAG0 + NRP;         // [NB][6] inverse diagonal blocks
     static constexpr int O_SBUF = O_INVD + 2 * NRP;      // [rows][3] scaled panel rows of the running factorisation
-    static constexpr int O_WC = O_SBUF + (COMM ? 3 * NRP : 96);   // [PC] comm pair weights (projection source), then [PC] rhs multipliers
+    static constexpr int O_WC = O_SBUF + (COMM ? 3 * NRP : 3 * BW);   // [PC] comm pair weights (projection source), then [PC] rhs multipliers
     static constexpr int O_RED = O_WC + 2 * PC;          // [2][NW][NRED]
-    static constexpr int O_ACT = O_RED + 2 * NW * NRED;  // int[KMAX]: original obstacle index of each kept slot, int keep[KMAX], int n_act
-    static constexpr int O_END = O_ACT + KMAX + 2;
+    static constexpr int O_ACT = O_RED + 2 * NW * NRED;  // int[KRAW]: original obstacle index of each kept slot, int keep[KRAW], int n_act
+    static constexpr int O_END = O_ACT + KRAW + 2;
+    static_assert(A_SIZE >= 3 * NV, "row weights do not fit under the reduced matrix");
+    static_assert(D * M * 36 >= 2 * NV, "directions do not fit under the projection blocks");
     static constexpr int SMEM_BYTES = O_END * 8;
-    // dual_out layout: [KMAX][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
-    static constexpr int DUAL_STRIDE = KMAX * M * 6 + NV * 6 + 2 * PC;   // (+ comm pairs: upper-side, lower-side multiplier)
+    // dual_out layout: [KRAW][M][6] LSC rows, then [NV][6] box rows (lb, ub, vel+, vel-, acc+, acc-)
+    static constexpr int DUAL_STRIDE = KRAW * M * 6 + NV * 6 + 2 * PC;   // (+ comm pairs: upper-side, lower-side multiplier)
 };
 
 // continuity map c[m][0..2] = T y[m-1][3..5]
@@ -219,11 +249,18 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// CTA barrier; a one-warp CTA only needs the warp-level one
+template <class C>
+__device__ __forceinline__ void cta_sync() {
+    if (C::NW == 1) __syncwarp(); else __syncthreads();
+}
+
 // CTA-wide all-reduce of 4 values: v[0], v[1] summed, v[2] min, v[3] max.  One barrier (ping-pong scratch).   // @phase reduce4
 template <class C>
 __device__ __forceinline__ void block_reduce4(double* v, double* red, int& phase) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a = warp_sum(v[0]), b = warp_sum(v[1]), c = warp_min(v[2]), d = warp_max(v[3]);
+    if (C::NW == 1) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; __syncwarp(); return; }
     double* buf = red + phase * C::NW * C::NRED;
     if (lane == 0) { buf[warp * 4 + 0] = a; buf[warp * 4 + 1] = b; buf[warp * 4 + 2] = c; buf[warp * 4 + 3] = d; }
     __syncthreads();
@@ -261,6 +298,13 @@ __device__ __forceinline__ double pivot_rcp(double x) {
 #endif
 }
 
+// rows below panel J that can be non-zero (up to the end of the next stage)
+template <class C>
+__device__ __forceinline__ int panel_rows_below(int J) {
+    const int last = (J * 3 / C::NZS + 2) * C::NZS;
+    return (last < C::NRP ? last : C::NRP) - 3 * J - 3;
+}
+
 template <class C>
 __device__ __forceinline__ int chol_banded(double* A, const double* diag0, double* pinv, double* sbuf,
                                            const int* pr_i, const int* pr_k) {   // @phase chol
@@ -271,7 +315,10 @@ __device__ __forceinline__ int chol_banded(double* A, const double* diag0, doubl
         const double p11 = A[c0 * C::LD + c0], p21 = A[(c0 + 1) * C::LD + c0], p31 = A[(c0 + 2) * C::LD + c0];
         const double p22 = A[(c0 + 1) * C::LD + c0 + 1], p32 = A[(c0 + 2) * C::LD + c0 + 1], p33 = A[(c0 + 2) * C::LD + c0 + 2];
         const int i = c0 + 3 + lane;
-        const bool row = lane < C::BW && i < C::NRP;
+        // the matrix is block tridiagonal over stages (NZS variables each): below the panel only the rest of its
+        // stage and the next stage are non-zero, and block elimination keeps it that way
+        const int R = panel_rows_below<C>(J);
+        const bool row = lane < R;
         double a0 = 0, a1 = 0, a2 = 0;
         if (row) { a0 = A[i * C::LD + c0]; a1 = A[i * C::LD + c0 + 1]; a2 = A[i * C::LD + c0 + 2]; }
         // 3x3 LDL^T with pivot guard (a non-positive pivot freezes that direction)
@@ -304,10 +351,12 @@ __device__ __forceinline__ int chol_banded(double* A, const double* diag0, doubl
             q[3] = r2 + m32 * m32 * r3; q[4] = m32 * r3; q[5] = r3;
         }
         __syncwarp();
+        const int npair = R * (R + 1) / 2;                      // pairs (di >= dk) with di < R come first in the lane order
 #pragma unroll
         for (int t = 0; t < C::NPR; t++) {
+            if (32 * t >= npair) break;
             const int ii = c0 + 3 + pr_i[t], kk = c0 + 3 + pr_k[t];
-            if (pr_i[t] >= 0 && ii < C::NRP) {
+            if (lane + 32 * t < npair) {
                 const double* si = sbuf + pr_i[t] * 3;
                 const double* tk = A + kk * C::LD + c0;
                 A[ii * C::LD + kk] -= si[0] * tk[0] + si[1] * tk[1] + si[2] * tk[2];
@@ -330,7 +379,7 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* pinv, 
         const int c0 = 3 * J;
         const double w0 = b[c0], w1 = b[c0 + 1], w2 = b[c0 + 2];
         const int i = c0 + 3 + lane;
-        if (lane < C::BW && i < C::NRP) {
+        if (lane < panel_rows_below<C>(J)) {
             const double* ab = A + i * C::LD + c0;
             b[i] = (b[i] - ab[0] * w0) - (ab[1] * w1 + ab[2] * w2);
         }
@@ -347,8 +396,9 @@ __device__ __forceinline__ void chol_solve(const double* A, const double* pinv, 
     for (int J = C::NB - 1; J >= 0; J--) {
         const int c0 = 3 * J;
         const double x0 = b[c0], x1 = b[c0 + 1], x2 = b[c0 + 2];
-        const int i = c0 - 1 - lane;                            // rows above the panel that couple to it
-        if (lane < C::BW && i >= 0)
+        const int i = c0 - 1 - lane;                            // rows above the panel that couple to it: back to the
+        const int first = (c0 / C::NZS - 1) * C::NZS;           // start of the previous stage
+        if (i >= first && i >= 0)
             b[i] = (b[i] - A[c0 * C::LD + i] * x0) - (A[(c0 + 1) * C::LD + i] * x1 + A[(c0 + 2) * C::LD + i] * x2);
         __syncwarp();
     }
@@ -542,12 +592,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     const bool cp_valid = cp < NCP;
     const int m_cp = cp / 6, i_cp = cp % 6;
     const bool lsc_thread = cp_valid && !(m_cp == 0 && i_cp < 3);       // traj_optimizer.cpp:404
-    const bool var_thread = tid < NV;
-    const int k_v = tid / NCP, cp_v = tid % NCP, m_v = cp_v / 6, i_v = cp_v % 6;
-    // box rows owned by a variable thread: 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc-
-    const bool has_bnd = var_thread && !(m_v == 0 && i_v < 3);          // :260-265
-    const bool has_vel = var_thread && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
-    const bool has_acc = var_thread && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
+    // box rows: variable v = tid + u NT (u < VPT) is owned by this thread; rows 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc-
+    constexpr int VPT = C::VPT, NBX = C::NBX;
     // communication-range pair of this thread (traj_optimizer.cpp:477-500), on the segment end points E_a = c[a][5]:
     //   |E_a - E_b| <= range/2 - radius  for b < a  (c[mi][0] = E_{mi-1});  E_a within range/2 - radius of the
     //   current position (mi = 0) and within range/2 - 1e-5 of next_waypoint (merged into one interval)
@@ -569,11 +615,21 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             c_hp = r1; c_hm = -r1;
         }
     }
-    const unsigned bmask = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u) | (has_comm ? 192u : 0u);
+    unsigned bmask[VPT];
+#pragma unroll
+    for (int u = 0; u < VPT; u++) {
+        const int v = tid + u * NT, m_v = (v % NCP) / 6, i_v = v % 6;
+        const bool on = v < NV;
+        const bool has_bnd = on && !(m_v == 0 && i_v < 3);              // :260-265
+        const bool has_vel = on && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
+        const bool has_acc = on && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
+        bmask[u] = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u) | ((u == 0 && has_comm) ? 192u : 0u);
+    }
 
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
-    if (K > C::KMAX) K = C::KMAX;
+    if (K > C::KRAW) K = C::KRAW;
+    if (p.klass_mode == 2 && p.klass[agent] == 0) return;                // solved by the light instance already
 
     // ---- Cholesky trailing-update pair assignment (fixed per lane)
     int pr_i[C::NPR], pr_k[C::NPR];
@@ -590,7 +646,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     }
 
     // ---- stage per-agent constants
-    if (tid < 36) sQ2[tid] = p.Q2[tid];
+    for (int e = tid; e < 36; e += NT) sQ2[e] = p.Q2[e];
     if (tid < D) {
         const int k = tid;
         const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
@@ -610,7 +666,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             s_lb[k * M + m] = lo; s_ub[k * M + m] = hi;
         }
     }
-    if (tid == 32) {
+    if (tid == (NT > 32 ? 32 : 8)) {
         // getTerminalSegments_old, traj_optimizer.cpp:530-538 (float norm of the point3d difference)
         const float dx = p.goal[agent * 3 + 0] - p.state[agent * 9 + 0], dy = p.goal[agent * 3 + 1] - p.state[agent * 9 + 1],
                     dz = p.goal[agent * 3 + 2] - p.state[agent * 9 + 2];
@@ -626,9 +682,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     // control point c[0][2] bounds control point (m, i) to a box of half-width (5m + i - 2) vmax_k dt / 5 around it.
     // Such rows are redundant for the feasible set, so the minimiser (and its multipliers: zero) is unchanged.
     int* s_act = reinterpret_cast<int*>(sm + C::O_ACT);
-    int* s_keep = s_act + C::KMAX;
-    for (int e = tid; e < C::KMAX; e += NT) s_keep[e] = (e < K && !p.presolve) ? 1 : 0;
-    __syncthreads();
+    int* s_keep = s_act + C::KRAW;
+    for (int e = tid; e < C::KRAW; e += NT) s_keep[e] = (e < K && !p.presolve) ? 1 : 0;
+    cta_sync<C>();
     if (p.presolve && lsc_thread) {
         const double steps = (double) (5 * m_cp + i_cp - 2);
         for (int oi = grp; oi < K; oi += G) {
@@ -641,19 +697,27 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (!(lo - b > 1e-6) && !zero_normal) s_keep[oi] = 1;      // benign race: every writer stores 1
         }
     }
-    __syncthreads();
-    if (tid < K && s_keep[tid]) {
+    cta_sync<C>();
+    for (int e = tid; e < K; e += NT) {
+        if (!s_keep[e]) continue;
         int pos = 0;
-        for (int u = 0; u < tid; u++) pos += s_keep[u];
-        s_act[pos] = tid;
+        for (int u = 0; u < e; u++) pos += s_keep[u];
+        if (pos < C::KMAX) s_act[pos] = e;
     }
     if (tid == 0) {
         int n = 0;
         for (int u = 0; u < K; u++) n += s_keep[u];
-        s_keep[C::KMAX] = n;
+        s_keep[C::KRAW] = n;
     }
-    __syncthreads();
-    K = s_keep[C::KMAX];                                               // kept obstacles, compacted into slots 0..K-1
+    cta_sync<C>();
+    K = s_keep[C::KRAW];                                               // kept obstacles, compacted into slots 0..K-1
+    if (p.klass_mode == 1) {
+        // light instance: agents with more kept obstacles than it holds go to the full-capacity instance
+        const bool over = K > C::KMAX;
+        if (tid == 0) p.klass[agent] = over ? 1 : 0;
+        if (over) return;
+    }
+    if (K > C::KMAX) K = C::KMAX;
     for (int e = tid; e < K * M; e += NT) {
         // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference
         // (traj_optimizer.cpp:409-411): here they become the constant row 0.c >= -1, which never binds
@@ -664,53 +728,67 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (sqrt((double) nsq) < 1e-5) { nx = 0.0; ny = 0.0; nz = 0.0; }
         s_nrm[e * 3] = nx; s_nrm[e * 3 + 1] = ny; s_nrm[e * 3 + 2] = nz;
     }
+    // full-space control points of the reduced vector yv (x0: the fixed initial points, null for directions)
+    auto expand = [&](const double* yv, const double* x0, double* out) {
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = tid + u * NT;
+            if (v < NV) out[v] = full_from_reduced<C>(yv, x0, v / NCP, (v % NCP) / 6, v % 6);
+        }
+    };
     // starting point: the free control points of initial_traj when given (the reference hands it to
     // TrajOptimizer::solve, traj_optimizer.cpp:18-21), else every free control point at the current position
     bool warm = p.warm_traj != nullptr;
     auto set_start = [&](bool from_traj) {
-        if (tid < NR) {
+        for (int r = tid; r < NR; r += NT) {
             int st, k, j;
-            if (C::TERM && tid >= (M - 1) * C::NZS) { st = M - 1; k = tid - (M - 1) * C::NZS; j = 2; }
-            else { st = tid / C::NZS; k = (tid % C::NZS) / 3; j = tid % 3; }
-            s_y[tid] = from_traj ? (double) p.warm_traj[(((size_t) agent * M + st) * 6 + 3 + j) * 3 + k]
-                                 : (double) p.state[agent * 9 + k];
+            if (C::TERM && r >= (M - 1) * C::NZS) { st = M - 1; k = r - (M - 1) * C::NZS; j = 2; }
+            else { st = r / C::NZS; k = (r % C::NZS) / 3; j = r % 3; }
+            s_y[r] = from_traj ? (double) p.warm_traj[(((size_t) agent * M + st) * 6 + 3 + j) * 3 + k]
+                               : (double) p.state[agent * 9 + k];
         }
-        __syncthreads();
-        if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
-        __syncthreads();
+        cta_sync<C>();
+        expand(s_y, s_x0, s_c);
+        cta_sync<C>();
     };
     set_start(warm);
 
     // ---- per-thread row state (registers): slack and multiplier of every owned row
     double ls[KPT], ll[KPT];
-    double bs[C::NBX], bl[C::NBX];
+    double bs[VPT][NBX], bl[VPT][NBX];
     // rows of this thread: obstacles grp, grp + G, ... < K on its control point (none for the fixed points)
     const int nrow = (lsc_thread && K > grp) ? (K - grp + G - 1) / G : 0;
 #pragma unroll
     for (int j = 0; j < KPT; j++) { ls[j] = 1.0; ll[j] = 0.0; }
 #pragma unroll
-    for (int e = 0; e < C::NBX; e++) { bs[e] = 1.0; bl[e] = 0.0; }
+    for (int u = 0; u < VPT; u++)
+#pragma unroll
+        for (int e = 0; e < NBX; e++) { bs[u][e] = 1.0; bl[u][e] = 0.0; }
 
     double red[4];
     {
-        red[0] = (double) (nrow + __popc(bmask)); red[1] = 0; red[2] = 0; red[3] = 0;
+        int nb = 0;
+#pragma unroll
+        for (int u = 0; u < VPT; u++) nb += __popc(bmask[u]);
+        red[0] = (double) (nrow + nb); red[1] = 0; red[2] = 0; red[3] = 0;
         block_reduce4<C>(red, s_red, red_phase);       // (barrier: s_c is complete after this)
     }
     const double n_rows = red[0];
 
     // helpers -----------------------------------------------------------------------------------
-    // directional change of the six box rows of this thread for a full-space direction dv
-    auto box_dq = [&](const double* dv, double* dq) {   // @phase row_helpers
-        const double* d = dv + k_v * NCP + cp_v;
+    // directional change of the six box rows of variable slot u for a full-space direction dv
+    auto box_dq = [&](const double* dv, double* dq, int u) {   // @phase row_helpers
+        const int v = tid + u * NT;
+        const double* d = dv + (v < NV ? v : 0);
         const double d0 = d[0];
         double dvv = 0.0, daa = 0.0;
-        if (has_vel) dvv = d[1] - d0;
-        if (has_acc) daa = d[2] - 2.0 * d[1] + d0;
+        if (bmask[u] & 4u) dvv = d[1] - d0;
+        if (bmask[u] & 16u) daa = d[2] - 2.0 * d[1] + d0;
         dq[0] = d0; dq[1] = -d0; dq[2] = -dvv; dq[3] = dvv; dq[4] = -daa; dq[5] = daa;
         if (C::COMM) {
             double dvc = 0.0;
             if (has_comm) dvc = dv[ca_idx] - (cb_idx >= 0 ? dv[cb_idx] : 0.0);
-            dq[C::NBX - 2] = -dvc; dq[C::NBX - 1] = dvc;
+            dq[NBX - 2] = -dvc; dq[NBX - 1] = dvc;
         }
     };
     auto load_cp = [&](const double* v, double& x, double& y, double& z) {
@@ -740,95 +818,107 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         T[0] += u * n[0]; T[1] += u * n[1];
         if (D == 3) T[2] += u * n[2];
     };
-    auto store_box = [&](const double* W, const double* u, bool withS) {
+    auto store_box = [&](const double* W, const double* u, bool withS, int slot) {
         // gradients of the rows: lb +e, ub -e, vel+ -(d), vel- +(d), acc+ -(d), acc- +(d)
-        if (withS) { s_wB[tid] = W[0] + W[1]; s_wV[tid] = W[2] + W[3]; s_wA[tid] = W[4] + W[5]; }
-        s_uB[tid] = u[0] - u[1]; s_uV[tid] = u[3] - u[2]; s_uA[tid] = u[5] - u[4];
+        const int v = tid + slot * NT;
+        if (v < NV) {
+            if (withS) { s_wB[v] = W[0] + W[1]; s_wV[v] = W[2] + W[3]; s_wA[v] = W[4] + W[5]; }
+            s_uB[v] = u[0] - u[1]; s_uV[v] = u[3] - u[2]; s_uA[v] = u[5] - u[4];
+        }
         if (C::COMM && has_comm) {
             // rows hp - v >= 0 (gradient -g) and v - hm >= 0 (gradient +g), g = e_a - e_b
-            if (withS) s_wC[tid] = W[C::NBX - 2] + W[C::NBX - 1];
-            s_wC[C::PC + tid] = u[C::NBX - 1] - u[C::NBX - 2];
+            if (withS) s_wC[tid] = W[NBX - 2] + W[NBX - 1];
+            s_wC[C::PC + tid] = u[NBX - 1] - u[NBX - 2];
         }
     };
 
     // sum the group slabs, build the 6x6 blocks (withS) and the full-space rhs  -grad f + A^T u, then project.
     auto assemble = [&](bool withS) {   // @phase assemble
-        __syncthreads();
-        for (int e = tid; e < NCP * D; e += NT) {
-            double a = slabT[e];
+        cta_sync<C>();
+        if (G > 1) {
+            for (int e = tid; e < NCP * D; e += NT) {
+                double a = slabT[e];
 #pragma unroll
-            for (int g = 1; g < G; g++) a += slabT[g * NCP * D + e];
-            slabT[e] = a;
-        }
-        if (withS) {
-            for (int e = tid; e < NCP * NS; e += NT) {
-                double a = slabS[e];
-#pragma unroll
-                for (int g = 1; g < G; g++) a += slabS[g * NCP * NS + e];
-                slabS[e] = a;
+                for (int g = 1; g < G; g++) a += slabT[g * NCP * D + e];
+                slabT[e] = a;
             }
-        }
-        __syncthreads();
-        if (withS && var_thread) {
-            // row a of the 6x6 block of (dimension k_v, segment m_v): jerk Gram + terminal + bounds on the diagonal,
-            // tri-diagonal velocity stencils (1,-1), penta-diagonal acceleration stencils (1,-2,1), LSC diagonal block
-            const int v0 = k_v * NCP + m_v * 6, a = i_v;
-            const double wv0 = a <= 4 ? s_wV[v0 + a] : 0.0, wvm = a >= 1 ? s_wV[v0 + a - 1] : 0.0;
-            const double wa0 = a <= 3 ? s_wA[v0 + a] : 0.0, wa1 = (a >= 1 && a <= 4) ? s_wA[v0 + a - 1] : 0.0,
-                         wa2 = a >= 2 ? s_wA[v0 + a - 2] : 0.0;
-            const int dd = (D == 3) ? symidx3(k_v, k_v) : symidx2(k_v, k_v);
-            double row[6];
+            if (withS) {
+                for (int e = tid; e < NCP * NS; e += NT) {
+                    double a = slabS[e];
 #pragma unroll
-            for (int b = 0; b < 6; b++) row[b] = sQ2[a * 6 + b];
-            // diagonal
-            double dg = s_wB[tid] + slabS[cp_v * NS + dd] + wv0 + wvm + wa0 + 4.0 * wa1 + wa2;
-            if (a == 5) dg += s_termw[m_v];
-            // neighbours: (a, a+1): -wV[a] - 2 wA[a] - 2 wA[a-1];  (a, a+2): wA[a];  mirrored for a-1, a-2
-            const double up1 = -wv0 - 2.0 * wa0 - 2.0 * wa1, dn1 = -wvm - 2.0 * wa1 - 2.0 * wa2;
-#pragma unroll
-            for (int b = 0; b < 6; b++) {
-                double add = 0.0;
-                if (b == a) add = dg;
-                else if (b == a + 1) add = up1;
-                else if (b == a - 1) add = dn1;
-                else if (b == a + 2) add = wa0;
-                else if (b == a - 2) add = wa2;
-                s_blk[(k_v * M + m_v) * 36 + a * 6 + b] = row[b] + add;
+                    for (int g = 1; g < G; g++) a += slabS[g * NCP * NS + e];
+                    slabS[e] = a;
+                }
             }
+            cta_sync<C>();
         }
-        if (var_thread) {
-            const int v0 = k_v * NCP + m_v * 6, a = i_v;
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = tid + u * NT;
+            if (v >= NV) continue;
+            const int k_v = v / NCP, cp_v = v % NCP, m_v = cp_v / 6, a = v % 6;
+            const int v0 = k_v * NCP + m_v * 6;
+            if (withS) {
+                // row a of the 6x6 block of (dimension k_v, segment m_v): jerk Gram + terminal + bounds on the diagonal,
+                // tri-diagonal velocity stencils (1,-1), penta-diagonal acceleration stencils (1,-2,1), LSC diagonal block
+                const double wv0 = a <= 4 ? s_wV[v0 + a] : 0.0, wvm = a >= 1 ? s_wV[v0 + a - 1] : 0.0;
+                const double wa0 = a <= 3 ? s_wA[v0 + a] : 0.0, wa1 = (a >= 1 && a <= 4) ? s_wA[v0 + a - 1] : 0.0,
+                             wa2 = a >= 2 ? s_wA[v0 + a - 2] : 0.0;
+                const int dd = (D == 3) ? symidx3(k_v, k_v) : symidx2(k_v, k_v);
+                double row[6];
+#pragma unroll
+                for (int b = 0; b < 6; b++) row[b] = sQ2[a * 6 + b];
+                // diagonal
+                double dg = s_wB[v] + slabS[cp_v * NS + dd] + wv0 + wvm + wa0 + 4.0 * wa1 + wa2;
+                if (a == 5) dg += s_termw[m_v];
+                // neighbours: (a, a+1): -wV[a] - 2 wA[a] - 2 wA[a-1];  (a, a+2): wA[a];  mirrored for a-1, a-2
+                const double up1 = -wv0 - 2.0 * wa0 - 2.0 * wa1, dn1 = -wvm - 2.0 * wa1 - 2.0 * wa2;
+#pragma unroll
+                for (int b = 0; b < 6; b++) {
+                    double add = 0.0;
+                    if (b == a) add = dg;
+                    else if (b == a + 1) add = up1;
+                    else if (b == a - 1) add = dn1;
+                    else if (b == a + 2) add = wa0;
+                    else if (b == a - 2) add = wa2;
+                    s_blk[(k_v * M + m_v) * 36 + a * 6 + b] = row[b] + add;
+                }
+            }
             double gr = 0.0;
 #pragma unroll
             for (int b = 0; b < 6; b++) gr += sQ2[a * 6 + b] * s_c[v0 + b];
             if (a == 5) gr += s_termw[m_v] * (s_c[v0 + 5] - s_goal[k_v]);
-            double au = s_uB[tid] + slabT[cp_v * D + k_v];
+            double au = s_uB[v] + slabT[cp_v * D + k_v];
             if (a >= 1) au += s_uV[v0 + a - 1];
             if (a <= 4) au -= s_uV[v0 + a];
             for (int i = (a - 2 > 0 ? a - 2 : 0); i <= (a < 3 ? a : 3); i++) au += s_uA[v0 + i] * ((a - i == 1) ? -2.0 : 1.0);
-            s_rfull[tid] = au - gr;
+            s_rfull[v] = au - gr;
         }
-        __syncthreads();
+        cta_sync<C>();
         if (withS) {
-            for (int e = tid; e < p.n_proj_ent; e += NT) {
-                const int4 h = p.proj_ent[e];
-                double val = 0.0;
-                for (int t = 0; t < h.z; t++) {
-                    const double2 ct = p.proj_term[h.y + t];
-                    val += ct.x * s_blk[(int) ct.y];
+            const ProjTerm* tab = (p.klass_mode == 1 ? p.proj_light : p.proj) + tid;
+            const int len = p.klass_mode == 1 ? p.proj_len_light : p.proj_len;
+            double val = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < len; i++) {
+                const ProjTerm t = tab[i * NT];
+                val = fma(t.coef, s_blk[t.src], val);
+                if (t.dest >= 0) {
+                    const int d = t.dest & PROJ_MASK;
+                    if (t.dest & PROJ_ONE) val = 1.0;                           // identity padding rows
+                    s_A[d] = val;
+                    if (t.dest & PROJ_DIAG) s_diag0[d / (C::LD + 1)] = val;
+                    val = 0.0;
                 }
-                if (h.z < 0) val = 1.0;                                     // identity padding rows
-                s_A[h.x] = val;
-                if (h.w >= 0) s_diag0[h.w] = val;
             }
         }
-        if (tid < C::NRP) {
-            double r = tid < NR ? reduce_from_full<C>(s_rfull, tid) : 0.0;
-            if (C::COMM && tid < NR) {
+        for (int r0 = tid; r0 < C::NRP; r0 += NT) {
+            double r = r0 < NR ? reduce_from_full<C>(s_rfull, r0) : 0.0;
+            if (C::COMM && r0 < NR) {
                 // end-point variables also collect A^T u of the comm pairs they appear in
                 int st = -1, k = 0;
-                if (C::TERM && tid >= (M - 1) * C::NZS) { st = M - 1; k = tid - (M - 1) * C::NZS; }
-                else if (tid % 3 == 2) { st = tid / C::NZS; k = (tid % C::NZS) / 3; }
+                if (C::TERM && r0 >= (M - 1) * C::NZS) { st = M - 1; k = r0 - (M - 1) * C::NZS; }
+                else if (r0 % 3 == 2) { st = r0 / C::NZS; k = (r0 % C::NZS) / 3; }
                 if (st >= 0) {
                     const double* uc = s_wC + C::PC + k * C::PP;
                     r += uc[st];                                                      // box pair of E_st
@@ -836,9 +926,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                     for (int a = st + 1; a < M; a++) r -= uc[M + a * (a - 1) / 2 + st];        // pairs (a, st): -g
                 }
             }
-            s_rhs[tid] = r;
+            s_rhs[r0] = r;
         }
-        __syncthreads();
+        cta_sync<C>();
     };
 
     int bad_piv = 0;
@@ -850,11 +940,28 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (factor) bad_piv += chol_banded<C>(s_A, s_diag0, s_invd, sm + C::O_SBUF, pr_i, pr_k);
             chol_solve<C>(s_A, s_invd, s_rhs);
         }
-        __syncthreads();
+        cta_sync<C>();
     };
 
     // ---------------------------------------------------------------- initial point   // @phase init_point
     // q of every row at the starting point is kept in ls[] / bs[] until s and lam are set.
+    auto box_q = [&](double* q, int u) {
+        const int v = tid + u * NT;
+        if (v < NV) {
+            const int k_v = v / NCP, m_v = (v % NCP) / 6;
+            const double* cc = s_c + v;
+            const double c0 = cc[0];
+            double dv = 0.0, da = 0.0;
+            if (bmask[u] & 4u) dv = cc[1] - c0;
+            if (bmask[u] & 16u) da = cc[2] - 2.0 * cc[1] + c0;
+            q[0] = c0 - s_lb[k_v * M + m_v]; q[1] = s_ub[k_v * M + m_v] - c0;
+            q[2] = s_vlim[k_v] - dv; q[3] = s_vlim[k_v] + dv; q[4] = s_alim[k_v] - da; q[5] = s_alim[k_v] + da;
+        }
+        if (C::COMM) {
+            const double vv = has_comm ? s_c[ca_idx] - (cb_idx >= 0 ? s_c[cb_idx] : 0.0) : 0.0;
+            q[NBX - 2] = c_hp - vv; q[NBX - 1] = vv - c_hm;
+        }
+    };
     auto rows_q = [&]() {
         double cx, cy, cz;
         if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
@@ -868,19 +975,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             ls[j] = q;
         }
-        if (var_thread) {
-            const double* cc = s_c + k_v * NCP + cp_v;
-            const double c0 = cc[0];
-            double dv = 0.0, da = 0.0;
-            if (has_vel) dv = cc[1] - c0;
-            if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
-            bs[0] = c0 - s_lb[k_v * M + m_v]; bs[1] = s_ub[k_v * M + m_v] - c0;
-            bs[2] = s_vlim[k_v] - dv; bs[3] = s_vlim[k_v] + dv; bs[4] = s_alim[k_v] - da; bs[5] = s_alim[k_v] + da;
-            if (C::COMM) {
-                const double v = has_comm ? s_c[ca_idx] - (cb_idx >= 0 ? s_c[cb_idx] : 0.0) : 0.0;
-                bs[C::NBX - 2] = c_hp - v; bs[C::NBX - 1] = v - c_hm;
-            }
-        }
+#pragma unroll
+        for (int u = 0; u < VPT; u++) box_q(bs[u], u);
     };
     rows_q();
     if (warm) {
@@ -889,12 +985,14 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
         for (int j = 0; j < KPT; j++) if (j < nrow) qmin = fmin(qmin, ls[j]);
 #pragma unroll
-        for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) qmin = fmin(qmin, bs[e]);
+        for (int u = 0; u < VPT; u++)
+#pragma unroll
+            for (int e = 0; e < NBX; e++) if (bmask[u] >> e & 1u) qmin = fmin(qmin, bs[u][e]);
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = 0;
         block_reduce4<C>(red, s_red, red_phase);
         if (red[2] < -p.warm_reject) {
             warm = false;
-            __syncthreads();
+            cta_sync<C>();
             set_start(false);
             rows_q();
         }
@@ -910,23 +1008,22 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             accum(S, T, n, 1.0, -ls[j], true);
         }
         store_slab(S, T, true);
-        if (var_thread) {
-            double W[C::NBX], u[C::NBX];
 #pragma unroll
-            for (int e = 0; e < C::NBX; e++) { const bool on = bmask >> e & 1u; W[e] = on ? 1.0 : 0.0; u[e] = on ? -bs[e] : 0.0; }
-            store_box(W, u, true);
+        for (int u = 0; u < VPT; u++) {
+            double W[NBX], uu[NBX];
+#pragma unroll
+            for (int e = 0; e < NBX; e++) { const bool on = bmask[u] >> e & 1u; W[e] = on ? 1.0 : 0.0; uu[e] = on ? -bs[u][e] : 0.0; }
+            store_box(W, uu, true, u);
         }
     }
     if (!warm) {
         assemble(true);
         factor_solve(true);
-        if (tid < NR) { s_dy[tid] = s_rhs[tid]; s_y[tid] += s_rhs[tid]; }
-        __syncthreads();
-        if (var_thread) {
-            s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
-            s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
-        }
-        __syncthreads();
+        for (int r = tid; r < NR; r += NT) { s_dy[r] = s_rhs[r]; s_y[r] += s_rhs[r]; }
+        cta_sync<C>();
+        expand(s_dy, nullptr, s_dc);
+        expand(s_y, s_x0, s_c);
+        cta_sync<C>();
     }
     double rp;      // the common primal residual s - q
     {
@@ -942,11 +1039,12 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             ls[j] += dq;
             qmin = fmin(qmin, ls[j]); qmax = fmax(qmax, ls[j]);
         }
-        if (var_thread) {
-            double dq[C::NBX] = {};
-            if (!warm) box_dq(s_dc, dq);
 #pragma unroll
-            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bs[e] += dq[e]; qmin = fmin(qmin, bs[e]); qmax = fmax(qmax, bs[e]); }
+        for (int u = 0; u < VPT; u++) {
+            double dq[NBX] = {};
+            if (!warm) box_dq(s_dc, dq, u);
+#pragma unroll
+            for (int e = 0; e < NBX; e++) if (bmask[u] >> e & 1u) { bs[u][e] += dq[e]; qmin = fmin(qmin, bs[u][e]); qmax = fmax(qmax, bs[u][e]); }
         }
         red[0] = 0; red[1] = 0; red[2] = qmin; red[3] = qmax;
         block_reduce4<C>(red, s_red, red_phase);
@@ -958,7 +1056,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
             for (int j = 0; j < KPT; j++) if (j < nrow) { ls[j] += shift_s; ll[j] = mu0 / ls[j]; }
 #pragma unroll
-            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bs[e] += shift_s; bl[e] = mu0 / bs[e]; }
+            for (int u = 0; u < VPT; u++)
+#pragma unroll
+                for (int e = 0; e < NBX; e++) if (bmask[u] >> e & 1u) { bs[u][e] += shift_s; bl[u][e] = mu0 / bs[u][e]; }
             rp = shift_s;
         } else {
             const double shift_s = (red[2] <= 0.0) ? 1.0 - red[2] : 0.0;        // alpha_p = -min(s) >= 0  -> s += 1 + alpha_p
@@ -966,7 +1066,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
             for (int j = 0; j < KPT; j++) if (j < nrow) { ll[j] = -ls[j] + shift_l; ls[j] += shift_s; }
 #pragma unroll
-            for (int e = 0; e < C::NBX; e++) if (bmask >> e & 1u) { bl[e] = -bs[e] + shift_l; bs[e] += shift_s; }
+            for (int u = 0; u < VPT; u++)
+#pragma unroll
+                for (int e = 0; e < NBX; e++) if (bmask[u] >> e & 1u) { bl[u][e] = -bs[u][e] + shift_l; bs[u][e] += shift_s; }
             rp = shift_s;
         }
     }
@@ -1002,24 +1104,25 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 accum(S, T, n, W, W * rp_new, true);
             }
             store_slab(S, T, true);
-            if (var_thread) {
-                double W[C::NBX], u[C::NBX], dqa[C::NBX], dq[C::NBX];
-                if (have_step) { box_dq(s_dca, dqa); box_dq(s_dc, dq); }
 #pragma unroll
-                for (int e = 0; e < C::NBX; e++) {
-                    W[e] = 0.0; u[e] = 0.0;
-                    if (!(bmask >> e & 1u)) continue;
+            for (int u = 0; u < VPT; u++) {
+                double W[NBX], uu[NBX], dqa[NBX], dq[NBX];
+                if (have_step) { box_dq(s_dca, dqa, u); box_dq(s_dc, dq, u); }
+#pragma unroll
+                for (int e = 0; e < NBX; e++) {
+                    W[e] = 0.0; uu[e] = 0.0;
+                    if (!(bmask[u] >> e & 1u)) continue;
                     if (have_step) {
-                        const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
-                        const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
-                        const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                        const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
-                        bs[e] += alpha * ds; bl[e] += alpha * dl;
+                        const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
+                        const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
+                        const double rc = bs[u][e] * bl[u][e] + dsa * dla - sigmu;
+                        const double ds = dq[e] - rp, dl = -(rc + bl[u][e] * ds) * rs;
+                        bs[u][e] += alpha * ds; bl[u][e] += alpha * dl;
                     }
-                    W[e] = bl[e] * fast_rcp(bs[e]); u[e] = W[e] * rp_new;
-                    sl += bs[e] * bl[e];
+                    W[e] = bl[u][e] * fast_rcp(bs[u][e]); uu[e] = W[e] * rp_new;
+                    sl += bs[u][e] * bl[u][e];
                 }
-                store_box(W, u, true);
+                store_box(W, uu, true, u);
             }
             rp = rp_new;
             red[0] = sl; red[1] = 0; red[2] = 0; red[3] = 0;
@@ -1033,15 +1136,15 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         // ---- predictor   // @phase predictor_glue
         assemble(true);
         factor_solve(true);
-        if (tid < NR) s_dy[tid] = s_rhs[tid];
-        __syncthreads();
-        if (var_thread) s_dca[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
-        __syncthreads();
+        for (int r = tid; r < NR; r += NT) s_dy[r] = s_rhs[r];
+        cta_sync<C>();
+        expand(s_dy, nullptr, s_dca);
+        cta_sync<C>();
         // ---- sweep B: affine step length and centering parameter   // @phase sweepB
         {
             double ax, ay, az;
             if (cp_valid) load_cp(s_dca, ax, ay, az); else { ax = ay = az = 0; }
-            MinRatio mr; mr.init();
+            double tmax = 0.0;                                   // max over rows of -dv / v (>= 1/2 for every row pair)
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
@@ -1049,26 +1152,30 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 const double* n = s_nrm + ((grp + G * j) * M + m_cp) * 3;
                 double dqa = n[0] * ax + n[1] * ay;
                 if (D == 3) dqa += n[2] * az;
-                const double W = ll[j] * fast_rcp(ls[j]);
+                const double rs = fast_rcp(ls[j]), W = ll[j] * rs;
                 const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
-                mr.add(ls[j], dsa); mr.add(ll[j], dla);
+                // inverse step to the boundary of both rows without a division: -dsa / s and -dla / lam = 1 + dsa / s
+                const double z = dsa * rs;
+                tmax = fmax(tmax, fmax(-z, 1.0 + z));
                 s1 += ls[j] * dla + ll[j] * dsa; s2 += dsa * dla;
             }
-            if (var_thread) {
-                double dqa[C::NBX];
-                box_dq(s_dca, dqa);
 #pragma unroll
-                for (int e = 0; e < C::NBX; e++) {
-                    if (!(bmask >> e & 1u)) continue;
-                    const double W = bl[e] * fast_rcp(bs[e]);
-                    const double dsa = dqa[e] - rp, dla = -bl[e] - W * dsa;
-                    mr.add(bs[e], dsa); mr.add(bl[e], dla);
-                    s1 += bs[e] * dla + bl[e] * dsa; s2 += dsa * dla;
+            for (int u = 0; u < VPT; u++) {
+                double dqa[NBX];
+                box_dq(s_dca, dqa, u);
+#pragma unroll
+                for (int e = 0; e < NBX; e++) {
+                    if (!(bmask[u] >> e & 1u)) continue;
+                    const double rs = fast_rcp(bs[u][e]), W = bl[u][e] * rs;
+                    const double dsa = dqa[e] - rp, dla = -bl[u][e] - W * dsa;
+                    const double z = dsa * rs;
+                    tmax = fmax(tmax, fmax(-z, 1.0 + z));
+                    s1 += bs[u][e] * dla + bl[u][e] * dsa; s2 += dsa * dla;
                 }
             }
-            red[0] = s1; red[1] = s2; red[2] = mr.value(); red[3] = 0;
+            red[0] = s1; red[1] = s2; red[2] = 0; red[3] = tmax;
             block_reduce4<C>(red, s_red, red_phase);
-            const double a = fmin(1.0, red[2]);
+            const double a = red[3] > 1.0 ? 1.0 / red[3] : 1.0;
             const double mu_aff = (mu * n_rows + a * red[0] + a * a * red[1]) / n_rows;
             double sg = mu_aff / mu;
             sg = sg * sg * sg;
@@ -1093,32 +1200,34 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 accum(S, T, n, 0.0, ll[j] + (ll[j] * rp - rc) * rs, false);
             }
             store_slab(S, T, false);
-            if (var_thread) {
-                double W[C::NBX], u[C::NBX], dqa[C::NBX];
-                box_dq(s_dca, dqa);
 #pragma unroll
-                for (int e = 0; e < C::NBX; e++) {
-                    W[e] = 0.0; u[e] = 0.0;
-                    if (!(bmask >> e & 1u)) continue;
-                    const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
-                    const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
-                    const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                    u[e] = bl[e] + (bl[e] * rp - rc) * rs;
+            for (int u = 0; u < VPT; u++) {
+                double W[NBX], uu[NBX], dqa[NBX];
+                box_dq(s_dca, dqa, u);
+#pragma unroll
+                for (int e = 0; e < NBX; e++) {
+                    W[e] = 0.0; uu[e] = 0.0;
+                    if (!(bmask[u] >> e & 1u)) continue;
+                    const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
+                    const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
+                    const double rc = bs[u][e] * bl[u][e] + dsa * dla - sigmu;
+                    uu[e] = bl[u][e] + (bl[u][e] * rp - rc) * rs;
                 }
-                store_box(W, u, false);
+                store_box(W, uu, false, u);
             }
         }
         assemble(false);
         factor_solve(false);
-        if (tid < NR) s_dy[tid] = s_rhs[tid];
-        __syncthreads();
-        if (var_thread) s_dc[tid] = full_from_reduced<C>(s_dy, nullptr, k_v, m_v, i_v);
-        __syncthreads();
+        for (int r = tid; r < NR; r += NT) s_dy[r] = s_rhs[r];
+        cta_sync<C>();
+        expand(s_dy, nullptr, s_dc);
+        cta_sync<C>();
         // ---- sweep D: step length of the combined direction   // @phase sweepD
         {
             double ax, ay, az, dx, dy, dz;
             if (cp_valid) { load_cp(s_dca, ax, ay, az); load_cp(s_dc, dx, dy, dz); } else { ax = ay = az = dx = dy = dz = 0; }
-            MinRatio mr; mr.init();
+            MinRatio mr; mr.init();                              // multiplier rows (float quotient)
+            double tmax = 0.0;                                   // slack rows: max of -ds / s through the known 1 / s
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
                 if (j >= nrow) break;
@@ -1129,38 +1238,40 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 const double dsa = dqa - rp, dla = -ll[j] - W * dsa;
                 const double rc = ls[j] * ll[j] + dsa * dla - sigmu;
                 const double ds = dq - rp, dl = -(rc + ll[j] * ds) * rs;
-                mr.add(ls[j], ds); mr.add(ll[j], dl);
+                tmax = fmax(tmax, -ds * rs); mr.add(ll[j], dl);
             }
-            if (var_thread) {
-                double dqa[C::NBX], dq[C::NBX];
-                box_dq(s_dca, dqa); box_dq(s_dc, dq);
 #pragma unroll
-                for (int e = 0; e < C::NBX; e++) {
-                    if (!(bmask >> e & 1u)) continue;
-                    const double rs = fast_rcp(bs[e]), Wo = bl[e] * rs;
-                    const double dsa = dqa[e] - rp, dla = -bl[e] - Wo * dsa;
-                    const double rc = bs[e] * bl[e] + dsa * dla - sigmu;
-                    const double ds = dq[e] - rp, dl = -(rc + bl[e] * ds) * rs;
-                    mr.add(bs[e], ds); mr.add(bl[e], dl);
+            for (int u = 0; u < VPT; u++) {
+                double dqa[NBX], dq[NBX];
+                box_dq(s_dca, dqa, u); box_dq(s_dc, dq, u);
+#pragma unroll
+                for (int e = 0; e < NBX; e++) {
+                    if (!(bmask[u] >> e & 1u)) continue;
+                    const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
+                    const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
+                    const double rc = bs[u][e] * bl[u][e] + dsa * dla - sigmu;
+                    const double ds = dq[e] - rp, dl = -(rc + bl[u][e] * ds) * rs;
+                    tmax = fmax(tmax, -ds * rs); mr.add(bl[u][e], dl);
                 }
             }
-            red[0] = 0; red[1] = 0; red[2] = mr.value(); red[3] = 0;
+            red[0] = 0; red[1] = 0; red[2] = mr.value(); red[3] = tmax;
             block_reduce4<C>(red, s_red, red_phase);
-            // (the ratio is a float quotient: a full step needs a margin above 1, otherwise stay 1% inside)
-            alpha = red[2] >= 1.0001 ? 1.0 : 0.99 * fmin(red[2], 1.0);
+            // (the ratios carry ~1e-7 relative error: a full step needs a margin above 1, otherwise stay 1% inside)
+            const double ratio = fmin(red[2], red[3] > 0.0 ? 1.0 / red[3] : 2.0);
+            alpha = ratio >= 1.0001 ? 1.0 : 0.99 * fmin(ratio, 1.0);
             have_step = true;
         }
         // the reduced iterate moves now; the rows follow in the next sweep A (s_dca / s_dc stay valid until then)
-        if (tid < NR) s_y[tid] += alpha * s_dy[tid];
-        __syncthreads();
-        if (var_thread) s_c[tid] = full_from_reduced<C>(s_y, s_x0, k_v, m_v, i_v);
+        for (int r = tid; r < NR; r += NT) s_y[r] += alpha * s_dy[r];
+        cta_sync<C>();
+        expand(s_y, s_x0, s_c);
         // (assemble() starts with a barrier before anything reads s_c)
     }
 
     // ---------------------------------------------------------------- outputs   // @phase outputs
     // true primal residual of the returned point, recomputed from the row constants
     double rp_true = 0.0;
-    __syncthreads();
+    cta_sync<C>();
     {
         double cx, cy, cz;
         if (cp_valid) load_cp(s_c, cx, cy, cz); else { cx = cy = cz = 0; }
@@ -1177,41 +1288,37 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             accum(S, T, n, 0.0, ll[j], false);
         }
         store_slab(S, T, false);
-        if (var_thread) {
-            const double* cc = s_c + k_v * NCP + cp_v;
-            const double c0 = cc[0];
-            double dv = 0.0, da = 0.0, q[C::NBX];
-            if (has_vel) dv = cc[1] - c0;
-            if (has_acc) da = cc[2] - 2.0 * cc[1] + c0;
-            q[0] = c0 - s_lb[k_v * M + m_v]; q[1] = s_ub[k_v * M + m_v] - c0;
-            q[2] = s_vlim[k_v] - dv; q[3] = s_vlim[k_v] + dv; q[4] = s_alim[k_v] - da; q[5] = s_alim[k_v] + da;
-            if (C::COMM) {
-                const double v = has_comm ? s_c[ca_idx] - (cb_idx >= 0 ? s_c[cb_idx] : 0.0) : 0.0;
-                q[C::NBX - 2] = c_hp - v; q[C::NBX - 1] = v - c_hm;
-            }
-            double W[C::NBX] = {}, u[C::NBX];
 #pragma unroll
-            for (int e = 0; e < C::NBX; e++) {
-                const bool on = bmask >> e & 1u;
-                u[e] = on ? bl[e] : 0.0;
-                if (on) rp_true = fmax(rp_true, fabs(bs[e] - q[e]));
+        for (int u = 0; u < VPT; u++) {
+            double q[NBX] = {};
+            box_q(q, u);
+            double W[NBX] = {}, uu[NBX];
+#pragma unroll
+            for (int e = 0; e < NBX; e++) {
+                const bool on = bmask[u] >> e & 1u;
+                uu[e] = on ? bl[u][e] : 0.0;
+                if (on) rp_true = fmax(rp_true, fabs(bs[u][e] - q[e]));
             }
-            store_box(W, u, false);
+            store_box(W, uu, false, u);
         }
         // stationarity || Z^T (grad f - A^T lam) ||_inf through the same projection (u = lam)
         assemble(false);
     }
     double rd_inf = 0.0, cost = 0.0;
-    if (tid < NR) rd_inf = fabs(s_rhs[tid]);
-    if (var_thread) {
+    for (int r = tid; r < NR; r += NT) rd_inf = fmax(rd_inf, fabs(s_rhs[r]));
+#pragma unroll
+    for (int u = 0; u < VPT; u++) {
+        const int v = tid + u * NT;
+        if (v >= NV) continue;
         // objective x'Px + q'x + c0 with P = w_c Q (no 1/2, traj_optimizer.cpp:294) + terminal terms (:301-315)
+        const int k_v = v / NCP, m_v = (v % NCP) / 6, i_v = v % 6;
         const int v0 = k_v * NCP + m_v * 6;
         double qc = 0.0;
 #pragma unroll
         for (int b = 0; b < 6; b++) qc += sQ2[i_v * 6 + b] * s_c[v0 + b];
-        cost = 0.5 * s_c[tid] * qc;
-        if (i_v == 5) { const double e = s_c[tid] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
-        p.ctrl_out[(size_t) agent * NV + tid] = s_c[tid];
+        cost += 0.5 * s_c[v] * qc;
+        if (i_v == 5) { const double e = s_c[v] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
+        p.ctrl_out[(size_t) agent * NV + v] = s_c[v];
     }
     red[0] = cost; red[1] = 0; red[2] = -rp_true; red[3] = rd_inf;
     block_reduce4<C>(red, s_red, red_phase);
@@ -1228,8 +1335,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     }
     if (p.dual_out) {
         double* du = p.dual_out + (size_t) agent * p.dual_stride;
-        for (int e = tid; e < C::KMAX * M * 6; e += NT) du[e] = 0.0;       // dropped / skipped rows: multiplier 0
-        __syncthreads();
+        for (int e = tid; e < C::KRAW * M * 6; e += NT) du[e] = 0.0;       // dropped / skipped rows: multiplier 0
+        cta_sync<C>();
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
             if (j >= nrow) break;
@@ -1237,15 +1344,18 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             const double* n = s_nrm + (slot * M + m_cp) * 3;
             if (!(n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0)) du[(s_act[slot] * M + m_cp) * 6 + i_cp] = ll[j];
         }
-        if (var_thread) {
-            // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2
-            const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
-            double* db = du + C::KMAX * M * 6 + tid * 6;
-            db[0] = (bmask & 1u) ? bl[0] : 0.0; db[1] = (bmask & 2u) ? bl[1] : 0.0;
-            db[2] = (bmask & 4u) ? bl[2] * sv : 0.0; db[3] = (bmask & 8u) ? bl[3] * sv : 0.0;
-            db[4] = (bmask & 16u) ? bl[4] * sa : 0.0; db[5] = (bmask & 32u) ? bl[5] * sa : 0.0;
-            if (C::COMM && has_comm) { double* dc = du + C::KMAX * M * 6 + NV * 6 + tid * 2; dc[0] = bl[C::NBX - 2]; dc[1] = bl[C::NBX - 1]; }
+        // back to the reference's row scaling: vel rows carry 5/dt, acc rows 20/dt^2
+        const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = tid + u * NT;
+            if (v >= NV) continue;
+            double* db = du + C::KRAW * M * 6 + v * 6;
+            db[0] = (bmask[u] & 1u) ? bl[u][0] : 0.0; db[1] = (bmask[u] & 2u) ? bl[u][1] : 0.0;
+            db[2] = (bmask[u] & 4u) ? bl[u][2] * sv : 0.0; db[3] = (bmask[u] & 8u) ? bl[u][3] * sv : 0.0;
+            db[4] = (bmask[u] & 16u) ? bl[u][4] * sa : 0.0; db[5] = (bmask[u] & 32u) ? bl[u][5] * sa : 0.0;
         }
+        if (C::COMM && has_comm) { double* dc = du + C::KRAW * M * 6 + NV * 6 + tid * 2; dc[0] = bl[0][NBX - 2]; dc[1] = bl[0][NBX - 1]; }
     }
 }
 

@@ -1,0 +1,90 @@
+// solve_instances.hpp -- the PDIP kernel instances, split over translation units so that nvcc compiles them in
+// parallel.  Each inst_<n>.cu defines LSCQP_TU (0..3) and includes this file; lscqp.cu sees only the declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include "host_common.hpp"
+
+namespace lscqp {
+
+struct InstanceInfo {
+    int dual_stride = 0, kmax = 0, nv = 0;
+    bool has_light = false;
+    ProjTable tab, tab_light;      // projection term streams of the full-capacity / light instance
+};
+
+// Looks the (M, dim, mode, comm) instance up in translation unit N: fills `info`, raises the dynamic shared-memory
+// limit of its kernels.  Returns 1 when found, 0 when the instance lives elsewhere, -1 on a CUDA error.
+int inst_query_0(const lscqp_config& cfg, InstanceInfo* info);
+int inst_query_1(const lscqp_config& cfg, InstanceInfo* info);
+int inst_query_2(const lscqp_config& cfg, InstanceInfo* info);
+int inst_query_3(const lscqp_config& cfg, InstanceInfo* info);
+// Launches the instance (light pass first when two_pass); returns the number of kernels launched, 0 when not here.
+int inst_launch_0(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+int inst_launch_1(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+int inst_launch_2(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+int inst_launch_3(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+
+#ifdef LSCQP_TU
+#if LSCQP_TU == 0
+#define LSCQP_TU_INSTANCES(X) X(5, 3, true, false) X(5, 3, false, false) X(5, 2, true, false) X(5, 2, false, false)
+#define LSCQP_TU_NAME(f) f##_0
+#elif LSCQP_TU == 1
+#define LSCQP_TU_INSTANCES(X) X(10, 2, true, false) X(10, 2, false, false)
+#define LSCQP_TU_NAME(f) f##_1
+#elif LSCQP_TU == 2
+#define LSCQP_TU_INSTANCES(X) X(10, 3, true, false) X(10, 3, false, false)
+#define LSCQP_TU_NAME(f) f##_2
+#else
+#define LSCQP_TU_INSTANCES(X) X(5, 3, true, true) X(5, 2, true, true) X(10, 3, true, true) X(10, 2, true, true)
+#define LSCQP_TU_NAME(f) f##_3
+#endif
+
+template <class C>
+static int set_smem_attr() {
+    return cudaFuncSetAttribute(pdip_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
+
+int LSCQP_TU_NAME(inst_query)(const lscqp_config& cfg, InstanceInfo* info) {
+    const bool term = cfg.planner_mode == LSCQP_MODE_LSC, comm = cfg.comm_range > 0;
+#define X(M_, D_, T_, C_)                                                           \
+    if (cfg.M == M_ && cfg.dim == D_ && term == T_ && comm == C_) {                 \
+        using I = Instance<M_, D_, T_, C_>;                                         \
+        using C = typename I::Full;                                                 \
+        if (set_smem_attr<C>()) return -1;                                          \
+        if (I::HAS_LIGHT && set_smem_attr<typename I::Light>()) return -1;          \
+        info->dual_stride = C::DUAL_STRIDE; info->kmax = C::KMAX; info->nv = C::NV; \
+        info->has_light = I::HAS_LIGHT;                                             \
+        info->tab = build_projection<C>();                                          \
+        if (I::HAS_LIGHT) info->tab_light = build_projection<C>(I::Light::NT);      \
+        return 1;                                                                   \
+    }
+    LSCQP_TU_INSTANCES(X)
+#undef X
+    return 0;
+}
+
+int LSCQP_TU_NAME(inst_launch)(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st) {
+    const bool term = cfg.planner_mode == LSCQP_MODE_LSC, comm = cfg.comm_range > 0;
+#define X(M_, D_, T_, C_)                                                           \
+    if (cfg.M == M_ && cfg.dim == D_ && term == T_ && comm == C_) {                 \
+        using I = Instance<M_, D_, T_, C_>;                                         \
+        using C = typename I::Full;                                                 \
+        int launched = 1;                                                           \
+        p.klass_mode = 0;                                                           \
+        if (I::HAS_LIGHT && two_pass) {                                             \
+            using L = typename I::Light;                                            \
+            p.klass_mode = 1;                                                       \
+            pdip_solve_kernel<L><<<n_agents, L::NT, L::SMEM_BYTES, st>>>(p);        \
+            p.klass_mode = 2;                                                       \
+            launched = 2;                                                           \
+        }                                                                           \
+        pdip_solve_kernel<C><<<n_agents, C::NT, C::SMEM_BYTES, st>>>(p);            \
+        return launched;                                                            \
+    }
+    LSCQP_TU_INSTANCES(X)
+#undef X
+    return 0;
+}
+#endif  // LSCQP_TU
+
+}  // namespace lscqp

@@ -1,0 +1,19 @@
+"""Builds liblscqp_<tag>.so variants (light-instance shapes) for scripts/ab_test.sh.  Development aid."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+
+VARIANTS = {
+    "g1k8c8": ("-DLSCQP_LIGHT_G=1", "-DLSCQP_LIGHT_KPT=8", "-DLSCQP_LIGHT_MINCTAS=8"),
+    "g1k8c10": ("-DLSCQP_LIGHT_G=1", "-DLSCQP_LIGHT_KPT=8", "-DLSCQP_LIGHT_MINCTAS=10"),
+    "g1k8c9": ("-DLSCQP_LIGHT_G=1", "-DLSCQP_LIGHT_KPT=8", "-DLSCQP_LIGHT_MINCTAS=9"),
+    "g1k8c12": ("-DLSCQP_LIGHT_G=1", "-DLSCQP_LIGHT_KPT=8", "-DLSCQP_LIGHT_MINCTAS=12"),
+    "g2k4c6": ("-DLSCQP_LIGHT_G=2", "-DLSCQP_LIGHT_KPT=4", "-DLSCQP_LIGHT_MINCTAS=6"),
+    "g2k4c4": ("-DLSCQP_LIGHT_G=2", "-DLSCQP_LIGHT_KPT=4", "-DLSCQP_LIGHT_MINCTAS=4"),
+}
+for tag in sys.argv[1:]:
+    out = os.path.join(g.ROOT, "lsc_dr_planner_b200", f"liblscqp_{tag}.so")
+    g.build_library(out, VARIANTS[tag])
+    print("built", out)

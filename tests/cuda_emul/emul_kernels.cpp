@@ -29,10 +29,20 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     const bool comm = cfg->comm_range > 0;
 #define X(M_, D_, T_, C_)                                                                   \
     if (cfg->M == M_ && cfg->dim == D_ && term == T_ && comm == C_) {                       \
-        using C = Cfg<M_, D_, T_, 4, 10, C_>;                                               \
+        using I = Instance<M_, D_, T_, C_>;                                                 \
+        using C = typename I::Full;                                                         \
         p.dual_stride = C::DUAL_STRIDE;                                                     \
         static const ProjTable tab = build_projection<C>();                                 \
-        p.proj_ent = tab.ent.data(); p.proj_term = tab.term.data(); p.n_proj_ent = (int) tab.ent.size(); \
+        p.proj = tab.term.data(); p.proj_len = tab.len;                                     \
+        static const ProjTable tabl = build_projection<C>(I::Light::NT);                    \
+        p.proj_light = tabl.term.data(); p.proj_len_light = tabl.len;                       \
+        std::vector<int> klass(n_agents + 1, 0);                                            \
+        if (I::HAS_LIGHT && (cfg->presolve & 1) && !(cfg->presolve & 2)) {                  \
+            using L = typename I::Light;                                                    \
+            p.klass = klass.data(); p.klass_mode = 1;                                       \
+            emu::launch(n_agents, L::NT, L::SMEM_BYTES, [&]() { pdip_solve_kernel<L>(p); }); \
+            p.klass_mode = 2;                                                               \
+        }                                                                                   \
         emu::launch(n_agents, C::NT, C::SMEM_BYTES, [&]() { pdip_solve_kernel<C>(p); });    \
         return 0;                                                                           \
     }
