@@ -60,8 +60,10 @@ typedef struct lscqp_config {
     int max_agents;                /* capacity of the staging buffers for the *_host calls     */
     int max_iter;                  /* interior-point iteration cap (0 = default 60)            */
     double tol;                    /* complementarity / primal tolerance (0 = default 1e-11)   */
-    int presolve;                  /* 1: drop obstacles whose rows are all proven inactive by
-                                      bound propagation through the velocity rows (exact)      */
+    int presolve;                  /* bit 0: drop obstacles whose rows are all proven inactive by
+                                      bound propagation through the velocity rows (exact);
+                                      bit 1: keep every agent on the full-capacity kernel
+                                      instance (no light-instance first pass)                   */
 } lscqp_config;
 
 typedef struct lscqp_handle lscqp_handle;
@@ -140,6 +142,26 @@ int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents,
         const int* obs_offsets, const int* obs_index,      /* [sum K] neighbour agent ids */
         double* ctrl_out, double* cost_out, int* status_out, int* iters_out);
 
+/* Batched GoalOptimizer::solve (src/goal_optimizer.cpp:7-165; called from
+ * TrajPlanner::goalPlanningWithGridBasedPlanner, src/traj_planner.cpp:545-550): the one-variable LP
+ *     min t,  0 <= t <= 1 + 1e-5,  n.((g - w) t + w - p) - d >= 0
+ * over the SFC faces of the last segment (use_sfc) and the LSC record (oi, M-1, n) of every obstacle, solved in
+ * closed form; goal_out = (g - w) * t + w in float arithmetic.  status_out: LSCQP_OK or LSCQP_INFEASIBLE (where the
+ * reference throws PlanningReport::QPFAILED).  Uses the packed planes of lscqp_assemble_lsc_batch.  Device pointers. */
+int lscqp_goal_batch(lscqp_handle* h, int n_agents,
+        const float*  goal,          /* [n_agents][3]  agent.current_goal_point (previous replan)  */
+        const float*  next_waypoint, /* [n_agents][3]  agent.next_waypoint                          */
+        const float*  sfc,           /* [n_agents][M][6] or NULL (use_sfc)                          */
+        const int*    obs_offsets, const double* normals, const double* rhs,
+        float*  goal_out,            /* [n_agents][3]  new current_goal_point                       */
+        double* t_out,               /* [n_agents]     optional: the LP optimum                     */
+        int*    status_out,          /* [n_agents]                                                  */
+        void* stream);
+/* Same with HOST buffers (copies in, solves, copies back, synchronises). */
+int lscqp_goal_host(lscqp_handle* h, int n_agents, const float* goal, const float* next_waypoint, const float* sfc,
+        const int* obs_offsets, const double* normals, const double* rhs,
+        float* goal_out, double* t_out, int* status_out);
+
 /* Device-side gather used by lscqp_replan_*: obs_traj[j] = own_traj[obs_index[j]] etc. */
 int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
         const float* own_traj, const double* agent_meta, const float* agent_goal, const float* state,
@@ -152,6 +174,11 @@ int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
  * the next state [n][9] at time `step`, and the shifted trajectory for the next replan. */
 int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step,
         float* traj_out, float* state_out, float* shifted_traj_out, void* stream);
+
+/* Measurement aid (bench.py): sustained FP64 FMA rate of the device in GFLOP/s from a register-resident DFMA
+ * microbenchmark (8 independent chains per thread), the denominator of the solve kernel's FP64 view
+ * (MEASURED_PEAKS.json holds only the HBM and bf16 peaks). */
+int lscqp_measure_fp64_peak(lscqp_handle* h, double* gflops_out);
 
 #ifdef __cplusplus
 }

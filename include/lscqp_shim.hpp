@@ -4,6 +4,7 @@
 // (/root/reference/include/traj_planner.hpp:104,110):
 //     DynamicPlanning::CollisionConstraints   include/collision_constraints.hpp:98-201 (LSC/SFC part)
 //     DynamicPlanning::TrajOptimizer          include/traj_optimizer.hpp:18-55
+//     DynamicPlanning::GoalOptimizer          include/goal_optimizer.hpp:18-38
 // with the same method names, argument meaning and error behaviour, so traj_planner.cpp compiles
 // against them unchanged apart from the include.  Plus BatchTrajOptimizer, the
 // single dispatch the serial loop of MultiSyncSimulator::plan (src/multi_sync_simulator.cpp:354-362)
@@ -221,6 +222,44 @@ private:
         lscqp_config c = make_lscqp_config(param, mission);
         if (lscqp_create(&c, 0, &handle) != 0) throw std::runtime_error(std::string("[TrajOptimizer] ") + lscqp_last_error());
     }
+    Param param;
+    Mission mission;
+    lscqp_handle* handle = nullptr;
+};
+
+// ---- GoalOptimizer (include/goal_optimizer.hpp:18-38, src/goal_optimizer.cpp:7-165) -------------
+// the second CPLEX call of a replan (TrajPlanner::goalPlanningWithGridBasedPlanner, traj_planner.cpp:545-550)
+class GoalOptimizer {
+public:
+    GoalOptimizer(const Param& p, const Mission& m) : param(p), mission(m) {
+        lscqp_config c = make_lscqp_config(param, mission);
+        c.comm_range = 0.0;                                                             // the goal LP has no comm rows
+        if (lscqp_create(&c, 0, &handle) != 0) throw std::runtime_error(std::string("[GoalOptimizer] ") + lscqp_last_error());
+    }
+    ~GoalOptimizer() { lscqp_destroy(handle); }
+    GoalOptimizer(const GoalOptimizer&) = delete;
+    GoalOptimizer& operator=(const GoalOptimizer&) = delete;
+
+    // returns the new current_goal_point; infeasible LP = throw PlanningReport::QPFAILED (goal_optimizer.cpp:94, 103)
+    point3d solve(const Agent& /*agent*/, const CollisionConstraints& constraints, const point3d& current_goal_point,
+                  const point3d& next_waypoint) {
+        const int M = param.M, D = param.world_dimension;
+        float goal[3], wp[3], out[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) { goal[k] = current_goal_point(k); wp[k] = next_waypoint(k); }
+        std::vector<double> normals, rhs;
+        constraints.pack(D, normals, rhs);
+        std::vector<float> sfc(M * 6);
+        for (int m = 0; m < M; m++)
+            for (int k = 0; k < 3; k++) { sfc[m * 6 + k] = constraints.getSFC(m).box_min(k); sfc[m * 6 + 3 + k] = constraints.getSFC(m).box_max(k); }
+        int offsets[2] = {0, (int) constraints.getObsSize()};
+        int status = 0;
+        int rc = lscqp_goal_host(handle, 1, goal, wp, param.world_use_octomap ? sfc.data() : nullptr, offsets, normals.data(),
+                                 rhs.data(), out, nullptr, &status);
+        if (rc != 0 || status != LSCQP_OK) throw PlanningReport::QPFAILED;
+        return point3d(out[0], out[1], out[2]);
+    }
+
+private:
     Param param;
     Mission mission;
     lscqp_handle* handle = nullptr;

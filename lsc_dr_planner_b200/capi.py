@@ -53,7 +53,8 @@ def load():
         _lib.lscqp_launch_count.restype = C.c_ulonglong
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
-                     "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy"):
+                     "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
+                     "lscqp_goal_host", "lscqp_measure_fp64_peak"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -128,6 +129,12 @@ class LscQp:
     def launches(self) -> int:
         return int(self.lib.lscqp_launch_count(self.h))
 
+    def measure_fp64_peak(self) -> float:
+        """sustained FP64 FMA rate of the device in GFLOP/s (register-resident DFMA microbenchmark)"""
+        out = C.c_double()
+        self._check(self.lib.lscqp_measure_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
     # ------------------------------------------------------------------ device entry points
     def solve_batch(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status,
                     iters=None, kkt=None, dual=None, stream=0, initial_traj=None, next_waypoint=None):
@@ -152,7 +159,19 @@ class LscQp:
         self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),
                                               _dp(shifted_out), C.c_void_p(stream)))
 
+    def goal_batch(self, n, goal, next_waypoint, sfc, obs_offsets, normals, rhs, goal_out, status, t_out=None, stream=0):
+        """batched GoalOptimizer::solve (goal_optimizer.cpp:7-165) on device tensors"""
+        self._check(self.lib.lscqp_goal_batch(self.h, n, _dp(goal), _dp(next_waypoint), _dp(sfc), _dp(obs_offsets),
+                                              _dp(normals), _dp(rhs), _dp(goal_out), _dp(t_out), _dp(status),
+                                              C.c_void_p(stream)))
+
     # ------------------------------------------------------------------ host entry points
+    def goal_host(self, n, goal, next_waypoint, sfc, obs_offsets, normals, rhs, goal_out, status, t_out=None):
+        self._check(self.lib.lscqp_goal_host(self.h, n, _hp(goal, np.float32), _hp(next_waypoint, np.float32),
+                                             _hp(sfc, np.float32), _hp(obs_offsets, np.int32), _hp(normals, np.float64),
+                                             _hp(rhs, np.float64), _hp(goal_out, np.float32), _hp(t_out, np.float64),
+                                             _hp(status, np.int32)))
+
     def solve_host(self, n, state, goal, limits, sfc, obs_offsets, normals, rhs, ctrl, cost, status, iters=None,
                    kkt=None, dual=None, initial_traj=None, next_waypoint=None):
         self._check(self.lib.lscqp_solve_host(self.h, n, _hp(state, np.float32), _hp(goal, np.float32),

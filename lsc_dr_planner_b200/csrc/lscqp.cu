@@ -11,6 +11,7 @@
 #include "solve_instances.hpp"
 #include "lsc_assemble.cuh"
 #include "step_kernel.cuh"
+#include "goal_kernel.cuh"
 
 using namespace lscqp;
 
@@ -47,7 +48,7 @@ struct lscqp_handle {
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
-    DevBuf d_proj_ent, d_proj_term, d_wp, d_klass;
+    DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout;
     bool two_pass = false;
     unsigned long long launches = 0;
 };
@@ -100,7 +101,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass};
+                      &h->d_klass, &h->d_gout};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -200,6 +201,63 @@ extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctr
     return 0;
 }
 
+extern "C" int lscqp_goal_batch(lscqp_handle* h, int n_agents, const float* goal, const float* next_waypoint,
+                                const float* sfc, const int* obs_offsets, const double* normals, const double* rhs,
+                                float* goal_out, double* t_out, int* status_out, void* stream) {
+    if (!h || n_agents < 0 || !goal || !next_waypoint || !obs_offsets || !goal_out || !status_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+    if (n_agents == 0) return 0;
+    GoalParams p;
+    p.n_agents = n_agents; p.M = h->cfg.M; p.dim = h->cfg.dim; p.use_sfc = h->cfg.use_sfc; p.feas_tol = 1e-6;
+    p.goal = goal; p.waypoint = next_waypoint; p.sfc = sfc; p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.goal_out = goal_out; p.t_out = t_out; p.status_out = status_out;
+    goal_lp_kernel<<<(n_agents + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 roofline denominator: SURVEY 8(d) asks for the achieved FP64 rate of the solve kernel against an on-box
+// FMA microbenchmark (MEASURED_PEAKS.json holds only HBM and bf16).  8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) fp64_fma_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0 - 1e-9, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;                      // never true: keeps the chains alive
+}
+
+extern "C" int lscqp_measure_fp64_peak(lscqp_handle* h, double* gflops_out) {
+    if (!h || !gflops_out) return fail(LSCQP_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    if (h->d_cost.reserve(64)) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0, h->stream));
+        fp64_fma_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->d_cost.as<double>(), iters, 1.0);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double gf = 2.0 * 8.0 * iters * (double) blocks * threads / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gf > best) best = gf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->launches += 4;
+    *gflops_out = best;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // HOST-buffer entry points: what a TrajOptimizer / simulator running on the CPU calls.
 #define RESERVE(buf, n) do { if ((buf).reserve(n)) return fail(LSCQP_E_CUDA, "cudaMalloc failed"); } while (0)
@@ -259,6 +317,45 @@ extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* stat
     if (iters_out) CK(cudaMemcpyAsync(iters_out, h->d_iters.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (kkt_out) CK(cudaMemcpyAsync(kkt_out, h->d_kkt.p, n_agents * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (dual_out) CK(cudaMemcpyAsync(dual_out, h->d_dual.p, (size_t) n_agents * h->dual_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int lscqp_goal_host(lscqp_handle* h, int n_agents, const float* goal, const float* next_waypoint,
+                               const float* sfc, const int* obs_offsets, const double* normals, const double* rhs,
+                               float* goal_out, double* t_out, int* status_out) {
+    if (!h || n_agents < 0 || !goal || !next_waypoint || !obs_offsets || !goal_out || !status_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (n_agents == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const int M = h->cfg.M;
+    const size_t sumK = (size_t) obs_offsets[n_agents];
+    if (sumK > 0 && (!normals || !rhs)) return fail(LSCQP_E_INVALID, "null planes");
+    cudaStream_t st = h->stream;
+    RESERVE(h->d_goal, n_agents * 3 * sizeof(float)); RESERVE(h->d_wp, n_agents * 3 * sizeof(float));
+    RESERVE(h->d_off, (n_agents + 1) * sizeof(int));
+    RESERVE(h->d_normals, (sumK * M * 3 + 1) * sizeof(double)); RESERVE(h->d_rhs, (sumK * M * 6 + 1) * sizeof(double));
+    RESERVE(h->d_gout, n_agents * 3 * sizeof(float)); RESERVE(h->d_cost, n_agents * sizeof(double));
+    RESERVE(h->d_status, n_agents * sizeof(int));
+    if (h->cfg.use_sfc) {
+        if (!sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+        RESERVE(h->d_sfc, (size_t) n_agents * M * 6 * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_sfc.p, sfc, (size_t) n_agents * M * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->d_goal.p, goal, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_wp.p, next_waypoint, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (sumK) {
+        CK(cudaMemcpyAsync(h->d_normals.p, normals, sumK * M * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_rhs.p, rhs, sumK * M * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    int rc = lscqp_goal_batch(h, n_agents, h->d_goal.as<float>(), h->d_wp.as<float>(), h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr,
+                              h->d_off.as<int>(), h->d_normals.as<double>(), h->d_rhs.as<double>(), h->d_gout.as<float>(),
+                              h->d_cost.as<double>(), h->d_status.as<int>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(goal_out, h->d_gout.p, n_agents * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (t_out) CK(cudaMemcpyAsync(t_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status_out, h->d_status.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -30,7 +30,7 @@
 #endif
 
 #ifndef LSCQP_LIGHT_MINCTAS
-#define LSCQP_LIGHT_MINCTAS 10
+#define LSCQP_LIGHT_MINCTAS 8
 #endif
 
 namespace lscqp {   // @phase helpers
@@ -548,7 +548,7 @@ struct MinRatio {   // @phase minratio
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS)
 pdip_solve_kernel(const SolveParams p) {   // @phase setup
-    constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, LD = C::LD, NS = C::NS;
+    constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, NS = C::NS;
     constexpr int G = C::G, KPT = C::KPT, NT = C::NT;
     LSCQP_DYN_SMEM(sm);
     const int tid = threadIdx.x, lane = tid & 31;

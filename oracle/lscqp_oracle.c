@@ -669,3 +669,58 @@ void orc_const_vel_traj(int M, int n, double dt, const float *pos, const float *
             time += dt / n;
         }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * GoalOptimizer (src/goal_optimizer.cpp:7-107 solve, :109-165 populatebyrow): the one-variable LP
+ *     min t   s.t.  0 <= t <= 1 + SP_EPSILON_FLOAT,
+ *                   n_r . ((g - w) t + w - p_r) - d_r >= 0      for every row r
+ * with g = current_goal_point, w = next_waypoint (point3d: the difference g - w is a float subtraction,
+ * :133-134, :152-153), rows = the 2 dim faces of the last segment's SFC box (Box::convertToLSCs,
+ * collision_constraints.cpp:37-59; only with world_use_octomap, :128-143) and the LSC record
+ * (oi, M-1, n) of every obstacle whose float normal is not shorter than SP_EPSILON_FLOAT (:146-162).
+ * Row r is written a_r t + b_r >= 0.  Rows come out in the reference's order. */
+int orc_goal_rows(const orc_config *cfg, const float *goal, const float *waypoint, int K,
+                  const float *lsc_point /* [K][M][n+1][3] */, const float *lsc_normal, const double *lsc_d,
+                  const float *sfc_last /* [6] box_min, box_max or NULL */, double *a, double *b) {
+    int N = cfg->n + 1, r = 0;
+    if (cfg->use_sfc && sfc_last) {
+        /* convertToLSCs: for each k: (p=0, n=+e_k, d=box_min_k) then (p=0, n=-e_k, d=-box_max_k) */
+        for (int k = 0; k < cfg->dim; k++) {
+            float diff = goal[k] - waypoint[k];
+            a[r] = 1.0 * (double) diff;  b[r] = 1.0 * ((double) waypoint[k] - 0.0) - (double) sfc_last[k];      r++;
+            a[r] = -1.0 * (double) diff; b[r] = -1.0 * ((double) waypoint[k] - 0.0) + (double) sfc_last[3 + k]; r++;
+        }
+    }
+    for (int oi = 0; oi < K; oi++) {
+        size_t rec = ((size_t) oi * cfg->M + (cfg->M - 1)) * N + cfg->n;
+        const float *nv = lsc_normal + rec * 3, *pv = lsc_point + rec * 3;
+        if (v3_norm(v3_load(nv)) < SP_EPSILON_FLOAT) continue;                    /* :148-150 */
+        double ar = 0, br = 0;
+        for (int k = 0; k < cfg->dim; k++) {
+            float diff = goal[k] - waypoint[k];
+            ar += (double) nv[k] * (double) diff;
+            br += (double) nv[k] * ((double) waypoint[k] - (double) pv[k]);
+        }
+        a[r] = ar; b[r] = br - lsc_d[rec]; r++;
+    }
+    return r;
+}
+
+/* Closed-form optimum of the LP above.  t* = max(0, max_{a_r > 0} -b_r / a_r); rows with a_r < 0 bound t from
+ * above, rows with a_r = 0 are pure feasibility tests.  Infeasible (the reference throws QPFAILED, :94, :103) when
+ * a row is violated at t* by more than feas_tol (CPLEX's default feasibility tolerance is 1e-6).
+ * Early-out g ~ w (:12-14).  Output: (g - w) * (float) t + w in float arithmetic (:51).  Returns 0 ok, 2 infeasible. */
+int orc_goal_solve(const orc_config *cfg, const float *goal, const float *waypoint, int nrows,
+                   const double *a, const double *b, double feas_tol, float *goal_out, double *t_out) {
+    v3 g = v3_load(goal), w = v3_load(waypoint);
+    (void) cfg;
+    if (v3_distance(g, w) < SP_EPSILON_FLOAT) { v3_store(goal_out, w); if (t_out) *t_out = 0.0; return 0; }
+    double t = 0.0;
+    for (int r = 0; r < nrows; r++) if (a[r] > 0 && -b[r] / a[r] > t) t = -b[r] / a[r];
+    if (t > 1.0 + SP_EPSILON_FLOAT) t = 1.0 + SP_EPSILON_FLOAT;
+    int status = 0;
+    for (int r = 0; r < nrows; r++) if (a[r] * t + b[r] < -feas_tol) status = 2;
+    if (t_out) *t_out = t;
+    v3_store(goal_out, v3_add(v3_scale(v3_sub(g, w), (float) t), w));
+    return status;
+}

@@ -103,6 +103,14 @@ void orc_get_state_at(int M, int n, double dt, const float *traj, double time, f
 void orc_shift_traj(int M, int n, const float *prev, float *out);
 void orc_const_vel_traj(int M, int n, double dt, const float *pos, const float *vel, float *out);
 
+/* GoalOptimizer, src/goal_optimizer.cpp:7-165: rows a t + b >= 0 of the one-variable LP (returns the row count,
+ * a / b sized 2 dim + K) and its closed-form optimum (0 ok | 2 infeasible = the reference's QPFAILED throw). */
+int orc_goal_rows(const orc_config *cfg, const float *goal, const float *waypoint, int K,
+                  const float *lsc_point, const float *lsc_normal, const double *lsc_d,
+                  const float *sfc_last, double *a, double *b);
+int orc_goal_solve(const orc_config *cfg, const float *goal, const float *waypoint, int nrows,
+                   const double *a, const double *b, double feas_tol, float *goal_out, double *t_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,6 +282,42 @@ def const_vel_traj(cfg: Config, pos, vel) -> np.ndarray:
     return out
 
 
+# ---------------------------------------------------------------- GoalOptimizer (src/goal_optimizer.cpp)
+def goal_rows(cfg: Config, goal, waypoint, lsc_point, lsc_normal, lsc_d, sfc_last=None):
+    """rows a t + b >= 0 of the one-variable goal LP (goal_optimizer.cpp:109-165), in the reference's order"""
+    goal, waypoint = _f32(goal), _f32(waypoint)
+    pt, nr, d = _f32(lsc_point), _f32(lsc_normal), _f64(lsc_d)
+    K = pt.shape[0]
+    a = np.zeros(2 * cfg.dim + K); b = np.zeros(2 * cfg.dim + K)
+    sfc = None if sfc_last is None else _f32(sfc_last)
+    cc = cfg.c()
+    n = lib().orc_goal_rows(C.byref(cc), _p(goal, C.c_float), _p(waypoint, C.c_float), K, _p(pt, C.c_float),
+                            _p(nr, C.c_float), _p(d, C.c_double), _p(sfc, C.c_float) if sfc is not None else None,
+                            _p(a, C.c_double), _p(b, C.c_double))
+    return a[:n].copy(), b[:n].copy()
+
+
+def goal_solve(cfg: Config, goal, waypoint, a, b, feas_tol: float = 1e-6):
+    """closed-form optimum of the goal LP; returns (goal_out f32[3], t, status) with status 0 ok | 2 infeasible"""
+    goal, waypoint = _f32(goal), _f32(waypoint)
+    a, b = _f64(a), _f64(b)
+    out = np.zeros(3, np.float32); t = C.c_double()
+    cc = cfg.c()
+    st = lib().orc_goal_solve(C.byref(cc), _p(goal, C.c_float), _p(waypoint, C.c_float), len(a), _p(a, C.c_double),
+                              _p(b, C.c_double), C.c_double(feas_tol), _p(out, C.c_float), C.byref(t))
+    return out, t.value, st
+
+
+def goal_solve_highs(a, b):
+    """the same LP through HiGHS (scipy.optimize.linprog): the independent solver standing in for CPLEX.
+    Returns (t, feasible)."""
+    from scipy.optimize import linprog
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    res = linprog([1.0], A_ub=-a[:, None] if len(a) else None, b_ub=b if len(a) else None,
+                  bounds=[(0.0, 1.0 + 1e-5)], method="highs")
+    return (float(res.x[0]) if res.status == 0 else float("nan")), res.status == 0
+
+
 # ---------------------------------------------------------------- HiGHS stand-in for CPLEX
 @dataclass
 class Solution:

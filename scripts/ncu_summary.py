@@ -39,6 +39,16 @@ for name, rep in (("pdip_solve_kernel", "prof_solve.ncu-rep"), ("lsc_assemble_ke
     rd = unit_bytes(*d["dram__bytes_read.sum"]); wr = unit_bytes(*d["dram__bytes_write.sum"])
     traffic[name + "_bytes_per_launch"] = rd + wr
     out.append(f"dram traffic per launch (read+write): {rd + wr:.0f} bytes")
+    try:
+        per_cyc = {op: float(d[f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"][0]) for op in ("dfma", "dadd", "dmul")}
+        cycles = float(d["smsp__cycles_elapsed.max"][0])
+        flops = (2 * per_cyc["dfma"] + per_cyc["dadd"] + per_cyc["dmul"]) * cycles
+        peak = 2 * float(d["sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained"][0])
+        traffic[name + "_fp64_flops_per_launch"] = flops
+        out.append(f"fp64 flops per launch (2 dfma + dadd + dmul thread instructions): {flops:.4g}  "
+                   f"= {100 * flops / cycles / peak:.2f} % of the FP64 issue peak ({peak:.0f} flop/cycle)")
+    except KeyError:
+        pass
     open(os.path.join(root, "profiles", f"{tag}_{name}_summary.txt"), "w").write("\n".join(out) + "\n")
 src = os.path.join(root, "gpurun_out", "launches.csv")
 if os.path.exists(src):

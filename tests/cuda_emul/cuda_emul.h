@@ -82,6 +82,16 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) {
     __syncwarp();
     return r;
 }
+inline int __any_sync(unsigned, int pred) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = pred ? 1.0 : 0.0;
+    __syncwarp();
+    const int w0 = s.cur & ~31, wn = std::min(32, s.nthreads - w0);
+    int r = 0;
+    for (int i = 0; i < wn; i++) r |= s.slot_d[w0 + i] != 0.0;
+    __syncwarp();
+    return r;
+}
 inline float __fdividef(float a, float b) { return a / b; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -6,6 +6,7 @@
 #include "../../lsc_dr_planner_b200/csrc/host_common.hpp"
 #include "../../lsc_dr_planner_b200/csrc/lsc_assemble.cuh"
 #include "../../lsc_dr_planner_b200/csrc/step_kernel.cuh"
+#include "../../lsc_dr_planner_b200/csrc/goal_kernel.cuh"
 
 using namespace lscqp;
 
@@ -75,6 +76,17 @@ extern "C" int emul_step_batch(const lscqp_config* cfg, int n_agents, const doub
     if (cfg->M == 5) emu::launch(blocks, 128, 64, [&]() { step_kernel<5>(p); });
     else if (cfg->M == 10) emu::launch(blocks, 128, 64, [&]() { step_kernel<10>(p); });
     else return LSCQP_E_INVALID;
+    return 0;
+}
+
+extern "C" int emul_goal_batch(const lscqp_config* cfg, int n_agents, const float* goal, const float* waypoint, const float* sfc,
+                               const int* obs_offsets, const double* normals, const double* rhs, float* goal_out,
+                               double* t_out, int* status_out) {
+    GoalParams p;
+    p.n_agents = n_agents; p.M = cfg->M; p.dim = cfg->dim; p.use_sfc = cfg->use_sfc && sfc; p.feas_tol = 1e-6;
+    p.goal = goal; p.waypoint = waypoint; p.sfc = sfc; p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
+    p.goal_out = goal_out; p.t_out = t_out; p.status_out = status_out;
+    emu::launch((n_agents + 3) / 4, 128, 64, [&]() { goal_lp_kernel(p); });
     return 0;
 }
 

@@ -60,3 +60,13 @@ def step(cfg, n, ctrl, t):
                                _p(state, np.float32), _p(shifted, np.float32))
     assert rc == 0, rc
     return traj, state, shifted
+
+
+def goal(cfg, n, goal_pt, waypoint, sfc, off, normals, rhs):
+    cc = capi.make_config(cfg)
+    out = np.zeros((n, 3), np.float32); t = np.zeros(n); status = np.zeros(n, np.int32)
+    rc = lib().emul_goal_batch(C.byref(cc), n, _p(goal_pt, np.float32), _p(waypoint, np.float32), _p(sfc, np.float32),
+                               _p(off, np.int32), _p(normals, np.float64), _p(rhs, np.float64), _p(out, np.float32),
+                               _p(t, np.float64), _p(status, np.int32))
+    assert rc == 0, rc
+    return out, t, status

@@ -1,5 +1,6 @@
 // tests/shim/shim_smoke.cpp -- exercises include/lscqp_shim.hpp the way traj_planner.cpp uses the reference classes:
-// CollisionConstraints::initializeLSC / setLSC, TrajOptimizer::solve, the QPFAILED throw, BatchTrajOptimizer::plan.
+// CollisionConstraints::initializeLSC / setLSC, TrajOptimizer::solve, the QPFAILED throw, GoalOptimizer::solve,
+// BatchTrajOptimizer::plan.
 // Prints the solution so the pytest wrapper can compare it with the Python / oracle path.
 #include <cstdio>
 #include "../../include/lscqp_shim.hpp"
@@ -38,6 +39,20 @@ int main(int argc, char** argv) {
     bool thrown = false;
     try { opt.solve(agent, constraints, initial, true); } catch (PlanningReport rep) { thrown = rep == PlanningReport::QPFAILED; }
     std::printf("qpfailed %d\n", (int) thrown);
+
+    // GoalOptimizer::solve as goalPlanningWithGridBasedPlanner calls it (traj_planner.cpp:545-550): one obstacle plane
+    // x <= 0.6 on the last control point, previous goal inside (x = 0.2), next waypoint outside (x = 1.0) -> t* = 0.5
+    constraints.initializeLSC(1);
+    for (int m = 0; m < param.M; m++) {
+        points_t obs(param.n + 1, point3d(1.0f, 0.0f, 1.0f));
+        constraints.setLSC(0, m, obs, point3d(-1, 0, 0), std::vector<double>(param.n + 1, 0.4));
+    }
+    GoalOptimizer gopt(param, mission);
+    point3d ng = gopt.solve(agent, constraints, point3d(0.2f, 0.5f, 1.0f), point3d(1.0f, 0.0f, 1.0f));
+    std::printf("goal %.9g %.9g %.9g\n", ng.x(), ng.y(), ng.z());
+    bool gthrown = false;      // previous goal outside as well: no t in [0, 1] satisfies the row
+    try { gopt.solve(agent, constraints, point3d(0.8f, 0.5f, 1.0f), point3d(1.0f, 0.0f, 1.0f)); } catch (PlanningReport rep) { gthrown = rep == PlanningReport::QPFAILED; }
+    std::printf("goalfailed %d\n", (int) gthrown);
 
     // batched dispatch: two agents swapping, each the other's neighbour
     std::vector<Agent> agents(2, agent);

@@ -349,6 +349,9 @@ def test_cpp_shim_end_to_end():
     assert cps[..., 0].max() <= 0.6 + 1e-6
     cost = float([l for l in out if l.startswith("cost")][0].split()[1])
     assert abs(cost - (xe @ qp.P @ xe + qp.q @ xe + qp.c0)) < 1e-6 * max(1.0, cost)
+    g = [float(v) for v in [l for l in out if l.startswith("goal ")][0].split()[1:]]
+    # t* = 0.5 on the segment from the waypoint (1, 0, 1) to the previous goal (0.2, 0.5, 1)
+    assert np.abs(np.array(g) - np.array([0.6, 0.25, 1.0])).max() < 1e-6 and "goalfailed 1" in out
     b = [l for l in out if l.startswith("batch")][0].split()
     assert b[1] == "0" and b[2] == "0" and float(b[3]) > 0.3 and float(b[4]) < 2.7
 
