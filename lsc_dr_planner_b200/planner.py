@@ -33,6 +33,9 @@ class DeviceBatch:
         self.obs_index = t(batch.obs_index.astype(np.int32))
         self.sfc = t(batch.sfc) if batch.sfc is not None else None
         self.next_waypoint = t(batch.next_waypoint) if cfg.comm_range > 0 else None
+        self.waypoint = t(batch.next_waypoint)                      # GoalOptimizer input (any configuration)
+        self.goal_new = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        self.goal_status = torch.empty((N,), dtype=torch.int32, device=dev)
         sk = max(self.sum_k, 1)
         self.obs_traj = torch.empty((sk, M, 6, 3), dtype=torch.float32, device=dev)
         self.obs_meta = torch.empty((sk, 4), dtype=torch.float32, device=dev)
@@ -76,6 +79,26 @@ class BatchPlanner:
 
     def replan_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0):
         self.assemble_device(d, generator, stream)
+        self.solve_device(d, stream=stream)
+
+    def goal_device(self, d: DeviceBatch, stream: int = 0):
+        """goalPlanningWithGridBasedPlanner for every agent (traj_planner.cpp:545-550): d.goal_new, d.goal_status from
+        the previous current_goal_point d.goal, the next waypoint and the planes of assemble_device"""
+        self.qp.goal_batch(d.n, d.goal, d.waypoint, d.sfc, d.obs_offsets, d.normals, d.rhs, d.goal_new, d.goal_status,
+                           stream=stream)
+
+    def plan_device(self, d: DeviceBatch, generator: int = capi.GEN_CLSC, stream: int = 0):
+        """One replan in the reference's stage order (TrajPlanner::planImpl, traj_planner.cpp:117-139, SURVEY appendix D):
+        LSC construction with the previous goal, goal LP, then the QP with the new goal.  Agents whose goal LP is
+        infeasible keep their previous goal and are reported through d.goal_status (the reference throws QPFAILED and
+        keeps initial_traj for them); launches must be stream-ordered by the caller (same stream)."""
+        import torch
+        self.assemble_device(d, generator, stream)
+        self.goal_device(d, stream)
+        ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+        with torch.cuda.stream(ext):
+            ok = (d.goal_status == 0).unsqueeze(1)
+            d.goal.copy_(torch.where(ok, d.goal_new, d.goal))
         self.solve_device(d, stream=stream)
 
     # ------------------------------------------------------------------ host-buffer path (what the reference calls)

@@ -328,7 +328,7 @@ class Solution:
     col_dual: np.ndarray
 
 
-def solve_highs(qp: QP, tol: float = 1e-9) -> Solution:
+def solve_highs(qp: QP, tol: float = 1e-9, time_limit: float | None = None) -> Solution:
     """Solve the restated model with HiGHS's QP active-set solver."""
     import scipy
     import scipy.sparse as sp
@@ -342,6 +342,8 @@ def solve_highs(qp: QP, tol: float = 1e-9) -> Solution:
     h.setOptionValue("output_flag", False)
     h.setOptionValue("primal_feasibility_tolerance", tol)
     h.setOptionValue("dual_feasibility_tolerance", tol)
+    if time_limit is not None:
+        h.setOptionValue("time_limit", float(time_limit))
     lp = hs.HighsLp()
     lp.num_col_ = nv; lp.num_row_ = A.shape[0]
     lp.col_cost_ = qp.q; lp.col_lower_ = lb; lp.col_upper_ = ub
@@ -361,6 +363,78 @@ def solve_highs(qp: QP, tol: float = 1e-9) -> Solution:
     status = h.modelStatusToString(h.getModelStatus())
     obj = float(x @ qp.P @ x + qp.q @ x + qp.c0)
     return Solution(status, x, obj, np.array(sol.row_dual), np.array(sol.col_dual))
+
+
+def solve_dense_ipm(qp: QP, tol: float = 1e-10, max_iter: int = 200) -> Solution:
+    """Second, independent checker solver: a textbook dense Mehrotra primal-dual interior-point method on the restated
+    model exactly as populatebyrow states it (all variables, equalities kept as equalities, numpy dense KKT solves) --
+    no equality elimination, no structure, nothing shared with the CUDA kernel.  Used where HiGHS' active-set QP
+    solver reports "Solve error" (it does on some dense communication-range models).  The duals are returned in the
+    layout polish() reads (row_dual over [Aeq; G], col_dual over the variable bounds)."""
+    nv, ne, ng = qp.q.size, qp.Aeq.shape[0], qp.G.shape[0]
+    rows, h, tag = [], [], []
+    for i in range(ng):
+        if qp.rhi[i] < INF:
+            rows.append(qp.G[i]); h.append(qp.rhi[i]); tag.append(("r", i))
+        if qp.rlo[i] > -INF:
+            rows.append(-qp.G[i]); h.append(-qp.rlo[i]); tag.append(("r", i))
+    for j in range(nv):
+        if qp.ub[j] < INF:
+            e = np.zeros(nv); e[j] = 1; rows.append(e); h.append(qp.ub[j]); tag.append(("c", j))
+        if qp.lb[j] > -INF:
+            e = np.zeros(nv); e[j] = -1; rows.append(e); h.append(-qp.lb[j]); tag.append(("c", j))
+    Gi = np.array(rows); h = np.array(h)
+    H = 2.0 * qp.P; A = qp.Aeq; b = qp.beq
+    x = np.zeros(nv); y = np.zeros(ne)
+    s = np.maximum(h - Gi @ x, 1.0); z = np.ones(len(h))
+    status = "Iteration limit"
+    for _ in range(max_iter):
+        rd = H @ x + qp.q + A.T @ y + Gi.T @ z
+        rp = A @ x - b
+        rg = Gi @ x + s - h
+        mu = float(s @ z) / len(h)
+        scale = max(1.0, float(np.abs(qp.q).max()), float(np.abs(H @ x).max()))
+        if (np.abs(rd).max() < 1e2 * tol * scale and max(np.abs(rp).max(initial=0.0), np.abs(rg).max()) < 1e2 * tol
+                and mu < tol):
+            status = "Optimal"
+            break
+        W = z / s
+        K = np.block([[H + Gi.T @ (W[:, None] * Gi), A.T], [A, np.zeros((ne, ne))]])
+        lu = np.linalg.inv(K + 1e-14 * np.eye(nv + ne))
+
+        def direction(rc):
+            rhs = np.concatenate([-rd + Gi.T @ (rc / s - W * rg), -rp])
+            d = lu @ rhs
+            dx = d[:nv]
+            ds = -rg - Gi @ dx
+            dz = -(rc + z * ds) / s
+            return dx, d[nv:], ds, dz
+
+        def step(ds, dz):
+            a = 1.0
+            for v, dv in ((s, ds), (z, dz)):
+                neg = dv < 0
+                if neg.any():
+                    with np.errstate(over="ignore"):
+                        a = min(a, float((-v[neg] / dv[neg]).min()))
+            return a
+        dxa, dya, dsa, dza = direction(s * z)
+        aa = step(dsa, dza)
+        mu_aff = float((s + aa * dsa) @ (z + aa * dza)) / len(h)
+        sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+        dx, dy, ds, dz = direction(s * z + dsa * dza - sigma * mu)
+        a = min(1.0, 0.995 * step(ds, dz))
+        x += a * dx; y += a * dy; s += a * ds; z += a * dz
+    row_dual = np.zeros(ne + ng); col_dual = np.zeros(nv)
+    row_dual[:ne] = y
+    for (kind, i), zi, si in zip(tag, z, s):
+        if zi <= si:                                   # inactive at the solution (interior-point active-set indicator)
+            continue
+        if kind == "r":
+            row_dual[ne + i] = max(row_dual[ne + i], zi)
+        else:
+            col_dual[i] = max(col_dual[i], zi)
+    return Solution(status, x, float(x @ qp.P @ x + qp.q @ x + qp.c0), row_dual, col_dual)
 
 
 def polish(qp: QP, sol: Solution, dual_tol: float = 1e-9, feas_tol: float = 1e-9):

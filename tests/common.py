@@ -56,7 +56,10 @@ def oracle_solution(qp: orc.QP):
     """(x, ok): HiGHS solution polished to ~1e-12; ok False when HiGHS failed or polish was refused"""
     sol = orc.solve_highs(qp)
     if sol.status != "Optimal":
-        return sol.x, False
+        sol = orc.solve_dense_ipm(qp)       # HiGHS' QP solver errors out on some dense comm-range models
+        if sol.status != "Optimal":
+            return sol.x, False
+        return orc.polish(qp, sol, dual_tol=1e-12)
     return orc.polish(qp, sol)
 
 

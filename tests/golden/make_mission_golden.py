@@ -1,0 +1,137 @@
+"""Regenerates tests/golden/mission_golden.npz (BASELINE configs 1 and 3).  Run in the build container only
+(it reads the reference's mission files, which do not travel to the GPU box):
+    python tests/golden/make_mission_golden.py
+
+  c1_*  config 1: missions/forest10/forest10_1.json, 10 agents, launch settings (2-D, M=10, communication range 3),
+        FIRST replan through the oracle in the reference's stage order (traj_planner.cpp:117-139):
+        generateCLSC -> GoalOptimizer -> TrajOptimizer (restated model + HiGHS, polished).
+  c3_*  config 3: 26 independent 10-agent instances of missions/maze10_dense/maze10_k.json rolled out in closed loop by
+        the oracle (LSC -> goal LP -> QP -> doStep -> shift) for R = 2..10 replans; the inputs of replan R+1 of every agent
+        (first 256 of 260) and their polished oracle solutions.
+The map pipeline (octomap SFC boxes) and the grid MAPF layer are outside the hot path: use_sfc is
+off and the next waypoint is the point one grid cell / one metre ahead on the straight line to the desired goal.
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from lsc_dr_planner_b200 import missions as MS  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+REF = "/root/reference"
+
+
+def ocfg(cfg):
+    return orc.Config(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, dt=cfg.dt, w_control=cfg.w_control,
+                      w_terminal=cfg.w_terminal, planner_mode=cfg.planner_mode, use_sfc=False, comm_range=cfg.comm_range,
+                      world_min=cfg.world_min, world_max=cfg.world_max, z_2d=cfg.z_2d)
+
+
+def plan_agent(cfgo, mission, a, state, goal_prev, wp, own, nbr, trajs, goals_prev, positions, final=True):
+    """one agent's replan through the oracle; returns (new_goal, goal_status, x or None, planes)"""
+    ag = orc.Agent(state[:3], state[3:6], state[6:9], goal_prev, next_waypoint=wp, max_vel=tuple(mission.max_vel[a]),
+                   max_acc=tuple(mission.max_acc[a]), radius=float(mission.radius[a]),
+                   nominal_velocity=float(mission.nominal_velocity[a]), downwash=float(mission.downwash[a]))
+    pt, nr, d = orc.generate_lsc(cfgo, orc.GEN_CLSC, ag, own, trajs[nbr], mission.radius[nbr], mission.downwash[nbr],
+                                 goals_prev[nbr], positions[nbr])
+    ar, br = orc.goal_rows(cfgo, goal_prev, wp, pt, nr, d)
+    new_goal, t, gst = orc.goal_solve(cfgo, goal_prev, wp, ar, br)
+    if gst != 0:
+        return goal_prev, gst, None, (pt, nr, d)
+    ag.goal = new_goal
+    qp = orc.qp_build(cfgo, ag, pt, nr, d)
+    # roll-out steps use the dense interior-point checker (50x faster on these models); the recorded step goes
+    # through HiGHS first, the two agree to the last digit after polish wherever HiGHS succeeds
+    sol = orc.solve_highs(qp, time_limit=20.0) if final else None
+    tol = 1e-9
+    if sol is None or sol.status != "Optimal":        # HiGHS "Solve error" on some dense comm-range models
+        sol = orc.solve_dense_ipm(qp); tol = 1e-12
+        if sol.status != "Optimal":
+            return new_goal, 0, None, (pt, nr, d)
+    x, ok = orc.polish(qp, sol, dual_tol=tol)
+    return new_goal, 0, (x, ok), (pt, nr, d)
+
+
+def waypoint(pos, desired, step):
+    v = desired.astype(np.float64) - pos.astype(np.float64)
+    dist = np.linalg.norm(v)
+    return (pos + v / max(dist, 1e-9) * min(dist, step)).astype(np.float32)
+
+
+def rollout(path, R, M=10, dim=2):
+    """closed loop of one mission for R replans; returns the inputs of replan R+1 and its oracle solutions"""
+    mission = MS.load_mission(path, dim, 1.0)
+    cfg = MS.launch_config(mission, M=M, dim=dim)
+    cfgo = ocfg(cfg)
+    n = mission.n_agents
+    state = np.zeros((n, 9), np.float32); state[:, :3] = mission.start
+    goal = mission.start.copy()                                   # agent_manager.cpp:9
+    trajs = np.stack([orc.const_vel_traj(cfgo, state[a, :3], state[a, 3:6]) for a in range(n)])
+    rec = None
+    for step in range(R + 1):
+        off, idx = MS.neighbours_linf(state[:, :3], cfg.comm_range)
+        wps = np.stack([waypoint(state[a, :3], mission.goal[a], 1.0) for a in range(n)])
+        new_goal = goal.copy(); new_trajs = trajs.copy(); sols = []; oks = []
+        for a in range(n):
+            nbr = idx[off[a]:off[a + 1]]
+            g, gst, sol, _ = plan_agent(cfgo, mission, a, state[a], goal[a], wps[a], trajs[a], nbr, trajs, goal, state[:, :3],
+                                        final=(step == R))
+            new_goal[a] = g
+            if sol is not None:
+                x, ok = sol
+                t = x.reshape(dim, M, 6).transpose(1, 2, 0)
+                tr = np.full((M, 6, 3), cfg.z_2d, np.float32); tr[..., :dim] = t.astype(np.float32)
+                new_trajs[a] = tr
+                sols.append(x); oks.append(ok)
+            else:
+                sols.append(np.full(dim * M * 6, np.nan)); oks.append(False)       # failsafe: keep initial_traj
+        if step == R:
+            rec = dict(state=state.copy(), goal_prev=goal.copy(), goal=new_goal.copy(), wp=wps, own=trajs.copy(), off=off, idx=idx,
+                       x=np.stack(sols), ok=np.array(oks), limits=np.concatenate([mission.max_vel, mission.max_acc,
+                       mission.radius[:, None], mission.nominal_velocity[:, None]], 1), meta=np.stack([mission.radius, mission.downwash], 1),
+                       world=np.array(mission.world_min + mission.world_max))
+            break
+        goal = new_goal
+        state = np.stack([orc.get_state_at(cfgo, new_trajs[a], cfg.dt) for a in range(n)])      # AgentManager::doStep
+        trajs = np.stack([orc.shift_traj(cfgo, new_trajs[a]) for a in range(n)])                 # traj_planner.cpp:287-297
+    return rec
+
+
+def _roll(args):
+    return rollout(*args)
+
+
+def main():
+    out = {}
+    r1 = rollout(os.path.join(REF, "missions/forest10/forest10_1.json"), 0)
+    for k, v in r1.items():
+        out["c1_" + k] = v
+    files = sorted(glob.glob(os.path.join(REF, "missions/maze10_dense/*.json")))[:26]       # lexicographic, mission.cpp:18-44
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        recs = pool.map(_roll, [(f, 2 + (i % 9)) for i, f in enumerate(files)], chunksize=1)   # replan indices 3..11
+    n0 = 0
+    keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta"]
+    cat = {k: [] for k in keys}; off = [0]; idx = []; world = []
+    for r in recs:
+        for k in keys:
+            cat[k].append(r[k])
+        idx.append(r["idx"] + n0); off.extend((r["off"][1:] + off[-1] - r["off"][0]).tolist())
+        n0 += r["state"].shape[0]; world.append(r["world"])
+    for k in keys:
+        out["c3_" + k] = np.concatenate(cat[k])
+    out["c3_off"] = np.array(off, np.int32); out["c3_idx"] = np.concatenate(idx).astype(np.int32)
+    out["c3_world"] = np.stack(world)
+    np.savez_compressed(os.path.join(HERE, "mission_golden.npz"), **out)
+    print("config 1: solved", int(r1["ok"].sum()), "of", len(r1["ok"]), "| config 3:", int(out["c3_ok"].sum()), "polished of", len(out["c3_ok"]),
+          "failed", int(np.isnan(out["c3_x"][:, 0]).sum()))
+
+
+if __name__ == "__main__":
+    main()
