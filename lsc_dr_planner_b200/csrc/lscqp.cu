@@ -50,6 +50,7 @@ struct lscqp_handle {
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
     DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout;
     bool two_pass = false;
+    int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
 };
 
@@ -79,6 +80,7 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     if (!found) { delete h; return fail(LSCQP_E_INVALID, "no kernel instance"); }
     h->dual_stride = info.dual_stride; h->kmax = info.kmax; h->nv = info.nv;
     h->two_pass = info.has_light && (cfg->presolve & 1) && !(cfg->presolve & 2);
+    if (const char* e = std::getenv("LSCQP_TWO_PASS_MIN")) h->two_pass_min = std::atoi(e);
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
     if (h->d_proj_ent.reserve(tab.term.size() * sizeof(ProjTerm)) || h->d_proj_term.reserve((tabl.term.size() + 1) * sizeof(ProjTerm)) ||
@@ -129,14 +131,17 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out; p.dual_stride = h->dual_stride;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (h->two_pass) {
+    // The light first pass pays off in the throughput regime (several waves of one-warp CTAs); a small batch is
+    // latency bound and finishes sooner on the 128-thread instance alone.
+    const bool two_pass = h->two_pass && n_agents >= h->two_pass_min;
+    if (two_pass) {
         if (h->d_klass.reserve((size_t) n_agents * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
         p.klass = h->d_klass.as<int>();
     }
-    int launched = inst_launch_0(h->cfg, p, n_agents, h->two_pass, st);
-    if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, h->two_pass, st);
-    if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, h->two_pass, st);
-    if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, h->two_pass, st);
+    int launched = inst_launch_0(h->cfg, p, n_agents, two_pass, st);
+    if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, two_pass, st);
+    if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, two_pass, st);
+    if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, two_pass, st);
     h->launches += launched;
     CK(cudaGetLastError());
     return 0;
@@ -373,6 +378,12 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     const int M = h->cfg.M;
     const size_t sumK = (size_t) obs_offsets[n_agents];
     if (sumK > 0 && !obs_index) return fail(LSCQP_E_INVALID, "null obs_index");
+    for (int a = 0; a < n_agents; a++) {
+        if (obs_offsets[a + 1] < obs_offsets[a] || obs_offsets[a + 1] - obs_offsets[a] > h->cfg.max_obs)
+            return fail(LSCQP_E_CAPACITY, "obstacle list of an agent is negative or above max_obs");
+    }
+    for (size_t j = 0; j < sumK; j++)
+        if (obs_index[j] < 0 || obs_index[j] >= n_agents) return fail(LSCQP_E_INVALID, "obs_index outside [0, n_agents)");
     cudaStream_t st = h->stream;
     RESERVE(h->d_state, n_agents * 9 * sizeof(float)); RESERVE(h->d_goal, n_agents * 3 * sizeof(float));
     RESERVE(h->d_limits, n_agents * 8 * sizeof(double)); RESERVE(h->d_off, (n_agents + 1) * sizeof(int));

@@ -15,7 +15,10 @@ import glob
 import os
 import sys
 
-import numpy as np
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):      # one BLAS thread per worker process
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -46,16 +49,50 @@ def plan_agent(cfgo, mission, a, state, goal_prev, wp, own, nbr, trajs, goals_pr
         return goal_prev, gst, None, (pt, nr, d)
     ag.goal = new_goal
     qp = orc.qp_build(cfgo, ag, pt, nr, d)
-    # roll-out steps use the dense interior-point checker (50x faster on these models); the recorded step goes
-    # through HiGHS first, the two agree to the last digit after polish wherever HiGHS succeeds
-    sol = orc.solve_highs(qp, time_limit=20.0) if final else None
-    tol = 1e-9
-    if sol is None or sol.status != "Optimal":        # HiGHS "Solve error" on some dense comm-range models
-        sol = orc.solve_dense_ipm(qp); tol = 1e-12
-        if sol.status != "Optimal":
-            return new_goal, 0, None, (pt, nr, d)
-    x, ok = orc.polish(qp, sol, dual_tol=tol)
+    # the dense interior-point checker solves these models in ~20 ms; HiGHS' active-set QP solver needs 1 s to minutes on
+    # the dense communication-range models and errors out on about half of them, so it is run afterwards on a subset
+    # under a wall-clock limit (highs_crosscheck) and the agreement is stored in the fixture
+    sol = orc.solve_dense_ipm(qp)
+    if sol.status != "Optimal":
+        return new_goal, 0, None, (pt, nr, d)
+    x, ok = orc.polish(qp, sol, dual_tol=1e-12)
+    if final:
+        HIGHS_JOBS.append((qp, x))
     return new_goal, 0, (x, ok), (pt, nr, d)
+
+
+HIGHS_JOBS = []          # (qp, polished x) of the recorded step, per process
+
+
+def _highs_one(qp, x, q):
+    sol = orc.solve_highs(qp, time_limit=25.0)
+    if sol.status != "Optimal":
+        q.put(np.nan); return
+    xh, ok = orc.polish(qp, sol)
+    q.put(float(np.abs(xh - x).max()) if ok else np.nan)
+
+
+def highs_crosscheck(jobs, limit_s=30.0, width=8):
+    """max |x_highs - x_ipm| per job (NaN: HiGHS failed, was not polishable, or ran over the wall-clock limit, in which
+    case its process is killed)"""
+    import multiprocessing as mp
+    import time
+    ctx = mp.get_context("fork")
+    out = np.full(len(jobs), np.nan)
+    for lo in range(0, len(jobs), width):
+        procs = []
+        for i in range(lo, min(lo + width, len(jobs))):
+            q = ctx.Queue()
+            p = ctx.Process(target=_highs_one, args=(jobs[i][0], jobs[i][1], q))
+            p.start(); procs.append((i, p, q))
+        t0 = time.time()
+        for i, p, q in procs:
+            p.join(max(0.1, limit_s - (time.time() - t0)))
+            if p.is_alive():
+                p.kill(); p.join()
+            elif not q.empty():
+                out[i] = q.get()
+    return out
 
 
 def waypoint(pos, desired, step):
@@ -95,7 +132,8 @@ def rollout(path, R, M=10, dim=2):
             rec = dict(state=state.copy(), goal_prev=goal.copy(), goal=new_goal.copy(), wp=wps, own=trajs.copy(), off=off, idx=idx,
                        x=np.stack(sols), ok=np.array(oks), limits=np.concatenate([mission.max_vel, mission.max_acc,
                        mission.radius[:, None], mission.nominal_velocity[:, None]], 1), meta=np.stack([mission.radius, mission.downwash], 1),
-                       world=np.array(mission.world_min + mission.world_max))
+                       world=np.array(mission.world_min + mission.world_max), highs_jobs=list(HIGHS_JOBS))
+            HIGHS_JOBS.clear()
             break
         goal = new_goal
         state = np.stack([orc.get_state_at(cfgo, new_trajs[a], cfg.dt) for a in range(n)])      # AgentManager::doStep
@@ -110,6 +148,7 @@ def _roll(args):
 def main():
     out = {}
     r1 = rollout(os.path.join(REF, "missions/forest10/forest10_1.json"), 0)
+    jobs = r1.pop("highs_jobs")
     for k, v in r1.items():
         out["c1_" + k] = v
     files = sorted(glob.glob(os.path.join(REF, "missions/maze10_dense/*.json")))[:26]       # lexicographic, mission.cpp:18-44
@@ -119,6 +158,9 @@ def main():
     n0 = 0
     keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta"]
     cat = {k: [] for k in keys}; off = [0]; idx = []; world = []
+    for r in recs[:3]:
+        jobs += r["highs_jobs"]
+    out["highs_maxdiff"] = highs_crosscheck(jobs)          # config 1 (10 QPs) + the first three config-3 instances
     for r in recs:
         for k in keys:
             cat[k].append(r[k])
@@ -130,7 +172,8 @@ def main():
     out["c3_world"] = np.stack(world)
     np.savez_compressed(os.path.join(HERE, "mission_golden.npz"), **out)
     print("config 1: solved", int(r1["ok"].sum()), "of", len(r1["ok"]), "| config 3:", int(out["c3_ok"].sum()), "polished of", len(out["c3_ok"]),
-          "failed", int(np.isnan(out["c3_x"][:, 0]).sum()))
+          "failed", int(np.isnan(out["c3_x"][:, 0]).sum()), "| HiGHS cross-check:", int(np.isfinite(out["highs_maxdiff"]).sum()), "of",
+          len(out["highs_maxdiff"]), "solved, max diff", np.nanmax(out["highs_maxdiff"]))
 
 
 if __name__ == "__main__":

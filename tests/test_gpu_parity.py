@@ -387,3 +387,17 @@ def test_communication_range_rows(M, dim, K, rng_):
         end = ctrl.reshape(64, dim, M, 6)[ok_agents][:, :, :, 5]
         dist = np.abs(end - batch.state[ok_agents][:, :dim, None]).max(axis=(1, 2))
         assert dist.max() <= 0.5 * rng_ - 0.15 + 1e-7 and dist.max() > 0.5 * rng_ - 0.15 - 1e-4
+
+
+def test_replan_host_rejects_bad_neighbour_lists():
+    """lscqp_replan_host validates the CSR neighbour lists before anything is launched (nothing written)"""
+    batch = W.make_forest_batch(16, K=4)
+    planner = BatchPlanner(batch.cfg, device=0)
+    b = planner.host_buffers(batch)
+    b["obs_index"][3] = 16                                    # outside [0, n_agents)
+    with pytest.raises(capi.LscqpError, match="obs_index"):
+        planner.replan_host_buffers(b, 16)
+    b["obs_index"][3] = 0
+    b["obs_offsets"][1] = 60                                  # 60 obstacles for agent 0 > max_obs
+    with pytest.raises(capi.LscqpError):
+        planner.replan_host_buffers(b, 16)
