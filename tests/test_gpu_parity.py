@@ -391,6 +391,7 @@ def test_communication_range_rows(M, dim, K, rng_):
 
 def test_replan_host_rejects_bad_neighbour_lists():
     """lscqp_replan_host validates the CSR neighbour lists before anything is launched (nothing written)"""
+    from lsc_dr_planner_b200.planner import BatchPlanner
     batch = W.make_forest_batch(16, K=4)
     planner = BatchPlanner(batch.cfg, device=0)
     b = planner.host_buffers(batch)
