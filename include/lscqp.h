@@ -167,6 +167,14 @@ int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
         const float* own_traj, const double* agent_meta, const float* agent_goal, const float* state,
         float* obs_traj, float* obs_meta, float* obs_goal, float* obs_position, void* stream);
 
+/* Neighbour selection on the device (MultiSyncSimulator::broadcastMsgs, src/multi_sync_simulator.cpp:305-352): for the
+ * agents [lo, lo + n_local) of a population of n_total, the ids of the K nearest other agents -- those within the
+ * Chebyshev communication range first (:319-328; comm_range <= 0: no filter), padded with the nearest out-of-range
+ * ones when fewer than K are in range -- in ascending id order.  state: [n_total][9] (position first);
+ * obs_index_out: [n_local][K], ready for lscqp_gather_obstacles with obs_offsets = K * arange. */
+int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, int K, double comm_range,
+        const float* state, int* obs_index_out, void* stream);
+
 /* Closed-loop glue on the device (AgentManager::doStep src/agent_manager.cpp:29-50 via
  * Trajectory::getStateAt src/trajectory.cpp:156-170, and the previous-solution shift
  * src/traj_planner.cpp:287-297, 402-411).  ctrl: [n][dim][M][6] doubles from the solve;

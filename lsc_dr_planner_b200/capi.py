@@ -54,7 +54,7 @@ def load():
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
-                     "lscqp_goal_host", "lscqp_measure_fp64_peak"):
+                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -154,6 +154,11 @@ class LscQp:
         self._check(self.lib.lscqp_gather_obstacles(self.h, n_obs, _dp(obs_index), _dp(own_traj), _dp(agent_meta),
                                                     _dp(agent_goal), _dp(state), _dp(obs_traj), _dp(obs_meta),
                                                     _dp(obs_goal), _dp(obs_position), C.c_void_p(stream)))
+
+    def select_neighbours(self, n_total, lo, n_local, K, comm_range, state, obs_index_out, stream=0):
+        """broadcastMsgs on the device: K nearest (in-range first) neighbour ids of the agents [lo, lo + n_local)"""
+        self._check(self.lib.lscqp_select_neighbours(self.h, n_total, lo, n_local, K, C.c_double(comm_range), _dp(state),
+                                                     _dp(obs_index_out), C.c_void_p(stream)))
 
     def step_batch(self, n, ctrl, step, traj_out, state_out=None, shifted_out=None, stream=0):
         self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),

@@ -8,7 +8,7 @@ src/multi_sync_simulator.cpp:81-129):
     failsafe       -> agents whose QP failed keep initial_traj (src/traj_planner.cpp:767-797)
     doStep         -> lscqp_step_batch: float trajectory, state at t = dt, shifted trajectory (device)
     exchange       -> one all-gather of trajectories / states per step (NCCL over NVLink on GPUs)
-Neighbour search uses torch (cdist + topk): it is simulator harness, not the hot path."""
+Neighbour search runs in the library too (lscqp_select_neighbours: radix select in shared memory, one CTA per agent)."""
 from __future__ import annotations
 
 import numpy as np
@@ -47,6 +47,7 @@ class ClosedLoopSim:
         # local scratch
         n, sk = max(self.n_local, 1), max(self.n_local * self.K, 1)
         self.obs_offsets = (torch.arange(self.n_local + 1, device=dev, dtype=torch.int32) * self.K).contiguous()
+        self.obs_index = torch.zeros((sk,), dtype=torch.int32, device=dev)
         self.obs_traj = torch.empty((sk, M, 6, 3), dtype=torch.float32, device=dev)
         self.obs_meta = torch.empty((sk, 4), dtype=torch.float32, device=dev)
         self.obs_goal = torch.empty((sk, 3), dtype=torch.float32, device=dev)
@@ -60,8 +61,13 @@ class ClosedLoopSim:
         self.traj_out = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev)
         self.state_out = torch.empty((n, 9), dtype=torch.float32, device=dev)
         self.shifted = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev)
-        self.failed_total = 0
+        self._failed = torch.zeros((), dtype=torch.int64, device=dev)
         self.steps = 0
+
+    @property
+    def failed_total(self) -> int:
+        """QPs that did not converge so far (reads the device counter: synchronises)"""
+        return int(self._failed.item())
 
     def _const_vel(self, state):
         torch = self.torch
@@ -71,17 +77,19 @@ class ClosedLoopSim:
         return (state[:, None, None, 0:3] + state[:, None, None, 3:6] * tt).contiguous()
 
     def neighbours(self):
-        """K nearest agents of every local agent (optionally within the L-inf communication range,
-        src/multi_sync_simulator.cpp:319-328); padded with the farthest ones when fewer are in range."""
-        torch = self.torch
-        pos = self.state[:, 0:3]
-        d = torch.cdist(pos[self.lo:self.hi], pos)
-        idx_self = torch.arange(self.lo, self.hi, device=self.dev)
-        d[torch.arange(self.n_local, device=self.dev), idx_self] = float("inf")
-        if self.comm_range > 0:
-            linf = (pos[self.lo:self.hi, None, :] - pos[None, :, :]).abs().amax(dim=-1)
-            d = torch.where(linf > self.comm_range, d + 1e6, d)
-        return torch.topk(d, self.K, dim=1, largest=False).indices.to(torch.int32).contiguous().view(-1)
+        """K nearest agents of every local agent (those within the L-inf communication range first,
+        src/multi_sync_simulator.cpp:319-328; padded with the nearest out-of-range ones when fewer are in range):
+        lscqp_select_neighbours, ids in ascending order"""
+        import os
+        if os.environ.get("LSCQP_CL_TORCH_KNN"):
+            torch = self.torch
+            pos = self.state[:, 0:3]
+            d = torch.cdist(pos[self.lo:self.hi], pos)
+            idx_self = torch.arange(self.lo, self.hi, device=self.dev)
+            d[torch.arange(self.n_local, device=self.dev), idx_self] = float("inf")
+            return torch.topk(d, self.K, dim=1, largest=False).indices.to(torch.int32).contiguous().view(-1)
+        self.planner.qp.select_neighbours(self.N, self.lo, self.n_local, self.K, self.comm_range, self.state, self.obs_index)
+        return self.obs_index
 
     def step(self):
         """one replan + one simulation step of length dt for the local shard, then the exchange"""
@@ -99,13 +107,20 @@ class ClosedLoopSim:
                                   self.obs_goal, self.obs_position, self.normals, self.rhs)
             qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
                            self.status, self.iters, initial_traj=own)
-            # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797)
+            # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797); done on the device
+            # without a host round trip so the launches of the next step can run ahead
             bad = self.status != 0
-            if bool(bad.any()):
-                D, M = self.cfg.dim, self.cfg.M
+            D = self.cfg.dim
+            import os
+            if os.environ.get("LSCQP_CL_SYNC_FAILSAFE"):
+                if bool(bad.any()):
+                    fallback = own.permute(0, 3, 1, 2)[:, :D].reshape(n, -1).to(torch.float64)
+                    self.ctrl[bad] = fallback[bad]
+                    self._failed += bad.sum()
+            else:
                 fallback = own.permute(0, 3, 1, 2)[:, :D].reshape(n, -1).to(torch.float64)
-                self.ctrl[bad] = fallback[bad]
-                self.failed_total += int(bad.sum())
+                torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
+                self._failed += bad.sum()
             qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted)
             new_traj, new_state = self.shifted, self.state_out
         else:

@@ -12,6 +12,7 @@
 #include "lsc_assemble.cuh"
 #include "step_kernel.cuh"
 #include "goal_kernel.cuh"
+#include "knn_kernel.cuh"
 
 using namespace lscqp;
 
@@ -50,6 +51,7 @@ struct lscqp_handle {
     DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
     DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout;
     bool two_pass = false;
+    size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
 };
@@ -201,6 +203,27 @@ extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctr
     const int blocks = (n_agents + 127) / 128;
     if (h->cfg.M == 5) step_kernel<5><<<blocks, 128, 0, st>>>(p);
     else step_kernel<10><<<blocks, 128, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, int K, double comm_range,
+                                       const float* state, int* obs_index_out, void* stream) {
+    if (!h || !state || !obs_index_out || n_total < 0 || n_local < 0 || lo < 0 || lo + n_local > n_total)
+        return fail(LSCQP_E_INVALID, "bad argument");
+    if (K < 0 || K > h->cfg.max_obs || K > n_total - 1) return fail(LSCQP_E_CAPACITY, "K above max_obs or n_total - 1");
+    if (n_local == 0 || K == 0) return 0;
+    const size_t smem = ((size_t) n_total + 256 + 2 * KNN_THREADS + 4) * sizeof(unsigned);
+    if (smem > 200 * 1024) return fail(LSCQP_E_CAPACITY, "n_total above the shared-memory capacity of the selection kernel");
+    if (smem > 48 * 1024 && smem > h->knn_smem) {
+        CK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        h->knn_smem = smem;
+    }
+    KnnParams p;
+    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = (float) comm_range;
+    p.state = state; p.obs_index = obs_index_out;
+    knn_select_kernel<<<n_local, KNN_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     h->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -92,6 +92,8 @@ inline int __any_sync(unsigned, int pred) {
     __syncwarp();
     return r;
 }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }   // fibers are cooperative
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __fdividef(float a, float b) { return a / b; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

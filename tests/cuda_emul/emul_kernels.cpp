@@ -7,6 +7,7 @@
 #include "../../lsc_dr_planner_b200/csrc/lsc_assemble.cuh"
 #include "../../lsc_dr_planner_b200/csrc/step_kernel.cuh"
 #include "../../lsc_dr_planner_b200/csrc/goal_kernel.cuh"
+#include "../../lsc_dr_planner_b200/csrc/knn_kernel.cuh"
 
 using namespace lscqp;
 
@@ -87,6 +88,13 @@ extern "C" int emul_goal_batch(const lscqp_config* cfg, int n_agents, const floa
     p.goal = goal; p.waypoint = waypoint; p.sfc = sfc; p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
     p.goal_out = goal_out; p.t_out = t_out; p.status_out = status_out;
     emu::launch((n_agents + 3) / 4, 128, 64, [&]() { goal_lp_kernel(p); });
+    return 0;
+}
+
+extern "C" int emul_select_neighbours(int n_total, int lo, int n_local, int K, double comm_range, const float* state, int* out) {
+    KnnParams p;
+    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = (float) comm_range; p.state = state; p.obs_index = out;
+    emu::launch(n_local, KNN_THREADS, ((size_t) n_total + 256 + 2 * KNN_THREADS + 4) * sizeof(unsigned) + 64, [&]() { knn_select_kernel(p); });
     return 0;
 }
 

@@ -70,3 +70,10 @@ def goal(cfg, n, goal_pt, waypoint, sfc, off, normals, rhs):
                                _p(t, np.float64), _p(status, np.int32))
     assert rc == 0, rc
     return out, t, status
+
+
+def select_neighbours(n_total, lo, n_local, K, comm_range, state):
+    out = np.zeros((n_local, K), np.int32)
+    rc = lib().emul_select_neighbours(n_total, lo, n_local, K, C.c_double(comm_range), _p(state, np.float32), _p(out, np.int32))
+    assert rc == 0, rc
+    return out

@@ -155,3 +155,30 @@ def test_solve_kernel_with_communication_range_rows(M, dim, K):
     assert checked >= 2
     # the comm rows must matter for at least one of these agents (otherwise the test proves nothing)
     assert np.abs(dual[:, -2 * dim * (M * (M - 1) // 2 + M):]).max() > 1e-6
+
+
+def _check_neighbours(state, lo, out, K, comm_range):
+    """every row holds K distinct other agents in ascending order; in-range agents come before out-of-range ones and
+    nearer before farther (float distances, ties at the cut allowed)"""
+    pos = state[:, :3].astype(np.float32)
+    for r, a in enumerate(range(lo, lo + out.shape[0])):
+        ids = out[r]
+        assert len(set(ids.tolist())) == K and a not in ids and (np.diff(ids) > 0).all()
+        d = pos - pos[a]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(np.float64)
+        if comm_range > 0:
+            d2 = d2 + 1e9 * (np.abs(d).max(axis=1) > np.float32(comm_range))
+        d2[a] = np.inf
+        rest = np.setdiff1d(np.arange(pos.shape[0]), np.append(ids, a))
+        if rest.size:
+            assert d2[ids].max() <= d2[rest].min() * (1 + 1e-6) + 1e-12, (a, d2[ids].max(), d2[rest].min())
+
+
+@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(300, 0, 300, 40, 0.0), (257, 100, 57, 9, 3.0), (64, 0, 64, 40, 1.0), (41, 0, 41, 40, 0.0)])
+def test_neighbour_selection_kernel(n_total, lo, n_local, K, comm):
+    rng = np.random.default_rng(n_total)
+    state = np.zeros((n_total, 9), np.float32)
+    state[:, :3] = rng.uniform(-6, 6, (n_total, 3)).astype(np.float32)
+    state[5, :3] = state[6, :3]                               # coincident agents: tie at distance zero
+    out = emul.select_neighbours(n_total, lo, n_local, K, comm, state)
+    _check_neighbours(state, lo, out, K, comm)

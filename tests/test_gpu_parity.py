@@ -402,3 +402,26 @@ def test_replan_host_rejects_bad_neighbour_lists():
     b["obs_offsets"][1] = 60                                  # 60 obstacles for agent 0 > max_obs
     with pytest.raises(capi.LscqpError):
         planner.replan_host_buffers(b, 16)
+
+
+@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(4096, 0, 4096, 40, 0.0), (1024, 256, 512, 40, 3.0), (15000, 14000, 1000, 17, 0.0)])
+def test_neighbour_selection_gpu(n_total, lo, n_local, K, comm):
+    """lscqp_select_neighbours (radix select per agent) against a numpy restatement of the broadcastMsgs filter"""
+    import torch
+    from test_emul_kernels import _check_neighbours
+    rng = np.random.default_rng(n_total)
+    state = np.zeros((n_total, 9), np.float32)
+    state[:, :3] = rng.uniform(-40, 40, (n_total, 3)).astype(np.float32)
+    cfg = W.PlannerConfig()
+    qp = capi.LscQp(cfg, device=0)
+    st = torch.from_numpy(state).cuda()
+    out = torch.zeros((n_local, K), dtype=torch.int32, device="cuda")
+    qp.select_neighbours(n_total, lo, n_local, K, comm, st, out)
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    sel = rng.choice(n_local, 64, replace=False)
+    _check_neighbours(state, lo, res, K, comm) if n_local <= 512 else [
+        _check_neighbours(state, lo + int(r), res[int(r):int(r) + 1], K, comm) for r in sel]
+    out2 = torch.zeros_like(out)
+    qp.select_neighbours(n_total, lo, n_local, K, comm, st, out2)
+    assert torch.equal(out, out2)                             # deterministic
