@@ -20,7 +20,7 @@ from .workloads import Batch
 
 class ClosedLoopSim:
     def __init__(self, batch: Batch, device: int = 0, rank: int = 0, world: int = 1, K: int = 40,
-                 comm_range: float = 0.0, generator: int = capi.GEN_LSC):
+                 comm_range: float = 0.0, generator: int = capi.GEN_LSC, use_graph: bool = False):
         import torch
         from .planner import BatchPlanner
         self.torch = torch
@@ -63,6 +63,8 @@ class ClosedLoopSim:
         self.shifted = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev)
         self._failed = torch.zeros((), dtype=torch.int64, device=dev)
         self.steps = 0
+        self.use_graph = use_graph
+        self._graph = None
 
     @property
     def failed_total(self) -> int:
@@ -76,59 +78,61 @@ class ClosedLoopSim:
         # Trajectory::planConstVelTraj (src/trajectory.cpp:77-89): time advances by dt/n per control point
         return (state[:, None, None, 0:3] + state[:, None, None, 3:6] * tt).contiguous()
 
-    def neighbours(self):
+    def neighbours(self, stream: int = 0):
         """K nearest agents of every local agent (those within the L-inf communication range first,
         src/multi_sync_simulator.cpp:319-328; padded with the nearest out-of-range ones when fewer are in range):
         lscqp_select_neighbours, ids in ascending order"""
-        import os
-        if os.environ.get("LSCQP_CL_TORCH_KNN"):
-            torch = self.torch
-            pos = self.state[:, 0:3]
-            d = torch.cdist(pos[self.lo:self.hi], pos)
-            idx_self = torch.arange(self.lo, self.hi, device=self.dev)
-            d[torch.arange(self.n_local, device=self.dev), idx_self] = float("inf")
-            return torch.topk(d, self.K, dim=1, largest=False).indices.to(torch.int32).contiguous().view(-1)
-        self.planner.qp.select_neighbours(self.N, self.lo, self.n_local, self.K, self.comm_range, self.state, self.obs_index)
+        self.planner.qp.select_neighbours(self.N, self.lo, self.n_local, self.K, self.comm_range, self.state,
+                                          self.obs_index, stream)
         return self.obs_index
 
-    def step(self):
-        """one replan + one simulation step of length dt for the local shard, then the exchange"""
+    def _step_impl(self, stream: int):
+        """one replan + one simulation step of length dt for the local shard, then the exchange; every launch goes to
+        `stream` (the current torch stream), nothing returns to the host"""
         torch = self.torch
         qp = self.planner.qp
         n, lo, hi = self.n_local, self.lo, self.hi
         if n > 0:
-            obs_index = self.neighbours()
+            obs_index = self.neighbours(stream)
             own = self.traj[lo:hi].contiguous()
             st, goal, lim, meta = (self.state[lo:hi].contiguous(), self.goal[lo:hi].contiguous(),
                                    self.limits[lo:hi].contiguous(), self.agent_meta[lo:hi].contiguous())
             qp.gather_obstacles(n * self.K, obs_index, self.traj, self.agent_meta, self.goal, self.state,
-                                self.obs_traj, self.obs_meta, self.obs_goal, self.obs_position)
+                                self.obs_traj, self.obs_meta, self.obs_goal, self.obs_position, stream)
             qp.assemble_lsc_batch(self.generator, n, own, meta, goal, self.obs_offsets, self.obs_traj, self.obs_meta,
-                                  self.obs_goal, self.obs_position, self.normals, self.rhs)
+                                  self.obs_goal, self.obs_position, self.normals, self.rhs, stream)
             qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
-                           self.status, self.iters, initial_traj=own)
+                           self.status, self.iters, stream=stream, initial_traj=own)
             # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797); done on the device
             # without a host round trip so the launches of the next step can run ahead
             bad = self.status != 0
-            D = self.cfg.dim
-            import os
-            if os.environ.get("LSCQP_CL_SYNC_FAILSAFE"):
-                if bool(bad.any()):
-                    fallback = own.permute(0, 3, 1, 2)[:, :D].reshape(n, -1).to(torch.float64)
-                    self.ctrl[bad] = fallback[bad]
-                    self._failed += bad.sum()
-            else:
-                fallback = own.permute(0, 3, 1, 2)[:, :D].reshape(n, -1).to(torch.float64)
-                torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
-                self._failed += bad.sum()
-            qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted)
+            fallback = own.permute(0, 3, 1, 2)[:, :self.cfg.dim].reshape(n, -1).to(torch.float64)
+            torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
+            self._failed += bad.sum()
+            qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted, stream)
             new_traj, new_state = self.shifted, self.state_out
         else:
             new_traj = self.shifted[:0]; new_state = self.state_out[:0]
-        self.traj = allgather_rows(new_traj[:n], self.N)
-        self.state = allgather_rows(new_state[:n], self.N)
-        if self.world == 1:
-            self.traj = self.traj.clone(); self.state = self.state.clone()
+        # the exchange (the only collective): every rank ends the step with all trajectories and states
+        self.traj.copy_(allgather_rows(new_traj[:n], self.N))
+        self.state.copy_(allgather_rows(new_state[:n], self.N))
+
+    def step(self):
+        """One closed-loop step.  With use_graph the step is captured once into a CUDA graph (library launches, the
+        few torch element-wise ops and the NCCL all-gather) after two eager steps and replayed afterwards: at a few
+        hundred agents per GPU the step is otherwise bound by the ~0.4 ms of host-side launch work."""
+        torch = self.torch
+        if self.use_graph and self._graph is not None:
+            self._graph.replay()
+        elif self.use_graph and self.steps >= 2:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_impl(torch.cuda.current_stream().cuda_stream)
+            self._graph = g                  # (capture does not execute: replay performs this step)
+            g.replay()
+        else:
+            self._step_impl(torch.cuda.current_stream().cuda_stream)
         self.steps += 1
 
     def min_separation_ratio(self) -> float:

@@ -16,19 +16,13 @@ w = make()
 t0 = time.perf_counter()
 while time.perf_counter() - t0 < 1.5:          # bring the clocks up before anything is timed
     w.step(); torch.cuda.synchronize()
-for knn in ("", "1", "", "1"):
-    for fs in ("", "1"):
-        os.environ.pop("LSCQP_CL_TORCH_KNN", None); os.environ.pop("LSCQP_CL_SYNC_FAILSAFE", None)
-        if knn: os.environ["LSCQP_CL_TORCH_KNN"] = "1"
-        if fs: os.environ["LSCQP_CL_SYNC_FAILSAFE"] = "1"
-        sim = make()
-        for _ in range(3): sim.step()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter(); a.record()
-        its = []
-        for s in range(200):
-            sim.step()
-            if s % 50 == 49: its.append(sim.iters.float().mean())
-        b.record(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-        print(f"torch_knn={knn or 0} sync_failsafe={fs or 0}: gpu {a.elapsed_time(b)/200:.3f} ms/step, cpu enqueue {(t1-t0)*5:.3f} ms/step, wall {(t2-t0)*5:.3f}, iters {[round(float(x),2) for x in its]}, failed {sim.failed_total}")
+for graph in (False, True, False, True):
+    sim = make(); sim.use_graph = graph
+    for _ in range(4): sim.step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); a.record()
+    for s in range(200):
+        sim.step()
+    b.record(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"n={n} graph={graph}: gpu {a.elapsed_time(b)/200:.3f} ms/step, cpu enqueue {(t1-t0)*5:.3f} ms/step, wall {(t2-t0)*5:.3f}, iters {float(sim.iters.float().mean()):.2f}, failed {sim.failed_total}, goal dist {sim.max_goal_distance():.4f}")

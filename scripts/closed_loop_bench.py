@@ -11,6 +11,7 @@ def main():
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--K", type=int, default=40)
+    ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph")
     args = ap.parse_args()
     import torch, torch.distributed as dist
     from lsc_dr_planner_b200 import workloads as W
@@ -28,7 +29,7 @@ def main():
     half = batch.cfg.world_max[0] - 0.5
     goal[:, :2] = np.clip(goal[:, :2], -half, half)
     batch.goal = goal.astype(np.float32)
-    sim = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K)
+    sim = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K, use_graph=args.graph)
     warm = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K)
     t_w = time.perf_counter()
     while time.perf_counter() - t_w < 1.0:            # a 0.3 s run is otherwise timed while the clocks are still ramping up
@@ -57,7 +58,7 @@ def main():
     if rank == 0:
         ms = float(t)
         print(json.dumps({"workload": f"closed loop, {args.agents} agents x {args.steps} replans, K={args.K} nearest neighbours re-selected every step",
-                          "n_gpus": world, "ms_per_replan_step": ms / args.steps, "replan_steps_per_s": args.steps / (ms * 1e-3),
+                          "n_gpus": world, "cuda_graph": bool(args.graph), "ms_per_replan_step": ms / args.steps, "replan_steps_per_s": args.steps / (ms * 1e-3),
                           "agent_qp_per_s": args.agents * args.steps / (ms * 1e-3), "min_safety_ratio": worst,
                           "qp_failures_total": float(f), "max_goal_distance_end": sim.max_goal_distance(),
                           "wall_s": time.perf_counter() - t0}))

@@ -425,3 +425,21 @@ def test_neighbour_selection_gpu(n_total, lo, n_local, K, comm):
     out2 = torch.zeros_like(out)
     qp.select_neighbours(n_total, lo, n_local, K, comm, st, out2)
     assert torch.equal(out, out2)                             # deterministic
+
+
+def test_closed_loop_cuda_graph_matches_eager():
+    """the captured step (library launches + torch glue in one CUDA graph) reproduces the eager loop bit for bit"""
+    import torch
+    from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
+    sims = []
+    for graph in (False, True):
+        batch = W.make_forest_batch(96, K=20, moving=False, seed=7)
+        batch.goal = (batch.state[:, :3] * [-1, -1, 1]).astype(np.float32)
+        sim = ClosedLoopSim(batch, device=0, K=20, use_graph=graph)
+        for _ in range(12):
+            sim.step()
+        torch.cuda.synchronize()
+        sims.append(sim)
+    assert sims[1]._graph is not None
+    assert torch.equal(sims[0].state, sims[1].state) and torch.equal(sims[0].traj, sims[1].traj)
+    assert sims[0].failed_total == sims[1].failed_total == 0
