@@ -160,10 +160,10 @@ def run_reference(args):
 
 
 def workload_config(args, n_agents):
-    return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (gather + LSC assembly + PDIP solve)",
+    return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (LSC assembly + PDIP solve)",
             "agents_per_gpu": n_agents, "K": args.K, "M": 5, "degree": 5, "dim": 3, "rows_per_qp": 27 * args.K + 414,
             "planner_mode": "lsc", "generator": "generateLSC", "l2": "flushed between timed steps (256 MiB write)",
-            "solver": "warm start from initial_traj, exact presolve (velocity-bound row pruning) on; see `variants` for off",
+            "solver": "warm start from initial_traj, exact presolve (velocity-bound row pruning, in assembly and solve) on; see `variants` for off",
             "parallelism": f"agents sharded over {args.gpus} rank(s), no data-path collective"}
 
 
@@ -211,7 +211,7 @@ def run_ours(args):
     for s in range(args.steps):
         flush.fill_(s & 0xFF)
         ev[s][0].record()
-        planner.assemble_device(d, capi.GEN_LSC, stream)
+        planner.assemble_fused_device(d, capi.GEN_LSC, stream)
         ev[s][1].record()
         planner.solve_device(d, stream=stream)
         ev[s][2].record()
@@ -293,6 +293,9 @@ def run_ours(args):
                     a.record(); fn(); b.record(); torch.cuda.synchronize()
                     tot += a.elapsed_time(b)
                 return tot / reps
+            ms = timed(lambda: planner.assemble_device(d, capi.GEN_LSC, stream))
+            variants["assemble_gathered_unpruned"] = {"ms": ms, "note": "gather kernel + every (obstacle, segment) plane, as lscqp_assemble_lsc_batch returns them"}
+            planner.assemble_fused_device(d, capi.GEN_LSC, stream)
             cfg3 = copy.copy(batch.cfg); cfg3.presolve = 3        # presolve on, light instances off (one pass, 128-thread CTAs)
             planner3 = BatchPlanner(cfg3, device=local)
             ms = timed(lambda: planner3.solve_device(d, stream=stream))

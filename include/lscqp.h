@@ -104,6 +104,24 @@ int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents,
         double* rhs_out,            /* [sum K][M][6]                                             */
         void* stream);
 
+/* Fused variant for obstacles that are agents of the same population (what MultiSyncSimulator::broadcastMsgs hands
+ * to every planner, src/multi_sync_simulator.cpp:305-352): the obstacles' trajectories / radii / goals / positions are
+ * read in place through obs_index from the population arrays (all_*: [n_total] rows; no gathered copies), and with
+ * prune != 0 an (obstacle, segment) pair whose rows provably cannot bind at any point the velocity rows allow is
+ * written as a zero normal -- a row the QP drops (traj_optimizer.cpp:409-411) -- without running the hull enumeration.
+ * The minimiser of the QP is unchanged; the planes are no longer the reference's for the dropped pairs, so
+ * GoalOptimizer (which reads the last control point's plane without the velocity rows) must use prune = 0. */
+int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prune, int n_agents,
+        const float* own_traj, const double* agent_meta, const float* agent_goal,
+        const float* state,          /* [n_agents][9]  (prune)                                   */
+        const double* limits,        /* [n_agents][8]  (prune)                                   */
+        const int* obs_offsets, const int* obs_index,
+        const float* all_traj,       /* [n_total][M][6][3]                                        */
+        const double* all_meta,      /* [n_total][2]   radius, downwash                           */
+        const float* all_goal,       /* [n_total][3]                                              */
+        const float* all_state,      /* [n_total][9]                                              */
+        double* normals_out, double* rhs_out, void* stream);
+
 /* Batched QP solve (TrajOptimizer::solve for every agent of the batch).  Device pointers. */
 int lscqp_solve_batch(lscqp_handle* h, int n_agents,
         const float*  state,        /* [n_agents][9]  position, velocity, acceleration          */

@@ -54,7 +54,7 @@ def load():
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
-                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours"):
+                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -148,6 +148,14 @@ class LscQp:
         self._check(self.lib.lscqp_assemble_lsc_batch(self.h, generator, n, _dp(own_traj), _dp(agent_meta), _dp(agent_goal),
                                                       _dp(obs_offsets), _dp(obs_traj), _dp(obs_meta), _dp(obs_goal),
                                                       _dp(obs_position), _dp(normals), _dp(rhs), C.c_void_p(stream)))
+
+    def assemble_lsc_fused(self, generator, prune, n, own_traj, agent_meta, agent_goal, state, limits, obs_offsets, obs_index,
+                           all_traj, all_meta, all_goal, all_state, normals, rhs, stream=0):
+        """gather-free assembly for obstacles that are agents of the same population, optionally pruned (exact)"""
+        self._check(self.lib.lscqp_assemble_lsc_fused(self.h, generator, int(prune), n, _dp(own_traj), _dp(agent_meta),
+                                                      _dp(agent_goal), _dp(state), _dp(limits), _dp(obs_offsets),
+                                                      _dp(obs_index), _dp(all_traj), _dp(all_meta), _dp(all_goal),
+                                                      _dp(all_state), _dp(normals), _dp(rhs), C.c_void_p(stream)))
 
     def gather_obstacles(self, n_obs, obs_index, own_traj, agent_meta, agent_goal, state, obs_traj, obs_meta, obs_goal,
                          obs_position, stream=0):

@@ -3,7 +3,7 @@
 Per step, for the agents a rank owns (what MultiSyncSimulator::run does serially,
 src/multi_sync_simulator.cpp:81-129):
     broadcastMsgs  -> neighbour lists from the all-gathered positions (K nearest within comm range)
-    constructLSC   -> lscqp_gather_obstacles + lscqp_assemble_lsc_batch   (device)
+    constructLSC   -> lscqp_assemble_lsc_fused: neighbours read in place, provably inactive pairs dropped (device)
     trajOptimization -> lscqp_solve_batch, started from the shifted previous solution (device)
     failsafe       -> agents whose QP failed keep initial_traj (src/traj_planner.cpp:767-797)
     doStep         -> lscqp_step_batch: float trajectory, state at t = dt, shifted trajectory (device)
@@ -48,10 +48,6 @@ class ClosedLoopSim:
         n, sk = max(self.n_local, 1), max(self.n_local * self.K, 1)
         self.obs_offsets = (torch.arange(self.n_local + 1, device=dev, dtype=torch.int32) * self.K).contiguous()
         self.obs_index = torch.zeros((sk,), dtype=torch.int32, device=dev)
-        self.obs_traj = torch.empty((sk, M, 6, 3), dtype=torch.float32, device=dev)
-        self.obs_meta = torch.empty((sk, 4), dtype=torch.float32, device=dev)
-        self.obs_goal = torch.empty((sk, 3), dtype=torch.float32, device=dev)
-        self.obs_position = torch.empty((sk, 3), dtype=torch.float32, device=dev)
         self.normals = torch.empty((sk, M, 3), dtype=torch.float64, device=dev)
         self.rhs = torch.empty((sk, M, 6), dtype=torch.float64, device=dev)
         self.ctrl = torch.empty((n, self.cfg.dim * M * 6), dtype=torch.float64, device=dev)
@@ -65,6 +61,7 @@ class ClosedLoopSim:
         self.steps = 0
         self.use_graph = use_graph
         self._graph = None
+        self.prune = bool(int(self.cfg.presolve) & 1)
 
     @property
     def failed_total(self) -> int:
@@ -97,10 +94,8 @@ class ClosedLoopSim:
             own = self.traj[lo:hi].contiguous()
             st, goal, lim, meta = (self.state[lo:hi].contiguous(), self.goal[lo:hi].contiguous(),
                                    self.limits[lo:hi].contiguous(), self.agent_meta[lo:hi].contiguous())
-            qp.gather_obstacles(n * self.K, obs_index, self.traj, self.agent_meta, self.goal, self.state,
-                                self.obs_traj, self.obs_meta, self.obs_goal, self.obs_position, stream)
-            qp.assemble_lsc_batch(self.generator, n, own, meta, goal, self.obs_offsets, self.obs_traj, self.obs_meta,
-                                  self.obs_goal, self.obs_position, self.normals, self.rhs, stream)
+            qp.assemble_lsc_fused(self.generator, self.prune, n, own, meta, goal, st, lim, self.obs_offsets, obs_index,
+                                  self.traj, self.agent_meta, self.goal, self.state, self.normals, self.rhs, stream)
             qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
                            self.status, self.iters, stream=stream, initial_traj=own)
             # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797); done on the device

@@ -29,6 +29,19 @@ struct AssembleParams {
     const float*  obs_position;  // [sumK][3]
     double* normals;             // [sumK][M][3]
     double* rhs;                 // [sumK][M][6]
+    // fused replan path (lscqp_assemble_lsc_fused): obstacles are read in place through obs_index from the
+    // population's own arrays (no gathered copies), and with `prune` the (obstacle, segment) pairs whose rows provably
+    // cannot bind at any point the velocity rows allow are written as zero normals (= rows the QP drops,
+    // traj_optimizer.cpp:409-411) without running the hull enumeration
+    const int*    obs_index;     // [sumK] ids into the all_* arrays, or null (use obs_*)
+    const float*  all_traj;      // [n_total][M][6][3]
+    const double* all_meta;      // [n_total][2]
+    const float*  all_goal;      // [n_total][3]
+    const float*  all_state;     // [n_total][9]
+    int prune;
+    const float*  state;         // [n][9]   (prune)
+    const double* limits;        // [n][8]   (prune)
+    double dt;
 };
 
 struct f3 { float x, y, z; };
@@ -230,22 +243,107 @@ template <int M>
 __global__ void __launch_bounds__(128)
 lsc_assemble_kernel(const AssembleParams p) {
     LSCQP_ASM_SMEM(s_own, M * 18);
+#ifdef LSCQP_CUDA_EMUL
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_own + M * 18 + 32);
+    int* s_cnt = reinterpret_cast<int*>(s_own + M * 18);
+    double* s_x0 = reinterpret_cast<double*>(s_own + M * 18 + 2);
+#else
+    __shared__ unsigned short s_list[40 * M];          // (obstacle, segment) pairs that need the hull enumeration
+    __shared__ int s_cnt[2];
+    __shared__ double s_x0[6];                         // fixed control point c[0][2], then vmax dt / 5
+#endif
     const int agent = blockIdx.x;
     if (agent >= p.n_agents) return;
     for (int e = threadIdx.x; e < M * 18; e += blockDim.x) s_own[e] = p.own_traj[(size_t) agent * M * 18 + e];
-    __syncthreads();
     const int obs0 = p.obs_offsets[agent], K = p.obs_offsets[agent + 1] - obs0;
     const double a_r = p.agent_meta[agent * 2 + 0], a_dw = p.agent_meta[agent * 2 + 1];
+    const bool prune = p.prune && p.dim == 3 && p.generator != 2 && K * M <= 40 * M;
+    if (prune && threadIdx.x < 3) {
+        // the same fixed third control point and velocity step the solve kernel's presolve uses
+        const int k = threadIdx.x;
+        const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
+                     acc = (double) p.state[agent * 9 + 6 + k];
+        const double c1 = pos + vel * p.dt / 5.0;
+        s_x0[k] = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - pos;
+        s_x0[3 + k] = p.limits[agent * 8 + k] * p.dt / 5.0;
+    }
+    if (threadIdx.x == 0) s_cnt[0] = 0;
+    __syncthreads();
 
-    for (int e = threadIdx.x; e < K * M; e += blockDim.x) {
+    auto obstacle = [&](size_t j, double& o_r, double& o_dw) -> size_t {
+        if (p.obs_index) {
+            const size_t src = (size_t) p.obs_index[j];
+            o_r = (double) (float) p.all_meta[src * 2 + 0]; o_dw = (double) (float) p.all_meta[src * 2 + 1];   // agent_manager.cpp:184-199
+            return src;
+        }
+        o_r = (double) p.obs_meta[j * 4 + 0]; o_dw = (double) p.obs_meta[j * 4 + 1];
+        return j;
+    };
+
+    int n_work = K * M;
+    if (prune) {
+        // Phase 1: a pair (oi, m) is dropped when  min_i u . r_i  >  R + 2 e_max  for the unit vector u along the
+        // centroid of the relative control points r_i (any unit u bounds the hull's distance to the origin from below):
+        // with n the hull's unit normal, every row reads  1/2 n . r_i + n . e >= 1/2 R  where e = T(c - c0_i) is the
+        // move of the control point away from the initial trajectory, and |e| <= |T(x0 - c0_i)| + steps |T(vmax dt/5)|
+        // for every c the velocity rows allow (T: z / downwash).  A margin of 1e-3 covers the float roundings.
+        for (int e = threadIdx.x; e < K * M; e += blockDim.x) {
+            const int oi = e / M, m = e % M;
+            const size_t j = (size_t) obs0 + oi;
+            double o_r, o_dw;
+            const size_t src = obstacle(j, o_r, o_dw);
+            bool drop = false;
+            if (!(p.generator == 1 && m == M - 1)) {
+                const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);
+                const double iz = 1.0 / downwash;
+                const float* ot = (p.obs_index ? p.all_traj : p.obs_traj) + (src * M + m) * 18;
+                double r[6][3], cx = 0, cy = 0, cz = 0, emax = 0;
+                const double vstep = sqrt(s_x0[3] * s_x0[3] + s_x0[4] * s_x0[4] + s_x0[5] * s_x0[5] * iz * iz);
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const double ox = (double) s_own[m * 18 + i * 3], oy = (double) s_own[m * 18 + i * 3 + 1], oz = (double) s_own[m * 18 + i * 3 + 2];
+                    r[i][0] = ox - (double) ot[i * 3]; r[i][1] = oy - (double) ot[i * 3 + 1]; r[i][2] = (oz - (double) ot[i * 3 + 2]) * iz;
+                    cx += r[i][0]; cy += r[i][1]; cz += r[i][2];
+                    if (m == 0 && i < 3) continue;                                      // no such rows (traj_optimizer.cpp:404)
+                    const double ex = s_x0[0] - ox, ey = s_x0[1] - oy, ez = (s_x0[2] - oz) * iz;
+                    emax = fmax(emax, sqrt(ex * ex + ey * ey + ez * ez) + (double) (5 * m + i - 2) * vstep);
+                }
+                const double cn = sqrt(cx * cx + cy * cy + cz * cz);
+                if (cn > 0.0) {
+                    double lb = 1e300;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) lb = fmin(lb, (r[i][0] * cx + r[i][1] * cy + r[i][2] * cz) / cn);
+                    drop = lb > (o_r + a_r) + 2.0 * emax + 1e-3;
+                }
+            }
+            if (drop) {
+                double* no = p.normals + (j * M + m) * 3;
+                no[0] = 0.0; no[1] = 0.0; no[2] = 0.0;
+                double* ro = p.rhs + (j * M + m) * 6;
+#pragma unroll
+                for (int i = 0; i < 6; i++) ro[i] = 0.0;
+            } else {
+                s_list[atomicAdd(&s_cnt[0], 1)] = (unsigned short) e;      // (order does not matter: pairs are independent)
+            }
+        }
+        __syncthreads();
+        n_work = s_cnt[0];
+    }
+
+    for (int w = threadIdx.x; w < n_work; w += blockDim.x) {
+        const int e = prune ? (int) s_list[w] : w;
         const int oi = e / M, m = e % M;
         const size_t j = (size_t) obs0 + oi;
-        const double o_r = (double) p.obs_meta[j * 4 + 0], o_dw = (double) p.obs_meta[j * 4 + 1];
+        double o_r, o_dw;
+        const size_t src = obstacle(j, o_r, o_dw);
         const double collision_dist = o_r + a_r;                                    // traj_planner.cpp:642, :661
         const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);            // downwashBetween :1229-1240
         const float dwf = (float) downwash;
         const bool transform = !(p.generator == 1 && p.dim == 2);                   // :666-672
-        const float* ot = p.obs_traj + (j * M + m) * 18;
+        const float* obase = p.obs_index ? p.all_traj : p.obs_traj;
+        const float* ot = obase + (src * M + m) * 18;
+        const float* ogoal = p.obs_index ? p.all_goal + src * 3 : p.obs_goal + j * 3;
+        const float* opos = p.obs_index ? p.all_state + src * 9 : p.obs_position + j * 3;
 
         f3 own[6], obs[6], own_t[6], obs_t[6];
 #pragma unroll
@@ -262,7 +360,7 @@ lsc_assemble_kernel(const AssembleParams p) {
         f3 pt[6];
         if (p.generator == 2) {                                                     // generateBVC :708-736
             f3 a0 = f3_make(s_own[0], s_own[1], __fdiv_rn(s_own[2], dwf));
-            const float* o0p = p.obs_traj + j * M * 18;
+            const float* o0p = obase + src * M * 18;
             f3 o0 = f3_make(o0p[0], o0p[1], __fdiv_rn(o0p[2], dwf));
             const f3 diff = f3_sub(a0, o0);
             normal = f3_normalized(diff);
@@ -270,7 +368,7 @@ lsc_assemble_kernel(const AssembleParams p) {
 #pragma unroll
             for (int i = 0; i < 6; i++) { d[i] = dd; pt[i] = obs[i]; }
         } else if (p.generator == 1 && m == M - 1) {                                // generateCLSC :691-703
-            const f3 og = f3_make(p.obs_goal[j * 3], p.obs_goal[j * 3 + 1], p.obs_goal[j * 3 + 2]);
+            const f3 og = f3_make(ogoal[0], ogoal[1], ogoal[2]);
             const f3 ag = f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]);
             const ClosestPts cp = closest_points_segments(obs_t[5], og, own_t[5], ag);
             normal = f3_normalized(f3_sub(cp.cp2, cp.cp1));
@@ -288,7 +386,7 @@ lsc_assemble_kernel(const AssembleParams p) {
             normal = f3_normalized(f3_make((float) v[0], (float) v[1], (float) v[2]));   // geometry.hpp:292, :1196
             if (p.generator == 0 && f3_norm(normal) < 1e-5) {                       // :626-634
                 f3 vec = f3_sub(f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]),
-                                f3_make(p.obs_position[j * 3], p.obs_position[j * 3 + 1], p.obs_position[j * 3 + 2]));
+                                f3_make(opos[0], opos[1], opos[2]));
                 vec.z = (float) ((double) vec.z / downwash);                        // coordinateTransform :1262-1266
                 normal = f3_normalized(vec);
             }

@@ -159,10 +159,35 @@ extern "C" int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_ag
     if ((generator == LSCQP_GEN_CLSC && (!obs_goal || !agent_goal)) || (generator == LSCQP_GEN_LSC && (!obs_position || !agent_goal)))
         return fail(LSCQP_E_INVALID, "generator needs goal / position arrays");
     if (n_agents == 0) return 0;
-    AssembleParams p;
+    AssembleParams p{};
     p.n_agents = n_agents; p.generator = generator; p.dim = h->cfg.dim;
     p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
     p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;
+    p.normals = normals_out; p.rhs = rhs_out;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
+    else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prune, int n_agents, const float* own_traj,
+                                        const double* agent_meta, const float* agent_goal, const float* state,
+                                        const double* limits, const int* obs_offsets, const int* obs_index,
+                                        const float* all_traj, const double* all_meta, const float* all_goal,
+                                        const float* all_state, double* normals_out, double* rhs_out, void* stream) {
+    if (!h || n_agents < 0 || !own_traj || !agent_meta || !agent_goal || !obs_offsets || !obs_index || !all_traj || !all_meta ||
+        !all_goal || !all_state || !normals_out || !rhs_out)
+        return fail(LSCQP_E_INVALID, "null argument");
+    if (generator < 0 || generator > 2) return fail(LSCQP_E_INVALID, "unknown generator");
+    if (prune && (!state || !limits)) return fail(LSCQP_E_INVALID, "prune needs state and limits");
+    if (n_agents == 0) return 0;
+    AssembleParams p{};
+    p.n_agents = n_agents; p.generator = generator; p.dim = h->cfg.dim;
+    p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
+    p.obs_index = obs_index; p.all_traj = all_traj; p.all_meta = all_meta; p.all_goal = all_goal; p.all_state = all_state;
+    p.prune = prune ? 1 : 0; p.state = state; p.limits = limits; p.dt = h->cfg.dt;
     p.normals = normals_out; p.rhs = rhs_out;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
@@ -434,13 +459,12 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     }
     CK(cudaMemcpyAsync(h->d_ameta.p, agent_meta, n_agents * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (sumK) CK(cudaMemcpyAsync(h->d_index.p, obs_index, sumK * sizeof(int), cudaMemcpyHostToDevice, st));
-    int rc = lscqp_gather_obstacles(h, (int) sumK, h->d_index.as<int>(), h->d_own.as<float>(), h->d_ameta.as<double>(),
-                                    h->d_goal.as<float>(), h->d_state.as<float>(), h->d_otraj.as<float>(),
-                                    h->d_ometa.as<float>(), h->d_ogoal.as<float>(), h->d_opos.as<float>(), st);
-    if (rc) return rc;
-    rc = lscqp_assemble_lsc_batch(h, generator, n_agents, h->d_own.as<float>(), h->d_ameta.as<double>(), h->d_goal.as<float>(),
-                                  h->d_off.as<int>(), h->d_otraj.as<float>(), h->d_ometa.as<float>(), h->d_ogoal.as<float>(),
-                                  h->d_opos.as<float>(), h->d_normals.as<double>(), h->d_rhs.as<double>(), st);
+    // obstacles are the batch's own agents: the assembly reads them in place through the index list (no gathered
+    // copies) and drops the (obstacle, segment) pairs that provably cannot bind (exact; presolve bit 0)
+    int rc = lscqp_assemble_lsc_fused(h, generator, h->cfg.presolve & 1, n_agents, h->d_own.as<float>(), h->d_ameta.as<double>(),
+                                      h->d_goal.as<float>(), h->d_state.as<float>(), h->d_limits.as<double>(), h->d_off.as<int>(),
+                                      h->d_index.as<int>(), h->d_own.as<float>(), h->d_ameta.as<double>(), h->d_goal.as<float>(),
+                                      h->d_state.as<float>(), h->d_normals.as<double>(), h->d_rhs.as<double>(), st);
     if (rc) return rc;
     rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
                            h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->cfg.comm_range > 0 ? h->d_wp.as<float>() : nullptr,

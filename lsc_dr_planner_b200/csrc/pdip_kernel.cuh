@@ -685,6 +685,19 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     int* s_keep = s_act + C::KRAW;
     for (int e = tid; e < C::KRAW; e += NT) s_keep[e] = (e < K && !p.presolve) ? 1 : 0;
     cta_sync<C>();
+    if (p.presolve) {
+        // the same reach box makes the bound rows (world box / SFC box, :238-270, :372-397) of a control point redundant
+        // when it lies strictly inside them: dropped (multipliers zero), exact like the obstacle rows below
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = tid + u * NT;
+            if (!(bmask[u] & 3u)) continue;
+            const int k_v = v / NCP, m_v = (v % NCP) / 6, i_v = v % 6;
+            const double reach = (double) (5 * m_v + i_v - 2) * s_vlim[k_v];
+            if (s_x0[k_v * 3 + 2] - reach - s_lb[k_v * M + m_v] > 1e-6 && s_ub[k_v * M + m_v] - (s_x0[k_v * 3 + 2] + reach) > 1e-6)
+                bmask[u] &= ~3u;
+        }
+    }
     if (p.presolve && lsc_thread) {
         const double steps = (double) (5 * m_cp + i_cp - 2);
         for (int oi = grp; oi < K; oi += G) {
@@ -767,13 +780,16 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     double red[4];
     {
-        int nb = 0;
+        int nb = 0, bnd = 0;
 #pragma unroll
-        for (int u = 0; u < VPT; u++) nb += __popc(bmask[u]);
-        red[0] = (double) (nrow + nb); red[1] = 0; red[2] = 0; red[3] = 0;
+        for (int u = 0; u < VPT; u++) { nb += __popc(bmask[u]); bnd |= (int) (bmask[u] & 3u); }
+        red[0] = (double) (nrow + nb); red[1] = 0; red[2] = 0; red[3] = (double) bnd;
         block_reduce4<C>(red, s_red, red_phase);       // (barrier: s_c is complete after this)
     }
     const double n_rows = red[0];
+    // CTA-uniform: no bound row left anywhere -> the row loops of the several-variables-per-thread instances start at
+    // the velocity rows (with one variable per thread the masked rows cost nothing worth a branch)
+    const int e_first = (VPT > 1 && !(red[3] > 0.0)) ? 2 : 0;
 
     // helpers -----------------------------------------------------------------------------------
     // directional change of the six box rows of variable slot u for a full-space direction dv
@@ -1111,7 +1127,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
                 for (int e = 0; e < NBX; e++) {
                     W[e] = 0.0; uu[e] = 0.0;
-                    if (!(bmask[u] >> e & 1u)) continue;
+                    if (e < e_first || !(bmask[u] >> e & 1u)) continue;
                     if (have_step) {
                         const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
                         const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
@@ -1165,7 +1181,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 box_dq(s_dca, dqa, u);
 #pragma unroll
                 for (int e = 0; e < NBX; e++) {
-                    if (!(bmask[u] >> e & 1u)) continue;
+                    if (e < e_first || !(bmask[u] >> e & 1u)) continue;
                     const double rs = fast_rcp(bs[u][e]), W = bl[u][e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[u][e] - W * dsa;
                     const double z = dsa * rs;
@@ -1207,7 +1223,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
                 for (int e = 0; e < NBX; e++) {
                     W[e] = 0.0; uu[e] = 0.0;
-                    if (!(bmask[u] >> e & 1u)) continue;
+                    if (e < e_first || !(bmask[u] >> e & 1u)) continue;
                     const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
                     const double rc = bs[u][e] * bl[u][e] + dsa * dla - sigmu;
@@ -1246,7 +1262,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
                 box_dq(s_dca, dqa, u); box_dq(s_dc, dq, u);
 #pragma unroll
                 for (int e = 0; e < NBX; e++) {
-                    if (!(bmask[u] >> e & 1u)) continue;
+                    if (e < e_first || !(bmask[u] >> e & 1u)) continue;
                     const double rs = fast_rcp(bs[u][e]), Wo = bl[u][e] * rs;
                     const double dsa = dqa[e] - rp, dla = -bl[u][e] - Wo * dsa;
                     const double rc = bs[u][e] * bl[u][e] + dsa * dla - sigmu;

@@ -65,11 +65,19 @@ class BatchPlanner:
         return DeviceBatch(batch, self.device)
 
     def assemble_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0):
-        """gather neighbours + LSC assembly (constructLSC for every agent)"""
+        """gather neighbours + LSC assembly (constructLSC for every agent): the reference's planes for every
+        (obstacle, segment), materialised obstacle copies (the layout lscqp_assemble_lsc_batch documents)"""
         self.qp.gather_obstacles(d.sum_k, d.obs_index, d.own_traj, d.agent_meta, d.goal, d.state,
                                  d.obs_traj, d.obs_meta, d.obs_goal, d.obs_position, stream)
         self.qp.assemble_lsc_batch(generator, d.n, d.own_traj, d.agent_meta, d.goal, d.obs_offsets, d.obs_traj,
                                    d.obs_meta, d.obs_goal, d.obs_position, d.normals, d.rhs, stream)
+
+    def assemble_fused_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0, prune: bool | None = None):
+        """the replan path's assembly: obstacles read in place through the neighbour ids (no gathered copies) and, with
+        presolve on, (obstacle, segment) pairs that provably cannot bind dropped before the hull enumeration (exact)"""
+        prune = bool(int(self.cfg.presolve) & 1) if prune is None else prune
+        self.qp.assemble_lsc_fused(generator, prune, d.n, d.own_traj, d.agent_meta, d.goal, d.state, d.limits, d.obs_offsets,
+                                   d.obs_index, d.own_traj, d.agent_meta, d.goal, d.state, d.normals, d.rhs, stream)
 
     def solve_device(self, d: DeviceBatch, want_kkt: bool = False, dual=None, stream: int = 0, warm: bool = True):
         """trajOptimization for every agent (initial_traj = the batch's own_traj as the solver's starting point)"""
@@ -78,7 +86,7 @@ class BatchPlanner:
                             initial_traj=d.own_traj if warm else None, next_waypoint=d.next_waypoint)
 
     def replan_device(self, d: DeviceBatch, generator: int = capi.GEN_LSC, stream: int = 0):
-        self.assemble_device(d, generator, stream)
+        self.assemble_fused_device(d, generator, stream)
         self.solve_device(d, stream=stream)
 
     def goal_device(self, d: DeviceBatch, stream: int = 0):
@@ -93,7 +101,7 @@ class BatchPlanner:
         infeasible keep their previous goal and are reported through d.goal_status (the reference throws QPFAILED and
         keeps initial_traj for them); launches must be stream-ordered by the caller (same stream)."""
         import torch
-        self.assemble_device(d, generator, stream)
+        self.assemble_fused_device(d, generator, stream, prune=False)     # the goal LP needs every last-point plane
         self.goal_device(d, stream)
         ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
         with torch.cuda.stream(ext):

@@ -26,8 +26,7 @@ print("step total       %.3f ms" % timed(sim.step))
 print("neighbours       %.3f ms" % timed(sim.neighbours))
 qp = sim.planner.qp; n = sim.n_local
 idx = sim.neighbours(); own = sim.traj.contiguous()
-print("gather           %.3f ms" % timed(lambda: qp.gather_obstacles(n * sim.K, idx, sim.traj, sim.agent_meta, sim.goal, sim.state, sim.obs_traj, sim.obs_meta, sim.obs_goal, sim.obs_position)))
-print("assemble         %.3f ms" % timed(lambda: qp.assemble_lsc_batch(sim.generator, n, own, sim.agent_meta, sim.goal, sim.obs_offsets, sim.obs_traj, sim.obs_meta, sim.obs_goal, sim.obs_position, sim.normals, sim.rhs)))
+print("assemble (fused) %.3f ms" % timed(lambda: qp.assemble_lsc_fused(sim.generator, sim.prune, n, own, sim.agent_meta, sim.goal, sim.state, sim.limits, sim.obs_offsets, idx, sim.traj, sim.agent_meta, sim.goal, sim.state, sim.normals, sim.rhs)))
 print("solve            %.3f ms" % timed(lambda: qp.solve_batch(n, sim.state, sim.goal, sim.limits, None, sim.obs_offsets, sim.normals, sim.rhs, sim.ctrl, sim.cost, sim.status, sim.iters, initial_traj=own)))
 print("iters mean %.2f  status!=0: %d" % (float(sim.iters.float().mean()), int((sim.status != 0).sum())))
 print("step kernel      %.3f ms" % timed(lambda: qp.step_batch(n, sim.ctrl, sim.cfg.dt, sim.traj_out, sim.state_out, sim.shifted)))

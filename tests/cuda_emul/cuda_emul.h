@@ -92,6 +92,7 @@ inline int __any_sync(unsigned, int pred) {
     __syncwarp();
     return r;
 }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }   // fibers are cooperative
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __fdividef(float a, float b) { return a / b; }

@@ -57,13 +57,29 @@ extern "C" int emul_assemble_lsc_batch(const lscqp_config* cfg, int generator, i
                                        const double* agent_meta, const float* agent_goal, const int* obs_offsets,
                                        const float* obs_traj, const float* obs_meta, const float* obs_goal,
                                        const float* obs_position, double* normals_out, double* rhs_out) {
-    AssembleParams p;
+    AssembleParams p{};
     p.n_agents = n_agents; p.generator = generator; p.dim = cfg->dim;
     p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
     p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;
     p.normals = normals_out; p.rhs = rhs_out;
-    if (cfg->M == 5) emu::launch(n_agents, 128, 5 * 18 * 4 + 64, [&]() { lsc_assemble_kernel<5>(p); });
-    else if (cfg->M == 10) emu::launch(n_agents, 128, 10 * 18 * 4 + 64, [&]() { lsc_assemble_kernel<10>(p); });
+    if (cfg->M == 5) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<5>(p); });
+    else if (cfg->M == 10) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<10>(p); });
+    else return LSCQP_E_INVALID;
+    return 0;
+}
+
+extern "C" int emul_assemble_lsc_fused(const lscqp_config* cfg, int generator, int prune, int n_agents, const float* own_traj,
+                                       const double* agent_meta, const float* agent_goal, const float* state, const double* limits,
+                                       const int* obs_offsets, const int* obs_index, const float* all_traj, const double* all_meta,
+                                       const float* all_goal, const float* all_state, double* normals_out, double* rhs_out) {
+    AssembleParams p{};
+    p.n_agents = n_agents; p.generator = generator; p.dim = cfg->dim;
+    p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
+    p.obs_index = obs_index; p.all_traj = all_traj; p.all_meta = all_meta; p.all_goal = all_goal; p.all_state = all_state;
+    p.prune = prune; p.state = state; p.limits = limits; p.dt = cfg->dt;
+    p.normals = normals_out; p.rhs = rhs_out;
+    if (cfg->M == 5) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<5>(p); });
+    else if (cfg->M == 10) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<10>(p); });
     else return LSCQP_E_INVALID;
     return 0;
 }

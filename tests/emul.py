@@ -77,3 +77,18 @@ def select_neighbours(n_total, lo, n_local, K, comm_range, state):
     rc = lib().emul_select_neighbours(n_total, lo, n_local, K, C.c_double(comm_range), _p(state, np.float32), _p(out, np.int32))
     assert rc == 0, rc
     return out
+
+
+def assemble_fused(cfg, generator, prune, batch):
+    """gather-free (optionally pruned) assembly of a whole workloads.Batch whose obstacles are its own agents"""
+    cc = capi.make_config(cfg)
+    n = batch.n_agents; sk = int(batch.obs_offsets[n])
+    normals = np.full((sk, cfg.M, 3), np.nan); rhs = np.full((sk, cfg.M, 6), np.nan)
+    meta = np.ascontiguousarray(batch.agent_meta, np.float64)
+    rc = lib().emul_assemble_lsc_fused(C.byref(cc), generator, int(prune), n, _p(batch.own_traj, np.float32), _p(meta, np.float64),
+                                       _p(batch.goal, np.float32), _p(batch.state, np.float32), _p(batch.limits, np.float64),
+                                       _p(batch.obs_offsets, np.int32), _p(batch.obs_index, np.int32), _p(batch.own_traj, np.float32),
+                                       _p(meta, np.float64), _p(batch.goal, np.float32), _p(batch.state, np.float32),
+                                       _p(normals, np.float64), _p(rhs, np.float64))
+    assert rc == 0, rc
+    return normals, rhs

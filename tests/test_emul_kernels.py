@@ -182,3 +182,38 @@ def test_neighbour_selection_kernel(n_total, lo, n_local, K, comm):
     state[5, :3] = state[6, :3]                               # coincident agents: tie at distance zero
     out = emul.select_neighbours(n_total, lo, n_local, K, comm, state)
     _check_neighbours(state, lo, out, K, comm)
+
+
+@pytest.mark.parametrize("generator,M,dim", [(0, 5, 3), (1, 5, 3), (1, 10, 2)])
+def test_fused_assembly_reads_in_place_and_prunes_exactly(generator, M, dim):
+    """lscqp_assemble_lsc_fused: (i) without prune the planes equal the gathered path bit for bit; (ii) with prune the
+    dropped (obstacle, segment) pairs are zero normals, the kept ones are unchanged, and the QP solutions do not move"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=1)
+    batch = W.make_forest_batch(48, K=20, cfg=cfg)
+    near_goals(batch)
+    batch.own_traj = np.ascontiguousarray(batch.own_traj)
+    n = 12
+    full = batch
+    n_ref, r_ref = emul.assemble(cfg, generator, batch.n_agents, batch.own_traj, batch.agent_meta, batch.goal, batch.obs_offsets,
+                                 batch.obs_traj(), batch.obs_meta(), batch.obs_goal(), batch.obs_position())
+    n0, r0 = emul.assemble_fused(cfg, generator, False, full)
+    assert np.array_equal(n0, n_ref) and np.array_equal(r0, r_ref)
+    n1, r1 = emul.assemble_fused(cfg, generator, True, full)
+    dropped = (n1 == 0).all(axis=2) & ~(n_ref == 0).all(axis=2)
+    kept = ~dropped
+    assert np.array_equal(n1[kept], n_ref[kept]) and np.array_equal(r1[kept], r_ref[kept]) and (r1[dropped] == 0).all()
+    if dim == 3:
+        assert dropped.mean() > 0.3, dropped.mean()            # most far pairs never reach the hull enumeration
+        if generator == 1:
+            assert not dropped[:, M - 1].any()                  # CLSC's last segment follows another rule: never pruned
+    else:
+        assert not dropped.any()                                # 2-D rows drop the z term: no pruning
+    sk = int(batch.obs_offsets[n])
+    args = (cfg, n, np.ascontiguousarray(batch.state[:n]), np.ascontiguousarray(batch.goal[:n]), np.ascontiguousarray(batch.limits[:n]),
+            None, np.ascontiguousarray(batch.obs_offsets[:n + 1]))
+    c_ref = emul.solve_batch(*args, np.ascontiguousarray(n_ref[:sk]), np.ascontiguousarray(r_ref[:sk]),
+                             initial_traj=np.ascontiguousarray(batch.own_traj[:n]))
+    c_pr = emul.solve_batch(*args, np.ascontiguousarray(n1[:sk]), np.ascontiguousarray(r1[:sk]),
+                            initial_traj=np.ascontiguousarray(batch.own_traj[:n]))
+    assert (c_ref[2] == 0).all() and (c_pr[2] == 0).all()
+    assert np.abs(c_ref[0] - c_pr[0]).max() < 1e-7, np.abs(c_ref[0] - c_pr[0]).max()

@@ -443,3 +443,31 @@ def test_closed_loop_cuda_graph_matches_eager():
     assert sims[1]._graph is not None
     assert torch.equal(sims[0].state, sims[1].state) and torch.equal(sims[0].traj, sims[1].traj)
     assert sims[0].failed_total == sims[1].failed_total == 0
+
+
+@pytest.mark.parametrize("generator,M,dim", [(capi.GEN_LSC, 5, 3), (capi.GEN_CLSC, 5, 3), (capi.GEN_CLSC, 10, 2)])
+def test_fused_pruned_assembly_is_exact_gpu(generator, M, dim):
+    """the replan path's assembly (neighbours read in place, provably inactive pairs dropped) against the materialised
+    one: kept planes bit-identical, dropped pairs zero, and the QP solutions unchanged at full batch size"""
+    import torch
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=capi.MODE_LSC)
+    batch = W.make_forest_batch(1024, K=40 if M == 5 else 9, cfg=cfg)
+    near_goals(batch)
+    planner = _planner(batch.cfg)
+    d = planner.upload(batch)
+    planner.assemble_device(d, generator)
+    planner.solve_device(d)
+    torch.cuda.synchronize()
+    n_ref, r_ref, c_ref, s_ref = d.normals.clone(), d.rhs.clone(), d.ctrl.clone(), d.status.clone()
+    planner.assemble_fused_device(d, generator, prune=False)
+    torch.cuda.synchronize()
+    assert torch.equal(d.normals, n_ref) and torch.equal(d.rhs, r_ref)
+    planner.assemble_fused_device(d, generator, prune=True)
+    planner.solve_device(d)
+    torch.cuda.synchronize()
+    dropped = (d.normals == 0).all(dim=2) & ~(n_ref == 0).all(dim=2)
+    assert torch.equal(d.normals[~dropped], n_ref[~dropped]) and torch.equal(d.rhs[~dropped], r_ref[~dropped])
+    assert float(dropped.float().mean()) > (0.5 if dim == 3 else -1.0)
+    ok = (s_ref == 0) & (d.status == 0)
+    assert int(ok.sum()) >= int((s_ref == 0).sum())
+    assert float((d.ctrl[ok] - c_ref[ok]).abs().max()) < 1e-6
