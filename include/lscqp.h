@@ -201,6 +201,13 @@ int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, i
 int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step,
         float* traj_out, float* state_out, float* shifted_traj_out, void* stream);
 
+/* TrajPlanner::isSolValid (src/traj_planner.cpp:990-1045) for every agent: SFC containment of the float control points
+ * (use_sfc; segment 0 from point phi on) and velocity / acceleration of the state at the replanning period within 1 %
+ * of the limits.  traj / state_at_step are the outputs of lscqp_step_batch (step = multisim time step).
+ * valid_out[a] = 1 | 0; in DLSC mode the reference re-runs the solver when the check fails (:763-766). */
+int lscqp_validate_batch(lscqp_handle* h, int n_agents, const float* traj, const float* state_at_step,
+        const double* limits, const float* sfc, int* valid_out, void* stream);
+
 /* Measurement aid (bench.py): sustained FP64 FMA rate of the device in GFLOP/s from a register-resident DFMA
  * microbenchmark (8 independent chains per thread), the denominator of the solve kernel's FP64 view
  * (MEASURED_PEAKS.json holds only the HBM and bf16 peaks). */

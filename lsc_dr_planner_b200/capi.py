@@ -54,7 +54,7 @@ def load():
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
-                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused"):
+                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -162,6 +162,11 @@ class LscQp:
         self._check(self.lib.lscqp_gather_obstacles(self.h, n_obs, _dp(obs_index), _dp(own_traj), _dp(agent_meta),
                                                     _dp(agent_goal), _dp(state), _dp(obs_traj), _dp(obs_meta),
                                                     _dp(obs_goal), _dp(obs_position), C.c_void_p(stream)))
+
+    def validate_batch(self, n, traj, state_at_step, limits, sfc, valid_out, stream=0):
+        """TrajPlanner::isSolValid for every agent (traj_planner.cpp:990-1045)"""
+        self._check(self.lib.lscqp_validate_batch(self.h, n, _dp(traj), _dp(state_at_step), _dp(limits), _dp(sfc),
+                                                  _dp(valid_out), C.c_void_p(stream)))
 
     def select_neighbours(self, n_total, lo, n_local, K, comm_range, state, obs_index_out, stream=0):
         """broadcastMsgs on the device: K nearest (in-range first) neighbour ids of the agents [lo, lo + n_local)"""

@@ -254,6 +254,20 @@ extern "C" int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int
     return 0;
 }
 
+extern "C" int lscqp_validate_batch(lscqp_handle* h, int n_agents, const float* traj, const float* state_at_step,
+                                    const double* limits, const float* sfc, int* valid_out, void* stream) {
+    if (!h || n_agents < 0 || !traj || !state_at_step || !limits || !valid_out) return fail(LSCQP_E_INVALID, "null argument");
+    if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+    if (n_agents == 0) return 0;
+    ValidateParams p;
+    p.n_agents = n_agents; p.M = h->cfg.M; p.dim = h->cfg.dim; p.use_sfc = h->cfg.use_sfc;
+    p.traj = traj; p.state = state_at_step; p.limits = limits; p.sfc = sfc; p.valid_out = valid_out;
+    validate_kernel<<<(n_agents + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int lscqp_goal_batch(lscqp_handle* h, int n_agents, const float* goal, const float* next_waypoint,
                                 const float* sfc, const int* obs_offsets, const double* normals, const double* rhs,
                                 float* goal_out, double* t_out, int* status_out, void* stream) {

@@ -96,4 +96,42 @@ step_kernel(const StepParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TrajPlanner::isSolValid (src/traj_planner.cpp:990-1045), the check trajOptimization applies to a solution before
+// accepting it in DLSC mode (:763-766): SFC containment of the float control points (segment 0: points phi..n only;
+// Box::isPointInBox with its SP_EPSILON_FLOAT slack, src/collision_constraints.cpp:81-111) when world_use_octomap, and
+// the velocity / acceleration of the state at the replanning period against the limits with 1 % tolerance.
+// (The LSC check is commented out in the reference, :1012-1027.)  Thread per agent.
+struct ValidateParams {
+    int n_agents, M, dim, use_sfc;
+    const float*  traj;      // [n][M][6][3]  result.desired_traj (float)
+    const float*  state;     // [n][9]        desired_traj.getStateAt(multisim_time_step)
+    const double* limits;    // [n][8]        max_vel[3], max_acc[3], ...
+    const float*  sfc;       // [n][M][6]     (use_sfc)
+    int* valid_out;          // [n]  1 valid | 0 not valid
+};
+
+__global__ void __launch_bounds__(128) validate_kernel(const ValidateParams p) {
+    const int agent = blockIdx.x * blockDim.x + threadIdx.x;
+    if (agent >= p.n_agents) return;
+    bool ok = true;
+    if (p.use_sfc) {
+        for (int m = 0; m < p.M; m++) {
+            const float* box = p.sfc + ((size_t) agent * p.M + m) * 6;
+            for (int i = (m == 0 ? 3 : 0); i < 6; i++) {                         // :995-1007
+                const float* c = p.traj + (((size_t) agent * p.M + m) * 6 + i) * 3;
+                for (int k = 0; k < 3; k++)
+                    ok = ok && ((double) c[k] > (double) box[k] - 1e-5) && ((double) c[k] < (double) box[3 + k] + 1e-5);
+            }
+        }
+    }
+    const double tol = 1.0 + 0.01;                                               // dyn_err_tol_ratio :1030
+    for (int k = 0; k < p.dim; k++) {
+        const double v = fabs((double) p.state[(size_t) agent * 9 + 3 + k]), a = fabs((double) p.state[(size_t) agent * 9 + 6 + k]);
+        if (v > p.limits[(size_t) agent * 8 + k] * tol) ok = false;              // :1033-1036
+        if (a > p.limits[(size_t) agent * 8 + 3 + k] * tol) ok = false;          // :1037-1040
+    }
+    p.valid_out[agent] = ok ? 1 : 0;
+}
+
 }  // namespace lscqp

@@ -724,3 +724,26 @@ int orc_goal_solve(const orc_config *cfg, const float *goal, const float *waypoi
     v3_store(goal_out, v3_add(v3_scale(v3_sub(g, w), (float) t), w));
     return status;
 }
+
+/* TrajPlanner::isSolValid src/traj_planner.cpp:990-1045 (Box::isPointInBox / isSegmentInBox
+ * src/collision_constraints.cpp:81-111); the LSC part is commented out in the reference (:1012-1027).
+ * state9 = desired_traj.getStateAt(multisim_time_step).  abs() there is the floating-point overload. */
+int orc_is_sol_valid(const orc_config *cfg, const orc_agent *ag, const float *traj /* [M][n+1][3] */,
+                     const float *state9, const float *sfc /* [M][6] or NULL */) {
+    int N = cfg->n + 1;
+    if (cfg->use_sfc && sfc) {
+        for (int m = 0; m < cfg->M; m++)
+            for (int i = (m == 0 ? cfg->phi : 0); i < N; i++) {
+                const float *c = traj + ((size_t) m * N + i) * 3, *b = sfc + (size_t) m * 6;
+                for (int k = 0; k < 3; k++)
+                    if (!((double) c[k] > (double) b[k] - SP_EPSILON_FLOAT && (double) c[k] < (double) b[3 + k] + SP_EPSILON_FLOAT))
+                        return 0;
+            }
+    }
+    double dyn_err_tol_ratio = 0.01;
+    for (int k = 0; k < cfg->dim; k++) {
+        if (fabs((double) state9[3 + k]) > ag->max_vel[k] * (1 + dyn_err_tol_ratio)) return 0;
+        if (fabs((double) state9[6 + k]) > ag->max_acc[k] * (1 + dyn_err_tol_ratio)) return 0;
+    }
+    return 1;
+}

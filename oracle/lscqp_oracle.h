@@ -103,6 +103,9 @@ void orc_get_state_at(int M, int n, double dt, const float *traj, double time, f
 void orc_shift_traj(int M, int n, const float *prev, float *out);
 void orc_const_vel_traj(int M, int n, double dt, const float *pos, const float *vel, float *out);
 
+/* TrajPlanner::isSolValid, src/traj_planner.cpp:990-1045 (1 valid | 0 not) */
+int orc_is_sol_valid(const orc_config *cfg, const orc_agent *ag, const float *traj, const float *state9, const float *sfc);
+
 /* GoalOptimizer, src/goal_optimizer.cpp:7-165: rows a t + b >= 0 of the one-variable LP (returns the row count,
  * a / b sized 2 dim + K) and its closed-form optimum (0 ok | 2 infeasible = the reference's QPFAILED throw). */
 int orc_goal_rows(const orc_config *cfg, const float *goal, const float *waypoint, int K,

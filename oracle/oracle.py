@@ -282,6 +282,15 @@ def const_vel_traj(cfg: Config, pos, vel) -> np.ndarray:
     return out
 
 
+def is_sol_valid(cfg: Config, ag: Agent, traj, state9, sfc=None) -> bool:
+    """TrajPlanner::isSolValid (src/traj_planner.cpp:990-1045)"""
+    traj, state9 = _f32(traj), _f32(state9)
+    sfc = None if sfc is None else _f32(sfc)
+    cc, ca = cfg.c(), ag.c()
+    return bool(lib().orc_is_sol_valid(C.byref(cc), C.byref(ca), _p(traj, C.c_float), _p(state9, C.c_float),
+                                       _p(sfc, C.c_float) if sfc is not None else None))
+
+
 # ---------------------------------------------------------------- GoalOptimizer (src/goal_optimizer.cpp)
 def goal_rows(cfg: Config, goal, waypoint, lsc_point, lsc_normal, lsc_d, sfc_last=None):
     """rows a t + b >= 0 of the one-variable goal LP (goal_optimizer.cpp:109-165), in the reference's order"""

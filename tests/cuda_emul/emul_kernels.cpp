@@ -114,4 +114,13 @@ extern "C" int emul_select_neighbours(int n_total, int lo, int n_local, int K, d
     return 0;
 }
 
+extern "C" int emul_validate_batch(const lscqp_config* cfg, int n_agents, const float* traj, const float* state, const double* limits,
+                                   const float* sfc, int* valid_out) {
+    ValidateParams p;
+    p.n_agents = n_agents; p.M = cfg->M; p.dim = cfg->dim; p.use_sfc = cfg->use_sfc && sfc;
+    p.traj = traj; p.state = state; p.limits = limits; p.sfc = sfc; p.valid_out = valid_out;
+    emu::launch((n_agents + 127) / 128, 128, 64, [&]() { validate_kernel(p); });
+    return 0;
+}
+
 extern "C" void emul_jerk_gram(int n, int phi, double dt, double* Q) { jerk_gram(n, phi, dt, Q); }

@@ -92,3 +92,12 @@ def assemble_fused(cfg, generator, prune, batch):
                                        _p(normals, np.float64), _p(rhs, np.float64))
     assert rc == 0, rc
     return normals, rhs
+
+
+def validate(cfg, n, traj, state, limits, sfc):
+    cc = capi.make_config(cfg)
+    out = np.zeros(n, np.int32)
+    rc = lib().emul_validate_batch(C.byref(cc), n, _p(traj, np.float32), _p(state, np.float32), _p(limits, np.float64),
+                                   _p(sfc, np.float32), _p(out, np.int32))
+    assert rc == 0, rc
+    return out

@@ -217,3 +217,27 @@ def test_fused_assembly_reads_in_place_and_prunes_exactly(generator, M, dim):
                             initial_traj=np.ascontiguousarray(batch.own_traj[:n]))
     assert (c_ref[2] == 0).all() and (c_pr[2] == 0).all()
     assert np.abs(c_ref[0] - c_pr[0]).max() < 1e-7, np.abs(c_ref[0] - c_pr[0]).max()
+
+
+@pytest.mark.parametrize("M,dim,use_sfc", [(5, 3, True), (10, 2, False), (5, 3, False)])
+def test_validate_kernel_matches_oracle_is_sol_valid(M, dim, use_sfc):
+    """isSolValid (traj_planner.cpp:990-1045): SFC containment + dynamic limits of the state at the replanning period"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=0, use_sfc=use_sfc)
+    batch = W.make_forest_batch(64, K=4, cfg=cfg)
+    rng = np.random.default_rng(3)
+    n = batch.n_agents
+    traj = np.ascontiguousarray(batch.own_traj)
+    cfgo = oracle_config(cfg)
+    state = np.stack([orc.get_state_at(cfgo, traj[a], cfg.dt) for a in range(n)])
+    state[::3, 3:6] *= rng.uniform(2.0, 6.0, (len(state[::3]), 3)).astype(np.float32)        # some beyond the limits
+    state[1::5, 6:9] *= 10.0
+    sfc = None
+    if use_sfc:
+        lo = traj.min(axis=2) - rng.uniform(-0.02, 0.3, (n, M, 3)); hi = traj.max(axis=2) + rng.uniform(-0.02, 0.3, (n, M, 3))
+        sfc = np.ascontiguousarray(np.concatenate([lo, hi], axis=2).astype(np.float32))
+    got = emul.validate(cfg, n, traj, np.ascontiguousarray(state), batch.limits, sfc)
+    want = np.array([orc.is_sol_valid(cfgo, orc.Agent(state[a, :3], state[a, 3:6], state[a, 6:9], batch.goal[a],
+                                                      max_vel=tuple(batch.limits[a, :3]), max_acc=tuple(batch.limits[a, 3:6])),
+                                      traj[a], state[a], None if sfc is None else sfc[a]) for a in range(n)], np.int32)
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < n

@@ -471,3 +471,31 @@ def test_fused_pruned_assembly_is_exact_gpu(generator, M, dim):
     ok = (s_ref == 0) & (d.status == 0)
     assert int(ok.sum()) >= int((s_ref == 0).sum())
     assert float((d.ctrl[ok] - c_ref[ok]).abs().max()) < 1e-6
+
+
+def test_validate_batch_gpu():
+    """lscqp_validate_batch (isSolValid) on the outputs of lscqp_step_batch, against the oracle"""
+    import torch
+    cfg = W.PlannerConfig(M=5, dim=3, planner_mode=capi.MODE_DLSC, use_sfc=True)
+    batch = W.make_forest_batch(256, K=8, cfg=cfg)
+    near_goals(batch)
+    rng = np.random.default_rng(9)
+    n, M = batch.n_agents, cfg.M
+    lo = batch.own_traj.min(axis=2) - rng.uniform(0.05, 0.6, (n, M, 3)); hi = batch.own_traj.max(axis=2) + rng.uniform(0.05, 0.6, (n, M, 3))
+    batch.sfc = np.ascontiguousarray(np.concatenate([lo, hi], axis=2).astype(np.float32))
+    batch.limits[::4, :3] = 0.2                                   # tight velocity limits: some solutions end up not valid
+    planner = _planner(cfg)
+    d = planner.upload(batch)
+    planner.replan_device(d)
+    dev = d.ctrl.device
+    traj = torch.empty((n, M, 6, 3), dtype=torch.float32, device=dev); state = torch.empty((n, 9), dtype=torch.float32, device=dev)
+    valid = torch.zeros(n, dtype=torch.int32, device=dev)
+    planner.qp.step_batch(n, d.ctrl, cfg.dt, traj, state)
+    state[1::7, 3:6] *= 3.0
+    planner.qp.validate_batch(n, traj, state, d.limits, d.sfc, valid)
+    torch.cuda.synchronize()
+    cfgo = oracle_config(cfg)
+    tr, st, got = traj.cpu().numpy(), state.cpu().numpy(), valid.cpu().numpy()
+    want = np.array([orc.is_sol_valid(cfgo, orc.Agent(st[a, :3], st[a, 3:6], st[a, 6:9], batch.goal[a], max_vel=tuple(batch.limits[a, :3]),
+                                                      max_acc=tuple(batch.limits[a, 3:6])), tr[a], st[a], batch.sfc[a]) for a in range(n)], np.int32)
+    assert np.array_equal(got, want) and 0 < want.sum() < n
