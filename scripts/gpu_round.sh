@@ -7,5 +7,6 @@ python scripts/ncu_summary.py ${1:-r01} > gpurun_out/ncu_summary.log 2>&1      #
 cp profiles/traffic.json gpurun_out/traffic.json
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json | cut -c1-600
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_reference.json | cut -c1-300
-timeout 600 python scripts/closed_loop_bench.py > gpurun_out/closed_loop_1gpu.json 2> gpurun_out/closed_loop.err; tail -2 gpurun_out/closed_loop.err; cat gpurun_out/closed_loop_1gpu.json
+timeout 600 python scripts/closed_loop_bench.py --graph > gpurun_out/closed_loop_1gpu.json 2> gpurun_out/closed_loop.err; tail -2 gpurun_out/closed_loop.err; cat gpurun_out/closed_loop_1gpu.json
+timeout 600 python scripts/closed_loop_bench.py --graph --agents 4096 --steps 100 > gpurun_out/closed_loop_4096_1gpu.json 2>> gpurun_out/closed_loop.err; cat gpurun_out/closed_loop_4096_1gpu.json
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
