@@ -239,8 +239,13 @@ __device__ __forceinline__ ClosestPts closest_points_segments(f3 l1s, f3 l1e, f3
 #define LSCQP_ASM_SMEM(name, count) __shared__ float name[count]
 #endif
 
+// (ptxas takes 255 registers when left alone; capped at 80 it spills ~300 bytes and three times as many CTAs fit: 0.20 -> 0.115 ms, measured --
+//  the kernel is latency bound on L2 reads of the neighbours' control points)
+#ifndef LSCQP_ASM_MINBLOCKS
+#define LSCQP_ASM_MINBLOCKS 6
+#endif
 template <int M>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, LSCQP_ASM_MINBLOCKS)
 lsc_assemble_kernel(const AssembleParams p) {
     LSCQP_ASM_SMEM(s_own, M * 18);
 #ifdef LSCQP_CUDA_EMUL

@@ -1,8 +1,7 @@
 #!/bin/bash
-# GPU visit: quick parity check of the default library, then A/B of prebuilt library variants
+# GPU visit: A/B of prebuilt library variants (liblscqp_<tag>.so copied over liblscqp.so in turn)
 mkdir -p gpurun_out
 cp lsc_dr_planner_b200/liblscqp.so /tmp/liblscqp_default.so
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
 for tag in "$@"; do
   cp lsc_dr_planner_b200/liblscqp_$tag.so lsc_dr_planner_b200/liblscqp.so
   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu 2>gpurun_out/ab_$tag.err | tee gpurun_out/ab_$tag.json | python -c "
