@@ -82,6 +82,14 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) {
     __syncwarp();
     return r;
 }
+inline double __shfl_sync(unsigned, double v, int src_lane) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = v;
+    __syncwarp();
+    const double r = s.slot_d[(s.cur & ~31) | (src_lane & 31)];
+    __syncwarp();
+    return r;
+}
 inline int __any_sync(unsigned, int pred) {
     emu::State& s = emu::st();
     s.slot_d[s.cur] = pred ? 1.0 : 0.0;
