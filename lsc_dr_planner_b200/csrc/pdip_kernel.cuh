@@ -29,6 +29,9 @@
 #define LSCQP_DYN_SMEM(name) extern __shared__ double name[]
 #endif
 
+#ifndef LSCQP_FULL_MINCTAS
+#define LSCQP_FULL_MINCTAS 4
+#endif
 #ifndef LSCQP_LIGHT_MINCTAS
 #define LSCQP_LIGHT_MINCTAS 8
 #endif
@@ -116,7 +119,7 @@ struct Cfg {
     static constexpr int VPT = (NV + NT - 1) / NT;       // variables (box-row owners) per thread
     static constexpr int KRAW = 40;                      // obstacle capacity of the ABI (lscqp_config.max_obs <= 40)
     // register budget: 65536 / (MIN_CTAS * NT) per thread (the light instances are shared-memory bound)
-    static constexpr int MIN_CTAS = NT > 128 ? 2 : (NT == 128 ? 3 : LSCQP_LIGHT_MINCTAS);
+    static constexpr int MIN_CTAS = NT > 128 ? 2 : (NT == 128 ? LSCQP_FULL_MINCTAS : LSCQP_LIGHT_MINCTAS);
     static_assert(!COMM || VPT == 1, "communication-range instances keep one variable per thread");
     static_assert(KMAX <= KRAW, "KMAX beyond the ABI capacity");
     // shared memory layout (doubles).  Two regions are shared by buffers whose lifetimes do not overlap:

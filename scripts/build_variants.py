@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 
 VARIANTS = {
+    "full3": ("-DLSCQP_FULL_MINCTAS=3",), "full4": ("-DLSCQP_FULL_MINCTAS=4",),
     "asm2": ("-DLSCQP_ASM_MINBLOCKS=2",), "asm4": ("-DLSCQP_ASM_MINBLOCKS=4",), "asm5": ("-DLSCQP_ASM_MINBLOCKS=5",),
     "asm6": ("-DLSCQP_ASM_MINBLOCKS=6",),
     "g1k8c8": ("-DLSCQP_LIGHT_G=1", "-DLSCQP_LIGHT_KPT=8", "-DLSCQP_LIGHT_MINCTAS=8"),
