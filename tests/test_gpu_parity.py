@@ -499,3 +499,24 @@ def test_validate_batch_gpu():
     want = np.array([orc.is_sol_valid(cfgo, orc.Agent(st[a, :3], st[a, 3:6], st[a, 6:9], batch.goal[a], max_vel=tuple(batch.limits[a, :3]),
                                                       max_acc=tuple(batch.limits[a, 3:6])), tr[a], st[a], batch.sfc[a]) for a in range(n)], np.int32)
     assert np.array_equal(got, want) and 0 < want.sum() < n
+
+
+def test_light_and_full_instances_agree_at_full_size():
+    """BASELINE's 4096-agent batch: the two-pass dispatch (one-warp light instance first) and the one-pass full-capacity
+    instance return the same solutions, statuses and (to the last iterations' noise) objective values"""
+    import copy
+    import torch
+    batch = W.make_forest_batch(4096, K=40)
+    outs = []
+    for presolve in (1, 3):                                  # 3 = presolve on, light instances off
+        cfg = copy.copy(batch.cfg); cfg.presolve = presolve
+        planner = _planner(cfg)
+        d = planner.upload(batch)
+        planner.replan_device(d)
+        torch.cuda.synchronize()
+        outs.append((d.ctrl.clone(), d.status.clone(), d.cost.clone(), d.iters.clone()))
+    (c1, s1, f1, i1), (c3, s3, f3, i3) = outs
+    assert int((s1 != 0).sum()) == 0 and int((s3 != 0).sum()) == 0
+    assert float((c1 - c3).abs().max()) < 2e-6
+    assert float(((f1 - f3).abs() / f3.abs().clamp(min=1.0)).max()) < 1e-8
+    assert abs(float(i1.float().mean()) - float(i3.float().mean())) < 0.2
