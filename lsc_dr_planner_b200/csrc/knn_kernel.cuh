@@ -5,8 +5,9 @@
 // are in range -- the nearest out-of-range ones as padding; their planes never bind).
 //
 // One CTA per agent.  Squared distances to all n_total agents go to shared memory as order-preserving unsigned keys
-// (non-negative float bits; bit 31 set for out-of-range agents, 0xFFFFFFFF for the agent itself), a 4-pass radix select
-// finds the K-th smallest key, and an ordered compaction writes the selected ids in ascending agent order (the order
+// (non-negative float bits; bit 31 set for out-of-range agents, 0xFFFFFFFF for the agent itself).  The K-th smallest key
+// is built bit by bit (32 counting passes over the keys: no atomics -- a radix histogram serialises on the handful of
+// exponent values distances share), and an ordered compaction writes the selected ids in ascending agent order (the order
 // broadcastMsgs emits them), ties at the threshold broken by the lower id: deterministic.
 #pragma once
 
@@ -20,6 +21,8 @@ struct KnnParams {
 };
 
 constexpr int KNN_THREADS = 128;
+// keys (skewed by one word per 32) + per-warp / per-thread counters
+inline size_t knn_smem_bytes(int n_total) { return ((size_t) n_total + (n_total >> 5) + 1 + 2 * KNN_THREADS + 8) * sizeof(unsigned); }
 
 __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams p) {
 #ifdef LSCQP_CUDA_EMUL
@@ -28,8 +31,8 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
     extern __shared__ unsigned knn_smem[];
 #endif
     unsigned* keys = knn_smem;                         // [n_total]
-    unsigned* hist = knn_smem + p.n_total;             // [256]
-    unsigned* cnt = hist + 256;                        // [2 * KNN_THREADS + 4]
+    unsigned* cnt = knn_smem + p.n_total + (p.n_total >> 5) + 1;   // [2 * KNN_THREADS + 4]
+    auto skew = [](int j) { return j + (j >> 5); };    // one pad word per 32 keys: the compaction's strided reads hit distinct banks
     const int tid = threadIdx.x, a = p.lo + blockIdx.x, N = p.n_total;
     if ((int) blockIdx.x >= p.n_local) return;
     const float ax = p.state[(size_t) a * 9], ay = p.state[(size_t) a * 9 + 1], az = p.state[(size_t) a * 9 + 2];
@@ -38,38 +41,34 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
         unsigned key = __float_as_uint(dx * dx + dy * dy + dz * dz) & 0x7FFFFFFFu;
         if (p.comm_range > 0.f && fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz)) > p.comm_range) key |= 0x80000000u;
         if (j == a) key = 0xFFFFFFFFu;
-        keys[j] = key;
+        keys[skew(j)] = key;
     }
-    // radix select: after the pass over byte b, `prefix` holds the top bytes of the K-th smallest key and `want` the
-    // rank still to be located inside that prefix
-    unsigned prefix = 0, mask = 0;
-    int want = p.K;                                    // 1-based rank
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int e = tid; e < 256; e += KNN_THREADS) hist[e] = 0;
+    __syncthreads();
+    // count(keys < t) over the CTA: per-thread count, warp shuffle sum, one shared-memory hop
+    auto count_below = [&](unsigned t) {
+        int c = 0;
+        for (int j = tid; j < N; j += KNN_THREADS) c += keys[skew(j)] < t;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((tid & 31) == 0) cnt[tid >> 5] = (unsigned) c;
         __syncthreads();
-        for (int j = tid; j < N; j += KNN_THREADS) {
-            const unsigned k = keys[j];
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-        }
+        int tot = 0;
+        for (int w = 0; w < KNN_THREADS / 32; w++) tot += (int) cnt[w];
         __syncthreads();
-        if (tid == 0) {
-            int acc = 0, b = 0;
-            for (; b < 255; b++) {
-                if (acc + (int) hist[b] >= want) break;
-                acc += (int) hist[b];
-            }
-            cnt[0] = (unsigned) b; cnt[1] = (unsigned) (want - acc);
-        }
-        __syncthreads();
-        prefix |= cnt[0] << shift; mask |= 255u << shift; want = (int) cnt[1];
-        __syncthreads();
+        return tot;
+    };
+    // the K-th smallest key is the largest T with count(keys < T) < K: set its bits from the top
+    unsigned prefix = 0;
+    for (int bit = 31; bit >= 0; bit--) {
+        const unsigned test = prefix | (1u << bit);
+        if (count_below(test) < p.K) prefix = test;
     }
+    const int want = p.K - count_below(prefix);        // how many of the keys equal to the threshold are taken
     const unsigned thr = prefix;                       // the K-th smallest key; `want` of the keys equal to it are taken
     // ordered compaction: thread t owns the contiguous id range [t * chunk, (t + 1) * chunk)
     const int chunk = (N + KNN_THREADS - 1) / KNN_THREADS;
     const int j0 = tid * chunk, j1 = (j0 + chunk < N) ? j0 + chunk : N;
     unsigned nl = 0, ne = 0;
-    for (int j = j0; j < j1; j++) { const unsigned k = keys[j]; nl += k < thr; ne += k == thr; }
+    for (int j = j0; j < j1; j++) { const unsigned k = keys[skew(j)]; nl += k < thr; ne += k == thr; }
     cnt[4 + tid] = nl; cnt[4 + KNN_THREADS + tid] = ne;
     __syncthreads();
     unsigned base_l = 0, base_e = 0, tot_l = 0;
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
     int* out = p.obs_index + (size_t) blockIdx.x * p.K;
     unsigned il = base_l, ie = base_e;
     for (int j = j0; j < j1; j++) {
-        const unsigned k = keys[j];
+        const unsigned k = keys[skew(j)];
         if (k < thr) { out[il + (ie < (unsigned) want ? ie : (unsigned) want)] = j; il++; }
         else if (k == thr) { if (ie < (unsigned) want) out[il + ie] = j; ie++; }
     }

@@ -239,7 +239,7 @@ extern "C" int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int
         return fail(LSCQP_E_INVALID, "bad argument");
     if (K < 0 || K > h->cfg.max_obs || K > n_total - 1) return fail(LSCQP_E_CAPACITY, "K above max_obs or n_total - 1");
     if (n_local == 0 || K == 0) return 0;
-    const size_t smem = ((size_t) n_total + 256 + 2 * KNN_THREADS + 4) * sizeof(unsigned);
+    const size_t smem = knn_smem_bytes(n_total);
     if (smem > 200 * 1024) return fail(LSCQP_E_CAPACITY, "n_total above the shared-memory capacity of the selection kernel");
     if (smem > 48 * 1024 && smem > h->knn_smem) {
         CK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

@@ -82,6 +82,7 @@ inline double __shfl_xor_sync(unsigned, double v, int mask) {
     __syncwarp();
     return r;
 }
+inline int __shfl_xor_sync(unsigned m, int v, int mask) { return (int) __shfl_xor_sync(m, (double) v, mask); }
 inline double __shfl_sync(unsigned, double v, int src_lane) {
     emu::State& s = emu::st();
     s.slot_d[s.cur] = v;

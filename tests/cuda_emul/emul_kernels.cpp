@@ -110,7 +110,7 @@ extern "C" int emul_goal_batch(const lscqp_config* cfg, int n_agents, const floa
 extern "C" int emul_select_neighbours(int n_total, int lo, int n_local, int K, double comm_range, const float* state, int* out) {
     KnnParams p;
     p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = (float) comm_range; p.state = state; p.obs_index = out;
-    emu::launch(n_local, KNN_THREADS, ((size_t) n_total + 256 + 2 * KNN_THREADS + 4) * sizeof(unsigned) + 64, [&]() { knn_select_kernel(p); });
+    emu::launch(n_local, KNN_THREADS, knn_smem_bytes(n_total) + 64, [&]() { knn_select_kernel(p); });
     return 0;
 }
 
