@@ -194,6 +194,13 @@ struct Instance {
     using Full = Cfg<M_, D_, T_, 4, 10, COMM_>;
     using Light = Cfg<M_, D_, T_, LSCQP_LIGHT_G, LSCQP_LIGHT_KPT, false>;
     static constexpr bool HAS_LIGHT = !COMM_;
+    // Communication-range configurations with few neighbours (the shipped 10-agent missions: K <= 9): half the threads
+    // (2 obstacle groups x 5 rows), so twice as many CTAs share an SM while the dense factorisation of each runs.
+    // Only where one variable per thread and one comm pair per thread still fit.
+    static constexpr int COMPACT_NT = 2 * (((6 * M_ + 31) / 32) * 32);
+    static constexpr bool HAS_COMPACT = COMM_ && D_ * 6 * M_ <= COMPACT_NT && D_ * (M_ * (M_ - 1) / 2 + M_) <= COMPACT_NT;
+    using Compact = Cfg<M_, D_, T_, 2, 5, HAS_COMPACT>;      // (a banded dummy where it does not apply: never launched)
+    static constexpr int COMPACT_KMAX = 10;
 };
 
 // kernel instances: (M, D, TERM, COMM) with 4 obstacle groups x 10 rows per thread (K <= 40)

@@ -52,9 +52,12 @@ int LSCQP_TU_NAME(inst_query)(const lscqp_config& cfg, InstanceInfo* info) {
         using C = typename I::Full;                                                 \
         if (set_smem_attr<C>()) return -1;                                          \
         if (I::HAS_LIGHT && set_smem_attr<typename I::Light>()) return -1;          \
+        if (I::HAS_COMPACT && set_smem_attr<typename I::Compact>()) return -1;      \
         info->dual_stride = C::DUAL_STRIDE; info->kmax = C::KMAX; info->nv = C::NV; \
         info->has_light = I::HAS_LIGHT;                                             \
         info->tab = build_projection<C>();                                          \
+        if (I::HAS_COMPACT && cfg.max_obs <= I::COMPACT_KMAX)                       \
+            info->tab = build_projection<typename I::Compact>();                    \
         if (I::HAS_LIGHT) info->tab_light = build_projection<C>(I::Light::NT);      \
         return 1;                                                                   \
     }
@@ -71,6 +74,11 @@ int LSCQP_TU_NAME(inst_launch)(const lscqp_config& cfg, SolveParams& p, int n_ag
         using C = typename I::Full;                                                 \
         int launched = 1;                                                           \
         p.klass_mode = 0;                                                           \
+        if (I::HAS_COMPACT && cfg.max_obs <= I::COMPACT_KMAX) {                     \
+            using K = typename I::Compact;                                          \
+            pdip_solve_kernel<K><<<n_agents, K::NT, K::SMEM_BYTES, st>>>(p);        \
+            return launched;                                                        \
+        }                                                                           \
         if (I::HAS_LIGHT && two_pass) {                                             \
             using L = typename I::Light;                                            \
             p.klass_mode = 1;                                                       \

@@ -104,7 +104,8 @@ def launch_config(mission: Mission, M: int = 10, dim: int = 2, comm_range: float
     control_input_weight 0.01, terminal_weight 1, communication range 3.  SFC boxes are an input of this path
     (octomap / dynamicEDT3D are out of scope), so use_sfc is off unless the caller supplies boxes."""
     return PlannerConfig(M=M, dim=dim, dt=0.2, w_control=0.01, w_terminal=1.0, planner_mode=1, use_sfc=False,
-                         comm_range=comm_range, world_min=mission.world_min, world_max=mission.world_max, z_2d=z_2d)
+                         comm_range=comm_range, world_min=mission.world_min, world_max=mission.world_max, z_2d=z_2d,
+                         max_obs=min(40, max(1, mission.n_agents - 1)))
 
 
 def first_replan_batch(mission: Mission, cfg: PlannerConfig, waypoint_step: float = 0.5) -> Batch:

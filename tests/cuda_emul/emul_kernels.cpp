@@ -38,6 +38,13 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
         p.proj = tab.term.data(); p.proj_len = tab.len;                                     \
         static const ProjTable tabl = build_projection<C>(I::Light::NT);                    \
         p.proj_light = tabl.term.data(); p.proj_len_light = tabl.len;                       \
+        if (I::HAS_COMPACT && cfg->max_obs <= I::COMPACT_KMAX) {                            \
+            using K = typename I::Compact;                                                  \
+            static const ProjTable tabk = build_projection<K>();                            \
+            p.proj = tabk.term.data(); p.proj_len = tabk.len;                               \
+            emu::launch(n_agents, K::NT, K::SMEM_BYTES, [&]() { pdip_solve_kernel<K>(p); }); \
+            return 0;                                                                       \
+        }                                                                                   \
         std::vector<int> klass(n_agents + 1, 0);                                            \
         if (I::HAS_LIGHT && (cfg->presolve & 1) && !(cfg->presolve & 2)) {                  \
             using L = typename I::Light;                                                    \

@@ -124,10 +124,11 @@ def test_step_kernel_matches_oracle():
             assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
 
 
-@pytest.mark.parametrize("M,dim,K", [(5, 3, 10), (10, 2, 9)])
-def test_solve_kernel_with_communication_range_rows(M, dim, K):
-    """communication-range rows (traj_optimizer.cpp:477-500; launch/simulation.launch sets range 3): dense instance"""
-    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=1, comm_range=0.7)       # tight enough to bind within the 1 s horizon
+@pytest.mark.parametrize("M,dim,K,max_obs", [(5, 3, 10, 40), (10, 2, 9, 40), (10, 2, 9, 10)])
+def test_solve_kernel_with_communication_range_rows(M, dim, K, max_obs):
+    """communication-range rows (traj_optimizer.cpp:477-500; launch/simulation.launch sets range 3): dense instance
+    (max_obs <= 10 selects the compact 128-thread instance of the 2-D configurations)"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=1, comm_range=0.7, max_obs=max_obs)   # tight enough to bind within the 1 s horizon
     batch = W.make_forest_batch(64, K=K, cfg=cfg)
     rng = np.random.default_rng(11)
     d = rng.normal(size=(64, 3)); d[:, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
