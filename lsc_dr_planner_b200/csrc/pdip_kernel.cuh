@@ -1100,7 +1100,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     // ---------------------------------------------------------------- main loop   // @phase sweepA
     int status = ST_MAX_ITER, it = 0;
-    double mu = 0.0, sigmu = 0.0, alpha = 0.0;
+    double mu = 0.0, sigmu = 0.0, alpha = 0.0, mu_first = 0.0;
     bool have_step = false;       // a (dca, dc, sigmu, alpha) step is pending and is applied by the next sweep A
     for (it = 0; it <= p.max_iter; it++) {
         // ---- sweep A: apply the pending step, then predictor weights of the new point
@@ -1156,6 +1156,9 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         }
         if (!(mu == mu)) { status = ST_NUMERICAL; break; }
         if (mu < p.mu_tol && fabs(rp) < p.rp_tol) { status = ST_OK; break; }
+        // an infeasible model drives the multipliers (and with them mu) to infinity: stop long before the overflow
+        if (it == 0) mu_first = mu;
+        if (mu > 1e12 * fmax(mu_first, 1.0)) { status = ST_INFEASIBLE; break; }
         if (it == p.max_iter) break;
 
         // ---- predictor   // @phase predictor_glue
@@ -1294,6 +1297,19 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     }
 
     // ---------------------------------------------------------------- outputs   // @phase outputs
+    // a numerical breakdown (NaN in the complementarity measure; seen on infeasible models whose pivots were all
+    // guarded) must not leak: the returned point is then the (finite) starting point, its multipliers zero
+    if (status == ST_NUMERICAL) {
+        cta_sync<C>();
+        set_start(p.warm_traj != nullptr);
+#pragma unroll
+        for (int j = 0; j < KPT; j++) { ls[j] = 1.0; ll[j] = 0.0; }
+#pragma unroll
+        for (int u = 0; u < VPT; u++)
+#pragma unroll
+            for (int e = 0; e < NBX; e++) { bs[u][e] = 1.0; bl[u][e] = 0.0; }
+        mu = -1.0;
+    }
     // true primal residual of the returned point, recomputed from the row constants
     double rp_true = 0.0;
     cta_sync<C>();

@@ -30,7 +30,7 @@ class DeviceBatch:
         self.own_traj = t(batch.own_traj)
         self.agent_meta = t(batch.agent_meta)
         self.obs_offsets = t(batch.obs_offsets.astype(np.int32))
-        self.obs_index = t(batch.obs_index.astype(np.int32))
+        self.obs_index = t(batch.obs_index.astype(np.int32)) if batch.obs_index.size else torch.zeros(1, dtype=torch.int32, device=dev)
         self.sfc = t(batch.sfc) if batch.sfc is not None else None
         self.next_waypoint = t(batch.next_waypoint) if cfg.comm_range > 0 else None
         self.waypoint = t(batch.next_waypoint)                      # GoalOptimizer input (any configuration)

@@ -164,7 +164,7 @@ def make_forest_batch(n_agents: int, K: int = 40, seed: int = 20260001,
     k = min(K, n_agents - 1)
     tree = cKDTree(pos)
     _, idx = tree.query(pos, k=k + 1)
-    idx = idx[:, 1:].astype(np.int32)
+    idx = np.asarray(idx).reshape(n_agents, k + 1)[:, 1:].astype(np.int32)
     state = np.concatenate([traj[:, 0, 0, :],
                             (5.0 / dt) * (traj[:, 0, 1, :] - traj[:, 0, 0, :]),
                             (20.0 / dt ** 2) * (traj[:, 0, 2, :] - 2 * traj[:, 0, 1, :] + traj[:, 0, 0, :])],

@@ -242,3 +242,25 @@ def test_validate_kernel_matches_oracle_is_sol_valid(M, dim, use_sfc):
                                       traj[a], state[a], None if sfc is None else sfc[a]) for a in range(n)], np.int32)
     assert np.array_equal(got, want)
     assert 0 < want.sum() < n
+
+
+def _infeasible_case():
+    """an agent whose CLSC rows (far antipodal goals: crossing goal lines) admit no point: captured from a GPU sweep
+    where the multipliers overflowed to NaN after 54 iterations (tests/golden/infeasible_case.npz)"""
+    g = np.load(os.path.join(GOLDEN, "infeasible_case.npz"))
+    cfg = W.PlannerConfig(M=int(g["M"]), dim=int(g["dim"]), planner_mode=int(g["mode"]), world_min=tuple(g["world"][:3]),
+                          world_max=tuple(g["world"][3:]))
+    off = np.array([0, g["normals"].shape[0]], np.int32)
+    return cfg, g, off
+
+
+def test_infeasible_model_is_detected_early_and_outputs_stay_finite():
+    cfg, g, off = _infeasible_case()
+    for warm in (True, False):
+        ctrl, cost, status, iters, kkt, dual = emul.solve_batch(
+            cfg, 1, g["state"][None].copy(), g["goal"][None].copy(), g["limits"][None].copy(), None, off,
+            np.ascontiguousarray(g["normals"]), np.ascontiguousarray(g["rhs"]),
+            initial_traj=g["own"][None].copy() if warm else None, want_dual=True)
+        assert status[0] == 2 and iters[0] < 45                     # LSCQP_INFEASIBLE, long before the iteration cap
+        assert np.isfinite(ctrl).all() and np.isfinite(cost).all() and np.isfinite(dual).all() and np.isfinite(kkt).all()
+        assert kkt[0, 1] > 1e-6                                     # the returned point does violate rows

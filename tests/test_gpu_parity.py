@@ -520,3 +520,17 @@ def test_light_and_full_instances_agree_at_full_size():
     assert float((c1 - c3).abs().max()) < 2e-6
     assert float(((f1 - f3).abs() / f3.abs().clamp(min=1.0)).max()) < 1e-8
     assert abs(float(i1.float().mean()) - float(i3.float().mean())) < 0.2
+
+
+def test_infeasible_case_from_the_sweep_gpu():
+    """the captured infeasible CLSC agent (tests/golden/infeasible_case.npz): reported, finite, stopped early"""
+    from test_emul_kernels import _infeasible_case
+    cfg, g, off = _infeasible_case()
+    qp = capi.LscQp(cfg, device=0)
+    nv = cfg.dim * cfg.M * 6
+    ctrl = np.zeros((1, nv)); cost = np.zeros(1); status = np.zeros(1, np.int32); iters = np.zeros(1, np.int32); kkt = np.zeros((1, 4))
+    qp.solve_host(1, g["state"][None].copy(), g["goal"][None].copy(), g["limits"][None].copy(), None, off,
+                  np.ascontiguousarray(g["normals"]), np.ascontiguousarray(g["rhs"]), ctrl, cost, status, iters=iters, kkt=kkt,
+                  initial_traj=g["own"][None].copy())
+    assert status[0] in (2, 3) and iters[0] < 45
+    assert np.isfinite(ctrl).all() and np.isfinite(cost).all() and np.isfinite(kkt).all()
