@@ -69,7 +69,15 @@ def main():
                           "qp_failures_total": float(f), "max_goal_distance_end": sim.max_goal_distance(),
                           "wall_s": time.perf_counter() - t0}))
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        # tear down in a safe order: a captured graph still holds NCCL kernels, and destroying the communicator under it
+        # can hang the process at exit (seen at 2 ranks); release the graph first, then leave without the destructor
+        torch.cuda.synchronize(); dist.barrier()
+        sim._graph = None
+        import gc; gc.collect(); torch.cuda.synchronize()
+        sys.stdout.flush()
+        if args.graph:
+            os._exit(0)
+        dist.destroy_process_group()
 
 if __name__ == "__main__":
     main()
