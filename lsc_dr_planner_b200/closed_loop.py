@@ -108,13 +108,19 @@ class ClosedLoopSim:
             new_traj, new_state = self.shifted, self.state_out
         else:
             new_traj = self.shifted[:0]; new_state = self.state_out[:0]
-        # the exchange (the only collective): every rank ends the step with all trajectories and states
-        self.traj.copy_(allgather_rows(new_traj[:n], self.N))
-        self.state.copy_(allgather_rows(new_state[:n], self.N))
+        if self.world == 1:
+            self.traj.copy_(new_traj[:n]); self.state.copy_(new_state[:n])
+
+    def _exchange(self):
+        """the only collective: every rank ends the step with all trajectories and states (eager: NCCL collectives inside
+        a captured graph hung intermittently at 2 ranks, so only the local compute is captured)"""
+        n = self.n_local
+        self.traj.copy_(allgather_rows(self.shifted[:n], self.N))
+        self.state.copy_(allgather_rows(self.state_out[:n], self.N))
 
     def step(self):
-        """One closed-loop step.  With use_graph the step is captured once into a CUDA graph (library launches, the
-        few torch element-wise ops and the NCCL all-gather) after two eager steps and replayed afterwards: at a few
+        """One closed-loop step.  With use_graph the local part of the step (library launches and the few torch
+        element-wise ops) is captured once into a CUDA graph after two eager steps and replayed afterwards: at a few
         hundred agents per GPU the step is otherwise bound by the ~0.4 ms of host-side launch work."""
         torch = self.torch
         if self.use_graph and self._graph is not None:
@@ -128,6 +134,8 @@ class ClosedLoopSim:
             g.replay()
         else:
             self._step_impl(torch.cuda.current_stream().cuda_stream)
+        if self.world > 1:
+            self._exchange()
         self.steps += 1
 
     def min_separation_ratio(self) -> float:

@@ -31,10 +31,13 @@ def main():
     batch.goal = goal.astype(np.float32)
     sim = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K, use_graph=args.graph)
     warm = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K)
-    t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 1.0:            # a 0.3 s run is otherwise timed while the clocks are still ramping up
+    # a 0.3 s run is otherwise timed while the clocks are still ramping up.  A fixed number of steps, NOT a time limit:
+    # every step holds a collective, so all ranks must execute the same count
+    for _ in range(max(200, 400_000 // max(args.agents // world, 256))):
         warm.step()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     del warm
     for _ in range(3):
         sim.step()
