@@ -264,3 +264,23 @@ def test_infeasible_model_is_detected_early_and_outputs_stay_finite():
         assert status[0] == 2 and iters[0] < 45                     # LSCQP_INFEASIBLE, long before the iteration cap
         assert np.isfinite(ctrl).all() and np.isfinite(cost).all() and np.isfinite(dual).all() and np.isfinite(kkt).all()
         assert kkt[0, 1] > 1e-6                                     # the returned point does violate rows
+
+
+def test_solve_kernel_m10_d3_instance_against_oracle():
+    """the largest banded instance (M = 10, 3-D: 84 reduced variables, 256-thread CTA) against the polished oracle"""
+    cfg = W.PlannerConfig(M=10, dim=3, planner_mode=1)
+    batch = W.make_forest_batch(48, K=12, cfg=cfg)
+    near_goals(batch)
+    agents = [2, 31]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    ctrl, cost, status, iters, kkt, _ = emul.solve_batch(batch.cfg, len(agents), st, goal, lim, None, off, normals, rhs,
+                                                         initial_traj=np.ascontiguousarray(batch.own_traj[agents]))
+    assert (status == 0).all() and kkt[:, 1].max() < 1e-9
+    checked = 0
+    for i, a in enumerate(agents):
+        xe, ok = oracle_solution(oracle_qp_from_planes(batch, a, normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]]))
+        if ok:
+            checked += 1
+            assert np.abs(ctrl[i] - xe).max() < 1e-5, np.abs(ctrl[i] - xe).max()
+    assert checked >= 1
