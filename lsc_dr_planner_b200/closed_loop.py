@@ -20,7 +20,8 @@ from .workloads import Batch
 
 class ClosedLoopSim:
     def __init__(self, batch: Batch, device: int = 0, rank: int = 0, world: int = 1, K: int = 40,
-                 comm_range: float = 0.0, generator: int = capi.GEN_LSC, use_graph: bool = False):
+                 comm_range: float = 0.0, generator: int = capi.GEN_LSC, use_graph: bool = False,
+                 goal_mode: str = "static"):
         import torch
         from .planner import BatchPlanner
         self.torch = torch
@@ -39,7 +40,11 @@ class ClosedLoopSim:
         M = self.cfg.M
         # global (replicated) per-agent data
         self.state = t(batch.state)                      # [N,9]
-        self.goal = t(batch.goal)                        # [N,3]
+        self.goal = t(batch.goal)                        # [N,3] current_goal_point
+        self.desired_goal = self.goal.clone()            # [N,3] desired_goal_point
+        assert goal_mode in ("static", "righthand")
+        self.goal_mode = goal_mode
+        self._seq = torch.zeros((), dtype=torch.int32, device=dev)      # planner_seq, on the device (graph-safe)
         self.agent_meta = t(batch.agent_meta)            # [N,2]
         self.limits = t(batch.limits)
         # first replan: constant-velocity trajectories from the current state (traj_planner.cpp:276-279, 400-401)
@@ -89,6 +94,16 @@ class ClosedLoopSim:
         torch = self.torch
         qp = self.planner.qp
         n, lo, hi = self.n_local, self.lo, self.hi
+        # goalPlanning (src/traj_planner.cpp:433-477): static goal, or the right-hand rule -- an agent that is slower than
+        # deadlock/velocity_threshold (0.1) after deadlock/seq_threshold (5) replans and still more than 0.2 m from its
+        # goal (isDeadlock, :904-923) aims at position + (desired - position) x e_z instead
+        self._seq += 1
+        if self.goal_mode == "righthand":
+            pos, vel = self.state[:, 0:3], self.state[:, 3:6]
+            to_goal = self.desired_goal - pos
+            dead = (self._seq > 5) & (vel.norm(dim=1) < 0.1) & (to_goal.norm(dim=1) > 0.2)
+            side = torch.stack([to_goal[:, 1], -to_goal[:, 0], torch.zeros_like(to_goal[:, 2])], dim=1)
+            self.goal.copy_(torch.where(dead[:, None], pos + side, self.desired_goal))
         if n > 0:
             obs_index = self.neighbours(stream)
             own = self.traj[lo:hi].contiguous()
@@ -149,4 +164,4 @@ class ClosedLoopSim:
         return float(d.min())
 
     def max_goal_distance(self) -> float:
-        return float((self.state[:, 0:3] - self.goal).norm(dim=1).max())
+        return float((self.state[:, 0:3] - self.desired_goal).norm(dim=1).max())

@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Fly one of the reference's mission files in the batched closed loop and write the reference's result files
 (log/simulation_*.csv rows and the log/summary_*.csv row).  The map pipeline and the grid MAPF layer are outside this
-repository's scope: agents head straight for their desired goals under LSC constraints (no static obstacles, no SFC).
-Without the waypoint layer this is the reference's "static" goal mode, which the symmetric swap missions deadlock in
-(that is what the reference's grid_based_planner + PIBT modes are for): measured on forest10 -- 600 replans, no QP
-failure, agent safety ratio 1.000003 throughout, 0.053 ms planning time per agent and replan, agents stopped 4.6 m short
-of their goals around the centre.  The run demonstrates the file formats and the safety of the batched planner, not
-mission completion.
+repository's scope: agents head for their desired goals under LSC constraints (no static obstacles, no SFC) with one of
+the reference's grid-free goal modes: "righthand" (goalPlanningWithRightHandRule, src/traj_planner.cpp:468-477 with
+isDeadlock :904-923) or "static".  Measured on forest10 (10 agents swapping across a circle of radius 4):
+  righthand  56 replans = 11.2 s flight time, 85.5 m total distance, agent safety ratio 1.00002, no QP failure, every
+             agent within 0.1 m of its goal  (the reference's own run of this mission, with static obstacles, SFC and
+             grid-based goals: 15.8 s, 103.2 m, 1.021 -- log/summary_LSC_10agents.csv)
+  static     deadlocks around the centre, as the symmetric swap must without a deadlock rule (600 replans, safety
+             ratio 1.000003, no QP failure, agents 4.6 m short of their goals)
 
   python scripts/run_mission.py missions/forest10/forest10_1.json --out gpurun_out/mission
 """
@@ -28,6 +30,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/mission")
     ap.add_argument("--max-steps", type=int, default=600)            # multisim/max_planner_iteration
     ap.add_argument("--dim", type=int, default=3)
+    ap.add_argument("--goal-mode", default="righthand", choices=["static", "righthand"])
     args = ap.parse_args()
     import torch
     from lsc_dr_planner_b200 import missions as MS, results as R, capi
@@ -37,7 +40,7 @@ def main():
     batch = MS.first_replan_batch(mission, cfg)
     batch.goal = mission.goal.copy()                                 # GoalMode static: fly to the desired goal
     n = mission.n_agents
-    sim = ClosedLoopSim(batch, device=0, K=min(40, n - 1), generator=capi.GEN_LSC)
+    sim = ClosedLoopSim(batch, device=0, K=min(40, n - 1), generator=capi.GEN_LSC, goal_mode=args.goal_mode)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     writer = R.SimulationCsvWriter(args.out + "_simulation.csv", n, time_step=cfg.dt, record_time_step=0.1, dt=cfg.dt)
     positions = [batch.state[:, :3].copy()]
@@ -57,10 +60,10 @@ def main():
                                planning_time=(float(st.mean()), float(st.min()), float(st.max())),
                                stage_times=dict(traj_optimization=float(st.mean())),
                                mission_file_name=args.mission or "forest10 (built in)", world_file_name="(none)", planner_mode="LSC",
-                               goal_mode="static", mapf_mode="none", communication_range=0.0, world_dimension=args.dim, M=cfg.M, dt=cfg.dt)
+                               goal_mode=args.goal_mode, mapf_mode="none", communication_range=0.0, world_dimension=args.dim, M=cfg.M, dt=cfg.dt)
     R.append_summary_csv(args.out + "_summary.csv", summary)
     print(json.dumps({"agents": n, "replans": s + 1, "flight_time_s": t, "flight_distance_m": dist, "safety_ratio_agent": ratio,
-                      "qp_failures": sim.failed_total, "goal_distance_end": sim.max_goal_distance(),
+                      "goal_mode": args.goal_mode, "qp_failures": sim.failed_total, "goal_distance_end": sim.max_goal_distance(),
                       "per_agent_planning_time_ms": float(st.mean() * 1e3), "files": [args.out + "_simulation.csv", args.out + "_summary.csv"]}))
 
 
