@@ -534,3 +534,30 @@ def test_infeasible_case_from_the_sweep_gpu():
                   initial_traj=g["own"][None].copy())
     assert status[0] in (2, 3) and iters[0] < 45
     assert np.isfinite(ctrl).all() and np.isfinite(cost).all() and np.isfinite(kkt).all()
+
+
+def test_closed_loop_right_hand_rule_completes_the_forest10_swap():
+    """the reference's forest10 mission (10 agents swapping across a circle) with the right-hand-rule goal mode
+    (traj_planner.cpp:468-477): every agent reaches its goal, collision-free, no QP failure; with static goals the
+    symmetric swap deadlocks (also collision-free)"""
+    from test_missions import FOREST10
+    from lsc_dr_planner_b200 import missions as MS
+    from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
+    mission = MS.parse_mission(FOREST10, 3, 1.0)
+    cfg = MS.launch_config(mission, M=5, dim=3, comm_range=0.0)
+    results = {}
+    for mode in ("righthand", "static"):
+        batch = MS.first_replan_batch(mission, cfg)
+        batch.goal = mission.goal.copy()
+        sim = ClosedLoopSim(batch, device=0, K=9, goal_mode=mode)
+        worst, steps = np.inf, 0
+        for steps in range(1, 121):
+            sim.step()
+            worst = min(worst, sim.min_separation_ratio())
+            if sim.max_goal_distance() < 0.1:
+                break
+        results[mode] = (steps, worst, sim.max_goal_distance(), sim.failed_total)
+    steps, worst, dist, failed = results["righthand"]
+    assert dist < 0.1 and steps < 100 and worst >= 1.0 - 1e-3 and failed == 0, results
+    steps, worst, dist, failed = results["static"]
+    assert dist > 1.0 and worst >= 1.0 - 1e-3 and failed == 0, results
