@@ -17,6 +17,9 @@
  *     entry points (which stage through pinned memory owned by the handle and include the
  *     host<->device copies).  `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *   - One handle per (device, host thread); calls on a handle are stream-ordered, not re-entrant.
+ *   - The *_host entry points validate the obstacle lists (every list within max_obs, every neighbour id inside the
+ *     batch) before anything is launched.  The device entry points cannot inspect device memory without a
+ *     synchronisation and trust obs_offsets / obs_index; a list longer than 40 obstacles is truncated to its first 40.
  *   - No CPU fallback exists: without a CUDA device lscqp_create fails with LSCQP_E_NODEVICE.
  */
 #ifndef LSCQP_H

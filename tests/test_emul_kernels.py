@@ -284,3 +284,26 @@ def test_solve_kernel_m10_d3_instance_against_oracle():
             checked += 1
             assert np.abs(ctrl[i] - xe).max() < 1e-5, np.abs(ctrl[i] - xe).max()
     assert checked >= 1
+
+
+@pytest.mark.parametrize("M,dim,mode,gen,K", [(5, 2, 1, 0, 12), (5, 3, 2, 2, 10), (10, 2, 0, 0, 6)])
+def test_solve_kernel_other_instances_against_oracle(M, dim, mode, gen, K):
+    """instances the golden file does not hold: 2-D with M = 5, BVC mode with generateBVC planes, DLSC with M = 10"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode)
+    batch = W.make_forest_batch(40, K=K, cfg=cfg)
+    near_goals(batch)
+    agents = [1, 17, 33]
+    off, normals, rhs = oracle_planes(batch, agents, gen)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    ctrl, cost, status, iters, kkt, _ = emul.solve_batch(batch.cfg, len(agents), st, goal, lim, None, off, normals, rhs,
+                                                         initial_traj=np.ascontiguousarray(batch.own_traj[agents]))
+    assert (status == 0).all() and kkt[:, 1].max() < 1e-9
+    checked = 0
+    for i, a in enumerate(agents):
+        qp = oracle_qp_from_planes(batch, a, normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]])
+        xe, ok = oracle_solution(qp)
+        if ok:
+            checked += 1
+            assert np.abs(ctrl[i] - xe).max() < 1e-5, (a, np.abs(ctrl[i] - xe).max())
+            assert abs(cost[i] - (xe @ qp.P @ xe + qp.q @ xe + qp.c0)) < 1e-6 * max(1.0, abs(cost[i]))
+    assert checked >= 2
