@@ -1,6 +1,7 @@
 // pdip_kernel.cuh -- batched primal-dual interior-point solve of the per-agent trajectory QP.
 //
-// One CTA per agent.  Replaces the CPLEX call of the reference
+// One CTA per agent -- a single warp in the light instances, 128 or 256 threads in the full-capacity ones (Cfg below,
+// host_common.hpp:Instance).  Replaces the CPLEX call of the reference
 // (src/traj_optimizer.cpp:18-156, model built by populatebyrow :216-514) for the whole batch the
 // serial loop src/multi_sync_simulator.cpp:354-362 walks.
 //
@@ -16,10 +17,11 @@
 //     n.c - b >= 0 (:400-437), box bounds (world box, intersected with the SFC box when given;
 //     :238-270, :372-397), velocity / acceleration differences (:440-474, rescaled to unit
 //     coefficients).  Slack s and multiplier lam of every row live in registers of the owning thread.
+//     An exact presolve drops the obstacles and bound rows no point allowed by the velocity rows can activate.
 //   * Mehrotra predictor-corrector on (y, s, lam).  Per iteration the row weights are accumulated
 //     into the structured full-space Hessian (6x6 blocks per (dim, segment) + 3x3 blocks per control
-//     point), projected to the reduced space, factorised by a banded Cholesky in shared memory
-//     (warp 0) and used for the two triangular solve pairs.
+//     point), projected to the reduced space (host-built per-thread term streams), factorised by a stage-aware
+//     banded block-LDL^T on a skewed band in shared memory (warp 0) and used for the two triangular solve pairs.
 #pragma once
 #include <math.h>
 
