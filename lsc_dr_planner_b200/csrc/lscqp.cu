@@ -48,7 +48,7 @@ struct lscqp_handle {
     cudaStream_t stream;
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
-    DevBuf d_own, d_ameta, d_index, d_otraj, d_ometa, d_ogoal, d_opos;
+    DevBuf d_own, d_ameta, d_index;
     DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout;
     bool two_pass = false;
     size_t knn_smem = 0;
@@ -104,7 +104,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
-                      &h->d_otraj, &h->d_ometa, &h->d_ogoal, &h->d_opos, &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
+                      &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
                       &h->d_klass, &h->d_gout};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
@@ -451,8 +451,7 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     RESERVE(h->d_limits, n_agents * 8 * sizeof(double)); RESERVE(h->d_off, (n_agents + 1) * sizeof(int));
     RESERVE(h->d_own, (size_t) n_agents * M * 18 * sizeof(float)); RESERVE(h->d_ameta, n_agents * 2 * sizeof(double));
     RESERVE(h->d_index, (sumK + 1) * sizeof(int));
-    RESERVE(h->d_otraj, (sumK * M * 18 + 1) * sizeof(float)); RESERVE(h->d_ometa, (sumK * 4 + 1) * sizeof(float));
-    RESERVE(h->d_ogoal, (sumK * 3 + 1) * sizeof(float)); RESERVE(h->d_opos, (sumK * 3 + 1) * sizeof(float));
+    // (no gathered obstacle copies: the assembly reads the neighbours in place through d_index)
     RESERVE(h->d_normals, (sumK * M * 3 + 1) * sizeof(double)); RESERVE(h->d_rhs, (sumK * M * 6 + 1) * sizeof(double));
     RESERVE(h->d_ctrl, (size_t) n_agents * h->nv * sizeof(double)); RESERVE(h->d_cost, n_agents * sizeof(double));
     RESERVE(h->d_status, n_agents * sizeof(int)); RESERVE(h->d_iters, n_agents * sizeof(int));
