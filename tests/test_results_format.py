@@ -56,3 +56,29 @@ def test_flight_metrics():
     dist, ratio = R.flight_metrics(pos, np.array([0.15, 0.15]), np.array([2.0, 2.0]))
     assert abs(dist - (0.2 + np.hypot(0.2, 0.6))) < 1e-12
     assert abs(ratio - np.hypot(0.6, 0.3) / 0.3) < 1e-12
+
+
+def test_simulation_csv_first_row_matches_the_reference_log():
+    """the reference's own golden log (log/simulation_1663743693.650981_LSC_10agents.csv: forest10, 2-D, world/z_2d = 0.6):
+    header identical, and the first data row -- every agent at rest at its start point at t = 0 -- identical field by field
+    except the planning-time column (a wall-clock measurement)"""
+    import json
+    from test_missions import FOREST10
+    from lsc_dr_planner_b200 import missions as MS
+    ref_header = ",".join(["id,t,px,py,pz,vx,vy,vz,ax,ay,az,planning_time"] * 10)
+    ref_first = ("0,0,4,0,0.6,0,0,0,0,0,0,1,0,3,2.5,0.6,0,0,0,0,0,0,2,0,1,4,0.6,0,0,0,0,0,0,3,0,-1,4,0.6,0,0,0,0,0,0,"
+                 "4,0,-3,2.5,0.6,0,0,0,0,0,0,5,0,-4,0,0.6,0,0,0,0,0,0,6,0,-3,-2.5,0.6,0,0,0,0,0,0,7,0,-1,-4,0.6,0,0,0,0,0,0,"
+                 "8,0,1,-4,0.6,0,0,0,0,0,0,9,0,3,-2.5,0.6,0,0,0,0,0,0")
+    mission = MS.parse_mission(json.loads(json.dumps(FOREST10)), world_dimension=2, world_z_2d=0.6)
+    cfg = MS.launch_config(mission, z_2d=0.6)
+    batch = MS.first_replan_batch(mission, cfg)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "sim.csv")
+        w = R.SimulationCsvWriter(p, mission.n_agents, time_step=0.2, record_time_step=0.1, dt=cfg.dt)
+        w.record(0.0, batch.own_traj, planning_time=0.0271518)
+        lines = open(p).read().splitlines()
+    assert lines[0] == ref_header
+    got = lines[1].split(",")
+    assert ",".join(",".join(got[i * 12:i * 12 + 11]) for i in range(10)) == ref_first
+    assert got[11] == "0.0271518"                      # same %g formatting as the reference's stream output
