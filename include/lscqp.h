@@ -17,9 +17,10 @@
  *     entry points (which stage through pinned memory owned by the handle and include the
  *     host<->device copies).  `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *   - One handle per (device, host thread); calls on a handle are stream-ordered, not re-entrant.
- *   - The *_host entry points validate the obstacle lists (every list within max_obs, every neighbour id inside the
- *     batch) before anything is launched.  The device entry points cannot inspect device memory without a
- *     synchronisation and trust obs_offsets / obs_index; a list longer than 40 obstacles is truncated to its first 40.
+ *   - Obstacle lists are never truncated.  The *_host entry points validate them (every list within max_obs, every
+ *     neighbour id inside the batch) before anything is launched and return LSCQP_E_CAPACITY / LSCQP_E_INVALID.  The
+ *     device entry points cannot inspect device memory without a synchronisation: an agent whose list is longer than
+ *     max_obs is reported through status_out = LSCQP_CAPACITY and left unsolved (ctrl_out = its starting point).
  *   - No CPU fallback exists: without a CUDA device lscqp_create fails with LSCQP_E_NODEVICE.
  */
 #ifndef LSCQP_H
@@ -39,6 +40,8 @@ extern "C" {
 #define LSCQP_MAX_ITER      1
 #define LSCQP_INFEASIBLE    2
 #define LSCQP_NUMERICAL     3
+#define LSCQP_CAPACITY      4      /* obstacle list longer than max_obs (or, without presolve, than the kernel instance
+                                      holds): nothing was dropped, the agent was not solved; ctrl_out = starting point */
 
 /* PlannerMode, include/sp_const.hpp:19-26 (same integer values) */
 #define LSCQP_MODE_DLSC 0
@@ -66,7 +69,9 @@ typedef struct lscqp_config {
     int presolve;                  /* bit 0: drop obstacles whose rows are all proven inactive by
                                       bound propagation through the velocity rows (exact);
                                       bit 1: keep every agent on the full-capacity kernel
-                                      instance (no light-instance first pass)                   */
+                                      instance (no light-instance first pass);
+                                      bit 2: light first pass at any batch size (default: only
+                                      from 1536 agents, below that a batch is latency bound)    */
 } lscqp_config;
 
 typedef struct lscqp_handle lscqp_handle;
@@ -89,6 +94,8 @@ int lscqp_destroy(lscqp_handle* h);
  * [dim*M*6][6] box rows = lb, ub, vel+, vel-, acc+, acc- of the variable's stencil, then with
  * comm_range > 0 [dim][M + M(M-1)/2][2] communication pairs = upper-side, lower-side). */
 int lscqp_dual_stride(const lscqp_handle* h);
+/* Number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+unsigned long long lscqp_launch_count(const lscqp_handle* h);
 int lscqp_max_obs_padded(const lscqp_handle* h);
 
 /* LSC assembly for agent-type obstacles: generateLSC / generateCLSC / generateBVC
@@ -146,6 +153,11 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
         double* dual_out,           /* [n_agents][lscqp_dual_stride] optional                   */
         void* stream);
 
+/* Diagnostics: which kernel instance solved each agent in the last lscqp_solve_batch call on this handle (0 = light
+ * one-warp instance, 1 = full-capacity instance); klass_out is a HOST array [n_agents]; synchronises `stream`.
+ * LSCQP_E_INVALID when that call ran the full-capacity instance alone. */
+int lscqp_last_instances(lscqp_handle* h, int n_agents, int* klass_out, void* stream);
+
 /* Same as lscqp_solve_batch with HOST buffers: copies inputs host->device, solves, copies
  * ctrl/cost/status (and the optional outputs) back, and synchronises the stream. */
 int lscqp_solve_host(lscqp_handle* h, int n_agents,
@@ -189,12 +201,14 @@ int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs_index,
         float* obs_traj, float* obs_meta, float* obs_goal, float* obs_position, void* stream);
 
 /* Neighbour selection on the device (MultiSyncSimulator::broadcastMsgs, src/multi_sync_simulator.cpp:305-352): for the
- * agents [lo, lo + n_local) of a population of n_total, the ids of the K nearest other agents -- those within the
- * Chebyshev communication range first (:319-328; comm_range <= 0: no filter), padded with the nearest out-of-range
- * ones when fewer than K are in range -- in ascending id order.  state: [n_total][9] (position first);
- * obs_index_out: [n_local][K], ready for lscqp_gather_obstacles with obs_offsets = K * arange. */
+ * agents [lo, lo + n_local) of a population of n_total, the ids of the other agents whose position is within the
+ * Chebyshev communication range (:319-328; comm_range <= 0: every other agent), in ascending id order, as a ragged CSR
+ * list -- exactly the reference's obstacle set.  K (<= max_obs) is the capacity per agent: an agent with more than K in
+ * range keeps its K nearest and overflow_out[a] holds its in-range count (0 = the list is complete); nothing is padded.
+ * state: [n_total][9] (position first); obs_offsets_out: [n_local + 1]; obs_index_out: capacity n_local * K;
+ * overflow_out: [n_local] or NULL.  Device pointers. */
 int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, int K, double comm_range,
-        const float* state, int* obs_index_out, void* stream);
+        const float* state, int* obs_offsets_out, int* obs_index_out, int* overflow_out, void* stream);
 
 /* Closed-loop glue on the device (AgentManager::doStep src/agent_manager.cpp:29-50 via
  * Trajectory::getStateAt src/trajectory.cpp:156-170, and the previous-solution shift

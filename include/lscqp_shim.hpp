@@ -158,8 +158,7 @@ inline lscqp_config make_lscqp_config(const Param& p, const Mission& m, int max_
     c.M = p.M; c.n = p.n; c.phi = p.phi; c.dim = p.world_dimension;
     c.dt = p.dt; c.w_control = p.control_input_weight; c.w_terminal = p.terminal_weight;
     c.planner_mode = (int) p.planner_mode; c.use_sfc = p.world_use_octomap ? 1 : 0;
-    // communication-range rows (traj_optimizer.cpp:477-500) exist in LSC mode only on the device side
-    c.comm_range = (p.planner_mode == PlannerMode::LSC) ? p.communication_range : 0.0;
+    c.comm_range = p.communication_range;      // rows of traj_optimizer.cpp:477-500, every planner mode
     for (int k = 0; k < 3; k++) { c.world_min[k] = (double) m.world_min(k); c.world_max[k] = (double) m.world_max(k); }
     c.z_2d = p.world_z_2d; c.max_obs = max_obs; c.max_agents = 1; c.max_iter = 0; c.tol = 0; c.presolve = 1;
     return c;

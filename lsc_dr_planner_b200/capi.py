@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblscqp.so")
 
 MODE_DLSC, MODE_LSC, MODE_BVC = 0, 1, 2
 GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
-STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL = 0, 1, 2, 3
+STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL, STATUS_CAPACITY = 0, 1, 2, 3, 4
 
 EXPORTS = ["lscqp_version", "lscqp_last_error", "lscqp_create", "lscqp_destroy", "lscqp_dual_stride",
            "lscqp_max_obs_padded", "lscqp_assemble_lsc_batch", "lscqp_solve_batch", "lscqp_solve_host",
@@ -54,7 +54,8 @@ def load():
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
-                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch"):
+                     "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch",
+                     "lscqp_last_instances"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -129,6 +130,12 @@ class LscQp:
     def launches(self) -> int:
         return int(self.lib.lscqp_launch_count(self.h))
 
+    def last_instances(self, n, stream=0) -> np.ndarray:
+        """kernel instance of every agent in the last two-pass solve_batch: 0 = light (one warp per QP), 1 = full capacity"""
+        out = np.zeros(n, np.int32)
+        self._check(self.lib.lscqp_last_instances(self.h, n, _hp(out, np.int32), C.c_void_p(stream)))
+        return out
+
     def measure_fp64_peak(self) -> float:
         """sustained FP64 FMA rate of the device in GFLOP/s (register-resident DFMA microbenchmark)"""
         out = C.c_double()
@@ -168,10 +175,13 @@ class LscQp:
         self._check(self.lib.lscqp_validate_batch(self.h, n, _dp(traj), _dp(state_at_step), _dp(limits), _dp(sfc),
                                                   _dp(valid_out), C.c_void_p(stream)))
 
-    def select_neighbours(self, n_total, lo, n_local, K, comm_range, state, obs_index_out, stream=0):
-        """broadcastMsgs on the device: K nearest (in-range first) neighbour ids of the agents [lo, lo + n_local)"""
+    def select_neighbours(self, n_total, lo, n_local, K, comm_range, state, obs_offsets_out, obs_index_out,
+                          overflow_out=None, stream=0):
+        """broadcastMsgs on the device: ragged CSR lists of the agents within the Chebyshev communication range of the agents
+        [lo, lo + n_local) (all others when comm_range <= 0); more than K in range -> K nearest + overflow_out = count"""
         self._check(self.lib.lscqp_select_neighbours(self.h, n_total, lo, n_local, K, C.c_double(comm_range), _dp(state),
-                                                     _dp(obs_index_out), C.c_void_p(stream)))
+                                                     _dp(obs_offsets_out), _dp(obs_index_out), _dp(overflow_out),
+                                                     C.c_void_p(stream)))
 
     def step_batch(self, n, ctrl, step, traj_out, state_out=None, shifted_out=None, stream=0):
         self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),

@@ -51,8 +51,10 @@ class ClosedLoopSim:
         self.traj = self._const_vel(self.state)          # [N,M,6,3] initial_traj / obs_pred_trajs of this step
         # local scratch
         n, sk = max(self.n_local, 1), max(self.n_local * self.K, 1)
-        self.obs_offsets = (torch.arange(self.n_local + 1, device=dev, dtype=torch.int32) * self.K).contiguous()
+        self.obs_offsets = torch.zeros((self.n_local + 1,), dtype=torch.int32, device=dev)     # ragged CSR, rebuilt every step
         self.obs_index = torch.zeros((sk,), dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros((n,), dtype=torch.int32, device=dev)   # in-range count where it exceeds K (else 0)
+        self._overflowed = torch.zeros((), dtype=torch.int64, device=dev)
         self.normals = torch.empty((sk, M, 3), dtype=torch.float64, device=dev)
         self.rhs = torch.empty((sk, M, 6), dtype=torch.float64, device=dev)
         self.ctrl = torch.empty((n, self.cfg.dim * M * 6), dtype=torch.float64, device=dev)
@@ -73,6 +75,11 @@ class ClosedLoopSim:
         """QPs that did not converge so far (reads the device counter: synchronises)"""
         return int(self._failed.item())
 
+    @property
+    def overflowed_total(self) -> int:
+        """(agent, replan) pairs whose in-range neighbours exceeded the capacity K (reads the device counter)"""
+        return int(self._overflowed.item())
+
     def _const_vel(self, state):
         torch = self.torch
         M, dt = self.cfg.M, self.cfg.dt
@@ -81,11 +88,11 @@ class ClosedLoopSim:
         return (state[:, None, None, 0:3] + state[:, None, None, 3:6] * tt).contiguous()
 
     def neighbours(self, stream: int = 0):
-        """K nearest agents of every local agent (those within the L-inf communication range first,
-        src/multi_sync_simulator.cpp:319-328; padded with the nearest out-of-range ones when fewer are in range):
-        lscqp_select_neighbours, ids in ascending order"""
+        """the reference's obstacle set of every local agent (src/multi_sync_simulator.cpp:319-328: the agents within the
+        L-inf communication range, all others when the range is <= 0) as a ragged CSR list, ids ascending; an agent with
+        more than K in range keeps its K nearest and is counted in `overflowed_total` (lscqp_select_neighbours)"""
         self.planner.qp.select_neighbours(self.N, self.lo, self.n_local, self.K, self.comm_range, self.state,
-                                          self.obs_index, stream)
+                                          self.obs_offsets, self.obs_index, self.overflow, stream)
         return self.obs_index
 
     def _step_impl(self, stream: int):
@@ -119,6 +126,7 @@ class ClosedLoopSim:
             fallback = own.permute(0, 3, 1, 2)[:, :self.cfg.dim].reshape(n, -1).to(torch.float64)
             torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
             self._failed += bad.sum()
+            self._overflowed += (self.overflow[:n] > 0).sum()
             qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted, stream)
             new_traj, new_state = self.shifted, self.state_out
         else:

@@ -57,7 +57,6 @@ inline int validate_config(const lscqp_config& c) {
     if (!(c.dim == 2 || c.dim == 3)) return LSCQP_E_INVALID;
     if (!(c.planner_mode == LSCQP_MODE_DLSC || c.planner_mode == LSCQP_MODE_LSC || c.planner_mode == LSCQP_MODE_BVC))
         return LSCQP_E_INVALID;
-    if (c.comm_range > 0 && c.planner_mode != LSCQP_MODE_LSC) return LSCQP_E_INVALID;   // comm rows are built for LSC mode
     if (c.max_obs < 0 || c.max_obs > 40) return LSCQP_E_INVALID;
     if (!(c.dt > 0) || !(c.w_control > 0) || !(c.w_terminal >= 0)) return LSCQP_E_INVALID;
     return 0;
@@ -77,6 +76,7 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     for (int k = 0; k < 3; k++) { p.world_min[k] = c.world_min[k]; p.world_max[k] = c.world_max[k]; }
     p.use_sfc = c.use_sfc;
     p.presolve = c.presolve & 1;
+    p.max_obs = c.max_obs;
     p.klass = nullptr; p.klass_mode = 0;
     p.comm_range = c.comm_range;
     double Q[36];
@@ -207,6 +207,7 @@ struct Instance {
 #define LSCQP_FOR_EACH_INSTANCE(X) \
     X(5, 3, true, false) X(5, 3, false, false) X(5, 2, true, false) X(5, 2, false, false) \
     X(10, 3, true, false) X(10, 3, false, false) X(10, 2, true, false) X(10, 2, false, false) \
-    X(5, 3, true, true) X(5, 2, true, true) X(10, 3, true, true) X(10, 2, true, true)
+    X(5, 3, true, true) X(5, 2, true, true) X(10, 3, true, true) X(10, 2, true, true) \
+    X(5, 3, false, true) X(5, 2, false, true) X(10, 3, false, true) X(10, 2, false, true)
 
 }  // namespace lscqp

@@ -1,23 +1,28 @@
 // knn_kernel.cuh -- neighbour selection for the closed loop (what MultiSyncSimulator::broadcastMsgs does,
-// src/multi_sync_simulator.cpp:305-352): the obstacles of agent qi are the other agents, restricted to those whose
-// current position is within the Chebyshev communication range (:319-328).  The batched kernels take at most
-// max_obs (<= 40) obstacles per agent, so the K nearest are kept (in-range agents first, then -- only when fewer than K
-// are in range -- the nearest out-of-range ones as padding; their planes never bind).
+// src/multi_sync_simulator.cpp:305-352): the obstacles of agent qi are the other agents whose current position is
+// within the Chebyshev communication range (:319-328; every other agent when the range is <= 0), in ascending id order.
+// The output is a ragged CSR list holding exactly that set.  The solve kernels hold at most max_obs obstacles per agent:
+// an agent with more than K in range keeps its K nearest and is *flagged* (overflow_out = its in-range count), so the
+// caller can raise max_obs or report it -- nothing is padded and nothing is dropped silently.
 //
-// One CTA per agent.  Squared distances to all n_total agents go to shared memory as order-preserving unsigned keys
-// (non-negative float bits; bit 31 set for out-of-range agents, 0xFFFFFFFF for the agent itself).  The K-th smallest key
-// is built bit by bit (32 counting passes over the keys: no atomics -- a radix histogram serialises on the handful of
-// exponent values distances share), and an ordered compaction writes the selected ids in ascending agent order (the order
-// broadcastMsgs emits them), ties at the threshold broken by the lower id: deterministic.
+// knn_select_kernel: one CTA per agent.  Squared distances to all n_total agents go to shared memory as order-preserving
+// unsigned keys (non-negative float bits; bit 31 set for out-of-range agents, 0xFFFFFFFF for the agent itself).  When more
+// than K agents are in range the K-th smallest key is built bit by bit (32 counting passes over the keys: no atomics -- a
+// radix histogram serialises on the handful of exponent values distances share); an ordered compaction then writes the
+// selected ids in ascending agent order (the order broadcastMsgs emits them), ties at the threshold broken by the lower
+// id: deterministic.  It writes a fixed-stride row per agent plus its count; knn_csr_kernel (one CTA: scan of the counts,
+// then a copy) turns the rows into the CSR arrays the assembly / solve kernels read.
 #pragma once
 
 namespace lscqp {
 
 struct KnnParams {
     int n_total, lo, n_local, K;
-    float comm_range;              // <= 0: no range filter
+    double comm_range;             // <= 0: no range filter (a double like Param::communication_range)
     const float* state;            // [n_total][9] position first
-    int* obs_index;                // [n_local][K]
+    int* obs_index;                // [n_local][K]  selected ids, ascending; entries beyond count[a] are not written
+    int* count;                    // [n_local]     number of selected ids (<= K)
+    int* overflow;                 // [n_local]     0, or the in-range count when it exceeds K (may be null)
 };
 
 constexpr int KNN_THREADS = 128;
@@ -39,7 +44,8 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
     for (int j = tid; j < N; j += KNN_THREADS) {
         const float dx = p.state[(size_t) j * 9] - ax, dy = p.state[(size_t) j * 9 + 1] - ay, dz = p.state[(size_t) j * 9 + 2] - az;
         unsigned key = __float_as_uint(dx * dx + dy * dy + dz * dz) & 0x7FFFFFFFu;
-        if (p.comm_range > 0.f && fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz)) > p.comm_range) key |= 0x80000000u;
+        // LInfinityDistance of the float positions, compared in double like multi_sync_simulator.cpp:321-326
+        if (p.comm_range > 0.0 && (double) fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz)) > p.comm_range) key |= 0x80000000u;
         if (j == a) key = 0xFFFFFFFFu;
         keys[skew(j)] = key;
     }
@@ -56,14 +62,23 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
         __syncthreads();
         return tot;
     };
-    // the K-th smallest key is the largest T with count(keys < T) < K: set its bits from the top
-    unsigned prefix = 0;
-    for (int bit = 31; bit >= 0; bit--) {
-        const unsigned test = prefix | (1u << bit);
-        if (count_below(test) < p.K) prefix = test;
+    const int n_in = count_below(0x80000000u);         // agents in range (the agent's own key is 0xFFFFFFFF)
+    if (tid == 0) {
+        p.count[blockIdx.x] = n_in < p.K ? n_in : p.K;
+        if (p.overflow) p.overflow[blockIdx.x] = n_in > p.K ? n_in : 0;
     }
-    const int want = p.K - count_below(prefix);        // how many of the keys equal to the threshold are taken
-    const unsigned thr = prefix;                       // the K-th smallest key; `want` of the keys equal to it are taken
+    unsigned thr = 0x80000000u;                        // everything in range ...
+    int want = 0;
+    if (n_in > p.K) {
+        // ... unless that exceeds the capacity: the K-th smallest key is the largest T with count(keys < T) < K
+        unsigned prefix = 0;
+        for (int bit = 31; bit >= 0; bit--) {
+            const unsigned test = prefix | (1u << bit);
+            if (count_below(test) < p.K) prefix = test;
+        }
+        want = p.K - count_below(prefix);              // how many of the keys equal to the threshold are taken
+        thr = prefix;
+    }
     // ordered compaction: thread t owns the contiguous id range [t * chunk, (t + 1) * chunk)
     const int chunk = (N + KNN_THREADS - 1) / KNN_THREADS;
     const int j0 = tid * chunk, j1 = (j0 + chunk < N) ? j0 + chunk : N;
@@ -86,6 +101,49 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_select_kernel(const KnnParams
         else if (k == thr) { if (ie < (unsigned) want) out[il + ie] = j; ie++; }
     }
     (void) tot_l;
+}
+
+// rows of knn_select_kernel -> CSR: offsets = exclusive scan of the counts, ids copied in order.  One CTA.
+struct KnnCsrParams {
+    int n_local, K;
+    const int* rows;               // [n_local][K]
+    const int* count;              // [n_local]
+    int* obs_offsets;              // [n_local + 1]
+    int* obs_index;                // [sum count]
+};
+
+constexpr int KNN_CSR_THREADS = 1024;
+
+__global__ void __launch_bounds__(KNN_CSR_THREADS) knn_csr_kernel(const KnnCsrParams p) {
+#ifdef LSCQP_CUDA_EMUL
+    int* s_warp = reinterpret_cast<int*>(emu_dyn_smem);
+#else
+    __shared__ int s_warp[KNN_CSR_THREADS / 32 + 1];
+#endif
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < p.n_local; base += KNN_CSR_THREADS) {
+        const int a = base + tid;
+        const int c = a < p.n_local ? p.count[a] : 0;
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < KNN_CSR_THREADS / 32 ? s_warp[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            s_warp[lane] = w;                                   // inclusive totals of the warps
+        }
+        __syncthreads();
+        const int off = carry + incl - c + (warp > 0 ? s_warp[warp - 1] : 0);
+        if (a < p.n_local) {
+            p.obs_offsets[a] = off;
+            for (int j = 0; j < c; j++) p.obs_index[off + j] = p.rows[(size_t) a * p.K + j];
+        }
+        carry += s_warp[KNN_CSR_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (tid == 0) p.obs_offsets[p.n_local] = carry;
 }
 
 }  // namespace lscqp

@@ -49,8 +49,8 @@ struct lscqp_handle {
     // device staging for the *_host entry points
     DevBuf d_state, d_goal, d_limits, d_sfc, d_off, d_normals, d_rhs, d_ctrl, d_cost, d_status, d_iters, d_kkt, d_dual;
     DevBuf d_own, d_ameta, d_index;
-    DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout;
-    bool two_pass = false;
+    DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout, d_knn;
+    bool two_pass = false, last_two_pass = false;
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
@@ -63,7 +63,7 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     if (!cfg || !out) return fail(LSCQP_E_INVALID, "null argument");
     int rc = validate_config(*cfg);
     if (rc) return fail(rc, "unsupported configuration (need n=5, phi=3, M in {5,10}, dim in {2,3}, "
-                            "mode in {DLSC,LSC,BVC}, comm_range>0 only in LSC mode, max_obs<=40)");
+                            "mode in {DLSC,LSC,BVC}, max_obs<=40)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(LSCQP_E_NODEVICE, "no CUDA device: liblscqp has no CPU fallback");
@@ -78,10 +78,12 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     if (!found) found = inst_query_1(*cfg, &info);
     if (!found) found = inst_query_2(*cfg, &info);
     if (!found) found = inst_query_3(*cfg, &info);
+    if (!found) found = inst_query_4(*cfg, &info);
     if (found < 0) { delete h; return fail(LSCQP_E_CUDA, "cudaFuncSetAttribute failed"); }
     if (!found) { delete h; return fail(LSCQP_E_INVALID, "no kernel instance"); }
     h->dual_stride = info.dual_stride; h->kmax = info.kmax; h->nv = info.nv;
     h->two_pass = info.has_light && (cfg->presolve & 1) && !(cfg->presolve & 2);
+    if (cfg->presolve & 4) h->two_pass_min = 0;            // light first pass at any batch size
     if (const char* e = std::getenv("LSCQP_TWO_PASS_MIN")) h->two_pass_min = std::atoi(e);
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
@@ -105,7 +107,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass, &h->d_gout};
+                      &h->d_klass, &h->d_gout, &h->d_knn};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -136,6 +138,7 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     // The light first pass pays off in the throughput regime (several waves of one-warp CTAs); a small batch is
     // latency bound and finishes sooner on the 128-thread instance alone.
     const bool two_pass = h->two_pass && n_agents >= h->two_pass_min;
+    h->last_two_pass = two_pass;
     if (two_pass) {
         if (h->d_klass.reserve((size_t) n_agents * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
         p.klass = h->d_klass.as<int>();
@@ -144,8 +147,19 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, two_pass, st);
     if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, two_pass, st);
     if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, two_pass, st);
+    if (!launched) launched = inst_launch_4(h->cfg, p, n_agents, two_pass, st);
     h->launches += launched;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// which kernel instance solved each agent in the last two-pass lscqp_solve_batch call (0 = light one-warp instance,
+// 1 = full-capacity instance); synchronises the stream.  Returns LSCQP_E_INVALID when the last call was one-pass.
+extern "C" int lscqp_last_instances(lscqp_handle* h, int n_agents, int* klass_out_host, void* stream) {
+    if (!h || !klass_out_host || n_agents < 0) return fail(LSCQP_E_INVALID, "null argument");
+    if (!h->last_two_pass || h->d_klass.bytes < (size_t) n_agents * sizeof(int)) return fail(LSCQP_E_INVALID, "last solve was one-pass");
+    CK(cudaMemcpyAsync(klass_out_host, h->d_klass.p, (size_t) n_agents * sizeof(int), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
     return 0;
 }
 
@@ -234,22 +248,30 @@ extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctr
 }
 
 extern "C" int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, int K, double comm_range,
-                                       const float* state, int* obs_index_out, void* stream) {
-    if (!h || !state || !obs_index_out || n_total < 0 || n_local < 0 || lo < 0 || lo + n_local > n_total)
+                                       const float* state, int* obs_offsets_out, int* obs_index_out, int* overflow_out,
+                                       void* stream) {
+    if (!h || !state || !obs_offsets_out || !obs_index_out || n_total < 0 || n_local < 0 || lo < 0 || lo + n_local > n_total)
         return fail(LSCQP_E_INVALID, "bad argument");
-    if (K < 0 || K > h->cfg.max_obs || K > n_total - 1) return fail(LSCQP_E_CAPACITY, "K above max_obs or n_total - 1");
-    if (n_local == 0 || K == 0) return 0;
+    if (K < 0 || K > h->cfg.max_obs) return fail(LSCQP_E_CAPACITY, "K above max_obs");
+    if (n_local == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t smem = knn_smem_bytes(n_total);
     if (smem > 200 * 1024) return fail(LSCQP_E_CAPACITY, "n_total above the shared-memory capacity of the selection kernel");
     if (smem > 48 * 1024 && smem > h->knn_smem) {
         CK(cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         h->knn_smem = smem;
     }
+    // fixed-stride rows + counts (scratch owned by the handle; allocate before any stream capture: the first call does)
+    if (h->d_knn.reserve(((size_t) n_local * (K > 0 ? K : 1) + n_local) * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
     KnnParams p;
-    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = (float) comm_range;
-    p.state = state; p.obs_index = obs_index_out;
-    knn_select_kernel<<<n_local, KNN_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    h->launches++;
+    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = comm_range;
+    p.state = state; p.obs_index = h->d_knn.as<int>(); p.count = p.obs_index + (size_t) n_local * (K > 0 ? K : 1);
+    p.overflow = overflow_out;
+    knn_select_kernel<<<n_local, KNN_THREADS, smem, st>>>(p);
+    KnnCsrParams c;
+    c.n_local = n_local; c.K = K; c.rows = p.obs_index; c.count = p.count; c.obs_offsets = obs_offsets_out; c.obs_index = obs_index_out;
+    knn_csr_kernel<<<1, KNN_CSR_THREADS, 0, st>>>(c);
+    h->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -329,6 +351,18 @@ extern "C" int lscqp_measure_fp64_peak(lscqp_handle* h, double* gflops_out) {
 // HOST-buffer entry points: what a TrajOptimizer / simulator running on the CPU calls.
 #define RESERVE(buf, n) do { if ((buf).reserve(n)) return fail(LSCQP_E_CUDA, "cudaMalloc failed"); } while (0)
 
+// every obstacle list of a host CSR must be non-negative and within the handle's capacity: the reference's model takes
+// every obstacle it is given (traj_optimizer.cpp:400-437), so a list this library cannot hold is an error, not a cut
+static int check_host_lists(const lscqp_handle* h, int n_agents, const int* obs_offsets) {
+    if (obs_offsets[0] != 0) return fail(LSCQP_E_INVALID, "obs_offsets[0] must be 0");
+    for (int a = 0; a < n_agents; a++) {
+        if (obs_offsets[a + 1] < obs_offsets[a]) return fail(LSCQP_E_INVALID, "obs_offsets must be non-decreasing");
+        if (obs_offsets[a + 1] - obs_offsets[a] > h->cfg.max_obs)
+            return fail(LSCQP_E_CAPACITY, "obstacle list of an agent is longer than max_obs");
+    }
+    return 0;
+}
+
 extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* state, const float* goal,
                                 const double* limits, const float* sfc, const float* next_waypoint, const int* obs_offsets,
                                 const double* normals, const double* rhs, const float* initial_traj, double* ctrl_out,
@@ -336,6 +370,7 @@ extern "C" int lscqp_solve_host(lscqp_handle* h, int n_agents, const float* stat
     if (!h || n_agents < 0 || !state || !goal || !limits || !obs_offsets || !ctrl_out || !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
+    if (int rc = check_host_lists(h, n_agents, obs_offsets)) return rc;
     CK(cudaSetDevice(h->device));
     const int M = h->cfg.M;
     const size_t sumK = (size_t) obs_offsets[n_agents];
@@ -394,6 +429,7 @@ extern "C" int lscqp_goal_host(lscqp_handle* h, int n_agents, const float* goal,
     if (!h || n_agents < 0 || !goal || !next_waypoint || !obs_offsets || !goal_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
+    if (int rc = check_host_lists(h, n_agents, obs_offsets)) return rc;
     CK(cudaSetDevice(h->device));
     const int M = h->cfg.M;
     const size_t sumK = (size_t) obs_offsets[n_agents];
@@ -436,14 +472,11 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
         !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
+    if (int rc = check_host_lists(h, n_agents, obs_offsets)) return rc;
     CK(cudaSetDevice(h->device));
     const int M = h->cfg.M;
     const size_t sumK = (size_t) obs_offsets[n_agents];
     if (sumK > 0 && !obs_index) return fail(LSCQP_E_INVALID, "null obs_index");
-    for (int a = 0; a < n_agents; a++) {
-        if (obs_offsets[a + 1] < obs_offsets[a] || obs_offsets[a + 1] - obs_offsets[a] > h->cfg.max_obs)
-            return fail(LSCQP_E_CAPACITY, "obstacle list of an agent is negative or above max_obs");
-    }
     for (size_t j = 0; j < sumK; j++)
         if (obs_index[j] < 0 || obs_index[j] >= n_agents) return fail(LSCQP_E_INVALID, "obs_index outside [0, n_agents)");
     cudaStream_t st = h->stream;

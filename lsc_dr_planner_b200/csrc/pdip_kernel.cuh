@@ -54,6 +54,7 @@ struct SolveParams {
     double world_min[3], world_max[3];
     int use_sfc;
     int presolve;               // drop obstacles whose rows are all proven inactive by velocity-bound propagation (exact)
+    int max_obs;                // lscqp_config.max_obs: a longer obstacle list is reported as ST_CAPACITY, never truncated
     const float*  state;        // [n][9]   position, velocity, acceleration
     const float*  goal;         // [n][3]   current_goal_point
     const double* limits;       // [n][8]   vmax[3], amax[3], radius, nominal_velocity
@@ -86,7 +87,7 @@ struct SolveParams {
     int     klass_mode;
 };
 
-enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3 };
+enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3, ST_CAPACITY = 4 };
 
 template <int M_, int D_, bool TERM_, int G_, int KPT_, bool COMM_ = false>
 struct Cfg {
@@ -633,8 +634,14 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
-    if (K > C::KRAW) K = C::KRAW;
     if (p.klass_mode == 2 && p.klass[agent] == 0) return;                // solved by the light instance already
+    // The reference's model takes every obstacle it is handed (traj_optimizer.cpp:400-437 loops over getObsSize()):
+    // a list this instance cannot hold is reported through status_out (LSCQP_CAPACITY), never silently shortened.
+    bool cap_fail = K < 0 || K > C::KRAW || K > p.max_obs;
+    if (cap_fail) {
+        if (p.klass_mode == 1) { if (tid == 0) p.klass[agent] = 1; return; }   // the full-capacity pass reports it
+        K = 0;
+    }
 
     // ---- Cholesky trailing-update pair assignment (fixed per lane)
     int pr_i[C::NPR], pr_k[C::NPR];
@@ -735,7 +742,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (tid == 0) p.klass[agent] = over ? 1 : 0;
         if (over) return;
     }
-    if (K > C::KMAX) K = C::KMAX;
+    if (K > C::KMAX) { cap_fail = true; K = 0; }                          // (only without presolve, or on the compact instance)
     for (int e = tid; e < K * M; e += NT) {
         // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference
         // (traj_optimizer.cpp:409-411): here they become the constant row 0.c >= -1, which never binds
@@ -770,6 +777,21 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         cta_sync<C>();
     };
     set_start(warm);
+    if (cap_fail) {
+        // finite outputs: the starting point (initial_traj when given), no multipliers
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = tid + u * NT;
+            if (v < NV) p.ctrl_out[(size_t) agent * NV + v] = s_c[v];
+        }
+        if (tid == 0) {
+            p.cost_out[agent] = 0.0; p.status_out[agent] = ST_CAPACITY;
+            if (p.iters_out) p.iters_out[agent] = 0;
+            if (p.kkt_out) for (int e = 0; e < 4; e++) p.kkt_out[agent * 4 + e] = 0.0;
+        }
+        if (p.dual_out) for (int e = tid; e < p.dual_stride; e += NT) p.dual_out[(size_t) agent * p.dual_stride + e] = 0.0;
+        return;
+    }
 
     // ---- per-thread row state (registers): slack and multiplier of every owned row
     double ls[KPT], ll[KPT];
@@ -1103,6 +1125,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     // ---------------------------------------------------------------- main loop   // @phase sweepA
     int status = ST_MAX_ITER, it = 0;
     double mu = 0.0, sigmu = 0.0, alpha = 0.0, mu_first = 0.0;
+    double res_scale = 1.0;       // prod (1 - alpha): what is left of the initial primal and dual residuals (both linear)
     bool have_step = false;       // a (dca, dc, sigmu, alpha) step is pending and is applied by the next sweep A
     for (it = 0; it <= p.max_iter; it++) {
         // ---- sweep A: apply the pending step, then predictor weights of the new point
@@ -1112,6 +1135,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (have_step && cp_valid) { load_cp(s_dca, ax, ay, az); load_cp(s_dc, dx, dy, dz); }
             else { ax = ay = az = dx = dy = dz = 0; }
             const double rp_new = have_step ? (1.0 - alpha) * rp : rp;
+            if (have_step) res_scale *= (1.0 - alpha);
             double sl = 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
@@ -1157,7 +1181,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             mu = red[0] / n_rows;
         }
         if (!(mu == mu)) { status = ST_NUMERICAL; break; }
-        if (mu < p.mu_tol && fabs(rp) < p.rp_tol) { status = ST_OK; break; }
+        // Stop: complementarity and primal residual small, and the initial *dual* residual -- which every step scales by
+        // (1 - alpha) like the primal one -- reduced by at least 1e-6 (a strictly interior warm start has rp = 0 from the
+        // first iteration, so the primal test alone would accept a run of short steps at a non-stationary point)
+        if (mu < p.mu_tol && fabs(rp) < p.rp_tol && res_scale < 1e-6) { status = ST_OK; break; }
         // an infeasible model drives the multipliers (and with them mu) to infinity: stop long before the overflow
         if (it == 0) mu_first = mu;
         if (mu > 1e12 * fmax(mu_first, 1.0)) { status = ST_INFEASIBLE; break; }

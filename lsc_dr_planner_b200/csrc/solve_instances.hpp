@@ -1,5 +1,5 @@
 // solve_instances.hpp -- the PDIP kernel instances, split over translation units so that nvcc compiles them in
-// parallel.  Each inst_<n>.cu defines LSCQP_TU (0..3) and includes this file; lscqp.cu sees only the declarations.
+// parallel.  Each inst_<n>.cu defines LSCQP_TU (0..4) and includes this file; lscqp.cu sees only the declarations.
 #pragma once
 #include <cuda_runtime.h>
 #include "host_common.hpp"
@@ -18,11 +18,13 @@ int inst_query_0(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_1(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_2(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_3(const lscqp_config& cfg, InstanceInfo* info);
+int inst_query_4(const lscqp_config& cfg, InstanceInfo* info);
 // Launches the instance (light pass first when two_pass); returns the number of kernels launched, 0 when not here.
 int inst_launch_0(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
 int inst_launch_1(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
 int inst_launch_2(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
 int inst_launch_3(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+int inst_launch_4(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
 
 #ifdef LSCQP_TU
 #if LSCQP_TU == 0
@@ -34,9 +36,12 @@ int inst_launch_3(const lscqp_config& cfg, SolveParams& p, int n_agents, bool tw
 #elif LSCQP_TU == 2
 #define LSCQP_TU_INSTANCES(X) X(10, 3, true, false) X(10, 3, false, false)
 #define LSCQP_TU_NAME(f) f##_2
-#else
+#elif LSCQP_TU == 3
 #define LSCQP_TU_INSTANCES(X) X(5, 3, true, true) X(5, 2, true, true) X(10, 3, true, true) X(10, 2, true, true)
 #define LSCQP_TU_NAME(f) f##_3
+#else   // communication-range rows without the terminal stop: DLSC / BVC modes (the reference's defaults, param.cpp:117,129)
+#define LSCQP_TU_INSTANCES(X) X(5, 3, false, true) X(5, 2, false, true) X(10, 3, false, true) X(10, 2, false, true)
+#define LSCQP_TU_NAME(f) f##_4
 #endif
 
 template <class C>

@@ -91,6 +91,25 @@ inline double __shfl_sync(unsigned, double v, int src_lane) {
     __syncwarp();
     return r;
 }
+inline int __shfl_up_sync(unsigned, int v, int delta) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = (double) v;
+    __syncwarp();
+    const int lane = s.cur & 31;
+    const int r = lane >= delta ? (int) s.slot_d[s.cur - delta] : v;
+    __syncwarp();
+    return r;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = pred ? 1.0 : 0.0;
+    __syncwarp();
+    const int w0 = s.cur & ~31, wn = std::min(32, s.nthreads - w0);
+    unsigned r = 0;
+    for (int i = 0; i < wn; i++) if (s.slot_d[w0 + i] != 0.0) r |= 1u << i;
+    __syncwarp();
+    return r;
+}
 inline int __any_sync(unsigned, int pred) {
     emu::State& s = emu::st();
     s.slot_d[s.cur] = pred ? 1.0 : 0.0;

@@ -114,10 +114,16 @@ extern "C" int emul_goal_batch(const lscqp_config* cfg, int n_agents, const floa
     return 0;
 }
 
-extern "C" int emul_select_neighbours(int n_total, int lo, int n_local, int K, double comm_range, const float* state, int* out) {
+extern "C" int emul_select_neighbours(int n_total, int lo, int n_local, int K, double comm_range, const float* state,
+                                      int* offsets_out, int* index_out, int* overflow_out) {
+    std::vector<int> rows((size_t) n_local * (K > 0 ? K : 1), -1), count(n_local, 0);
     KnnParams p;
-    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = (float) comm_range; p.state = state; p.obs_index = out;
+    p.n_total = n_total; p.lo = lo; p.n_local = n_local; p.K = K; p.comm_range = comm_range; p.state = state;
+    p.obs_index = rows.data(); p.count = count.data(); p.overflow = overflow_out;
     emu::launch(n_local, KNN_THREADS, knn_smem_bytes(n_total) + 64, [&]() { knn_select_kernel(p); });
+    KnnCsrParams c;
+    c.n_local = n_local; c.K = K; c.rows = rows.data(); c.count = count.data(); c.obs_offsets = offsets_out; c.obs_index = index_out;
+    emu::launch(1, KNN_CSR_THREADS, 1024, [&]() { knn_csr_kernel(c); });
     return 0;
 }
 

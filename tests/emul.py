@@ -73,10 +73,12 @@ def goal(cfg, n, goal_pt, waypoint, sfc, off, normals, rhs):
 
 
 def select_neighbours(n_total, lo, n_local, K, comm_range, state):
-    out = np.zeros((n_local, K), np.int32)
-    rc = lib().emul_select_neighbours(n_total, lo, n_local, K, C.c_double(comm_range), _p(state, np.float32), _p(out, np.int32))
+    """-> (offsets [n_local+1], ids [sumK], overflow [n_local])"""
+    off = np.zeros(n_local + 1, np.int32); idx = np.full(max(n_local * K, 1), -1, np.int32); over = np.zeros(n_local, np.int32)
+    rc = lib().emul_select_neighbours(n_total, lo, n_local, K, C.c_double(comm_range), _p(state, np.float32), _p(off, np.int32),
+                                      _p(idx, np.int32), _p(over, np.int32))
     assert rc == 0, rc
-    return out
+    return off, idx[:off[-1]], over
 
 
 def assemble_fused(cfg, generator, prune, batch):

@@ -44,7 +44,7 @@ def test_create_fails_loudly_without_device_or_on_bad_config():
     bad = capi.make_config(W.PlannerConfig(M=7))
     assert lib.lscqp_create(C.byref(bad), 0, C.byref(h)) == -1          # LSCQP_E_INVALID
     assert b"unsupported" in lib.lscqp_last_error()
-    bad = capi.make_config(W.PlannerConfig(comm_range=3.0, planner_mode=0))      # comm rows exist in LSC mode only
+    bad = capi.make_config(W.PlannerConfig(max_obs=4096))                        # above the ABI's obstacle capacity
     assert lib.lscqp_create(C.byref(bad), 0, C.byref(h)) == -1
     if not torch.cuda.is_available():
         ok = capi.make_config(W.PlannerConfig())

@@ -124,11 +124,13 @@ def test_step_kernel_matches_oracle():
             assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
 
 
-@pytest.mark.parametrize("M,dim,K,max_obs", [(5, 3, 10, 40), (10, 2, 9, 40), (10, 2, 9, 10)])
-def test_solve_kernel_with_communication_range_rows(M, dim, K, max_obs):
+@pytest.mark.parametrize("M,dim,K,max_obs,mode", [(5, 3, 10, 40, 1), (10, 2, 9, 40, 1), (10, 2, 9, 10, 1),
+                                                  (5, 3, 10, 40, 0), (10, 2, 9, 10, 2)])
+def test_solve_kernel_with_communication_range_rows(M, dim, K, max_obs, mode):
     """communication-range rows (traj_optimizer.cpp:477-500; launch/simulation.launch sets range 3): dense instance
-    (max_obs <= 10 selects the compact 128-thread instance of the 2-D configurations)"""
-    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=1, comm_range=0.7, max_obs=max_obs)   # tight enough to bind within the 1 s horizon
+    (max_obs <= 10 selects the compact 128-thread instance of the 2-D configurations).  The rows have no mode condition
+    in the reference -- its defaults are mode dlsc + range 3 (param.cpp:117,129) -- so DLSC (0) and BVC (2) run them too."""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode, comm_range=0.7, max_obs=max_obs)   # tight enough to bind within the 1 s horizon
     batch = W.make_forest_batch(64, K=K, cfg=cfg)
     rng = np.random.default_rng(11)
     d = rng.normal(size=(64, 3)); d[:, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
@@ -158,31 +160,72 @@ def test_solve_kernel_with_communication_range_rows(M, dim, K, max_obs):
     assert np.abs(dual[:, -2 * dim * (M * (M - 1) // 2 + M):]).max() > 1e-6
 
 
-def _check_neighbours(state, lo, out, K, comm_range):
-    """every row holds K distinct other agents in ascending order; in-range agents come before out-of-range ones and
-    nearer before farther (float distances, ties at the cut allowed)"""
+@pytest.mark.parametrize("max_obs,k_over,presolve", [(40, 45, True), (40, 45, False), (12, 13, True), (12, 13, 3)])
+def test_obstacle_lists_above_capacity_are_reported_not_truncated(max_obs, k_over, presolve):
+    """the reference's model takes every obstacle it is handed (traj_optimizer.cpp:400-437 loops over getObsSize()); a
+    list longer than lscqp_config.max_obs is reported per agent (LSCQP_CAPACITY, ctrl = starting point) -- never cut to
+    the first max_obs -- and the other agents of the batch are solved as usual"""
+    cfg = W.PlannerConfig(max_obs=max_obs, presolve=presolve)
+    batch = W.make_forest_batch(64, K=min(max_obs, 12), cfg=cfg)
+    agents = [0, 1, 2]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    k = off[1] - off[0]
+    reps = -(-k_over // k)
+    n1 = np.concatenate([normals[off[1]:off[2]]] * reps)[:k_over]; r1 = np.concatenate([rhs[off[1]:off[2]]] * reps)[:k_over]
+    normals2 = np.ascontiguousarray(np.concatenate([normals[:off[1]], n1, normals[off[2]:]]))
+    rhs2 = np.ascontiguousarray(np.concatenate([rhs[:off[1]], r1, rhs[off[2]:]]))
+    off2 = np.array([0, k, k + k_over, 2 * k + k_over], np.int32)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    warm = np.ascontiguousarray(batch.own_traj[agents])
+    ref = emul.solve_batch(cfg, 3, st, goal, lim, None, off, normals, rhs, initial_traj=warm)
+    got = emul.solve_batch(cfg, 3, st, goal, lim, None, off2, normals2, rhs2, initial_traj=warm)
+    assert list(got[2]) == [0, 4, 0] and list(ref[2]) == [0, 0, 0]
+    assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[0][2], ref[0][2])
+    start = np.transpose(warm[1].astype(np.float64), (2, 0, 1)).reshape(-1)
+    # (the first three control points of segment 0 follow the initial state, the rest is initial_traj)
+    assert np.isfinite(got[0][1]).all() and np.abs(got[0][1] - start).max() < 1e-5
+
+
+def _check_neighbours(state, lo, off, idx, over, K, comm_range, rows=None):
+    """CSR list of agent a = exactly the reference's obstacle set (multi_sync_simulator.cpp:319-328: every other agent whose
+    L-inf distance is not above the range; all others when the range is <= 0) in ascending id order; when that set is
+    larger than the capacity K: its K nearest (float distances, ties at the cut allowed) and overflow = the set's size"""
     pos = state[:, :3].astype(np.float32)
-    for r, a in enumerate(range(lo, lo + out.shape[0])):
-        ids = out[r]
-        assert len(set(ids.tolist())) == K and a not in ids and (np.diff(ids) > 0).all()
+    assert off[0] == 0 and len(idx) == off[-1]
+    for r in (range(len(off) - 1) if rows is None else rows):
+        a = lo + r
+        ids = idx[off[r]:off[r + 1]]
         d = pos - pos[a]
-        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(np.float64)
-        if comm_range > 0:
-            d2 = d2 + 1e9 * (np.abs(d).max(axis=1) > np.float32(comm_range))
-        d2[a] = np.inf
-        rest = np.setdiff1d(np.arange(pos.shape[0]), np.append(ids, a))
-        if rest.size:
-            assert d2[ids].max() <= d2[rest].min() * (1 + 1e-6) + 1e-12, (a, d2[ids].max(), d2[rest].min())
+        linf = np.abs(d).max(axis=1).astype(np.float64)
+        in_range = np.ones(pos.shape[0], bool) if comm_range <= 0 else ~(linf > comm_range)
+        in_range[a] = False
+        want = np.where(in_range)[0]
+        assert (np.diff(ids) > 0).all()
+        if len(want) <= K:
+            assert np.array_equal(ids, want), (a, ids, want)
+            assert over[r] == 0
+        else:
+            assert over[r] == len(want) and len(ids) == K and in_range[ids].all()
+            d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(np.float64)
+            rest = np.setdiff1d(want, ids)
+            if K > 0:
+                assert d2[ids].max() <= d2[rest].min() * (1 + 1e-6) + 1e-12, (a, d2[ids].max(), d2[rest].min())
 
 
-@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(300, 0, 300, 40, 0.0), (257, 100, 57, 9, 3.0), (64, 0, 64, 40, 1.0), (41, 0, 41, 40, 0.0)])
+@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(300, 0, 300, 40, 0.0), (257, 100, 57, 9, 3.0), (64, 0, 64, 40, 1.0),
+                                                       (41, 0, 41, 40, 0.0), (200, 0, 200, 40, 2.5), (50, 10, 30, 0, 3.0),
+                                                       (1500, 700, 40, 12, 0.1)])
 def test_neighbour_selection_kernel(n_total, lo, n_local, K, comm):
     rng = np.random.default_rng(n_total)
     state = np.zeros((n_total, 9), np.float32)
     state[:, :3] = rng.uniform(-6, 6, (n_total, 3)).astype(np.float32)
     state[5, :3] = state[6, :3]                               # coincident agents: tie at distance zero
-    out = emul.select_neighbours(n_total, lo, n_local, K, comm, state)
-    _check_neighbours(state, lo, out, K, comm)
+    if comm == 0.1:                                           # (float) 0.1 > 0.1: a neighbour at exactly (float) 0.1 is out of range
+        state[lo + 1, :3] = state[lo, :3]; state[lo + 1, 0] = state[lo, 0] + np.float32(0.1)
+    off, idx, over = emul.select_neighbours(n_total, lo, n_local, K, comm, state)
+    _check_neighbours(state, lo, off, idx, over, K, comm)
+    if comm > 0 and K > 0:
+        assert (over == 0).any()                              # the ragged case is exercised (lists shorter than K, none padded)
 
 
 @pytest.mark.parametrize("generator,M,dim", [(0, 5, 3), (1, 5, 3), (1, 10, 2)])

@@ -356,12 +356,14 @@ def test_cpp_shim_end_to_end():
     assert b[1] == "0" and b[2] == "0" and float(b[3]) > 0.3 and float(b[4]) < 2.7
 
 
-@pytest.mark.parametrize("M,dim,K,rng_", [(10, 2, 9, 0.7), (5, 3, 12, 0.7), (10, 2, 9, 3.0)])
-def test_communication_range_rows(M, dim, K, rng_):
+@pytest.mark.parametrize("M,dim,K,rng_,mode", [(10, 2, 9, 0.7, 1), (5, 3, 12, 0.7, 1), (10, 2, 9, 3.0, 1),
+                                               (5, 3, 12, 3.0, 0), (5, 3, 12, 0.7, 0), (10, 2, 9, 0.7, 2)])
+def test_communication_range_rows(M, dim, K, rng_, mode):
     """the launch-file shape (M=10, 2-D, communication_range 3, generateCLSC) and a binding range: rows of
-    traj_optimizer.cpp:477-500 through the dense instance, assembly on the device"""
+    traj_optimizer.cpp:477-500 through the dense instance, assembly on the device.  mode 0 / range 3 is the reference's
+    own default parameter set (param.cpp:117,129: mode/planner = dlsc, communication/range = 3.0)."""
     import torch
-    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=capi.MODE_LSC, comm_range=rng_)
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode, comm_range=rng_)
     batch = W.make_forest_batch(64, K=K, cfg=cfg)
     r = np.random.default_rng(11)
     d = r.normal(size=(64, 3)); d[:, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
@@ -369,19 +371,20 @@ def test_communication_range_rows(M, dim, K, rng_):
     batch.next_waypoint = (batch.state[:, :3] + r.uniform(-0.05, 0.05, (64, 3))).astype(np.float32)
     if dim == 2:
         batch.next_waypoint[:, 2] = cfg.z_2d; batch.goal[:, 2] = cfg.z_2d
+    gen = {1: capi.GEN_CLSC, 0: capi.GEN_LSC, 2: capi.GEN_BVC}[mode]      # constructLSC, traj_planner.cpp:552-569
     planner = _planner(batch.cfg)
     dev = planner.upload(batch)
-    planner.replan_device(dev, capi.GEN_CLSC)
+    planner.replan_device(dev, gen)
     torch.cuda.synchronize()
     status = dev.status.cpu().numpy(); ctrl = dev.ctrl.cpu().numpy(); cost = dev.cost.cpu().numpy()
     # a 0.2 m leash can be infeasible for agents that cannot brake in time: those must be *reported*, the rest solved
     ok_agents = np.where(status == 0)[0]
     assert len(ok_agents) >= (64 if rng_ > 1 else 8), np.bincount(status)
     agents = [int(a) for a in ok_agents[:4]]
-    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_CLSC)
+    off, normals, rhs = oracle_planes(batch, agents, gen)
     _check_against_oracle(batch, agents, off, normals, rhs, ctrl[agents], cost[agents], status[agents], min_checked=2)
     for a in np.where(status != 0)[0][:2]:         # the oracle agrees that the reported ones have no solution
-        o2, n2, r2 = oracle_planes(batch, [int(a)], orc.GEN_CLSC)
+        o2, n2, r2 = oracle_planes(batch, [int(a)], gen)
         assert orc.solve_highs(oracle_qp_from_planes(batch, int(a), n2, r2)).status != "Optimal"
     if rng_ < 1:      # the range must actually bind: end points stay within range/2 - radius of the start
         end = ctrl.reshape(64, dim, M, 6)[ok_agents][:, :, :, 5]
@@ -400,13 +403,48 @@ def test_replan_host_rejects_bad_neighbour_lists():
         planner.replan_host_buffers(b, 16)
     b["obs_index"][3] = 0
     b["obs_offsets"][1] = 60                                  # 60 obstacles for agent 0 > max_obs
-    with pytest.raises(capi.LscqpError):
+    with pytest.raises(capi.LscqpError, match="max_obs"):
         planner.replan_host_buffers(b, 16)
 
 
-@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(4096, 0, 4096, 40, 0.0), (1024, 256, 512, 40, 3.0), (15000, 14000, 1000, 17, 0.0)])
+def test_solve_and_goal_host_reject_lists_above_capacity_and_device_path_reports_them():
+    """no entry point shortens an obstacle list: lscqp_solve_host / lscqp_goal_host return LSCQP_E_CAPACITY (the shim then
+    throws QPFAILED), the device entry point reports the agent through status_out = LSCQP_CAPACITY"""
+    import torch
+    cfg = W.PlannerConfig(max_obs=12)
+    batch = W.make_forest_batch(64, K=12, cfg=cfg)
+    agents = [0, 1, 2]
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    k = 12
+    n1 = np.concatenate([normals[off[1]:off[2]], normals[off[1]:off[1] + 1]]); r1 = np.concatenate([rhs[off[1]:off[2]], rhs[off[1]:off[1] + 1]])
+    normals2 = np.ascontiguousarray(np.concatenate([normals[:off[1]], n1, normals[off[2]:]]))
+    rhs2 = np.ascontiguousarray(np.concatenate([rhs[:off[1]], r1, rhs[off[2]:]]))
+    off2 = np.array([0, k, 2 * k + 1, 3 * k + 1], np.int32)
+    planner = _planner(cfg)
+    with pytest.raises(capi.LscqpError, match="max_obs"):
+        _solve_host(planner, batch, agents, off2, normals2, rhs2)
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents])
+    gout = np.zeros((3, 3), np.float32); gst = np.zeros(3, np.int32)
+    with pytest.raises(capi.LscqpError, match="max_obs"):
+        planner.qp.goal_host(3, goal, goal, None, off2, normals2, rhs2, gout, gst)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ctrl = torch.zeros((3, 90), dtype=torch.float64, device="cuda"); cost = torch.zeros(3, dtype=torch.float64, device="cuda")
+    status = torch.full((3,), -1, dtype=torch.int32, device="cuda")
+    warm = t(batch.own_traj[agents])
+    planner.qp.solve_batch(3, t(st), t(goal), t(batch.limits[agents]), None, t(off2), t(normals2), t(rhs2), ctrl, cost, status,
+                           initial_traj=warm)
+    torch.cuda.synchronize()
+    assert status.cpu().tolist() == [0, capi.STATUS_CAPACITY, 0]
+    ref = _solve_host(planner, batch, agents, off, normals, rhs, warm=True)
+    got = ctrl.cpu().numpy()
+    assert np.array_equal(got[0], ref[0][0]) and np.array_equal(got[2], ref[0][2]) and np.isfinite(got[1]).all()
+
+
+@pytest.mark.parametrize("n_total,lo,n_local,K,comm", [(4096, 0, 4096, 40, 0.0), (1024, 256, 512, 40, 3.0), (15000, 14000, 1000, 17, 0.0),
+                                                       (4096, 0, 4096, 40, 6.0), (3000, 100, 2000, 5, 4.0)])
 def test_neighbour_selection_gpu(n_total, lo, n_local, K, comm):
-    """lscqp_select_neighbours (radix select per agent) against a numpy restatement of the broadcastMsgs filter"""
+    """lscqp_select_neighbours against a numpy restatement of the broadcastMsgs filter: ragged CSR lists holding exactly
+    the in-range agents; K nearest + overflow flag only where more than K are in range"""
     import torch
     from test_emul_kernels import _check_neighbours
     rng = np.random.default_rng(n_total)
@@ -415,16 +453,20 @@ def test_neighbour_selection_gpu(n_total, lo, n_local, K, comm):
     cfg = W.PlannerConfig()
     qp = capi.LscQp(cfg, device=0)
     st = torch.from_numpy(state).cuda()
-    out = torch.zeros((n_local, K), dtype=torch.int32, device="cuda")
-    qp.select_neighbours(n_total, lo, n_local, K, comm, st, out)
-    torch.cuda.synchronize()
-    res = out.cpu().numpy()
-    sel = rng.choice(n_local, 64, replace=False)
-    _check_neighbours(state, lo, res, K, comm) if n_local <= 512 else [
-        _check_neighbours(state, lo + int(r), res[int(r):int(r) + 1], K, comm) for r in sel]
-    out2 = torch.zeros_like(out)
-    qp.select_neighbours(n_total, lo, n_local, K, comm, st, out2)
-    assert torch.equal(out, out2)                             # deterministic
+
+    def run():
+        off = torch.zeros((n_local + 1,), dtype=torch.int32, device="cuda")
+        idx = torch.full((n_local * K,), -1, dtype=torch.int32, device="cuda")
+        over = torch.zeros((n_local,), dtype=torch.int32, device="cuda")
+        qp.select_neighbours(n_total, lo, n_local, K, comm, st, off, idx, over)
+        torch.cuda.synchronize()
+        return off.cpu().numpy(), idx.cpu().numpy(), over.cpu().numpy()
+    off, idx, over = run()
+    sel = range(n_local) if n_local <= 512 else [int(r) for r in rng.choice(n_local, 64, replace=False)]
+    _check_neighbours(state, lo, off, idx[:off[-1]], over, K, comm, rows=sel)
+    assert (np.diff(off) <= K).all() and (idx[off[-1]:] == -1).all()
+    off2, idx2, over2 = run()
+    assert np.array_equal(off, off2) and np.array_equal(idx, idx2) and np.array_equal(over, over2)    # deterministic
 
 
 def test_closed_loop_cuda_graph_matches_eager():
@@ -520,6 +562,44 @@ def test_light_and_full_instances_agree_at_full_size():
     assert float((c1 - c3).abs().max()) < 2e-6
     assert float(((f1 - f3).abs() / f3.abs().clamp(min=1.0)).max()) < 1e-8
     assert abs(float(i1.float().mean()) - float(i3.float().mean())) < 0.2
+
+
+def test_bench_batch_light_instance_and_pruned_assembly_against_oracle():
+    """The kernels the bench number is made of, against the oracle on hardware: BASELINE's 4096-agent batch through the
+    fused pruned assembly and the two-pass solve; 64 sampled agents that the one-warp *light* instance solved
+    (lscqp_last_instances) are compared with the oracle's optimum of the reference's full model (all 40 obstacles, all
+    rows) at 1e-5 m, and their pruned planes with the oracle's planes: a kept (obstacle, segment) pair carries the
+    reference's normal (<= 1 float ulp) and constants, a dropped pair (zero normal) is strictly inactive at the optimum."""
+    import torch
+    batch = W.make_forest_batch(4096, K=40)
+    planner = _planner(batch.cfg)
+    d = planner.upload(batch)
+    planner.replan_device(d)
+    torch.cuda.synchronize()
+    klass = planner.qp.last_instances(4096)
+    assert (klass == 0).mean() > 0.9                          # the light instance is what the bench measures
+    status = d.status.cpu().numpy(); ctrl = d.ctrl.cpu().numpy(); cost = d.cost.cpu().numpy()
+    normals_d = d.normals.cpu().numpy(); rhs_d = d.rhs.cpu().numpy()
+    assert (status == 0).all()
+    rng = np.random.default_rng(64)
+    agents = [int(a) for a in rng.choice(np.where(klass == 0)[0], 64, replace=False)]
+    agents += [int(a) for a in np.where(klass == 1)[0][:4]]   # and a few the full-capacity pass took over
+    off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
+    errs = _check_against_oracle(batch, agents, off, normals, rhs, ctrl[agents], cost[agents], status[agents], min_checked=60)
+    print("light-instance parity: max |ctrl - oracle| = %.2e, median %.2e over %d agents" % (errs.max(), np.median(errs), len(errs)))
+    M = batch.cfg.M
+    kept = dropped = 0
+    for i, a in enumerate(agents[:16]):
+        sl_o = slice(off[i], off[i + 1]); sl_d = slice(batch.obs_offsets[a], batch.obs_offsets[a + 1])
+        nd, rd, no, ro = normals_d[sl_d], rhs_d[sl_d], normals[sl_o], rhs[sl_o]
+        zero = (nd == 0).all(axis=2)                          # [K, M] pairs the pruning dropped
+        assert np.abs(nd[~zero] - no[~zero]).max() <= 2.4e-7 and np.abs(rd[~zero] - ro[~zero]).max() <= 2e-6
+        x = ctrl[a].reshape(3, M, 6)
+        q = np.einsum("kmd,dmi->kmi", no, x) - ro             # row values of the reference's planes at the optimum
+        q[:, 0, :3] = np.inf                                  # (no rows on the first three control points)
+        assert q[zero].min() > 1e-6, (a, q[zero].min())
+        kept += int((~zero).sum()); dropped += int(zero.sum())
+    assert kept > 0 and dropped > kept
 
 
 def test_infeasible_case_from_the_sweep_gpu():
