@@ -52,7 +52,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -168,6 +168,129 @@ def workload_config(args, n_agents):
 
 
 # ------------------------------------------------------------------------------------------------
+def closed_loop_batch(W, n_agents, K=40):
+    """BASELINE config 5 population: every agent at rest (first replan of a mission), goals 12 m away in a random
+    direction (clipped to the world): collision-prone but finite"""
+    b = W.make_forest_batch(n_agents, K=K, seed=20260005, moving=False)
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(0, 2 * np.pi, n_agents)
+    g = b.state[:, :3] + np.stack([12 * np.cos(ang), 12 * np.sin(ang), np.zeros(n_agents)], 1)
+    half = b.cfg.world_max[0] - 0.5
+    g[:, :2] = np.clip(g[:, :2], -half, half)
+    b.goal = g.astype(np.float32)
+    return b
+
+
+def run_strong(args, torch, dist, W, capi, rank, world, local, flush):
+    """BASELINE config 4: 4096 agents with synthetic random LSC half-spaces, N fixed, agents sharded over the ranks
+    (strong scaling).  One step = PDIP solve of the rank's shard + the exchange of the solved trajectories with every
+    rank (lscqp_step_exchange stores them into all ranks' blocks over NVLink, lscqp_exchange_begin waits for everyone's
+    flag and copies them out) -- the gather is inside the timed region."""
+    from lsc_dr_planner_b200.planner import BatchPlanner
+    from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
+    from lsc_dr_planner_b200.sharding import shard_range
+    N = args.strong_agents
+    pop = W.make_forest_batch(N, K=args.K, seed=20260004)
+    off, nrm, rhs = W.make_synthetic_planes(pop, K=args.K)
+    lo, hi = shard_range(N, rank, world)
+    n = hi - lo
+    dev = torch.device("cuda", local)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    # the sim object provides the replicated arrays and the connected exchange; its own step() is not used here
+    sim = ClosedLoopSim(pop, device=local, rank=rank, world=world, K=args.K, exchange="p2p")
+    qp = sim.planner.qp
+    state, goal, lim = t(pop.state[lo:hi]), t(pop.goal[lo:hi]), t(pop.limits[lo:hi])
+    own = t(pop.own_traj[lo:hi])
+    offs = t((off[lo:hi + 1] - off[lo]).astype(np.int32))
+    normals, rhs_d = t(nrm[off[lo]:off[hi]]), t(rhs[off[lo]:off[hi]])
+    ctrl = torch.empty((n, 90), dtype=torch.float64, device=dev); cost = torch.empty((n,), dtype=torch.float64, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev); iters = torch.empty((n,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    p2p = sim.exchange == "p2p"
+    shifted = torch.empty((n, 5, 6, 3), dtype=torch.float32, device=dev); st_out = torch.empty((n, 9), dtype=torch.float32, device=dev)
+    traj_out = torch.empty((n, 5, 6, 3), dtype=torch.float32, device=dev)
+
+    def step():
+        qp.solve_batch(n, state, goal, lim, None, offs, normals, rhs_d, ctrl, cost, status, iters, stream=stream, initial_traj=own)
+        if p2p:
+            qp.step_exchange(lo, n, ctrl, status, own, pop.cfg.dt, None, stream)
+            qp.exchange_begin(sim.traj, sim.state, stream)
+        else:
+            from lsc_dr_planner_b200.sharding import allgather_rows
+            qp.step_batch(n, ctrl, pop.cfg.dt, traj_out, st_out, shifted, stream)
+            sim.traj.copy_(allgather_rows(shifted, N)); sim.state.copy_(allgather_rows(st_out, N))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev[s][0].record(); step(); ev[s][1].record()
+    barrier()
+    ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    ok = int((status != 0).sum().item()) == 0
+    # the gathered result: every rank must hold every agent's shifted solution
+    ref_last = sim.traj[:, -1, -1, :].clone()
+    timeouts = sim.exchange_timeouts
+    tt = torch.tensor([ms, float(timeouts), 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    chk = ref_last.to(torch.float64).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        lo_chk, hi_chk = chk.clone(), chk.clone()
+        dist.all_reduce(lo_chk, op=dist.ReduceOp.MIN); dist.all_reduce(hi_chk, op=dist.ReduceOp.MAX)
+        same = bool((lo_chk == hi_chk).item())
+    else:
+        same = True
+    ms_step = float(tt[0]) / args.steps
+    return {"workload": f"config 4: {N} agents total, synthetic random LSC half-spaces (K={args.K}, M=5, D=3), agents sharded "
+                        f"over {world} rank(s); step = PDIP solve of the shard + exchange of the solved trajectories with every rank",
+            "scaling": "strong", "agents_total": N, "agents_per_rank": n, "ms_per_step": ms_step,
+            "value": N / (ms_step * 1e-3), "unit": UNIT, "exchange": "p2p stores into every rank's block over NVLink (CUDA IPC) + flag wait"
+            if p2p else "nccl all_gather_into_tensor", "exchange_in_timed_region": True, "bytes_published_per_rank_per_step": n * (90 + 9) * 4 * world,
+            "all_solved": float(tt[2]) == 0.0, "exchange_timeouts": int(tt[1]), "every_rank_holds_the_same_population": same}
+
+
+def run_closed_loop(args, torch, dist, W, capi, rank, world, local, exchange, graph=True):
+    """BASELINE config 5: 1024 agents x 200 closed-loop replans, agents sharded over the ranks; per replan: neighbour
+    selection, LSC assembly, PDIP solve, failsafe + doStep + shift, exchange of the new trajectories with every rank."""
+    from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
+    N, T = args.loop_agents, args.loop_steps
+    b = closed_loop_batch(W, N)
+    # communication/range = 3.0 is the reference's default (param.cpp:117): the obstacle set of an agent is every agent
+    # within 3 m (L-inf) of it, as broadcastMsgs builds it -- about 8 in this forest, never above the capacity of 40
+    sim = ClosedLoopSim(b, device=local, rank=rank, world=world, K=40, comm_range=3.0, use_graph=graph, exchange=exchange)
+    for _ in range(4):
+        sim.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(T):
+        sim.step()
+    e.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(e) / T
+    tt = torch.tensor([ms, float(sim.failed_total), float(sim.exchange_timeouts), float(sim.overflowed_total)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt[:1], op=dist.ReduceOp.MAX)
+        rest = tt[1:].clone(); dist.all_reduce(rest, op=dist.ReduceOp.SUM); tt[1:] = rest
+    out = {"workload": f"config 5: closed loop, {N} agents x {T} replans, agents sharded over {world} rank(s) ({sim.n_local} per rank), "
+                       "neighbours re-selected every replan (every agent within the reference's default communication range 3.0, ragged lists)",
+           "ms_per_replan": float(tt[0]), "replans_per_s": 1e3 / float(tt[0]), "agent_qp_per_s": N / (float(tt[0]) * 1e-3),
+           "exchange": sim.exchange, "cuda_graph": bool(graph and sim._graph is not None),
+           "exchange_in_timed_region": True, "qp_failures": int(tt[1]), "exchange_timeouts": int(tt[2]),
+           "neighbour_overflows": int(tt[3]), "min_safety_ratio_end": sim.min_separation_ratio(),
+           "goal_distance_end": sim.max_goal_distance()}
+    sim._graph = None
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -198,6 +321,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value): inputs in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         planner.replan_device(d, capi.GEN_LSC, stream)
     torch.cuda.synchronize()
@@ -206,7 +330,6 @@ def run_ours(args):
           for _ in range(args.steps)]
     launches0 = planner.qp.launches
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s & 0xFF)
@@ -232,13 +355,29 @@ def run_ours(args):
         planner.replan_host_buffers(hb, n_agents)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
-    clocks = sampler.stop() if sampler else None
     assert (hb["status"] == 0).all()
 
     tt = torch.tensor([t_step.sum(), e2e_s, t_sol.mean(), t_asm.mean()], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms, e2e_s, sol_ms, asm_ms = (float(x) for x in tt.tolist())
+
+    # ---- sharded workloads, measured at every N (all ranks take part): config 4 strong scaling, config 5 closed loop
+    sharded = {}
+    if not args.no_sharded:
+        for name, fn in (("strong", lambda: run_strong(args, torch, dist, W, capi, rank, world, local, flush)),
+                         ("closed_loop", lambda: run_closed_loop(args, torch, dist, W, capi, rank, world, local, "p2p")),
+                         ("closed_loop_nccl", (lambda: run_closed_loop(args, torch, dist, W, capi, rank, world, local, "nccl"))
+                          if world > 1 else None)):
+            if fn is None:
+                continue
+            try:
+                sharded[name] = fn()
+            except Exception as exc:          # a failure here must not take the contract line down (all ranks raise alike)
+                sharded[name] = {"error": repr(exc)}
+            barrier()
+    clocks = sampler.stop() if sampler else None
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = world * n_agents / (ms_per_step * 1e-3)
@@ -278,9 +417,12 @@ def run_ours(args):
                                           "frac": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9 / hbm,
                                           "algorithmic_bytes_per_qp": ab["assemble"]}},
                 "wall_s_timed_region": wall}
+        line.update(sharded)
         # secondary numbers (same timing method, 5 steps each): presolve off, and config-4 style synthetic planes
         variants = {}
         try:
+            if world > 1 or args.no_variants:
+                raise StopIteration
             import copy
             def timed(fn, reps=5):
                 for _ in range(3):
@@ -306,11 +448,6 @@ def run_ours(args):
             variants["solve_no_presolve"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
             ms = timed(lambda: planner2.solve_device(d, stream=stream, warm=False))
             variants["solve_no_presolve_cold_start"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
-            off, nrm, rhs_ = W.make_synthetic_planes(batch, K=args.K)
-            d.normals.copy_(torch.from_numpy(nrm).to(d.normals.device)); d.rhs.copy_(torch.from_numpy(rhs_).to(d.rhs.device))
-            ms = timed(lambda: planner.solve_device(d, stream=stream))
-            ok = int((d.status != 0).sum().item()) == 0
-            variants["solve_synthetic_planes_config4"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item()), "all_ok": ok}
             # the shape the reference's own published timings are for (launch/simulation.launch, 2-D, M = 10,
             # K <= 9 neighbours, communication range 3, generateCLSC -> GoalOptimizer -> TrajOptimizer; 4.58 / 6.64 ms per QP
             # with CPLEX on the authors' workstation): one full plan (assembly + goal LP + QP) for 4096 such agents
@@ -333,36 +470,8 @@ def run_ours(args):
                 "reference_published_ms_per_qp": [4.58, 6.64],
                 "note": "assembly (CLSC) + goal LP + dense communication-range QP instance; agents the reference would fail "
                         "(infeasible goal LP / QP) are counted as work, not as solved"}
-            if world == 1:
-                # BASELINE config 5 on one GPU: 1024 agents x 200 closed-loop replans (neighbour selection, assembly, solve,
-                # doStep, shift per replan; the local step captured in a CUDA graph).  A fixed number of warm-up steps.
-                from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
-                bC = W.make_forest_batch(1024, K=40, seed=20260005, moving=False)
-                rngc = np.random.default_rng(5)
-                ang = rngc.uniform(0, 2 * np.pi, 1024)
-                gC = bC.state[:, :3] + np.stack([12 * np.cos(ang), 12 * np.sin(ang), np.zeros(1024)], 1)
-                halfC = bC.cfg.world_max[0] - 0.5
-                gC[:, :2] = np.clip(gC[:, :2], -halfC, halfC)
-                bC.goal = gC.astype(np.float32)
-                warm_sim = ClosedLoopSim(bC, device=local, K=40)
-                for _ in range(400):
-                    warm_sim.step()
-                torch.cuda.synchronize()
-                del warm_sim
-                simC = ClosedLoopSim(bC, device=local, K=40, use_graph=True)
-                for _ in range(4):
-                    simC.step()
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(200):
-                    simC.step()
-                b.record(); torch.cuda.synchronize()
-                msC = a.elapsed_time(b) / 200
-                variants["closed_loop_config5_1024x200_1gpu"] = {
-                    "ms_per_replan": msC, "agent_qp_per_s": 1024 / (msC * 1e-3), "qp_failures": simC.failed_total,
-                    "min_safety_ratio": simC.min_separation_ratio(), "goal_distance_end": simC.max_goal_distance()}
-                simC._graph = None
+        except StopIteration:
+            pass
         except Exception as exc:  # secondary numbers must never break the contract line
             variants["error"] = repr(exc)
         line["variants"] = variants
@@ -377,6 +486,7 @@ def run_ours(args):
                                     "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)",
                                     "ms_per_qp_one_core": 1e3 * per_qp}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -393,6 +503,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--ref-sample", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the config-4 strong-scaling and config-5 closed-loop blocks")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--strong-agents", type=int, default=4096, help="population of the strong-scaling block (config 4)")
+    ap.add_argument("--loop-agents", type=int, default=1024, help="population of the closed-loop block (config 5)")
+    ap.add_argument("--loop-steps", type=int, default=200)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

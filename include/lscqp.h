@@ -218,6 +218,35 @@ int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, i
 int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step,
         float* traj_out, float* state_out, float* shifted_traj_out, void* stream);
 
+/* ---- Peer exchange for the sharded closed loop (BASELINE config 5: agents sharded over GPUs, one exchange of the solved
+ * trajectories per replan).  Stands in for MultiSyncSimulator::broadcastMsgs (src/multi_sync_simulator.cpp:305-352), which
+ * copies every agent's state and prev_traj (AgentManager::getAgent, src/agent_manager.cpp:184-199) to every planner.
+ * Each rank owns one exchange block in its HBM, mapped into every peer through CUDA IPC; lscqp_step_exchange fuses the
+ * failsafe + doStep + shift with the all-gather: the new rows are stored straight into every rank's block over NVLink and
+ * a per-rank sequence flag is raised; lscqp_exchange_begin (first launch of the next step) waits for all flags and copies
+ * the rows into the rank's replicated arrays.  No host involvement per step: both launches can be captured in a CUDA graph.
+ *   create : allocates the local block for a population of n_total agents; ipc_handle_out receives 64 bytes
+ *            (a cudaIpcMemHandle_t) to be exchanged between the ranks by the caller (e.g. torch.distributed.all_gather)
+ *   connect: all_ipc_handles = world x 64 bytes in rank order (the own entry is ignored)
+ *   begin  : traj [n_total][M][6][3], state [n_total][9] (device): overwritten with the rows published for this step;
+ *            a no-op before the first publish.  A peer that does not arrive within ~2 s raises the time-out counter
+ *            (lscqp_exchange_status) instead of hanging the device.
+ *   step_exchange: ctrl [n_local][dim][M][6] of the agents [lo, lo + n_local); status / fallback_traj (both or neither):
+ *            agents with status != 0 keep fallback_traj (TrajPlanner::trajOptimization's catch branch,
+ *            src/traj_planner.cpp:767-797); traj_out (optional) receives the float trajectories [n_local][M][6][3].
+ *            Every rank must call it once per step with n_local >= 1.
+ *   status : out3 = { steps published, wait time-outs, failsafe uses } of this rank (synchronises the stream). */
+int lscqp_exchange_create(lscqp_handle* h, int n_total, int world, int rank, void* ipc_handle_out);
+int lscqp_exchange_connect(lscqp_handle* h, const void* all_ipc_handles);
+int lscqp_exchange_begin(lscqp_handle* h, float* traj, float* state, void* stream);
+int lscqp_step_exchange(lscqp_handle* h, int lo, int n_local, const double* ctrl, const int* status,
+        const float* fallback_traj, double step, float* traj_out, void* stream);
+int lscqp_exchange_status(lscqp_handle* h, unsigned long long* out3, void* stream);
+int lscqp_exchange_destroy(lscqp_handle* h);
+/* single-process wiring (several handles, one per device, in one process): the peers' blocks as plain device pointers */
+void* lscqp_exchange_local_base(lscqp_handle* h);
+int lscqp_exchange_connect_ptrs(lscqp_handle* h, void* const* bases);
+
 /* TrajPlanner::isSolValid (src/traj_planner.cpp:990-1045) for every agent: SFC containment of the float control points
  * (use_sfc; segment 0 from point phi on) and velocity / acceleration of the state at the replanning period within 1 %
  * of the limits.  traj / state_at_step are the outputs of lscqp_step_batch (step = multisim time step).

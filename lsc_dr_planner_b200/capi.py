@@ -52,10 +52,13 @@ def load():
         _lib.lscqp_last_error.restype = C.c_char_p
         _lib.lscqp_launch_count.restype = C.c_ulonglong
         _lib.lscqp_launch_count.argtypes = [C.c_void_p]
+        _lib.lscqp_exchange_local_base.restype = C.c_void_p
+        _lib.lscqp_exchange_local_base.argtypes = [C.c_void_p]
         for name in ("lscqp_solve_batch", "lscqp_assemble_lsc_batch", "lscqp_solve_host", "lscqp_replan_host",
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
                      "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch",
-                     "lscqp_last_instances"):
+                     "lscqp_last_instances", "lscqp_exchange_create", "lscqp_exchange_connect", "lscqp_exchange_begin",
+                     "lscqp_step_exchange", "lscqp_exchange_status", "lscqp_exchange_destroy", "lscqp_exchange_connect_ptrs"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -186,6 +189,30 @@ class LscQp:
     def step_batch(self, n, ctrl, step, traj_out, state_out=None, shifted_out=None, stream=0):
         self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),
                                               _dp(shifted_out), C.c_void_p(stream)))
+
+    # ------------------------------------------------------------------ peer exchange (sharded closed loop)
+    def exchange_create(self, n_total, world, rank) -> bytes:
+        """allocate this rank's exchange block; returns its 64-byte CUDA IPC handle (to be all-gathered by the caller)"""
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.lscqp_exchange_create(self.h, n_total, world, rank, buf))
+        return bytes(buf)
+
+    def exchange_connect(self, all_handles: bytes):
+        """all_handles: world x 64 bytes in rank order"""
+        self._check(self.lib.lscqp_exchange_connect(self.h, C.c_char_p(all_handles)))
+
+    def exchange_begin(self, traj, state, stream=0):
+        self._check(self.lib.lscqp_exchange_begin(self.h, _dp(traj), _dp(state), C.c_void_p(stream)))
+
+    def step_exchange(self, lo, n_local, ctrl, status, fallback_traj, step, traj_out=None, stream=0):
+        self._check(self.lib.lscqp_step_exchange(self.h, lo, n_local, _dp(ctrl), _dp(status), _dp(fallback_traj),
+                                                 C.c_double(step), _dp(traj_out), C.c_void_p(stream)))
+
+    def exchange_status(self, stream=0) -> tuple[int, int, int]:
+        """(steps published, wait time-outs, failsafe uses) of this rank; synchronises the stream"""
+        out = (C.c_ulonglong * 3)()
+        self._check(self.lib.lscqp_exchange_status(self.h, out, C.c_void_p(stream)))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def goal_batch(self, n, goal, next_waypoint, sfc, obs_offsets, normals, rhs, goal_out, status, t_out=None, stream=0):
         """batched GoalOptimizer::solve (goal_optimizer.cpp:7-165) on device tensors"""

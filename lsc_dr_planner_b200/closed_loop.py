@@ -6,22 +6,25 @@ src/multi_sync_simulator.cpp:81-129):
     constructLSC   -> lscqp_assemble_lsc_fused: neighbours read in place, provably inactive pairs dropped (device)
     trajOptimization -> lscqp_solve_batch, started from the shifted previous solution (device)
     failsafe       -> agents whose QP failed keep initial_traj (src/traj_planner.cpp:767-797)
-    doStep         -> lscqp_step_batch: float trajectory, state at t = dt, shifted trajectory (device)
-    exchange       -> one all-gather of trajectories / states per step (NCCL over NVLink on GPUs)
+    doStep + exchange -> lscqp_step_exchange: failsafe, float trajectory, state at t = dt, shifted trajectory, stored
+                      straight into every rank's exchange block over NVLink (CUDA IPC peer memory) + a sequence flag;
+                      lscqp_exchange_begin at the start of the next step waits for all flags and copies the rows out.
+                      The whole step is device-side and is captured in one CUDA graph.  exchange="nccl" keeps the
+                      library all-gather (torch.distributed) as the comparison / fallback path.
 Neighbour search runs in the library too (lscqp_select_neighbours: radix select in shared memory, one CTA per agent)."""
 from __future__ import annotations
 
 import numpy as np
 
 from . import capi
-from .sharding import allgather_rows, shard_range
+from .sharding import all_agree, allgather_handles, allgather_rows, shard_range
 from .workloads import Batch
 
 
 class ClosedLoopSim:
     def __init__(self, batch: Batch, device: int = 0, rank: int = 0, world: int = 1, K: int = 40,
                  comm_range: float = 0.0, generator: int = capi.GEN_LSC, use_graph: bool = False,
-                 goal_mode: str = "static"):
+                 goal_mode: str = "static", exchange: str = "p2p"):
         import torch
         from .planner import BatchPlanner
         self.torch = torch
@@ -69,11 +72,41 @@ class ClosedLoopSim:
         self.use_graph = use_graph
         self._graph = None
         self.prune = bool(int(self.cfg.presolve) & 1)
+        assert exchange in ("p2p", "nccl")
+        self.exchange = exchange
+        if exchange == "p2p":
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """every rank allocates its exchange block and maps the others' through CUDA IPC; the 64-byte handles travel
+        through torch.distributed (plumbing).  If any rank cannot map a peer, all ranks fall back to the NCCL all-gather."""
+        qp = self.planner.qp
+        ok = True
+        try:
+            handle = qp.exchange_create(self.N, self.world, self.rank)
+        except capi.LscqpError:
+            ok, handle = False, bytes(64)
+        if self.world > 1:
+            handles, ok = allgather_handles(handle, ok, device=self.dev)
+            if ok:
+                try:
+                    qp.exchange_connect(handles)
+                except capi.LscqpError:
+                    ok = False
+            ok = all_agree(ok, device=self.dev)
+        if not ok:
+            self.exchange = "nccl"
 
     @property
     def failed_total(self) -> int:
         """QPs that did not converge so far (reads the device counter: synchronises)"""
+        if self.exchange == "p2p":
+            return self.planner.qp.exchange_status(self.torch.cuda.current_stream().cuda_stream)[2]
         return int(self._failed.item())
+
+    @property
+    def exchange_timeouts(self) -> int:
+        return self.planner.qp.exchange_status(self.torch.cuda.current_stream().cuda_stream)[1] if self.exchange == "p2p" else 0
 
     @property
     def overflowed_total(self) -> int:
@@ -101,6 +134,9 @@ class ClosedLoopSim:
         torch = self.torch
         qp = self.planner.qp
         n, lo, hi = self.n_local, self.lo, self.hi
+        p2p = self.exchange == "p2p"
+        if p2p:
+            qp.exchange_begin(self.traj, self.state, stream)           # rows every rank published at the end of the last step
         # goalPlanning (src/traj_planner.cpp:433-477): static goal, or the right-hand rule -- an agent that is slower than
         # deadlock/velocity_threshold (0.1) after deadlock/seq_threshold (5) replans and still more than 0.2 m from its
         # goal (isDeadlock, :904-923) aims at position + (desired - position) x e_z instead
@@ -111,40 +147,40 @@ class ClosedLoopSim:
             dead = (self._seq > 5) & (vel.norm(dim=1) < 0.1) & (to_goal.norm(dim=1) > 0.2)
             side = torch.stack([to_goal[:, 1], -to_goal[:, 0], torch.zeros_like(to_goal[:, 2])], dim=1)
             self.goal.copy_(torch.where(dead[:, None], pos + side, self.desired_goal))
-        if n > 0:
-            obs_index = self.neighbours(stream)
-            own = self.traj[lo:hi].contiguous()
-            st, goal, lim, meta = (self.state[lo:hi].contiguous(), self.goal[lo:hi].contiguous(),
-                                   self.limits[lo:hi].contiguous(), self.agent_meta[lo:hi].contiguous())
-            qp.assemble_lsc_fused(self.generator, self.prune, n, own, meta, goal, st, lim, self.obs_offsets, obs_index,
-                                  self.traj, self.agent_meta, self.goal, self.state, self.normals, self.rhs, stream)
-            qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
-                           self.status, self.iters, stream=stream, initial_traj=own)
-            # failsafe: keep initial_traj where the QP did not converge (traj_planner.cpp:795-797); done on the device
-            # without a host round trip so the launches of the next step can run ahead
-            bad = self.status != 0
-            fallback = own.permute(0, 3, 1, 2)[:, :self.cfg.dim].reshape(n, -1).to(torch.float64)
-            torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
-            self._failed += bad.sum()
-            self._overflowed += (self.overflow[:n] > 0).sum()
-            qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted, stream)
-            new_traj, new_state = self.shifted, self.state_out
-        else:
-            new_traj = self.shifted[:0]; new_state = self.state_out[:0]
+        assert n > 0, "every rank needs at least one agent"
+        obs_index = self.neighbours(stream)
+        own = self.traj[lo:hi]                                         # (contiguous row blocks: views, no copies)
+        st, goal, lim, meta = self.state[lo:hi], self.goal[lo:hi], self.limits[lo:hi], self.agent_meta[lo:hi]
+        qp.assemble_lsc_fused(self.generator, self.prune, n, own, meta, goal, st, lim, self.obs_offsets, obs_index,
+                              self.traj, self.agent_meta, self.goal, self.state, self.normals, self.rhs, stream)
+        qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
+                       self.status, self.iters, stream=stream, initial_traj=own)
+        self._overflowed += (self.overflow[:n] > 0).sum()
+        if p2p:
+            # failsafe (keep initial_traj where the QP did not converge, traj_planner.cpp:795-797) + doStep + shift +
+            # publish to every rank, one kernel
+            qp.step_exchange(lo, n, self.ctrl, self.status, own, self.cfg.dt, self.traj_out, stream)
+            return
+        bad = self.status != 0
+        fallback = own.permute(0, 3, 1, 2)[:, :self.cfg.dim].reshape(n, -1).to(torch.float64)
+        torch.where(bad[:, None], fallback, self.ctrl, out=self.ctrl)
+        self._failed += bad.sum()
+        qp.step_batch(n, self.ctrl, self.cfg.dt, self.traj_out, self.state_out, self.shifted, stream)
         if self.world == 1:
-            self.traj.copy_(new_traj[:n]); self.state.copy_(new_state[:n])
+            self.traj.copy_(self.shifted[:n]); self.state.copy_(self.state_out[:n])
 
     def _exchange(self):
-        """the only collective: every rank ends the step with all trajectories and states (eager: NCCL collectives inside
-        a captured graph hung intermittently at 2 ranks, so only the local compute is captured)"""
+        """exchange="nccl": every rank ends the step with all trajectories and states through two library all-gathers
+        (eager: NCCL collectives inside a captured graph hung intermittently at 2 ranks, so only the local compute is
+        captured on this path; the p2p path has no such limit)"""
         n = self.n_local
         self.traj.copy_(allgather_rows(self.shifted[:n], self.N))
         self.state.copy_(allgather_rows(self.state_out[:n], self.N))
 
     def step(self):
-        """One closed-loop step.  With use_graph the local part of the step (library launches and the few torch
-        element-wise ops) is captured once into a CUDA graph after two eager steps and replayed afterwards: at a few
-        hundred agents per GPU the step is otherwise bound by the ~0.4 ms of host-side launch work."""
+        """One closed-loop step.  With use_graph the step (library launches and the few torch element-wise ops) is
+        captured once into a CUDA graph after two eager steps and replayed afterwards: at a few hundred agents per GPU
+        the step is otherwise bound by the host-side launch work.  On the p2p path the exchange is part of the graph."""
         torch = self.torch
         if self.use_graph and self._graph is not None:
             self._graph.replay()
@@ -157,14 +193,25 @@ class ClosedLoopSim:
             g.replay()
         else:
             self._step_impl(torch.cuda.current_stream().cuda_stream)
-        if self.world > 1:
+        if self.world > 1 and self.exchange == "nccl":
             self._exchange()
         self.steps += 1
 
-    def min_separation_ratio(self) -> float:
-        """min over pairs of (downwash-scaled distance) / (r_i + r_j) at the current positions (>= 1 is safe)"""
+    def sync_state(self):
+        """make self.traj / self.state hold the rows of the last step (on the p2p path they are copied out of the inbox
+        by the next step's first launch; call this before reading them on the host)"""
+        if self.exchange == "p2p":
+            self.planner.qp.exchange_begin(self.traj, self.state, self.torch.cuda.current_stream().cuda_stream)
+        self.torch.cuda.synchronize()
+
+    def min_separation_ratio(self, state=None) -> float:
+        """min over pairs of (downwash-scaled distance) / (r_i + r_j) at the current positions (>= 1 is safe), or at the
+        positions of a state snapshot"""
         torch = self.torch
-        pos = self.state[:, 0:3].to(torch.float64).clone()
+        if state is None:
+            self.sync_state()
+            state = self.state
+        pos = state[:, 0:3].to(torch.float64).clone()
         r = self.agent_meta[:, 0]; dw = self.agent_meta[:, 1]
         pos[:, 2] = pos[:, 2] / dw
         d = torch.cdist(pos, pos) / (r[:, None] + r[None, :])
@@ -172,4 +219,5 @@ class ClosedLoopSim:
         return float(d.min())
 
     def max_goal_distance(self) -> float:
+        self.sync_state()
         return float((self.state[:, 0:3] - self.desired_goal).norm(dim=1).max())

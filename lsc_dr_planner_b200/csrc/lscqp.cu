@@ -40,6 +40,7 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+struct Exchange;
 struct lscqp_handle {
     lscqp_config cfg;
     int device;
@@ -54,6 +55,7 @@ struct lscqp_handle {
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
+    Exchange* xchg = nullptr;          // peer exchange of the sharded closed loop (lscqp_exchange_*)
 };
 
 extern "C" const char* lscqp_version(void) { return "lscqp-b200 0.1 (sm_100a)"; }
@@ -101,9 +103,11 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     return 0;
 }
 
+extern "C" int lscqp_exchange_destroy(lscqp_handle* h);
 extern "C" int lscqp_destroy(lscqp_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    lscqp_exchange_destroy(h);
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
@@ -231,19 +235,153 @@ extern "C" int lscqp_gather_obstacles(lscqp_handle* h, int n_obs, const int* obs
     return 0;
 }
 
+static int launch_step(lscqp_handle* h, int n_agents, const double* ctrl, double step, float* traj_out, float* state_out,
+                       float* shifted_out, const int* status, const float* fallback, const ExchangePeers* peers, int lo,
+                       cudaStream_t st) {
+    StepParams p;
+    p.n_agents = n_agents; p.dim = h->cfg.dim; p.dt = h->cfg.dt; p.step = step; p.z_2d = h->cfg.z_2d;
+    p.ctrl = ctrl; p.traj_out = traj_out; p.state_out = state_out; p.shifted_out = shifted_out;
+    p.status = status; p.fallback = fallback; p.peers = peers; p.lo = lo;
+    const int blocks = (n_agents + STEP_WARPS - 1) / STEP_WARPS;
+    if (h->cfg.M == 5) step_kernel<5><<<blocks, STEP_WARPS * 32, 0, st>>>(p);
+    else step_kernel<10><<<blocks, STEP_WARPS * 32, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step, float* traj_out,
                                 float* state_out, float* shifted_traj_out, void* stream) {
     if (!h || n_agents < 0 || !ctrl || !traj_out) return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
-    StepParams p;
-    p.n_agents = n_agents; p.dim = h->cfg.dim; p.dt = h->cfg.dt; p.step = step; p.z_2d = h->cfg.z_2d;
-    p.ctrl = ctrl; p.traj_out = traj_out; p.state_out = state_out; p.shifted_out = shifted_traj_out;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int blocks = (n_agents + 127) / 128;
-    if (h->cfg.M == 5) step_kernel<5><<<blocks, 128, 0, st>>>(p);
-    else step_kernel<10><<<blocks, 128, 0, st>>>(p);
+    return launch_step(h, n_agents, ctrl, step, traj_out, state_out, shifted_traj_out, nullptr, nullptr, nullptr, 0,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer exchange of the sharded closed loop (step_kernel.cuh: ExchangeBlock): one block per rank, mapped into every
+// peer with CUDA IPC; the step kernel publishes into all of them over NVLink, exchange_begin waits and copies.
+struct Exchange {
+    ExchangePeers host{};                 // pointers as seen from this process
+    ExchangePeers* dev = nullptr;         // device copy read by the kernels
+    void* local = nullptr;                // base of the local block (cudaMalloc)
+    void* mapped[EXCHANGE_MAX_WORLD] = {};   // IPC mappings of the peers' blocks
+    size_t bytes = 0;
+};
+
+static void exchange_layout(void* base, int world, int n_total, int row, ExchangeBlock& b) {
+    char* c = static_cast<char*>(base);
+    b.ctl = reinterpret_cast<unsigned long long*>(c);                       // [4] (+ padding to 64 bytes)
+    b.flags = reinterpret_cast<unsigned long long*>(c + 64);                // [EXCHANGE_MAX_WORLD]
+    b.inbox = reinterpret_cast<float*>(c + 64 + 8 * EXCHANGE_MAX_WORLD);
+    (void) world; (void) n_total; (void) row;
+}
+static size_t exchange_bytes(int n_total, int row) { return 64 + 8 * EXCHANGE_MAX_WORLD + (size_t) 2 * n_total * row * sizeof(float); }
+
+extern "C" int lscqp_exchange_create(lscqp_handle* h, int n_total, int world, int rank, void* ipc_handle_out) {
+    if (!h || n_total <= 0 || world < 1 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || !ipc_handle_out)
+        return fail(LSCQP_E_INVALID, "bad argument");
+    if (h->xchg) return fail(LSCQP_E_INVALID, "exchange already created on this handle");
+    CK(cudaSetDevice(h->device));
+    Exchange* x = new Exchange();
+    const int row = h->cfg.M * 18 + 9;
+    x->bytes = exchange_bytes(n_total, row);
+    if (cudaMalloc(&x->local, x->bytes) != cudaSuccess) { delete x; return fail(LSCQP_E_CUDA, "cudaMalloc failed"); }
+    cudaMemset(x->local, 0, x->bytes);
+    x->host.world = world; x->host.rank = rank; x->host.n_total = n_total; x->host.row = row;
+    exchange_layout(x->local, world, n_total, row, x->host.blk[rank]);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "lscqp.h documents a 64-byte handle");
+    cudaIpcMemHandle_t ih;
+    std::memset(&ih, 0, sizeof(ih));
+    if (world > 1 && cudaIpcGetMemHandle(&ih, x->local) != cudaSuccess) {
+        const std::string msg = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+        cudaFree(x->local); delete x;
+        return fail(LSCQP_E_CUDA, msg);
+    }
+    std::memcpy(ipc_handle_out, &ih, sizeof(ih));
+    if (cudaMalloc(&x->dev, sizeof(ExchangePeers)) != cudaSuccess) { cudaFree(x->local); delete x; return fail(LSCQP_E_CUDA, "cudaMalloc failed"); }
+    h->xchg = x;
+    if (world == 1) CK(cudaMemcpy(x->dev, &x->host, sizeof(ExchangePeers), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int lscqp_exchange_connect(lscqp_handle* h, const void* all_ipc_handles) {
+    if (!h || !h->xchg || !all_ipc_handles) return fail(LSCQP_E_INVALID, "exchange not created / null handles");
+    Exchange* x = h->xchg;
+    CK(cudaSetDevice(h->device));
+    const char* hs = static_cast<const char*>(all_ipc_handles);
+    for (int r = 0; r < x->host.world; r++) {
+        if (r == x->host.rank) continue;
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, hs + (size_t) r * sizeof(ih), sizeof(ih));
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(LSCQP_E_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        x->mapped[r] = base;
+        exchange_layout(base, x->host.world, x->host.n_total, x->host.row, x->host.blk[r]);
+    }
+    CK(cudaMemcpy(x->dev, &x->host, sizeof(ExchangePeers), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// In-process wiring for tests and single-process multi-GPU drivers: the peers' blocks are given as plain device
+// pointers (lscqp_exchange_local_base of the other handles; peer access must be enabled by the caller).
+extern "C" void* lscqp_exchange_local_base(lscqp_handle* h) { return (h && h->xchg) ? h->xchg->local : nullptr; }
+extern "C" int lscqp_exchange_connect_ptrs(lscqp_handle* h, void* const* bases) {
+    if (!h || !h->xchg || !bases) return fail(LSCQP_E_INVALID, "exchange not created / null bases");
+    Exchange* x = h->xchg;
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < x->host.world; r++)
+        if (r != x->host.rank) exchange_layout(bases[r], x->host.world, x->host.n_total, x->host.row, x->host.blk[r]);
+    CK(cudaMemcpy(x->dev, &x->host, sizeof(ExchangePeers), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int lscqp_exchange_begin(lscqp_handle* h, float* traj, float* state, void* stream) {
+    if (!h || !h->xchg || !traj || !state) return fail(LSCQP_E_INVALID, "exchange not created / null argument");
+    ExchangeBeginParams p;
+    p.peers = h->xchg->dev; p.traj = traj; p.state = state;
+    p.timeout_cycles = 4000000000ll;                          // ~2 s at 1.9 GHz: a missing peer must not hang the device
+    const size_t total = (size_t) h->xchg->host.n_total * h->xchg->host.row;
+    int blocks = (int) ((total + 256 * 8 - 1) / (256 * 8));
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    exchange_begin_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lscqp_step_exchange(lscqp_handle* h, int lo, int n_local, const double* ctrl, const int* status,
+                                   const float* fallback_traj, double step, float* traj_out, void* stream) {
+    if (!h || !h->xchg || n_local <= 0 || lo < 0 || lo + n_local > h->xchg->host.n_total || !ctrl)
+        return fail(LSCQP_E_INVALID, "exchange not created / bad argument (every rank must publish at least one agent)");
+    if ((status == nullptr) != (fallback_traj == nullptr)) return fail(LSCQP_E_INVALID, "status and fallback_traj go together");
+    return launch_step(h, n_local, ctrl, step, traj_out, nullptr, nullptr, status, fallback_traj, h->xchg->dev, lo,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+// counters of the local block: out[0] = steps published, out[1] = wait time-outs seen, out[2] = failsafe uses; synchronises
+extern "C" int lscqp_exchange_status(lscqp_handle* h, unsigned long long* out3, void* stream) {
+    if (!h || !h->xchg || !out3) return fail(LSCQP_E_INVALID, "exchange not created / null argument");
+    unsigned long long ctl[4];
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(ctl, h->xchg->host.blk[h->xchg->host.rank].ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out3[0] = ctl[0]; out3[1] = ctl[2]; out3[2] = ctl[3];
+    return 0;
+}
+
+extern "C" int lscqp_exchange_destroy(lscqp_handle* h) {
+    if (!h || !h->xchg) return 0;
+    Exchange* x = h->xchg;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < EXCHANGE_MAX_WORLD; r++) if (x->mapped[r]) cudaIpcCloseMemHandle(x->mapped[r]);
+    if (x->dev) cudaFree(x->dev);
+    if (x->local) cudaFree(x->local);
+    delete x;
+    h->xchg = nullptr;
     return 0;
 }
 

@@ -12,6 +12,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--K", type=int, default=40)
     ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     import torch, torch.distributed as dist
     from lsc_dr_planner_b200 import workloads as W
@@ -29,8 +30,8 @@ def main():
     half = batch.cfg.world_max[0] - 0.5
     goal[:, :2] = np.clip(goal[:, :2], -half, half)
     batch.goal = goal.astype(np.float32)
-    sim = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K, use_graph=args.graph)
-    warm = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K)
+    sim = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K, use_graph=args.graph, exchange=args.exchange)
+    warm = ClosedLoopSim(batch, device=local, rank=rank, world=world, K=args.K, exchange="nccl")
     # a 0.3 s run is otherwise timed while the clocks are still ramping up.  A fixed number of steps, NOT a time limit:
     # every step holds a collective, so all ranks must execute the same count
     for _ in range(max(200, 400_000 // max(args.agents // world, 256))):
@@ -52,13 +53,10 @@ def main():
     for s in range(args.steps):
         sim.step()
         if s % 10 == 0:
-            snaps.append(sim.state.clone())          # (the safety metric is evaluated after the timed region: its fp64
-    ev1.record(); torch.cuda.synchronize()           #  all-pairs distance costs several replans' worth of time)
-    cur = sim.state
-    for snap in snaps:
-        sim.state = snap
-        worst = min(worst, sim.min_separation_ratio())
-    sim.state = cur
+            snaps.append(sim.state.clone())          # (state at the start of this step; the safety metric is evaluated after
+    ev1.record(); torch.cuda.synchronize()           #  the timed region: its fp64 all-pairs distance costs several replans)
+    for snap in snaps + [None]:
+        worst = min(worst, sim.min_separation_ratio(snap))
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     f = torch.tensor([float(sim.failed_total)], dtype=torch.float64, device="cuda")
@@ -67,7 +65,7 @@ def main():
     if rank == 0:
         ms = float(t)
         print(json.dumps({"workload": f"closed loop, {args.agents} agents x {args.steps} replans, K={args.K} nearest neighbours re-selected every step",
-                          "n_gpus": world, "cuda_graph": bool(args.graph), "ms_per_replan_step": ms / args.steps, "replan_steps_per_s": args.steps / (ms * 1e-3),
+                          "n_gpus": world, "cuda_graph": bool(args.graph), "exchange": sim.exchange, "exchange_timeouts": sim.exchange_timeouts, "ms_per_replan_step": ms / args.steps, "replan_steps_per_s": args.steps / (ms * 1e-3),
                           "agent_qp_per_s": args.agents * args.steps / (ms * 1e-3), "min_safety_ratio": worst,
                           "qp_failures_total": float(f), "max_goal_distance_end": sim.max_goal_distance(),
                           "wall_s": time.perf_counter() - t0}))

@@ -51,8 +51,9 @@ def main():
         step_times.append(ev0.elapsed_time(ev1) * 1e-3 / n)          # the reference reports per-agent planning time
         writer.record(t, sim.traj_out.cpu().numpy(), step_times[-1])
         t += cfg.dt
+        done = sim.max_goal_distance() < 0.1                            # (synchronises sim.state with the step just made)
         positions.append(sim.state[:, :3].cpu().numpy())
-        if sim.max_goal_distance() < 0.1:                            # plan/goal_threshold
+        if done:                            # plan/goal_threshold
             break
     dist, ratio = R.flight_metrics(np.stack(positions), mission.radius, mission.downwash)
     st = np.array(step_times)

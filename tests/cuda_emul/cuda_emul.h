@@ -122,6 +122,9 @@ inline int __any_sync(unsigned, int pred) {
 }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }   // fibers are cooperative
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline void __threadfence_system() {}
+inline void __threadfence() {}
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __fdividef(float a, float b) { return a / b; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

@@ -91,15 +91,60 @@ extern "C" int emul_assemble_lsc_fused(const lscqp_config* cfg, int generator, i
     return 0;
 }
 
+static void emul_launch_step(const lscqp_config* cfg, const StepParams& p) {
+    const int blocks = (p.n_agents + STEP_WARPS - 1) / STEP_WARPS;
+    if (cfg->M == 5) emu::launch(blocks, STEP_WARPS * 32, STEP_WARPS * 5 * 18 * 4 + 64, [&]() { step_kernel<5>(p); });
+    else emu::launch(blocks, STEP_WARPS * 32, STEP_WARPS * 10 * 18 * 4 + 64, [&]() { step_kernel<10>(p); });
+}
+
 extern "C" int emul_step_batch(const lscqp_config* cfg, int n_agents, const double* ctrl, double step, float* traj_out,
-                               float* state_out, float* shifted_out) {
+                               float* state_out, float* shifted_out, const int* status, const float* fallback) {
+    if (cfg->M != 5 && cfg->M != 10) return LSCQP_E_INVALID;
     StepParams p;
     p.n_agents = n_agents; p.dim = cfg->dim; p.dt = cfg->dt; p.step = step; p.z_2d = cfg->z_2d;
     p.ctrl = ctrl; p.traj_out = traj_out; p.state_out = state_out; p.shifted_out = shifted_out;
-    const int blocks = (n_agents + 127) / 128;
-    if (cfg->M == 5) emu::launch(blocks, 128, 64, [&]() { step_kernel<5>(p); });
-    else if (cfg->M == 10) emu::launch(blocks, 128, 64, [&]() { step_kernel<10>(p); });
-    else return LSCQP_E_INVALID;
+    p.status = status; p.fallback = fallback; p.peers = nullptr; p.lo = 0;
+    emul_launch_step(cfg, p);
+    return 0;
+}
+
+// The peer exchange on the emulator: `world` ranks simulated in one process (their blocks are plain host arrays), one
+// closed-loop exchange step = every rank publishes its shard with step_kernel, then every rank runs exchange_begin.
+// blocks: world pointers to zero-initialised buffers of emul_exchange_bytes(); ctrl / status / fallback: [n_total] rows;
+// traj / state: [world][n_total] replicated arrays (outputs).
+extern "C" long emul_exchange_bytes(int n_total, int M) { return 64 + 8 * EXCHANGE_MAX_WORLD + (long) 2 * n_total * (M * 18 + 9) * 4; }
+extern "C" int emul_exchange_step(const lscqp_config* cfg, int world, int n_total, void* const* blocks, const double* ctrl,
+                                  const int* status, const float* fallback, double step, float* traj, float* state,
+                                  int skip_rank) {
+    const int M = cfg->M, row = M * 18 + 9;
+    std::vector<ExchangePeers> peers(world);
+    for (int r = 0; r < world; r++) {
+        peers[r].world = world; peers[r].rank = r; peers[r].n_total = n_total; peers[r].row = row;
+        for (int q = 0; q < world; q++) {
+            char* c = static_cast<char*>(blocks[q]);
+            peers[r].blk[q].ctl = reinterpret_cast<unsigned long long*>(c);
+            peers[r].blk[q].flags = reinterpret_cast<unsigned long long*>(c + 64);
+            peers[r].blk[q].inbox = reinterpret_cast<float*>(c + 64 + 8 * EXCHANGE_MAX_WORLD);
+        }
+    }
+    const int per = (n_total + world - 1) / world;
+    for (int r = 0; r < world; r++) {
+        if (r == skip_rank) continue;                       // (a rank that never publishes: the others must time out)
+        const int lo = std::min(n_total, r * per), hi = std::min(n_total, lo + per);
+        StepParams p;
+        p.n_agents = hi - lo; p.dim = cfg->dim; p.dt = cfg->dt; p.step = step; p.z_2d = cfg->z_2d;
+        p.ctrl = ctrl + (size_t) lo * cfg->dim * M * 6; p.traj_out = nullptr; p.state_out = nullptr; p.shifted_out = nullptr;
+        p.status = status ? status + lo : nullptr; p.fallback = fallback ? fallback + (size_t) lo * M * 18 : nullptr;
+        p.peers = &peers[r]; p.lo = lo;
+        emul_launch_step(cfg, p);
+    }
+    for (int r = 0; r < world; r++) {
+        if (r == skip_rank) continue;
+        ExchangeBeginParams b;
+        b.peers = &peers[r]; b.traj = traj + (size_t) r * n_total * M * 18; b.state = state + (size_t) r * n_total * 9;
+        b.timeout_cycles = 0;
+        emu::launch(3, 256, 64, [&]() { exchange_begin_kernel(b); });
+    }
     return 0;
 }
 

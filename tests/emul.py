@@ -53,13 +53,39 @@ def assemble(cfg, generator, n, own_traj, agent_meta, agent_goal, off, obs_traj,
     return normals, rhs
 
 
-def step(cfg, n, ctrl, t):
+def step(cfg, n, ctrl, t, status=None, fallback=None):
     cc = capi.make_config(cfg)
     traj = np.zeros((n, cfg.M, 6, 3), np.float32); state = np.zeros((n, 9), np.float32); shifted = np.zeros_like(traj)
     rc = lib().emul_step_batch(C.byref(cc), n, _p(ctrl, np.float64), C.c_double(t), _p(traj, np.float32),
-                               _p(state, np.float32), _p(shifted, np.float32))
+                               _p(state, np.float32), _p(shifted, np.float32), _p(status, np.int32), _p(fallback, np.float32))
     assert rc == 0, rc
     return traj, state, shifted
+
+
+class ExchangeSim:
+    """`world` ranks of the peer exchange simulated in one process on the emulator (step_kernel publishing into every
+    rank's block, exchange_begin_kernel copying the inbox out)"""
+
+    def __init__(self, cfg, world, n_total):
+        self.cfg, self.world, self.n = cfg, world, n_total
+        lib().emul_exchange_bytes.restype = C.c_long
+        nb = lib().emul_exchange_bytes(n_total, cfg.M)
+        self.blocks = [np.zeros(nb // 8 + 1, np.uint64) for _ in range(world)]
+        self.ptrs = (C.c_void_p * world)(*[b.ctypes.data for b in self.blocks])
+        self.traj = np.zeros((world, n_total, cfg.M, 6, 3), np.float32)
+        self.state = np.zeros((world, n_total, 9), np.float32)
+
+    def step(self, ctrl, t, status=None, fallback=None, skip_rank=-1):
+        cc = capi.make_config(self.cfg)
+        rc = lib().emul_exchange_step(C.byref(cc), self.world, self.n, self.ptrs, _p(ctrl, np.float64), _p(status, np.int32),
+                                      _p(fallback, np.float32), C.c_double(t), _p(self.traj, np.float32),
+                                      _p(self.state, np.float32), skip_rank)
+        assert rc == 0, rc
+
+    def counters(self, rank):
+        """(steps published, time-outs, failsafe uses)"""
+        c = self.blocks[rank]
+        return int(c[0]), int(c[2]), int(c[3])
 
 
 def goal(cfg, n, goal_pt, waypoint, sfc, off, normals, rhs):

@@ -109,19 +109,55 @@ def test_step_kernel_matches_oracle():
         cfg = W.PlannerConfig(M=M, dim=dim)
         batch = W.make_forest_batch(64, K=4, cfg=cfg)
         cfgo = oracle_config(cfg)
-        traj = batch.own_traj[:8].astype(np.float64) + np.random.default_rng(2).normal(0, 1e-3, batch.own_traj[:8].shape)
-        ctrl = np.ascontiguousarray(np.transpose(traj, (0, 3, 1, 2))[:, :dim].reshape(8, -1))
-        got_traj, got_state, got_shift = emul.step(batch.cfg, 8, ctrl, 0.1)
-        for a in range(8):
-            want = traj[a].astype(np.float32)
-            if dim == 2:
-                want[..., 2] = np.float32(cfg.z_2d)
-            assert np.array_equal(got_traj[a], want)
-            st = orc.get_state_at(cfgo, want, 0.1)
-            if dim == 2:
-                st[2] = np.float32(cfg.z_2d)
-            assert np.allclose(got_state[a], st, rtol=2e-6, atol=2e-6)
-            assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
+        n = 19                                                    # not a multiple of the warps per CTA
+        traj = batch.own_traj[:n].astype(np.float64) + np.random.default_rng(2).normal(0, 1e-3, batch.own_traj[:n].shape)
+        ctrl = np.ascontiguousarray(np.transpose(traj, (0, 3, 1, 2))[:, :dim].reshape(n, -1))
+        # failsafe (traj_planner.cpp:767-797): agents 3 and 7 did not solve and keep initial_traj
+        status = np.zeros(n, np.int32); status[[3, 7]] = [2, 1]
+        fallback = np.ascontiguousarray(batch.own_traj[:n])
+        for st_, fb_ in ((None, None), (status, fallback)):
+            got_traj, got_state, got_shift = emul.step(batch.cfg, n, ctrl, 0.1, st_, fb_)
+            for a in range(n):
+                want = traj[a].astype(np.float32)
+                if dim == 2:
+                    want[..., 2] = np.float32(cfg.z_2d)
+                if st_ is not None and status[a] != 0:
+                    want = fallback[a]
+                assert np.array_equal(got_traj[a], want)
+                st = orc.get_state_at(cfgo, want, 0.1)
+                if dim == 2:
+                    st[2] = np.float32(cfg.z_2d)
+                assert np.allclose(got_state[a], st, rtol=2e-6, atol=2e-6)
+                assert np.array_equal(got_shift[a], orc.shift_traj(cfgo, want))
+
+
+@pytest.mark.parametrize("world,n_total,M,dim", [(2, 37, 5, 3), (3, 20, 10, 2), (1, 9, 5, 3), (8, 64, 5, 3)])
+def test_peer_exchange_publishes_every_shard_to_every_rank(world, n_total, M, dim):
+    """the fused step + all-gather of the sharded closed loop (lscqp_step_exchange / lscqp_exchange_begin), `world` ranks
+    simulated on the emulator: after a step every rank holds the shifted trajectory and the new state of every agent,
+    identical to the unsharded step kernel's; the double-buffered inbox survives consecutive steps; failsafe uses are
+    counted; a rank that never publishes makes the others time out (counter raised, arrays untouched) instead of hanging"""
+    cfg = W.PlannerConfig(M=M, dim=dim)
+    batch = W.make_forest_batch(max(n_total, 16), K=4, cfg=cfg)
+    sim = emul.ExchangeSim(cfg, world, n_total)
+    rng = np.random.default_rng(world)
+    fallback = np.ascontiguousarray(batch.own_traj[:n_total])
+    for it in range(3):
+        traj = batch.own_traj[:n_total].astype(np.float64) + rng.normal(0, 1e-3, batch.own_traj[:n_total].shape)
+        ctrl = np.ascontiguousarray(np.transpose(traj, (0, 3, 1, 2))[:, :dim].reshape(n_total, -1))
+        status = np.zeros(n_total, np.int32); status[it] = 3
+        sim.step(ctrl, cfg.dt, status, fallback)
+        _, want_state, want_shift = emul.step(cfg, n_total, ctrl, cfg.dt, status, fallback)
+        for r in range(world):
+            assert np.array_equal(sim.traj[r], want_shift), (it, r)
+            assert np.array_equal(sim.state[r], want_state), (it, r)
+            assert sim.counters(r)[:2] == (it + 1, 0)
+    assert sum(sim.counters(r)[2] for r in range(world)) == 3
+    if world > 1:
+        before = sim.traj.copy()
+        sim.step(ctrl, cfg.dt, status, fallback, skip_rank=world - 1)
+        for r in range(world - 1):
+            assert sim.counters(r)[1] == 1 and np.array_equal(sim.traj[r], before[r])
 
 
 @pytest.mark.parametrize("M,dim,K,max_obs,mode", [(5, 3, 10, 40, 1), (10, 2, 9, 40, 1), (10, 2, 9, 10, 1),

@@ -474,17 +474,20 @@ def test_closed_loop_cuda_graph_matches_eager():
     import torch
     from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
     sims = []
-    for graph in (False, True):
+    for graph, exchange in ((False, "p2p"), (True, "p2p"), (False, "nccl")):
         batch = W.make_forest_batch(96, K=20, moving=False, seed=7)
         batch.goal = (batch.state[:, :3] * [-1, -1, 1]).astype(np.float32)
-        sim = ClosedLoopSim(batch, device=0, K=20, use_graph=graph)
+        sim = ClosedLoopSim(batch, device=0, K=20, use_graph=graph, exchange=exchange)
         for _ in range(12):
             sim.step()
-        torch.cuda.synchronize()
+        sim.sync_state()
         sims.append(sim)
-    assert sims[1]._graph is not None
+    assert sims[1]._graph is not None and sims[0].exchange == "p2p" and sims[2].exchange == "nccl"
     assert torch.equal(sims[0].state, sims[1].state) and torch.equal(sims[0].traj, sims[1].traj)
-    assert sims[0].failed_total == sims[1].failed_total == 0
+    # the fused failsafe + step + publish kernel against the separate torch failsafe + lscqp_step_batch path
+    assert torch.equal(sims[0].state, sims[2].state) and torch.equal(sims[0].traj, sims[2].traj)
+    assert sims[0].failed_total == sims[1].failed_total == sims[2].failed_total == 0
+    assert sims[0].exchange_timeouts == 0 and float((sims[0].state[:, :3] - torch.from_numpy(batch.state[:, :3]).cuda()).abs().max()) > 0.5
 
 
 @pytest.mark.parametrize("generator,M,dim", [(capi.GEN_LSC, 5, 3), (capi.GEN_CLSC, 5, 3), (capi.GEN_CLSC, 10, 2)])

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lsc_dr_planner_b200.sharding import allgather_rows, shard_range, shard_sizes
+from lsc_dr_planner_b200.sharding import all_agree, allgather_handles, allgather_rows, shard_range, shard_sizes
 
 
 def test_shard_ranges_partition_the_agents():
@@ -37,6 +37,14 @@ def _worker(rank, world, port, n_total, q):
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ok = ok and float(t) == float(world)
+        # plumbing of the peer exchange (ClosedLoopSim._connect_peers): 64-byte handles in rank order + success flags
+        mine = bytes([(rank * 37 + i) % 251 for i in range(64)])
+        handles, all_ok = allgather_handles(mine, ok=True)
+        ok = ok and all_ok and len(handles) == 64 * world
+        for r in range(world):
+            ok = ok and handles[64 * r:64 * (r + 1)] == bytes([(r * 37 + i) % 251 for i in range(64)])
+        _, all_ok = allgather_handles(mine, ok=(rank != world - 1))        # one rank could not create its block
+        ok = ok and not all_ok and not all_agree(rank != 0) and all_agree(True)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
