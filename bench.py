@@ -280,10 +280,34 @@ def run_closed_loop(args, torch, dist, W, capi, rank, world, local, exchange, gr
     if world > 1:
         dist.all_reduce(tt[:1], op=dist.ReduceOp.MAX)
         rest = tt[1:].clone(); dist.all_reduce(rest, op=dist.ReduceOp.SUM); tt[1:] = rest
+    # the exchange alone (publish the shard into every rank's block + wait for everyone + copy out), same agents, outside the loop
+    ex_us = None
+    if sim.exchange == "p2p":
+        qp = sim.planner.qp
+        stream = torch.cuda.current_stream().cuda_stream
+        own = sim.traj[sim.lo:sim.hi]
+        def ex():
+            qp.step_exchange(sim.lo, sim.n_local, sim.ctrl, sim.status, own, sim.cfg.dt, None, stream)
+            qp.exchange_begin(sim.traj, sim.state, stream)
+        for _ in range(10):
+            ex()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for _ in range(100):
+            ex()
+        e2.record(); torch.cuda.synchronize()
+        t2 = torch.tensor([a2.elapsed_time(e2) * 10.0], dtype=torch.float64, device="cuda")      # us per exchange
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ex_us = float(t2)
     out = {"workload": f"config 5: closed loop, {N} agents x {T} replans, agents sharded over {world} rank(s) ({sim.n_local} per rank), "
                        "neighbours re-selected every replan (every agent within the reference's default communication range 3.0, ragged lists)",
            "ms_per_replan": float(tt[0]), "replans_per_s": 1e3 / float(tt[0]), "agent_qp_per_s": N / (float(tt[0]) * 1e-3),
            "exchange": sim.exchange, "cuda_graph": bool(graph and sim._graph is not None),
+           "exchange_us_eager": ex_us,
            "exchange_in_timed_region": True, "qp_failures": int(tt[1]), "exchange_timeouts": int(tt[2]),
            "neighbour_overflows": int(tt[3]), "min_safety_ratio_end": sim.min_separation_ratio(),
            "goal_distance_end": sim.max_goal_distance()}
@@ -406,7 +430,8 @@ def run_ours(args):
                 "kernel_ms": {"assemble": asm_ms, "solve": sol_ms}, "pdip_iterations_mean": iters_mean,
                 "e2e": {"value": world * n_agents / e2e_s, "unit": UNIT, "h2d_bytes_per_step": planner.h2d_bytes(hb),
                         "d2h_bytes_per_step": planner.d2h_bytes(hb), "ms_per_step": 1e3 * e2e_s,
-                        "api": "lscqp_replan_host (C ABI, pinned host buffers)"},
+                        "api": "lscqp_replan_host (C ABI, pinned host buffers: inputs copied host->device inside the call, "
+                               "outputs stored by the solve kernel straight into the pinned result arrays)"},
                 "roofline": {"kernel": "pdip_solve_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                              "algorithmic_bytes_per_qp": ab["solve"],

@@ -601,6 +601,15 @@ extern "C" int lscqp_goal_host(lscqp_handle* h, int n_agents, const float* goal,
     return 0;
 }
 
+// device-visible alias of a host pointer when it lies in pinned (page-locked, UVA-mapped) memory, else null
+static void* mapped_alias(const void* host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
 extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, const float* state, const float* goal,
                                  const double* limits, const float* sfc, const float* next_waypoint, const float* own_traj,
                                  const double* agent_meta,
@@ -610,13 +619,13 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
         !cost_out || !status_out)
         return fail(LSCQP_E_INVALID, "null argument");
     if (n_agents == 0) return 0;
+    if (h->cfg.use_sfc && !sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
+    if (h->cfg.comm_range > 0 && !next_waypoint) return fail(LSCQP_E_INVALID, "comm_range set but next_waypoint is null");
     if (int rc = check_host_lists(h, n_agents, obs_offsets)) return rc;
     CK(cudaSetDevice(h->device));
     const int M = h->cfg.M;
     const size_t sumK = (size_t) obs_offsets[n_agents];
     if (sumK > 0 && !obs_index) return fail(LSCQP_E_INVALID, "null obs_index");
-    for (size_t j = 0; j < sumK; j++)
-        if (obs_index[j] < 0 || obs_index[j] >= n_agents) return fail(LSCQP_E_INVALID, "obs_index outside [0, n_agents)");
     cudaStream_t st = h->stream;
     RESERVE(h->d_state, n_agents * 9 * sizeof(float)); RESERVE(h->d_goal, n_agents * 3 * sizeof(float));
     RESERVE(h->d_limits, n_agents * 8 * sizeof(double)); RESERVE(h->d_off, (n_agents + 1) * sizeof(int));
@@ -624,25 +633,44 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     RESERVE(h->d_index, (sumK + 1) * sizeof(int));
     // (no gathered obstacle copies: the assembly reads the neighbours in place through d_index)
     RESERVE(h->d_normals, (sumK * M * 3 + 1) * sizeof(double)); RESERVE(h->d_rhs, (sumK * M * 6 + 1) * sizeof(double));
-    RESERVE(h->d_ctrl, (size_t) n_agents * h->nv * sizeof(double)); RESERVE(h->d_cost, n_agents * sizeof(double));
-    RESERVE(h->d_status, n_agents * sizeof(int)); RESERVE(h->d_iters, n_agents * sizeof(int));
+    // Outputs in pinned host memory are written by the solve kernel itself through their device alias (every QP stores
+    // its 720 bytes when it finishes, so the device->host transfer overlaps the rest of the batch); pageable outputs
+    // are staged in device buffers and copied back after the kernel.
+    double* k_ctrl = static_cast<double*>(mapped_alias(ctrl_out));
+    double* k_cost = static_cast<double*>(mapped_alias(cost_out));
+    int* k_status = static_cast<int*>(mapped_alias(status_out));
+    int* k_iters = iters_out ? static_cast<int*>(mapped_alias(iters_out)) : nullptr;
+    const bool direct = k_ctrl && k_cost && k_status && (!iters_out || k_iters);
+    if (!direct) {
+        RESERVE(h->d_ctrl, (size_t) n_agents * h->nv * sizeof(double)); RESERVE(h->d_cost, n_agents * sizeof(double));
+        RESERVE(h->d_status, n_agents * sizeof(int)); RESERVE(h->d_iters, n_agents * sizeof(int));
+        k_ctrl = h->d_ctrl.as<double>(); k_cost = h->d_cost.as<double>(); k_status = h->d_status.as<int>(); k_iters = h->d_iters.as<int>();
+    }
+    // host -> device: queue every copy first (largest first), then validate the neighbour ids while they are in flight
+    CK(cudaMemcpyAsync(h->d_own.p, own_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (sumK) CK(cudaMemcpyAsync(h->d_index.p, obs_index, sumK * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_limits.p, limits, n_agents * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_state.p, state, n_agents * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_ameta.p, agent_meta, n_agents * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_goal.p, goal, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     if (h->cfg.use_sfc) {
-        if (!sfc) return fail(LSCQP_E_INVALID, "use_sfc set but sfc is null");
         RESERVE(h->d_sfc, (size_t) n_agents * M * 6 * sizeof(float));
         CK(cudaMemcpyAsync(h->d_sfc.p, sfc, (size_t) n_agents * M * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(h->d_state.p, state, n_agents * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_goal.p, goal, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_limits.p, limits, n_agents * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_off.p, obs_offsets, (n_agents + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_own.p, own_traj, (size_t) n_agents * M * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
     if (h->cfg.comm_range > 0) {
-        if (!next_waypoint) return fail(LSCQP_E_INVALID, "comm_range set but next_waypoint is null");
         RESERVE(h->d_wp, n_agents * 3 * sizeof(float));
         CK(cudaMemcpyAsync(h->d_wp.p, next_waypoint, n_agents * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(h->d_ameta.p, agent_meta, n_agents * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (sumK) CK(cudaMemcpyAsync(h->d_index.p, obs_index, sumK * sizeof(int), cudaMemcpyHostToDevice, st));
+    {
+        unsigned bad = 0;
+        const unsigned lim = (unsigned) n_agents;
+        for (size_t j = 0; j < sumK; j++) bad |= (unsigned) ((unsigned) obs_index[j] >= lim);   // (negative ids wrap above lim)
+        if (bad) {
+            cudaStreamSynchronize(st);                           // nothing is launched, no output is written
+            return fail(LSCQP_E_INVALID, "obs_index outside [0, n_agents)");
+        }
+    }
     // obstacles are the batch's own agents: the assembly reads them in place through the index list (no gathered
     // copies) and drops the (obstacle, segment) pairs that provably cannot bind (exact; presolve bit 0)
     int rc = lscqp_assemble_lsc_fused(h, generator, h->cfg.presolve & 1, n_agents, h->d_own.as<float>(), h->d_ameta.as<double>(),
@@ -653,13 +681,14 @@ extern "C" int lscqp_replan_host(lscqp_handle* h, int generator, int n_agents, c
     rc = lscqp_solve_batch(h, n_agents, h->d_state.as<float>(), h->d_goal.as<float>(), h->d_limits.as<double>(),
                            h->cfg.use_sfc ? h->d_sfc.as<float>() : nullptr, h->cfg.comm_range > 0 ? h->d_wp.as<float>() : nullptr,
                            h->d_off.as<int>(), h->d_normals.as<double>(),
-                           h->d_rhs.as<double>(), h->d_own.as<float>(), h->d_ctrl.as<double>(), h->d_cost.as<double>(),
-                           h->d_status.as<int>(), h->d_iters.as<int>(), nullptr, nullptr, st);
+                           h->d_rhs.as<double>(), h->d_own.as<float>(), k_ctrl, k_cost, k_status, k_iters, nullptr, nullptr, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctrl_out, h->d_ctrl.p, (size_t) n_agents * h->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cost_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status_out, h->d_status.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (iters_out) CK(cudaMemcpyAsync(iters_out, h->d_iters.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!direct) {
+        CK(cudaMemcpyAsync(ctrl_out, h->d_ctrl.p, (size_t) n_agents * h->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cost_out, h->d_cost.p, n_agents * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status_out, h->d_status.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (iters_out) CK(cudaMemcpyAsync(iters_out, h->d_iters.p, n_agents * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     return 0;
 }
