@@ -146,6 +146,8 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     if (two_pass) {
         if (h->d_klass.reserve((size_t) n_agents * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
         p.klass = h->d_klass.as<int>();
+        // (routing the remainder of the light pass's last round to the full-capacity pass was measured: 1.65 vs 1.52 ms
+        //  per 4096 QPs -- the QPs' durations spread over 8..11 iterations, so the rounds do not end together)
     }
     int launched = inst_launch_0(h->cfg, p, n_agents, two_pass, st);
     if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, two_pass, st);

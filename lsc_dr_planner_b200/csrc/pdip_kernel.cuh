@@ -18,6 +18,10 @@
 //     :238-270, :372-397), velocity / acceleration differences (:440-474, rescaled to unit
 //     coefficients).  Slack s and multiplier lam of every row live in registers of the owning thread.
 //     An exact presolve drops the obstacles and bound rows no point allowed by the velocity rows can activate.
+//   * The QP is solved in agent-local coordinates: every control point is taken relative to the agent's current position
+//     (the jerk cost and all difference rows are shift invariant; goal, bounds and row constants are shifted once at
+//     start-up, the position is added back on output).  Iterates then stay within the ~1 m the horizon can reach, so
+//     their floating-point grid is 10-60x finer than at world coordinates of up to +-64 m.
 //   * Mehrotra predictor-corrector on (y, s, lam).  Per iteration the row weights are accumulated
 //     into the structured full-space Hessian (6x6 blocks per (dim, segment) + 3x3 blocks per control
 //     point), projected to the reduced space (host-built per-thread term streams), factorised by a stage-aware
@@ -138,7 +142,8 @@ struct Cfg {
     static constexpr int O_VLIM = O_X0 + 3 * D;          // [D]
     static constexpr int O_ALIM = O_VLIM + D;            // [D]
     static constexpr int O_GOAL = O_ALIM + D;            // [D]
-    static constexpr int O_LB = O_GOAL + D;              // [D][M]
+    static constexpr int O_ORG = O_GOAL + D;             // [D] origin of the local coordinates: the agent's current position
+    static constexpr int O_LB = O_ORG + D;               // [D][M]
     static constexpr int O_UB = O_LB + D * M;            // [D][M]
     static constexpr int O_TERMW = O_UB + D * M;         // [M] terminal weights, then the distance to the goal
     static constexpr int O_NRM = O_TERMW + M + 1;        // [KMAX][M][3]
@@ -571,6 +576,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     double* s_vlim = sm + C::O_VLIM;
     double* s_alim = sm + C::O_ALIM;
     double* s_goal = sm + C::O_GOAL;
+    double* s_org = sm + C::O_ORG;
     double* s_lb = sm + C::O_LB;
     double* s_ub = sm + C::O_UB;
     double* s_termw = sm + C::O_TERMW;
@@ -610,9 +616,10 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         const int kc = tid / C::PP, r = tid % C::PP;
         const double r1 = 0.5 * p.comm_range - p.limits[agent * 8 + 6], r2 = 0.5 * p.comm_range - 1e-5;
         if (r < M) {
-            const double pos = (double) p.state[agent * 9 + kc], wp = (double) p.next_waypoint[agent * 3 + kc];
+            // (local coordinates: the current position is the origin)
+            const double wp = (double) p.next_waypoint[agent * 3 + kc] - (double) p.state[agent * 9 + kc];
             ca_idx = kc * NCP + r * 6 + 5;
-            c_hp = fmin(pos + r1, wp + r2); c_hm = fmax(pos - r1, wp - r2);
+            c_hp = fmin(r1, wp + r2); c_hm = fmax(-r1, wp - r2);
         } else {
             int e = r - M, a = 1;
             while (a * (a + 1) / 2 <= e) a++;                     // pair e -> (a, b), 0 <= b < a <= M-1
@@ -663,19 +670,20 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         const int k = tid;
         const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
                      acc = (double) p.state[agent * 9 + 6 + k];
-        // c0 = pos; 5/dt (c1 - c0) = vel; 20/dt^2 (c2 - 2 c1 + c0) = acc    (traj_optimizer.cpp:321-338)
-        const double c0 = pos, c1 = pos + vel * p.dt / 5.0, c2 = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - c0;
+        // c0 = pos; 5/dt (c1 - c0) = vel; 20/dt^2 (c2 - 2 c1 + c0) = acc    (traj_optimizer.cpp:321-338), relative to pos
+        const double c0 = 0.0, c1 = vel * p.dt / 5.0, c2 = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - c0;
+        s_org[k] = pos;
         s_x0[k * 3 + 0] = c0; s_x0[k * 3 + 1] = c1; s_x0[k * 3 + 2] = c2;
         s_vlim[k] = p.limits[agent * 8 + k] * p.dt / 5.0;                 // :448-453 scaled to unit coefficients
         s_alim[k] = p.limits[agent * 8 + 3 + k] * p.dt * p.dt / 20.0;     // :462-471
-        s_goal[k] = (double) p.goal[agent * 3 + k];
+        s_goal[k] = (double) p.goal[agent * 3 + k] - pos;
         for (int m = 0; m < M; m++) {
             double lo = p.world_min[k], hi = p.world_max[k];              // :252-253
             if (p.use_sfc) {                                               // :372-397, Box::convertToLSCs
                 lo = fmax(lo, (double) p.sfc[((size_t) agent * M + m) * 6 + k]);
                 hi = fmin(hi, (double) p.sfc[((size_t) agent * M + m) * 6 + 3 + k]);
             }
-            s_lb[k * M + m] = lo; s_ub[k * M + m] = hi;
+            s_lb[k * M + m] = lo - pos; s_ub[k * M + m] = hi - pos;
         }
     }
     if (tid == (NT > 32 ? 32 : 8)) {
@@ -715,7 +723,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         for (int oi = grp; oi < K; oi += G) {
             const double* g = p.normals + ((size_t) (obs0 + oi) * M + m_cp) * 3;
             const double nx = g[0], ny = g[1], nz = (D == 3) ? g[2] : 0.0;
-            const double b = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp];
+            double b = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp] - (nx * s_org[0] + ny * s_org[1]);
+            if (D == 3) b -= nz * s_org[2];
             double lo = nx * s_x0[2] + ny * s_x0[5] - steps * (fabs(nx) * s_vlim[0] + fabs(ny) * s_vlim[1]);
             if (D == 3) lo += nz * s_x0[8] - steps * fabs(nz) * s_vlim[2];
             const bool zero_normal = (float) nx == 0.0f && (float) ny == 0.0f && (D == 2 || (float) nz == 0.0f);
@@ -769,8 +778,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             int st, k, j;
             if (C::TERM && r >= (M - 1) * C::NZS) { st = M - 1; k = r - (M - 1) * C::NZS; j = 2; }
             else { st = r / C::NZS; k = (r % C::NZS) / 3; j = r % 3; }
-            s_y[r] = from_traj ? (double) p.warm_traj[(((size_t) agent * M + st) * 6 + 3 + j) * 3 + k]
-                               : (double) p.state[agent * 9 + k];
+            s_y[r] = from_traj ? (double) p.warm_traj[(((size_t) agent * M + st) * 6 + 3 + j) * 3 + k] - s_org[k] : 0.0;
         }
         cta_sync<C>();
         expand(s_y, s_x0, s_c);
@@ -782,7 +790,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 #pragma unroll
         for (int u = 0; u < VPT; u++) {
             const int v = tid + u * NT;
-            if (v < NV) p.ctrl_out[(size_t) agent * NV + v] = s_c[v];
+            if (v < NV) p.ctrl_out[(size_t) agent * NV + v] = s_c[v] + s_org[v / NCP];
         }
         if (tid == 0) {
             p.cost_out[agent] = 0.0; p.status_out[agent] = ST_CAPACITY;
@@ -1019,8 +1027,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
-            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
-            if (D == 3) q += n[2] * cz;
+            double q = n[0] * (cx + s_org[0]) + n[1] * (cy + s_org[1]) - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
+            if (D == 3) q += n[2] * (cz + s_org[2]);
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             ls[j] = q;
         }
@@ -1351,8 +1359,8 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
             if (j >= nrow) break;
             const int oi = grp + G * j;
             const double* n = s_nrm + (oi * M + m_cp) * 3;
-            double q = n[0] * cx + n[1] * cy - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
-            if (D == 3) q += n[2] * cz;
+            double q = n[0] * (cx + s_org[0]) + n[1] * (cy + s_org[1]) - p.rhs[((size_t) (obs0 + s_act[oi]) * M + m_cp) * 6 + i_cp];
+            if (D == 3) q += n[2] * (cz + s_org[2]);
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) q = 1.0;
             rp_true = fmax(rp_true, fabs(ls[j] - q));
             accum(S, T, n, 0.0, ll[j], false);
@@ -1388,7 +1396,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         for (int b = 0; b < 6; b++) qc += sQ2[i_v * 6 + b] * s_c[v0 + b];
         cost += 0.5 * s_c[v] * qc;
         if (i_v == 5) { const double e = s_c[v] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
-        p.ctrl_out[(size_t) agent * NV + v] = s_c[v];
+        p.ctrl_out[(size_t) agent * NV + v] = s_c[v] + s_org[k_v];
     }
     red[0] = cost; red[1] = 0; red[2] = -rp_true; red[3] = rd_inf;
     block_reduce4<C>(red, s_red, red_phase);
