@@ -218,6 +218,33 @@ int lscqp_select_neighbours(lscqp_handle* h, int n_total, int lo, int n_local, i
 int lscqp_step_batch(lscqp_handle* h, int n_agents, const double* ctrl, double step,
         float* traj_out, float* state_out, float* shifted_traj_out, void* stream);
 
+/* ---- Static map and Safe Flight Corridors (TrajPlanner::generateSFC, src/traj_planner.cpp:738-753).
+ * lscqp_map_set builds, once per world, what MapManager::updateOctreeFromCSV (src/map_manager.cpp:262-305) and
+ * DynamicEDTOctomap(maxdist) (src/map_manager.cpp:59-80) hold in the reference: the occupied cells of the world's boxes
+ * (boxes: HOST array [n_boxes][6] = centre xyz, size xyz -- one row of a world CSV; param.world_resolution; the world
+ * box is lscqp_config.world_min/max) and the Euclidean-nearest occupied cell of every cell within max_dist
+ * (the reference passes 1.0).  lscqp_map_get copies them back (HOST arrays; occ [nx][ny][nz] bytes, closest
+ * [nx][ny][nz] packed x | y << 10 | z << 20 or -1; either may be NULL).
+ * lscqp_sfc_batch (device pointers) fills / advances the corridors sfc [n_agents][M][6] (box_min, box_max per segment,
+ * the array lscqp_solve_batch takes) for every agent, one CTA each:
+ *   LSCQP_SFC_INIT       CollisionConstraints::initializeSFC (src/collision_constraints.cpp:366-383): point = current
+ *                        position; all M corridors = the box grown around its grid cell; status 1, or 0 where the
+ *                        reference throws "Invalid initial SFC" (corridors untouched)
+ *   LSCQP_SFC_FROM_POINT constructSFCFromPoint (:396-411, :669-694): corridors shift by one segment, the last one is grown
+ *                        from point = initial_traj.lastPoint() towards goal = agent.current_goal_point (setAxisCand
+ *                        :1134-1170); status 1, or 0 = no valid box, previous corridor reused
+ *   LSCQP_SFC_FROM_HULL  constructSFCFromConvexHull (:413-436, :696-777; goal mode grid_based_planner): hull = {point,
+ *                        goal} first together with next_waypoint (status 2), else alone inside the previous corridor
+ *                        (status 1), else the previous corridor again (status 0)
+ * limits: [n_agents][8] as for lscqp_solve_batch (the agent radius at [6] is the margin). */
+#define LSCQP_SFC_INIT        0
+#define LSCQP_SFC_FROM_POINT  1
+#define LSCQP_SFC_FROM_HULL   2
+int lscqp_map_set(lscqp_handle* h, const double* boxes, int n_boxes, double resolution, double max_dist);
+int lscqp_map_get(lscqp_handle* h, int* n3, unsigned char* occ_out, int* closest_out);
+int lscqp_sfc_batch(lscqp_handle* h, int mode, int n_agents, const float* point, const float* goal,
+        const float* next_waypoint, const double* limits, float* sfc, int* status_out, void* stream);
+
 /* ---- Peer exchange for the sharded closed loop (BASELINE config 5: agents sharded over GPUs, one exchange of the solved
  * trajectories per replan).  Stands in for MultiSyncSimulator::broadcastMsgs (src/multi_sync_simulator.cpp:305-352), which
  * copies every agent's state and prev_traj (AgentManager::getAgent, src/agent_manager.cpp:184-199) to every planner.

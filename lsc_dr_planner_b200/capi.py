@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblscqp.so")
 
 MODE_DLSC, MODE_LSC, MODE_BVC = 0, 1, 2
 GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
+SFC_INIT, SFC_FROM_POINT, SFC_FROM_HULL = 0, 1, 2
 STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL, STATUS_CAPACITY = 0, 1, 2, 3, 4
 
 EXPORTS = ["lscqp_version", "lscqp_last_error", "lscqp_create", "lscqp_destroy", "lscqp_dual_stride",
@@ -58,7 +59,8 @@ def load():
                      "lscqp_gather_obstacles", "lscqp_step_batch", "lscqp_create", "lscqp_destroy", "lscqp_goal_batch",
                      "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch",
                      "lscqp_last_instances", "lscqp_exchange_create", "lscqp_exchange_connect", "lscqp_exchange_begin",
-                     "lscqp_step_exchange", "lscqp_exchange_status", "lscqp_exchange_destroy", "lscqp_exchange_connect_ptrs"):
+                     "lscqp_step_exchange", "lscqp_exchange_status", "lscqp_exchange_destroy", "lscqp_exchange_connect_ptrs",
+                     "lscqp_map_set", "lscqp_map_get", "lscqp_sfc_batch"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -189,6 +191,27 @@ class LscQp:
     def step_batch(self, n, ctrl, step, traj_out, state_out=None, shifted_out=None, stream=0):
         self._check(self.lib.lscqp_step_batch(self.h, n, _dp(ctrl), C.c_double(step), _dp(traj_out), _dp(state_out),
                                               _dp(shifted_out), C.c_void_p(stream)))
+
+    # ------------------------------------------------------------------ static map + Safe Flight Corridors
+    def map_set(self, boxes, resolution: float = 0.1, max_dist: float = 1.0):
+        """world boxes [n][6] (centre xyz, size xyz: the rows of a world CSV) -> occupancy grid + nearest-obstacle field
+        on the device (MapManager::updateOctreeFromCSV + DynamicEDTOctomap(maxdist))"""
+        b = np.ascontiguousarray(np.asarray(boxes, np.float64).reshape(-1, 6))
+        self._check(self.lib.lscqp_map_set(self.h, _hp(b, np.float64) if b.size else C.c_void_p(0), b.shape[0],
+                                           C.c_double(resolution), C.c_double(max_dist)))
+
+    def map_get(self):
+        """(occupancy [nx, ny, nz] uint8, closest [nx, ny, nz] packed int32) copied back from the device"""
+        n3 = (C.c_int * 3)()
+        self._check(self.lib.lscqp_map_get(self.h, n3, C.c_void_p(0), C.c_void_p(0)))
+        occ = np.zeros(tuple(n3), np.uint8); cl = np.zeros(tuple(n3), np.int32)
+        self._check(self.lib.lscqp_map_get(self.h, n3, C.c_void_p(occ.ctypes.data), C.c_void_p(cl.ctypes.data)))
+        return occ, cl
+
+    def sfc_batch(self, mode, n, point, goal, next_waypoint, limits, sfc, status, stream=0):
+        """TrajPlanner::generateSFC for every agent: SFC_INIT / SFC_FROM_POINT / SFC_FROM_HULL on sfc [n][M][6] (device)"""
+        self._check(self.lib.lscqp_sfc_batch(self.h, mode, n, _dp(point), _dp(goal), _dp(next_waypoint), _dp(limits), _dp(sfc),
+                                             _dp(status), C.c_void_p(stream)))
 
     # ------------------------------------------------------------------ peer exchange (sharded closed loop)
     def exchange_create(self, n_total, world, rank) -> bytes:

@@ -24,7 +24,7 @@ from .workloads import Batch
 class ClosedLoopSim:
     def __init__(self, batch: Batch, device: int = 0, rank: int = 0, world: int = 1, K: int = 40,
                  comm_range: float = 0.0, generator: int = capi.GEN_LSC, use_graph: bool = False,
-                 goal_mode: str = "static", exchange: str = "p2p"):
+                 goal_mode: str = "static", exchange: str = "p2p", world_boxes=None, world_resolution: float = 0.1):
         import torch
         from .planner import BatchPlanner
         self.torch = torch
@@ -72,6 +72,16 @@ class ClosedLoopSim:
         self.use_graph = use_graph
         self._graph = None
         self.prune = bool(int(self.cfg.presolve) & 1)
+        # Safe Flight Corridors against the static map (world_use_octomap; TrajPlanner::generateSFC, traj_planner.cpp:738-753)
+        self.use_sfc = bool(self.cfg.use_sfc)
+        self.sfc = None
+        if self.use_sfc:
+            assert world_boxes is not None, "cfg.use_sfc needs the world's boxes (a world CSV)"
+            self.planner.qp.map_set(world_boxes, world_resolution, 1.0)
+            wb = torch.tensor(list(self.cfg.world_min) + list(self.cfg.world_max), dtype=torch.float32, device=dev)
+            self.sfc = wb.repeat(n, M, 1).contiguous()                  # (an agent without a valid start box keeps the world box)
+            self.sfc_status = torch.zeros((n,), dtype=torch.int32, device=dev)
+            self._sfc_invalid = torch.zeros((), dtype=torch.int64, device=dev)
         assert exchange in ("p2p", "nccl")
         self.exchange = exchange
         if exchange == "p2p":
@@ -134,6 +144,7 @@ class ClosedLoopSim:
         torch = self.torch
         qp = self.planner.qp
         n, lo, hi = self.n_local, self.lo, self.hi
+        M_ = self.cfg.M
         p2p = self.exchange == "p2p"
         if p2p:
             qp.exchange_begin(self.traj, self.state, stream)           # rows every rank published at the end of the last step
@@ -153,7 +164,15 @@ class ClosedLoopSim:
         st, goal, lim, meta = self.state[lo:hi], self.goal[lo:hi], self.limits[lo:hi], self.agent_meta[lo:hi]
         qp.assemble_lsc_fused(self.generator, self.prune, n, own, meta, goal, st, lim, self.obs_offsets, obs_index,
                               self.traj, self.agent_meta, self.goal, self.state, self.normals, self.rhs, stream)
-        qp.solve_batch(n, st, goal, lim, None, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
+        if self.use_sfc:
+            # constructSFC after constructLSC (planImpl, traj_planner.cpp:117-139): the first replan grows one box around the
+            # start cell for all segments (:739-741), later ones shift and grow the last box from the end of initial_traj
+            if self.steps == 0:
+                qp.sfc_batch(capi.SFC_INIT, n, st[:, 0:3].contiguous(), None, None, lim, self.sfc, self.sfc_status, stream)
+                self._sfc_invalid += (self.sfc_status == 0).sum()
+            else:
+                qp.sfc_batch(capi.SFC_FROM_POINT, n, own[:, M_ - 1, 5].contiguous(), goal, None, lim, self.sfc, self.sfc_status, stream)
+        qp.solve_batch(n, st, goal, lim, self.sfc, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
                        self.status, self.iters, stream=stream, initial_traj=own)
         self._overflowed += (self.overflow[:n] > 0).sum()
         if p2p:

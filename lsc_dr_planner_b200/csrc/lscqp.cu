@@ -1,6 +1,7 @@
 // lscqp.cu -- liblscqp.so: the C ABI of include/lscqp.h on top of the sm_100a kernels.
 // No CPU path exists here: every entry point launches CUDA kernels or fails with an error code.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include "step_kernel.cuh"
 #include "goal_kernel.cuh"
 #include "knn_kernel.cuh"
+#include "sfc_kernel.cuh"
 
 using namespace lscqp;
 
@@ -55,6 +57,9 @@ struct lscqp_handle {
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
+    DevBuf d_occ, d_closest, d_boxes;   // static map (lscqp_map_set)
+    MapView map{};
+    bool has_map = false;
     Exchange* xchg = nullptr;          // peer exchange of the sharded closed loop (lscqp_exchange_*)
 };
 
@@ -111,7 +116,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass, &h->d_gout, &h->d_knn};
+                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -442,6 +447,68 @@ extern "C" int lscqp_goal_batch(lscqp_handle* h, int n_agents, const float* goal
     p.goal = goal; p.waypoint = next_waypoint; p.sfc = sfc; p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs;
     p.goal_out = goal_out; p.t_out = t_out; p.status_out = status_out;
     goal_lp_kernel<<<(n_agents + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Static map + Safe Flight Corridors (sfc_kernel.cuh)
+extern "C" int lscqp_map_set(lscqp_handle* h, const double* boxes, int n_boxes, double resolution, double max_dist) {
+    if (!h || n_boxes < 0 || (n_boxes > 0 && !boxes) || !(resolution > 0) || !(max_dist > 0)) return fail(LSCQP_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    MapView m{};
+    m.res = resolution; m.inv_res = 1.0 / resolution;
+    size_t cells = 1;
+    for (int k = 0; k < 3; k++) {
+        m.world_min[k] = (float) h->cfg.world_min[k]; m.world_max[k] = (float) h->cfg.world_max[k];     // Mission::world_min/max are point3d
+        m.key0[k] = (int) std::floor(m.inv_res * (double) m.world_min[k]);
+        m.n[k] = (int) std::floor(m.inv_res * (double) m.world_max[k]) - m.key0[k] + 1;
+        if (m.n[k] < 1 || m.n[k] > 1023) return fail(LSCQP_E_CAPACITY, "map needs 1..1023 cells per axis");
+        cells *= (size_t) m.n[k];
+    }
+    m.maxd2 = (int) std::pow(max_dist / resolution, 2);
+    if (h->d_occ.reserve(cells) || h->d_closest.reserve(cells * sizeof(int)) || h->d_boxes.reserve((size_t) (n_boxes > 0 ? n_boxes : 1) * 6 * sizeof(double)))
+        return fail(LSCQP_E_CUDA, "cudaMalloc failed");
+    m.occ = h->d_occ.as<unsigned char>(); m.closest = h->d_closest.as<int>();
+    cudaStream_t st = h->stream;
+    CK(cudaMemsetAsync(h->d_occ.p, 0, cells, st));
+    if (n_boxes > 0) {
+        CK(cudaMemcpyAsync(h->d_boxes.p, boxes, (size_t) n_boxes * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+        OccParams op{m, h->d_occ.as<unsigned char>(), h->d_boxes.as<double>(), n_boxes};
+        occupancy_kernel<<<n_boxes, 256, 0, st>>>(op);
+    }
+    EdtParams ep{m, h->d_closest.as<int>()};
+    edt_closest_kernel<<<(unsigned) ((cells + 127) / 128), 128, 0, st>>>(ep);
+    h->launches += n_boxes > 0 ? 2 : 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    h->map = m; h->has_map = true;
+    return 0;
+}
+
+extern "C" int lscqp_map_get(lscqp_handle* h, int* n3, unsigned char* occ_out_host, int* closest_out_host) {
+    if (!h || !h->has_map || !n3) return fail(LSCQP_E_INVALID, "no map set / null argument");
+    CK(cudaSetDevice(h->device));
+    const size_t cells = (size_t) h->map.n[0] * h->map.n[1] * h->map.n[2];
+    for (int k = 0; k < 3; k++) n3[k] = h->map.n[k];
+    if (occ_out_host) CK(cudaMemcpy(occ_out_host, h->d_occ.p, cells, cudaMemcpyDeviceToHost));
+    if (closest_out_host) CK(cudaMemcpy(closest_out_host, h->d_closest.p, cells * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int lscqp_sfc_batch(lscqp_handle* h, int mode, int n_agents, const float* point, const float* goal,
+                               const float* next_waypoint, const double* limits, float* sfc, int* status_out, void* stream) {
+    if (!h || n_agents < 0 || !point || !limits || !sfc || !status_out) return fail(LSCQP_E_INVALID, "null argument");
+    if (!h->has_map) return fail(LSCQP_E_INVALID, "lscqp_map_set has not been called on this handle");
+    if (mode < SFC_INIT || mode > SFC_FROM_HULL) return fail(LSCQP_E_INVALID, "unknown mode");
+    if (mode != SFC_INIT && !goal) return fail(LSCQP_E_INVALID, "goal is null");
+    if (mode == SFC_FROM_HULL && !next_waypoint) return fail(LSCQP_E_INVALID, "next_waypoint is null");
+    if (n_agents == 0) return 0;
+    SfcParams p;
+    p.map = h->map; p.mode = mode; p.n_agents = n_agents; p.M = h->cfg.M;
+    p.point = point; p.goal = goal; p.waypoint = next_waypoint; p.limits = limits; p.sfc = sfc; p.status = status_out;
+    sfc_kernel<<<n_agents, SFC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     h->launches++;
     CK(cudaGetLastError());
     return 0;

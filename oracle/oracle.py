@@ -33,8 +33,8 @@ GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
 
 def build(force: bool = False) -> None:
     """Compile the C restatement (and oracle/_ref when /root/reference is present)."""
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(
-            os.path.join(_HERE, "lscqp_oracle.c")):
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(
+            os.path.join(_HERE, f)) for f in ("lscqp_oracle.c", "sfc_oracle.c", "lscqp_oracle.h")):
         subprocess.run(["make", "-C", _HERE, "_build/liblscqp_oracle.so"], check=True,
                        stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/openGJK/openGJK.cpp") and (force or not os.path.exists(_REF)):
@@ -111,6 +111,12 @@ def lib():
         _lib.orc_terminal_segments.restype = C.c_int
         _lib.orc_qp_build.restype = C.c_int
         _lib.orc_build_aeq_base.restype = C.c_int
+        _lib.orc_map_build.restype = C.c_void_p
+        _lib.orc_map_occupancy.restype = C.c_void_p
+        _lib.orc_map_closest.restype = C.c_void_p
+        for f in ("orc_map_free", "orc_map_dims", "orc_map_occupancy", "orc_map_closest", "orc_is_obstacle_in_sfc", "orc_expand_sfc",
+                  "orc_sfc_initialize", "orc_sfc_from_point", "orc_sfc_from_convex_hull"):
+            getattr(_lib, f).argtypes = None
     return _lib
 
 
@@ -540,3 +546,62 @@ def kkt_certificate(qp: QP, x: np.ndarray) -> dict:
     return {"stationarity": float(np.abs(res).max()), "primal_eq": prim_eq, "primal_ineq": prim_ineq,
             "n_active": int(act.size), "max_multiplier": float(z.max()) if z.size else 0.0,
             "grad_scale": float(np.abs(grad).max())}
+
+
+# ------------------------------------------------------------------------------------------------
+# Safe Flight Corridor construction (oracle/sfc_oracle.c).  PARITY UNPINNED: octomap / dynamicEDT3D absent.
+class Map:
+    """occupancy grid + nearest-obstacle queries of a world CSV (MapManager::updateOctreeFromCSV + DynamicEDTOctomap)"""
+
+    def __init__(self, boxes, world_min, world_max, resolution: float = 0.1, max_dist: float = 1.0):
+        self.boxes = np.ascontiguousarray(np.asarray(boxes, np.float64).reshape(-1, 6))
+        self.world_min = np.asarray(world_min, np.float32); self.world_max = np.asarray(world_max, np.float32)
+        self.res = float(resolution)
+        self.h = C.c_void_p(lib().orc_map_build(_p(self.boxes, C.c_double), C.c_int(self.boxes.shape[0]), C.c_double(self.res),
+                                                _p(self.world_min, C.c_float), _p(self.world_max, C.c_float), C.c_double(max_dist)))
+        n3 = (C.c_int * 3)(); k0 = (C.c_int * 3)()
+        self.maxd2 = lib().orc_map_dims(self.h, n3, k0)
+        self.n = tuple(n3); self.key0 = tuple(k0)
+
+    def __del__(self):
+        try:
+            lib().orc_map_free(self.h)
+        except Exception:
+            pass
+
+    def occupancy(self) -> np.ndarray:
+        ptr = lib().orc_map_occupancy(self.h)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=self.n).copy()
+
+    def closest(self) -> np.ndarray:
+        """[nx, ny, nz, 3] nearest occupied cell of every cell (-1: none within max_dist); slow (brute force)"""
+        ptr = lib().orc_map_closest(self.h)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int)), shape=self.n + (3,)).copy()
+
+    def is_obstacle_in_sfc(self, box, margin: float) -> bool:
+        b = np.ascontiguousarray(box, np.float32).reshape(6)
+        return bool(lib().orc_is_obstacle_in_sfc(self.h, _p(b, C.c_float), C.c_double(margin)))
+
+    def expand_sfc(self, initial, margin: float, goal=None):
+        """(ok, box): CollisionConstraints::expandSFC, goal-directed axis order when `goal` is given"""
+        b = np.ascontiguousarray(initial, np.float32).reshape(6); out = np.zeros(6, np.float32)
+        g = None if goal is None else np.ascontiguousarray(goal, np.float32)
+        ok = lib().orc_expand_sfc(self.h, _p(b, C.c_float), None if g is None else _p(g, C.c_float), C.c_double(margin), _p(out, C.c_float))
+        return bool(ok), out
+
+    def sfc_initialize(self, position, radius: float):
+        pos = np.ascontiguousarray(position, np.float32); out = np.zeros(6, np.float32)
+        ok = lib().orc_sfc_initialize(self.h, _p(pos, C.c_float), C.c_double(radius), _p(out, C.c_float))
+        return bool(ok), out
+
+    def sfc_from_point(self, point, goal, prev, radius: float):
+        pt = np.ascontiguousarray(point, np.float32); g = np.ascontiguousarray(goal, np.float32)
+        pv = np.ascontiguousarray(prev, np.float32).reshape(6); out = np.zeros(6, np.float32)
+        ok = lib().orc_sfc_from_point(self.h, _p(pt, C.c_float), _p(g, C.c_float), _p(pv, C.c_float), C.c_double(radius), _p(out, C.c_float))
+        return int(ok), out
+
+    def sfc_from_convex_hull(self, hull2, next_waypoint, prev, radius: float):
+        h2 = np.ascontiguousarray(hull2, np.float32).reshape(2, 3); w = np.ascontiguousarray(next_waypoint, np.float32)
+        pv = np.ascontiguousarray(prev, np.float32).reshape(6); out = np.zeros(6, np.float32)
+        ok = lib().orc_sfc_from_convex_hull(self.h, _p(h2, C.c_float), _p(w, C.c_float), _p(pv, C.c_float), C.c_double(radius), _p(out, C.c_float))
+        return int(ok), out

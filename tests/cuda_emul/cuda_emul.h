@@ -65,6 +65,7 @@ inline void __syncthreads() {
     if (++s.arrived == s.nthreads) { s.arrived = 0; s.gen++; return; }
     while (s.gen == g) emu::yield();
 }
+inline int __syncthreads_or(int pred);
 inline void __syncwarp(unsigned = 0xffffffffu) {
     emu::State& s = emu::st();
     const int w = s.cur >> 5;
@@ -120,6 +121,21 @@ inline int __any_sync(unsigned, int pred) {
     __syncwarp();
     return r;
 }
+inline int __syncthreads_or(int pred) {
+    // two accumulators keyed by the parity of the barrier generation, each tagged with the generation it belongs to
+    // (a thread that runs ahead into the next barrier must not disturb the value the others still have to read)
+    emu::State& s = emu::st();
+    static int acc[2] = {0, 0};
+    static unsigned long tag[2] = {~0ul, ~0ul};
+    const unsigned long g = s.gen;
+    const int slot = (int) (g & 1);
+    if (tag[slot] != g) { acc[slot] = 0; tag[slot] = g; }
+    if (pred) acc[slot] = 1;
+    __syncthreads();
+    return acc[slot];
+}
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }   // fibers are cooperative
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }

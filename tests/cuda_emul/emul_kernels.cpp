@@ -8,6 +8,7 @@
 #include "../../lsc_dr_planner_b200/csrc/step_kernel.cuh"
 #include "../../lsc_dr_planner_b200/csrc/goal_kernel.cuh"
 #include "../../lsc_dr_planner_b200/csrc/knn_kernel.cuh"
+#include "../../lsc_dr_planner_b200/csrc/sfc_kernel.cuh"
 
 using namespace lscqp;
 
@@ -182,3 +183,57 @@ extern "C" int emul_validate_batch(const lscqp_config* cfg, int n_agents, const 
 }
 
 extern "C" void emul_jerk_gram(int n, int phi, double dt, double* Q) { jerk_gram(n, phi, dt, Q); }
+
+// Safe Flight Corridors on the emulator: the map kernels + sfc_kernel on host arrays.
+struct EmulMap { MapView m; std::vector<unsigned char> occ; std::vector<int> closest; };
+extern "C" void* emul_map_build(const lscqp_config* cfg, const double* boxes, int n_boxes, double res, double max_dist) {
+    EmulMap* e = new EmulMap();
+    MapView& m = e->m;
+    m.res = res; m.inv_res = 1.0 / res;
+    size_t cells = 1;
+    for (int k = 0; k < 3; k++) {
+        m.world_min[k] = (float) cfg->world_min[k]; m.world_max[k] = (float) cfg->world_max[k];
+        m.key0[k] = (int) std::floor(m.inv_res * (double) m.world_min[k]);
+        m.n[k] = (int) std::floor(m.inv_res * (double) m.world_max[k]) - m.key0[k] + 1;
+        cells *= (size_t) m.n[k];
+    }
+    m.maxd2 = (int) std::pow(max_dist / res, 2);
+    e->occ.assign(cells, 0); e->closest.assign(cells, -1);
+    m.occ = e->occ.data(); m.closest = e->closest.data();
+    if (n_boxes > 0) {
+        OccParams op{m, e->occ.data(), boxes, n_boxes};
+        emu::launch(n_boxes, 256, 64, [&]() { occupancy_kernel(op); });
+    }
+    return e;
+}
+// (the brute-force window scan of every cell is too slow on the fiber emulator: only the listed cells are computed)
+extern "C" int emul_map_edt_cells(void* map, const long* cells, int n) {
+    EmulMap* e = static_cast<EmulMap*>(map);
+    // run edt_closest_kernel's body for single cells: one emulated CTA of 128 threads covers 128 consecutive cells
+    for (int i = 0; i < n; i++) {
+        const long blk = cells[i] / 128;
+        EdtParams ep{e->m, e->closest.data()};
+        emu::State& s = emu::st(); (void) s;
+        // launch a 1-CTA grid whose blockIdx is forced through an offset copy of the params: emulate by temporary remap
+        struct Local { static void run(const EdtParams& p, long blk) {
+            blockIdx.x = (unsigned) blk; edt_closest_kernel(p); } };
+        emu::launch(1, 128, 64, [&]() { Local::run(ep, blk); });
+    }
+    return 0;
+}
+extern "C" const unsigned char* emul_map_occ(void* map, int* n3) {
+    EmulMap* e = static_cast<EmulMap*>(map);
+    for (int k = 0; k < 3; k++) n3[k] = e->m.n[k];
+    return e->occ.data();
+}
+extern "C" int* emul_map_closest(void* map) { return static_cast<EmulMap*>(map)->closest.data(); }
+extern "C" void emul_map_free(void* map) { delete static_cast<EmulMap*>(map); }
+extern "C" int emul_sfc_batch(void* map, int mode, int M, int n_agents, const float* point, const float* goal, const float* waypoint,
+                              const double* limits, float* sfc, int* status) {
+    EmulMap* e = static_cast<EmulMap*>(map);
+    SfcParams p;
+    p.map = e->m; p.mode = mode; p.n_agents = n_agents; p.M = M;
+    p.point = point; p.goal = goal; p.waypoint = waypoint; p.limits = limits; p.sfc = sfc; p.status = status;
+    emu::launch(n_agents, SFC_THREADS, 64, [&]() { sfc_kernel(p); });
+    return 0;
+}

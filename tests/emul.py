@@ -129,3 +129,46 @@ def validate(cfg, n, traj, state, limits, sfc):
                                    _p(sfc, np.float32), _p(out, np.int32))
     assert rc == 0, rc
     return out
+
+
+class EmulMap:
+    """the map kernels (occupancy_kernel, edt_closest_kernel) and sfc_kernel on the emulator"""
+
+    def __init__(self, cfg, boxes, resolution=0.1, max_dist=1.0):
+        self.cfg = cfg
+        self.cc = capi.make_config(cfg)
+        self.boxes = np.ascontiguousarray(np.asarray(boxes, np.float64).reshape(-1, 6))
+        lib().emul_map_build.restype = C.c_void_p
+        lib().emul_map_occ.restype = C.c_void_p
+        lib().emul_map_closest.restype = C.c_void_p
+        self.h = C.c_void_p(lib().emul_map_build(C.byref(self.cc), _p(self.boxes, np.float64), self.boxes.shape[0],
+                                                 C.c_double(resolution), C.c_double(max_dist)))
+        n3 = (C.c_int * 3)()
+        self._occ_ptr = lib().emul_map_occ(self.h, n3)
+        self.n = tuple(n3)
+
+    def __del__(self):
+        try:
+            lib().emul_map_free(self.h)
+        except Exception:
+            pass
+
+    def occupancy(self):
+        return np.ctypeslib.as_array(C.cast(self._occ_ptr, C.POINTER(C.c_ubyte)), shape=self.n).copy()
+
+    def closest_view(self):
+        """packed nearest-occupied-cell table [nx, ny, nz] (writable view)"""
+        return np.ctypeslib.as_array(C.cast(lib().emul_map_closest(self.h), C.POINTER(C.c_int)), shape=self.n)
+
+    def edt_cells(self, cells):
+        """run edt_closest_kernel for the CTAs holding the given linear cell indices"""
+        c = np.ascontiguousarray(cells, np.int64)
+        assert lib().emul_map_edt_cells(self.h, c.ctypes.data_as(C.POINTER(C.c_long)), len(c)) == 0
+
+    def sfc(self, mode, point, goal, waypoint, limits, sfc):
+        n = point.shape[0]
+        status = np.full(n, -1, np.int32)
+        rc = lib().emul_sfc_batch(self.h, mode, self.cfg.M, n, _p(point, np.float32), _p(goal, np.float32), _p(waypoint, np.float32),
+                                  _p(limits, np.float64), _p(sfc, np.float32), _p(status, np.int32))
+        assert rc == 0
+        return status

@@ -8,8 +8,12 @@
   c3_*  config 3: 26 independent 10-agent instances of missions/maze10_dense/maze10_k.json rolled out in closed loop by
         the oracle (LSC -> goal LP -> QP -> doStep -> shift) for R = 2..10 replans; the inputs of replan R+1 of every agent
         (first 256 of 260) and their polished oracle solutions.
-The map pipeline (octomap SFC boxes) and the grid MAPF layer are outside the hot path: use_sfc is
-off and the next waypoint is the point one grid cell / one metre ahead on the straight line to the desired goal.
+Safe Flight Corridors are ON (world_use_octomap, as the shipped launches run): every mission is paired with its world
+file like the reference pairs them (lexicographic order of both directories, multi_sync_simulator_node.cpp:48-49), the
+corridors are built by the oracle's restatement of generateSFC (initializeSFC on the first replan, afterwards
+constructSFCFromConvexHull -- the goal mode of the launches is grid_based_planner), and they enter the goal LP and the QP.
+The grid MAPF layer is outside the hot path: the next waypoint is the point one metre ahead on the straight line to the
+desired goal.
 """
 import glob
 import os
@@ -32,23 +36,23 @@ REF = "/root/reference"
 
 def ocfg(cfg):
     return orc.Config(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, dt=cfg.dt, w_control=cfg.w_control,
-                      w_terminal=cfg.w_terminal, planner_mode=cfg.planner_mode, use_sfc=False, comm_range=cfg.comm_range,
+                      w_terminal=cfg.w_terminal, planner_mode=cfg.planner_mode, use_sfc=True, comm_range=cfg.comm_range,
                       world_min=cfg.world_min, world_max=cfg.world_max, z_2d=cfg.z_2d)
 
 
-def plan_agent(cfgo, mission, a, state, goal_prev, wp, own, nbr, trajs, goals_prev, positions, final=True):
+def plan_agent(cfgo, mission, a, state, goal_prev, wp, own, nbr, trajs, goals_prev, positions, sfc, final=True):
     """one agent's replan through the oracle; returns (new_goal, goal_status, x or None, planes)"""
     ag = orc.Agent(state[:3], state[3:6], state[6:9], goal_prev, next_waypoint=wp, max_vel=tuple(mission.max_vel[a]),
                    max_acc=tuple(mission.max_acc[a]), radius=float(mission.radius[a]),
                    nominal_velocity=float(mission.nominal_velocity[a]), downwash=float(mission.downwash[a]))
     pt, nr, d = orc.generate_lsc(cfgo, orc.GEN_CLSC, ag, own, trajs[nbr], mission.radius[nbr], mission.downwash[nbr],
                                  goals_prev[nbr], positions[nbr])
-    ar, br = orc.goal_rows(cfgo, goal_prev, wp, pt, nr, d)
+    ar, br = orc.goal_rows(cfgo, goal_prev, wp, pt, nr, d, sfc_last=sfc[-1])
     new_goal, t, gst = orc.goal_solve(cfgo, goal_prev, wp, ar, br)
     if gst != 0:
         return goal_prev, gst, None, (pt, nr, d)
     ag.goal = new_goal
-    qp = orc.qp_build(cfgo, ag, pt, nr, d)
+    qp = orc.qp_build(cfgo, ag, pt, nr, d, sfc)
     # the dense interior-point checker solves these models in ~20 ms; HiGHS' active-set QP solver needs 1 s to minutes on
     # the dense communication-range models and errors out on about half of them, so it is run afterwards on a subset
     # under a wall-clock limit (highs_crosscheck) and the agreement is stored in the fixture
@@ -101,12 +105,15 @@ def waypoint(pos, desired, step):
     return (pos + v / max(dist, 1e-9) * min(dist, step)).astype(np.float32)
 
 
-def rollout(path, R, M=10, dim=2):
+def rollout(path, world_path, R, M=10, dim=2):
     """closed loop of one mission for R replans; returns the inputs of replan R+1 and its oracle solutions"""
     mission = MS.load_mission(path, dim, 1.0)
     cfg = MS.launch_config(mission, M=M, dim=dim)
     cfgo = ocfg(cfg)
     n = mission.n_agents
+    boxes = MS.load_world_csv(world_path)
+    world_map = orc.Map(boxes, mission.world_min, mission.world_max, 0.1, 1.0)
+    sfcs = np.zeros((n, M, 6), np.float32)
     state = np.zeros((n, 9), np.float32); state[:, :3] = mission.start
     goal = mission.start.copy()                                   # agent_manager.cpp:9
     trajs = np.stack([orc.const_vel_traj(cfgo, state[a, :3], state[a, 3:6]) for a in range(n)])
@@ -115,10 +122,20 @@ def rollout(path, R, M=10, dim=2):
         off, idx = MS.neighbours_linf(state[:, :3], cfg.comm_range)
         wps = np.stack([waypoint(state[a, :3], mission.goal[a], 1.0) for a in range(n)])
         new_goal = goal.copy(); new_trajs = trajs.copy(); sols = []; oks = []
+        sfc_prev = sfcs.copy(); sfc_status = np.zeros(n, np.int32)
+        for a in range(n):                                         # generateSFC, traj_planner.cpp:738-753 (after the LSCs)
+            if step == 0:
+                ok_, box = world_map.sfc_initialize(state[a, :3], float(mission.radius[a]))
+                if not ok_:
+                    raise RuntimeError(f"{path}: invalid initial SFC for agent {a} (the reference throws here)")
+                sfcs[a, :] = box; sfc_status[a] = 1
+            else:
+                st_, box = world_map.sfc_from_convex_hull([trajs[a, M - 1, 5], goal[a]], wps[a], sfcs[a, M - 1].copy(), float(mission.radius[a]))
+                sfcs[a, :M - 1] = sfcs[a, 1:].copy(); sfcs[a, M - 1] = box; sfc_status[a] = st_
         for a in range(n):
             nbr = idx[off[a]:off[a + 1]]
             g, gst, sol, _ = plan_agent(cfgo, mission, a, state[a], goal[a], wps[a], trajs[a], nbr, trajs, goal, state[:, :3],
-                                        final=(step == R))
+                                        sfcs[a], final=(step == R))
             new_goal[a] = g
             if sol is not None:
                 x, ok = sol
@@ -132,7 +149,8 @@ def rollout(path, R, M=10, dim=2):
             rec = dict(state=state.copy(), goal_prev=goal.copy(), goal=new_goal.copy(), wp=wps, own=trajs.copy(), off=off, idx=idx,
                        x=np.stack(sols), ok=np.array(oks), limits=np.concatenate([mission.max_vel, mission.max_acc,
                        mission.radius[:, None], mission.nominal_velocity[:, None]], 1), meta=np.stack([mission.radius, mission.downwash], 1),
-                       world=np.array(mission.world_min + mission.world_max), highs_jobs=list(HIGHS_JOBS))
+                       world=np.array(mission.world_min + mission.world_max), highs_jobs=list(HIGHS_JOBS),
+                       sfc=sfcs.copy(), sfc_prev=sfc_prev, sfc_status=sfc_status, boxes=boxes, first=np.full(n, step == 0))
             HIGHS_JOBS.clear()
             break
         goal = new_goal
@@ -147,17 +165,18 @@ def _roll(args):
 
 def main():
     out = {}
-    r1 = rollout(os.path.join(REF, "missions/forest10/forest10_1.json"), 0)
+    r1 = rollout(os.path.join(REF, "missions/forest10/forest10_1.json"), os.path.join(REF, "world/forest/forest1.csv"), 0)
     jobs = r1.pop("highs_jobs")
     for k, v in r1.items():
         out["c1_" + k] = v
     files = sorted(glob.glob(os.path.join(REF, "missions/maze10_dense/*.json")))[:26]       # lexicographic, mission.cpp:18-44
+    worlds = sorted(glob.glob(os.path.join(REF, "world/maze/dense/*.csv")))[:26]
     import multiprocessing as mp
     with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
-        recs = pool.map(_roll, [(f, 2 + (i % 9)) for i, f in enumerate(files)], chunksize=1)   # replan indices 3..11
+        recs = pool.map(_roll, [(f, w, 2 + (i % 9)) for i, (f, w) in enumerate(zip(files, worlds))], chunksize=1)   # replan indices 3..11
     n0 = 0
-    keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta"]
-    cat = {k: [] for k in keys}; off = [0]; idx = []; world = []
+    keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta", "sfc", "sfc_prev", "sfc_status"]
+    cat = {k: [] for k in keys}; off = [0]; idx = []; world = []; boxes = []; boxes_off = [0]
     for r in recs[:3]:
         jobs += r["highs_jobs"]
     out["highs_maxdiff"] = highs_crosscheck(jobs)          # config 1 (10 QPs) + the first three config-3 instances
@@ -166,10 +185,12 @@ def main():
             cat[k].append(r[k])
         idx.append(r["idx"] + n0); off.extend((r["off"][1:] + off[-1] - r["off"][0]).tolist())
         n0 += r["state"].shape[0]; world.append(r["world"])
+        boxes.append(r["boxes"]); boxes_off.append(boxes_off[-1] + r["boxes"].shape[0])
     for k in keys:
         out["c3_" + k] = np.concatenate(cat[k])
     out["c3_off"] = np.array(off, np.int32); out["c3_idx"] = np.concatenate(idx).astype(np.int32)
     out["c3_world"] = np.stack(world)
+    out["c3_boxes"] = np.concatenate(boxes); out["c3_boxes_off"] = np.array(boxes_off, np.int32)   # world boxes of instance i
     np.savez_compressed(os.path.join(HERE, "mission_golden.npz"), **out)
     print("config 1: solved", int(r1["ok"].sum()), "of", len(r1["ok"]), "| config 3:", int(out["c3_ok"].sum()), "polished of", len(out["c3_ok"]),
           "failed", int(np.isnan(out["c3_x"][:, 0]).sum()), "| HiGHS cross-check:", int(np.isfinite(out["highs_maxdiff"]).sum()), "of",
