@@ -244,6 +244,9 @@ int lscqp_map_set(lscqp_handle* h, const double* boxes, int n_boxes, double reso
 int lscqp_map_get(lscqp_handle* h, int* n3, unsigned char* occ_out, int* closest_out);
 int lscqp_sfc_batch(lscqp_handle* h, int mode, int n_agents, const float* point, const float* goal,
         const float* next_waypoint, const double* limits, float* sfc, int* status_out, void* stream);
+/* the same with HOST buffers (copies in, runs, copies sfc / status back, synchronises) */
+int lscqp_sfc_host(lscqp_handle* h, int mode, int n_agents, const float* point, const float* goal,
+        const float* next_waypoint, const double* limits, float* sfc, int* status_out);
 
 /* ---- Peer exchange for the sharded closed loop (BASELINE config 5: agents sharded over GPUs, one exchange of the solved
  * trajectories per replan).  Stands in for MultiSyncSimulator::broadcastMsgs (src/multi_sync_simulator.cpp:305-352), which

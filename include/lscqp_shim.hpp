@@ -13,6 +13,7 @@
 #include <array>
 #include <cmath>
 #include <cstddef>
+#include <memory>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -55,6 +56,7 @@ struct Param {                                 // the fields the QP reads (src/p
     PlannerMode planner_mode = PlannerMode::LSC;
     SlackMode slack_mode = SlackMode::NONE;
     bool world_use_octomap = false, log_solver = false;
+    double world_resolution = 0.1;
     std::string package_path;
 };
 struct Mission { point3d world_min{-5, -5, 0}, world_max{5, 5, 2.5}; };               // include/mission.hpp (point3d there too)
@@ -103,9 +105,48 @@ public:
 typedef std::vector<std::vector<LSCs>> RSFCs;
 typedef std::vector<Box> SFCs;
 
+// The static map behind the corridors: what MapManager holds as octree + DynamicEDTOctomap (src/map_manager.cpp:59-80,
+// 262-305), here the occupancy grid and nearest-obstacle field liblscqp keeps in HBM.  boxes: the rows of a world CSV.
+class StaticMap {
+public:
+    StaticMap(const Param& p, const Mission& m, const std::vector<std::array<double, 6>>& boxes, double max_dist = 1.0) {
+        lscqp_config c{};
+        c.M = p.M; c.n = p.n; c.phi = p.phi; c.dim = p.world_dimension; c.dt = p.dt; c.w_control = p.control_input_weight;
+        c.w_terminal = p.terminal_weight; c.planner_mode = (int) p.planner_mode <= 2 ? (int) p.planner_mode : 0;
+        for (int k = 0; k < 3; k++) { c.world_min[k] = (double) m.world_min(k); c.world_max[k] = (double) m.world_max(k); }
+        c.z_2d = p.world_z_2d; c.max_obs = 40; c.presolve = 1;
+        if (lscqp_create(&c, 0, &handle) != 0) throw std::runtime_error(std::string("[StaticMap] ") + lscqp_last_error());
+        std::vector<double> flat;
+        for (const auto& b : boxes) flat.insert(flat.end(), b.begin(), b.end());
+        if (lscqp_map_set(handle, flat.data(), (int) boxes.size(), p.world_resolution, max_dist) != 0) {
+            const std::string msg = lscqp_last_error();
+            lscqp_destroy(handle);
+            throw std::runtime_error("[StaticMap] " + msg);
+        }
+    }
+    ~StaticMap() { lscqp_destroy(handle); }
+    StaticMap(const StaticMap&) = delete;
+    StaticMap& operator=(const StaticMap&) = delete;
+    lscqp_handle* handle = nullptr;
+};
+
 class CollisionConstraints {
 public:
     CollisionConstraints(const Param& p, const Mission&) : param(p) { sfcs.resize(p.M); }
+    void setDistmap(std::shared_ptr<StaticMap> map) { distmap_ptr = std::move(map); }    // collision_constraints.hpp:136
+
+    // ---- Safe Flight Corridors (src/collision_constraints.cpp:366-436), grown by lscqp_sfc_host against the static map
+    void initializeSFC(const point3d& agent_position, double agent_radius) {            // :366-383
+        if (sfc_call(LSCQP_SFC_INIT, agent_position, point3d(), point3d(), agent_radius) == 0)
+            throw std::invalid_argument("[CollisionConstraints] Invalid initial SFC");
+    }
+    void constructSFCFromPoint(const point3d& point, const point3d& goal_point, double agent_radius) {      // :396-411
+        sfc_call(LSCQP_SFC_FROM_POINT, point, goal_point, point3d(), agent_radius);
+    }
+    void constructSFCFromConvexHull(const points_t& convex_hull, const point3d& next_waypoint, double agent_radius) {   // :413-436
+        if (convex_hull.size() != 2) throw std::invalid_argument("[lscqp] the convex hull of generateSFC holds two points (traj_planner.cpp:745-747)");
+        sfc_call(LSCQP_SFC_FROM_HULL, convex_hull[0], convex_hull[1], next_waypoint, agent_radius);
+    }
     void initializeLSC(size_t N_obs) {                                                  // collision_constraints.cpp:385-394
         lscs.assign(N_obs, std::vector<LSCs>(param.M, LSCs(param.n + 1)));
     }
@@ -123,6 +164,7 @@ public:
         for (int i = 0; i < param.n + 1; i++) lscs[oi][m][i] = LSC(p, n, d);
     }
     void setSFC(int m, const Box& b) { sfcs[m] = b; }                                   // :541-543
+    int last_sfc_status = 0;                   // lscqp_sfc_batch status of the last corridor update (0: previous corridor reused)
 
     // Packed planes for lscqp_solve_*: normal[oi][m] and rhs = n.p + d (the constant of traj_optimizer.cpp:413-429).
     // The reference's generators write one normal per (obstacle, segment); anything else is rejected.
@@ -144,6 +186,23 @@ public:
             }
     }
 private:
+    int sfc_call(int mode, const point3d& point, const point3d& goal, const point3d& wp, double radius) {
+        if (!distmap_ptr) throw std::runtime_error("[CollisionConstraints] setDistmap has not been called");
+        const int M = param.M;
+        std::vector<float> boxes((size_t) M * 6);
+        for (int m = 0; m < M; m++)
+            for (int k = 0; k < 3; k++) { boxes[m * 6 + k] = sfcs[m].box_min(k); boxes[m * 6 + 3 + k] = sfcs[m].box_max(k); }
+        const float pt[3] = {point(0), point(1), point(2)}, g[3] = {goal(0), goal(1), goal(2)}, w[3] = {wp(0), wp(1), wp(2)};
+        const double limits[8] = {0, 0, 0, 0, 0, 0, radius, 0};
+        int status = 0;
+        if (lscqp_sfc_host(distmap_ptr->handle, mode, 1, pt, g, w, limits, boxes.data(), &status) != 0)
+            throw std::runtime_error(std::string("[CollisionConstraints] ") + lscqp_last_error());
+        for (int m = 0; m < M; m++)
+            for (int k = 0; k < 3; k++) { sfcs[m].box_min(k) = boxes[m * 6 + k]; sfcs[m].box_max(k) = boxes[m * 6 + 3 + k]; }
+        last_sfc_status = status;
+        return status;
+    }
+    std::shared_ptr<StaticMap> distmap_ptr;
     Param param;
     RSFCs lscs;
     SFCs sfcs;

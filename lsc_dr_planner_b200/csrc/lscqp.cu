@@ -514,6 +514,34 @@ extern "C" int lscqp_sfc_batch(lscqp_handle* h, int mode, int n_agents, const fl
     return 0;
 }
 
+// host-buffer variant (what the CollisionConstraints shim calls for one agent): stages, launches, copies back, synchronises
+extern "C" int lscqp_sfc_host(lscqp_handle* h, int mode, int n_agents, const float* point, const float* goal,
+                              const float* next_waypoint, const double* limits, float* sfc, int* status_out) {
+    if (!h || n_agents < 0 || !point || !limits || !sfc || !status_out) return fail(LSCQP_E_INVALID, "null argument");
+    if (mode != SFC_INIT && !goal) return fail(LSCQP_E_INVALID, "goal is null");
+    if (mode == SFC_FROM_HULL && !next_waypoint) return fail(LSCQP_E_INVALID, "next_waypoint is null");
+    if (n_agents == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t) n_agents, M = (size_t) h->cfg.M;
+    if (h->d_state.reserve(n * 9 * sizeof(float)) || h->d_goal.reserve(n * 3 * sizeof(float)) || h->d_wp.reserve(n * 3 * sizeof(float)) ||
+        h->d_limits.reserve(n * 8 * sizeof(double)) || h->d_sfc.reserve(n * M * 6 * sizeof(float)) || h->d_status.reserve(n * sizeof(int)))
+        return fail(LSCQP_E_CUDA, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(h->d_state.p, point, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (goal) CK(cudaMemcpyAsync(h->d_goal.p, goal, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (next_waypoint) CK(cudaMemcpyAsync(h->d_wp.p, next_waypoint, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_limits.p, limits, n * 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_sfc.p, sfc, n * M * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = lscqp_sfc_batch(h, mode, n_agents, h->d_state.as<float>(), goal ? h->d_goal.as<float>() : nullptr,
+                             next_waypoint ? h->d_wp.as<float>() : nullptr, h->d_limits.as<double>(), h->d_sfc.as<float>(),
+                             h->d_status.as<int>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sfc, h->d_sfc.p, n * M * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status_out, h->d_status.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP64 roofline denominator: SURVEY 8(d) asks for the achieved FP64 rate of the solve kernel against an on-box
 // FMA microbenchmark (MEASURED_PEAKS.json holds only HBM and bf16).  8 independent DFMA chains per thread.

@@ -14,7 +14,7 @@
 // Arithmetic follows the reference's types exactly (box corners and points are float, the resolution, the margin and
 // every product with them double, narrowed on assignment); the _rn intrinsics keep nvcc from contracting what the
 // reference's host compiler evaluates as separate operations.  Ties between equally near occupied cells go to the lowest
-// (x, y, z) index (the reference's brushfire order is not specified; see oracle/sfc_oracle.c).
+// (x, y, z) index (the reference's brushfire order is not specified).
 #pragma once
 #include <math.h>
 

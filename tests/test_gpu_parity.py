@@ -354,6 +354,28 @@ def test_cpp_shim_end_to_end():
     assert np.abs(np.array(g) - np.array([0.6, 0.25, 1.0])).max() < 1e-6 and "goalfailed 1" in out
     b = [l for l in out if l.startswith("batch")][0].split()
     assert b[1] == "0" and b[2] == "0" and float(b[3]) > 0.3 and float(b[4]) < 2.7
+    # CollisionConstraints::initializeSFC / constructSFCFromPoint / constructSFCFromConvexHull against the oracle, bit for bit
+    m = orc.Map(np.array([[2.0, 0.0, 1.25, 0.5, 0.5, 2.5]]), (-5, -5, 0), (5, 5, 2.5))
+    line = lambda key: [l for l in out if l.startswith(key + " ")][0].split()[1:]
+    f32 = lambda vals: np.array([float(v) for v in vals], np.float32)
+    ok, box = m.sfc_initialize((1.0, 0.3, 1.0), 0.15)
+    v = line("sfc_init")
+    assert ok and np.array_equal(f32(v[:6]), box) and v[7] == "1"
+    st1, box1 = m.sfc_from_point((1.2, 0.35, 1.0), (3.0, 2.0, 1.0), box, 0.15)
+    v = line("sfc_point")
+    assert int(v[0]) == st1 and np.array_equal(f32(v[1:]), box1)
+    st2, box2 = m.sfc_from_convex_hull([(1.2, 0.35, 1.0), (1.3, 0.5, 1.0)], (1.4, 1.0, 1.0), box1, 0.15)
+    v = line("sfc_hull")
+    assert int(v[0]) == st2 and np.array_equal(f32(v[1:]), box2)
+    assert "sfc_invalid 1" in out
+    xq, xmax = (float(t) for t in line("sfc_qp"))
+    okq, boxq = m.sfc_initialize((1.3, 0.0, 1.0), 0.15)
+    cfgs = orc.Config(world_min=(-5, -5, 0), world_max=(5, 5, 2.5), use_sfc=True)
+    ags = orc.Agent(np.array([1.3, 0, 1]), np.zeros(3), np.zeros(3), np.array([4, 0, 1]))
+    qps = orc.qp_build(cfgs, ags, np.zeros((0, 5, 6, 3), np.float32), np.zeros((0, 5, 6, 3), np.float32), np.zeros((0, 5, 6)), np.tile(boxq, (5, 1)))
+    xs, oks = oracle_solution(qps)
+    # the corridor stops short of the pillar (x_max 1.65 < 1.75) and bounds the QP: without it the end point would pass 1.75
+    assert okq and abs(xmax - boxq[3]) < 1e-7 and xmax < 1.7 and xq <= xmax + 1e-6 and abs(xq - xs.reshape(3, 5, 6)[0, -1, -1]) < 1e-5
 
 
 @pytest.mark.parametrize("M,dim,K,rng_,mode", [(10, 2, 9, 0.7, 1), (5, 3, 12, 0.7, 1), (10, 2, 9, 3.0, 1),
