@@ -124,6 +124,33 @@ def cpu_reference_rate(batch, n_sample: int, cores: int, pool=None) -> tuple[flo
     return n_sample / wall, per_qp
 
 
+def cpu_pdip_rate(batch, n_sample: int, cores: int) -> dict:
+    """SURVEY 8(d) baseline (ii): the SAME algorithm class as the kernel (Mehrotra interior point) in C, -O3 -march=native,
+    OpenMP over the agents (oracle/pdip_cpu.c; LSC generation + model build + solve per agent, the reference's per-agent
+    path), compiled on this machine"""
+    from oracle import oracle as orc
+    cfg = batch.cfg
+    cfgo = orc.Config(M=cfg.M, n=cfg.n, phi=cfg.phi, dim=cfg.dim, dt=cfg.dt, w_control=cfg.w_control, w_terminal=cfg.w_terminal,
+                      planner_mode=cfg.planner_mode, use_sfc=False, comm_range=0.0, world_min=cfg.world_min, world_max=cfg.world_max,
+                      z_2d=cfg.z_2d)
+    n = min(n_sample, batch.n_agents)
+    agents = [orc.Agent(position=batch.state[a, :3], velocity=batch.state[a, 3:6], acceleration=batch.state[a, 6:9], goal=batch.goal[a],
+                        max_vel=tuple(batch.limits[a, :3]), max_acc=tuple(batch.limits[a, 3:6]), radius=float(batch.agent_meta[a, 0]),
+                        nominal_velocity=float(batch.limits[a, 7]), downwash=float(batch.agent_meta[a, 1])) for a in range(n)]
+    off = batch.obs_offsets[:n + 1]
+    run = lambda th: orc.replan_batch_pdip(cfgo, orc.GEN_LSC, agents, batch.own_traj, off, batch.obs_index, batch.agent_meta[:, 0],
+                                           batch.agent_meta[:, 1], batch.goal, batch.state[:, :3], threads=th)
+    run(cores)                                                       # warm-up (thread pool, page faults)
+    _, status, iters, sec = run(cores)
+    _, _, _, sec1 = orc.replan_batch_pdip(cfgo, orc.GEN_LSC, agents[:max(8, n // 16)], batch.own_traj, off[:max(8, n // 16) + 1], batch.obs_index,
+                                          batch.agent_meta[:, 0], batch.agent_meta[:, 1], batch.goal, batch.state[:, :3], threads=1)
+    return {"value": n / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "solver": "Mehrotra predictor-corrector in C (oracle/pdip_cpu.c: populatebyrow's model as it stands, equalities kept, "
+                      "pivoted LU of the KKT matrix), gcc -O3 -march=native, OpenMP over agents",
+            "sample": f"first {n} agent-QPs of the same batch, LSC generation + model build + solve", "solved": int((status == 0).sum()),
+            "iterations_mean": float(iters.mean()), "ms_per_qp_one_core": 1e3 * sec1 / max(8, n // 16)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; CPLEX itself is absent) on all host cores"""
     rank = int(os.environ.get("RANK", "0"))
@@ -154,7 +181,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.agents),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)", "ms_per_qp_one_core": 1e3 * per_qp},
+                             "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)", "ms_per_qp_one_core": 1e3 * per_qp,
+                             "same_algorithm": cpu_pdip_rate(batch, 4 * n_sample, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -509,7 +537,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n_s} agent-QPs of the same batch, LSC generation + model build + solve",
                                     "solver": "restated populatebyrow + HiGHS 1.12 (CPLEX 20.1 absent)",
-                                    "ms_per_qp_one_core": 1e3 * per_qp}
+                                    "ms_per_qp_one_core": 1e3 * per_qp,
+                                    "same_algorithm": cpu_pdip_rate(batch, 4 * n_s, cores)}
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:

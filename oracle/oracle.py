@@ -41,6 +41,46 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
 
 
+_PDIP = os.path.join(_HERE, "_build", "libpdip_cpu.so")
+
+
+def _cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build_pdip(force: bool = False) -> None:
+    """Compile oracle/pdip_cpu.c with -O3 -march=native -fopenmp for THIS machine (rebuilt when the CPU model changes:
+    the prebuilt file travels to the GPU box, whose host CPU may differ)."""
+    stamp = _PDIP + ".cpu"
+    srcs = [os.path.join(_HERE, f) for f in ("pdip_cpu.c", "lscqp_oracle.c", "lscqp_oracle.h")]
+    stale = (not os.path.exists(_PDIP) or not os.path.exists(stamp) or open(stamp).read() != _cpu_model()
+             or os.path.getmtime(_PDIP) < max(os.path.getmtime(f) for f in srcs))
+    if force or stale:
+        if os.path.exists(_PDIP):
+            os.unlink(_PDIP)
+        subprocess.run(["make", "-C", _HERE, "_build/libpdip_cpu.so"], check=True, stdout=subprocess.DEVNULL)
+        open(stamp, "w").write(_cpu_model())
+
+
+_pdip = None
+
+
+def pdip_lib():
+    global _pdip
+    if _pdip is None:
+        build_pdip()
+        _pdip = C.CDLL(_PDIP)
+        _pdip.orc_pdip_solve.restype = C.c_int
+        _pdip.orc_replan_batch_pdip.restype = C.c_double
+    return _pdip
+
+
 class _Cfg(C.Structure):
     _fields_ = [("M", C.c_int), ("n", C.c_int), ("phi", C.c_int), ("phi_n", C.c_int), ("dim", C.c_int),
                 ("dt", C.c_double), ("w_control", C.c_double), ("w_terminal", C.c_double),
@@ -605,3 +645,136 @@ class Map:
         pv = np.ascontiguousarray(prev, np.float32).reshape(6); out = np.zeros(6, np.float32)
         ok = lib().orc_sfc_from_convex_hull(self.h, _p(h2, C.c_float), _p(w, C.c_float), _p(pv, C.c_float), C.c_double(radius), _p(out, C.c_float))
         return int(ok), out
+
+
+# ------------------------------------------------------------------------------------------------
+# Interior-point CPU solver (oracle/pdip_cpu.c): third checker solver and the same-algorithm-class CPU baseline
+def solve_pdip_c(qp: "QP", tol: float = 1e-10, max_iter: int = 100) -> "Solution":
+    """Mehrotra PDIP in C on the restated model as it stands (equalities kept, quasi-definite KKT + LDL')"""
+    nv, ne, ng = qp.q.size, qp.Aeq.shape[0], qp.G.shape[0]
+    x = np.zeros(nv); info = np.zeros(4)
+    arr = lambda a: np.ascontiguousarray(a, np.float64)
+    P, q, A, b, G, rlo, rhi, lb, ub = (arr(v) for v in (qp.P, qp.q, qp.Aeq, qp.beq, qp.G, qp.rlo, qp.rhi, qp.lb, qp.ub))
+    st = pdip_lib().orc_pdip_solve(nv, ne, ng, _p(P, C.c_double), _p(q, C.c_double), _p(A, C.c_double), _p(b, C.c_double),
+                                   _p(G, C.c_double), _p(rlo, C.c_double), _p(rhi, C.c_double), _p(lb, C.c_double),
+                                   _p(ub, C.c_double), C.c_double(tol), max_iter, _p(x, C.c_double), _p(info, C.c_double))
+    status = {0: "Optimal", 1: "Iteration limit", 3: "Numerical"}[st]
+    sol = Solution(status, x, float(x @ qp.P @ x + qp.q @ x + qp.c0), np.zeros(ne + ng), np.zeros(nv))
+    sol.iterations = int(info[0])
+    return sol
+
+
+def replan_batch_pdip(cfg: "Config", generator: int, agents: list, own_traj, obs_offsets, obs_index, radius, downwash, goal,
+                      position, threads: int = 0):
+    """The reference's per-agent path (LSC generation + model build + interior-point solve) for a whole batch in C with
+    OpenMP over the agents.  Returns (ctrl [n, nv], status [n], iters [n], seconds of the parallel region)."""
+    n = len(agents)
+    nv = cfg.dim * cfg.M * (cfg.n + 1)
+    cc = cfg.c()
+    ags = (_Agent * n)(*[a.c() for a in agents])
+    dw = np.ascontiguousarray(downwash, np.float64)
+    own = np.ascontiguousarray(own_traj, np.float32); off = np.ascontiguousarray(obs_offsets, np.int32); idx = np.ascontiguousarray(obs_index, np.int32)
+    rf = np.ascontiguousarray(radius, np.float32); df = np.ascontiguousarray(downwash, np.float32)
+    g = np.ascontiguousarray(goal, np.float32); pos = np.ascontiguousarray(position, np.float32)
+    ctrl = np.zeros((n, nv)); status = np.zeros(n, np.int32); iters = np.zeros(n, np.int32)
+    sec = pdip_lib().orc_replan_batch_pdip(C.byref(cc), generator, n, ags, _p(dw, C.c_double), _p(own, C.c_float), _p(off, C.c_int),
+                                           _p(idx, C.c_int), _p(rf, C.c_float), _p(df, C.c_float), _p(g, C.c_float),
+                                           _p(pos, C.c_float), _p(ctrl, C.c_double), _p(status, C.c_int), _p(iters, C.c_int), threads)
+    return ctrl, status, iters, float(sec)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPLEX-LP files of the restated models: the format cplex.exportModel("QPmodel_trajOpt.lp") writes when param.log_solver is
+# set (src/traj_optimizer.cpp:45-49).  Anyone with CPLEX can solve tests/golden/lp/*.lp and close the pin on the fixture
+# solutions; HiGHS reads the same files (read_lp_highs), which is how the writer itself is tested.
+def variable_names(M: int, n: int, dim: int) -> list[str]:
+    """x_m_i / y_m_i / z_m_i in the order of populatebyrow (traj_optimizer.cpp:238-270)"""
+    return [f"{'xyz'[k]}_{m}_{i}" for k in range(dim) for m in range(M) for i in range(n + 1)]
+
+
+def _lp_num(v: float) -> str:
+    return repr(float(v))
+
+
+def write_lp(qp: QP, path: str, names: list[str] | None = None, comment: str = "") -> None:
+    """min x'Px + q'x + c0  s.t.  Aeq x = beq, rlo <= G x <= rhi, lb <= x <= ub as a CPLEX LP file.  The quadratic part is
+    written in the format's [ ... ] / 2 bracket (twice the entries of P, both triangles merged)."""
+    nv = qp.q.size
+    names = names or [f"v{j}" for j in range(nv)]
+    out = []
+    if comment:
+        out += ["\\ " + line for line in comment.splitlines()]
+    out.append("Minimize")
+    lin = " ".join(f"{'+' if qp.q[j] >= 0 else '-'} {_lp_num(abs(qp.q[j]))} {names[j]}" for j in range(nv) if qp.q[j] != 0.0)
+    out.append(" obj: " + (lin if lin else f"0 {names[0]}"))
+    quad = []
+    for i in range(nv):
+        if qp.P[i, i] != 0.0:
+            quad.append(f"{'+' if qp.P[i, i] >= 0 else '-'} {_lp_num(abs(2.0 * qp.P[i, i]))} {names[i]} ^2")
+        for j in range(i + 1, nv):
+            c = 2.0 * (qp.P[i, j] + qp.P[j, i])
+            if c != 0.0:
+                quad.append(f"{'+' if c >= 0 else '-'} {_lp_num(abs(c))} {names[i]} * {names[j]}")
+    for k in range(0, len(quad), 6):
+        out.append("   " + ("+ [ " if k == 0 else "") + " ".join(quad[k:k + 6]))
+    if quad:
+        out.append("   ] / 2")
+    if qp.c0 != 0.0:                                      # constant of the terminal cost (part of getObjValue, :100)
+        out.append(f"   {'+' if qp.c0 >= 0 else '-'} {_lp_num(abs(qp.c0))} objconst")
+    out.append("Subject To")
+
+    def row(coefs):
+        nz = np.nonzero(coefs)[0]
+        return " ".join(f"{'+' if coefs[j] >= 0 else '-'} {_lp_num(abs(coefs[j]))} {names[j]}" for j in nz) if len(nz) else f"0 {names[0]}"
+    for e in range(qp.Aeq.shape[0]):
+        out.append(f" e{e}: {row(qp.Aeq[e])} = {_lp_num(qp.beq[e])}")
+    for r in range(qp.G.shape[0]):
+        lo, hi = qp.rlo[r], qp.rhi[r]
+        if lo > -INF and hi < INF:
+            out.append(f" c{r}: {row(qp.G[r])} >= {_lp_num(lo)}")
+            out.append(f" c{r}u: {row(qp.G[r])} <= {_lp_num(hi)}")
+        elif hi < INF:
+            out.append(f" c{r}: {row(qp.G[r])} <= {_lp_num(hi)}")
+        else:
+            out.append(f" c{r}: {row(qp.G[r])} >= {_lp_num(lo)}")
+    out.append("Bounds")
+    for j in range(nv):
+        lo, hi = qp.lb[j], qp.ub[j]
+        if lo <= -INF and hi >= INF:
+            out.append(f" {names[j]} free")
+        else:
+            out.append(f" {'-inf' if lo <= -INF else _lp_num(lo)} <= {names[j]} <= {'+inf' if hi >= INF else _lp_num(hi)}")
+    if qp.c0 != 0.0:
+        out.append(" objconst = 1")
+    out.append("End")
+    opener = __import__("gzip").open if path.endswith(".gz") else open
+    with opener(path, "wt") as f:
+        f.write("\n".join(out) + "\n")
+
+
+def solve_lp_file_highs(path: str, tol: float = 1e-9, time_limit: float | None = 60.0):
+    """read a CPLEX-LP file with HiGHS (Highs::readModel) and solve it; returns (status, {name: value}, objective)"""
+    import gzip, shutil, tempfile
+    from scipy.optimize._highspy import _core as hs
+    tmp = None
+    if path.endswith(".gz"):
+        tmp = tempfile.NamedTemporaryFile(suffix=".lp", delete=False)
+        with gzip.open(path, "rb") as f:
+            shutil.copyfileobj(f, tmp)
+        tmp.close(); path = tmp.name
+    h = hs._Highs()
+    h.setOptionValue("output_flag", False)
+    h.setOptionValue("primal_feasibility_tolerance", tol); h.setOptionValue("dual_feasibility_tolerance", tol)
+    if time_limit:
+        h.setOptionValue("time_limit", float(time_limit))
+    st = h.readModel(path)
+    h.run()
+    sol = h.getSolution()
+    lp = h.getLp()
+    names = list(lp.col_names_)
+    vals = dict(zip(names, sol.col_value))
+    status = h.modelStatusToString(h.getModelStatus())
+    obj = h.getInfo().objective_function_value
+    if tmp:
+        os.unlink(tmp.name)
+    return status, vals, obj

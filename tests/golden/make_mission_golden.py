@@ -62,10 +62,14 @@ def plan_agent(cfgo, mission, a, state, goal_prev, wp, own, nbr, trajs, goals_pr
     x, ok = orc.polish(qp, sol, dual_tol=1e-12)
     if final:
         HIGHS_JOBS.append((qp, x))
+        # third solver: the interior-point method in C (oracle/pdip_cpu.c: equalities kept, pivoted LU)
+        sc = orc.solve_pdip_c(qp)
+        PDIP_DIFF.append(float(np.abs(sc.x - x).max()) if sc.status == "Optimal" else np.nan)
     return new_goal, 0, (x, ok), (pt, nr, d)
 
 
 HIGHS_JOBS = []          # (qp, polished x) of the recorded step, per process
+PDIP_DIFF = []           # max |x_pdip_c - x| of the recorded step's QPs, per process (NaN: not solved)
 
 
 def _highs_one(qp, x, q):
@@ -150,8 +154,9 @@ def rollout(path, world_path, R, M=10, dim=2):
                        x=np.stack(sols), ok=np.array(oks), limits=np.concatenate([mission.max_vel, mission.max_acc,
                        mission.radius[:, None], mission.nominal_velocity[:, None]], 1), meta=np.stack([mission.radius, mission.downwash], 1),
                        world=np.array(mission.world_min + mission.world_max), highs_jobs=list(HIGHS_JOBS),
-                       sfc=sfcs.copy(), sfc_prev=sfc_prev, sfc_status=sfc_status, boxes=boxes, first=np.full(n, step == 0))
-            HIGHS_JOBS.clear()
+                       sfc=sfcs.copy(), sfc_prev=sfc_prev, sfc_status=sfc_status, boxes=boxes, first=np.full(n, step == 0),
+                       pdip_maxdiff=np.array(PDIP_DIFF + [np.nan] * (n - len(PDIP_DIFF))))
+            HIGHS_JOBS.clear(); PDIP_DIFF.clear()
             break
         goal = new_goal
         state = np.stack([orc.get_state_at(cfgo, new_trajs[a], cfg.dt) for a in range(n)])      # AgentManager::doStep
@@ -175,11 +180,23 @@ def main():
     with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
         recs = pool.map(_roll, [(f, w, 2 + (i % 9)) for i, (f, w) in enumerate(zip(files, worlds))], chunksize=1)   # replan indices 3..11
     n0 = 0
-    keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta", "sfc", "sfc_prev", "sfc_status"]
+    keys = ["state", "goal_prev", "goal", "wp", "own", "x", "ok", "limits", "meta", "sfc", "sfc_prev", "sfc_status", "pdip_maxdiff"]
     cat = {k: [] for k in keys}; off = [0]; idx = []; world = []; boxes = []; boxes_off = [0]
     for r in recs[:3]:
         jobs += r["highs_jobs"]
     out["highs_maxdiff"] = highs_crosscheck(jobs)          # config 1 (10 QPs) + the first three config-3 instances
+    # the same models as CPLEX-LP files (what cplex.exportModel writes, traj_optimizer.cpp:45-49): config 1 and the first
+    # config-3 instance, for anyone with CPLEX to close the pin; lp_index maps file k to its fixture row
+    lpdir = os.path.join(HERE, "lp")
+    os.makedirs(lpdir, exist_ok=True)
+    for f in glob.glob(os.path.join(lpdir, "*.lp.gz")):
+        os.unlink(f)
+    names = orc.variable_names(10, 5, 2)
+    for k, (qp, x) in enumerate(jobs[:20]):
+        tag = f"c1_agent{k}" if k < 10 else f"c3_agent{k - 10}"
+        orc.write_lp(qp, os.path.join(lpdir, tag + ".lp.gz"), names,
+                     comment=f"lsc_dr_planner agent QP ({tag}), restated populatebyrow (src/traj_optimizer.cpp:216-514)\n"
+                             f"fixture optimum objective {float(x @ qp.P @ x + qp.q @ x + qp.c0)!r}")
     for r in recs:
         for k in keys:
             cat[k].append(r[k])
@@ -193,7 +210,8 @@ def main():
     out["c3_boxes"] = np.concatenate(boxes); out["c3_boxes_off"] = np.array(boxes_off, np.int32)   # world boxes of instance i
     np.savez_compressed(os.path.join(HERE, "mission_golden.npz"), **out)
     print("config 1: solved", int(r1["ok"].sum()), "of", len(r1["ok"]), "| config 3:", int(out["c3_ok"].sum()), "polished of", len(out["c3_ok"]),
-          "failed", int(np.isnan(out["c3_x"][:, 0]).sum()), "| HiGHS cross-check:", int(np.isfinite(out["highs_maxdiff"]).sum()), "of",
+          "failed", int(np.isnan(out["c3_x"][:, 0]).sum()), "| C PDIP agrees (<1e-6) on", int((out["c3_pdip_maxdiff"] < 1e-6).sum()), "of 260, max",
+          np.nanmax(out["c3_pdip_maxdiff"]), "| HiGHS cross-check:", int(np.isfinite(out["highs_maxdiff"]).sum()), "of",
           len(out["highs_maxdiff"]), "solved, max diff", np.nanmax(out["highs_maxdiff"]))
 
 

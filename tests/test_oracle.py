@@ -164,3 +164,28 @@ def test_highs_solution_matches_golden():
     qp = oracle_qp_from_planes(batch, a, normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]])
     x, ok = oracle_solution(qp)
     assert ok and np.abs(x - g["m5d3lsc_x"][0]).max() < 1e-8
+
+
+def test_interior_point_c_solver_matches_the_golden_solutions():
+    """oracle/pdip_cpu.c (third, independent solver; also bench.py's same-algorithm-class CPU baseline) on the committed
+    golden QPs, and its batched OpenMP driver on a small batch"""
+    g = np.load(os.path.join(GOLDEN, "qp_golden.npz"))
+    for name, cfg, K in (("m5d3lsc", W.PlannerConfig(M=5, dim=3, planner_mode=1), 40), ("m10d2lsc", W.PlannerConfig(M=10, dim=2, planner_mode=1), 9)):
+        batch = W.make_forest_batch(64, K=K, cfg=cfg)
+        off, normals, rhs = g[name + "_off"], g[name + "_normals"], g[name + "_rhs"]
+        agents = [0, 5, 11, 17, 23, 42]
+        for x, i in zip(g[name + "_x"][:2], [int(v) for v in g[name + "_keep"][:2]]):
+            qp = oracle_qp_from_planes(batch, agents[i], normals[off[i]:off[i + 1]], rhs[off[i]:off[i + 1]])
+            sol = orc.solve_pdip_c(qp)
+            assert sol.status == "Optimal" and np.abs(sol.x - x).max() < 1e-6, (name, i, sol.status, np.abs(sol.x - x).max())
+    cfg = W.PlannerConfig()
+    batch = W.make_forest_batch(32, K=12, cfg=cfg)
+    ctrl, status, iters, sec = orc.replan_batch_pdip(oracle_config(cfg), orc.GEN_LSC, [oracle_agent(batch, a) for a in range(32)],
+                                                     batch.own_traj, batch.obs_offsets, batch.obs_index, batch.agent_meta[:, 0],
+                                                     batch.agent_meta[:, 1], batch.goal, batch.state[:, :3], threads=2)
+    assert (status == 0).mean() > 0.9 and sec > 0
+    for a in (0, 7):
+        o, n_, r_ = oracle_planes(batch, [a], orc.GEN_LSC)
+        xe, ok = oracle_solution(oracle_qp_from_planes(batch, a, n_, r_))
+        if ok and status[a] == 0:
+            assert np.abs(ctrl[a] - xe).max() < 1e-6
