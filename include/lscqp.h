@@ -47,11 +47,15 @@ extern "C" {
 #define LSCQP_MODE_DLSC 0
 #define LSCQP_MODE_LSC  1
 #define LSCQP_MODE_BVC  2
+#define LSCQP_MODE_RECIPROCALRSFC 4   /* SlackMode::COLLISIONCONSTRAINT (src/param.cpp:157-161): the LSC rows carry free,
+                                         cost-less slacks (traj_optimizer.cpp:272-283, 423-425) and cannot bind; z bounds of
+                                         segment 0 relaxed to +-100 (:255-258) */
 
 /* LSC generator selected by TrajPlanner::constructLSC, src/traj_planner.cpp:552-569 */
 #define LSCQP_GEN_LSC   0          /* generateLSC  :611-657 */
 #define LSCQP_GEN_CLSC  1          /* generateCLSC :659-706 (mode lsc + grid_based_planner) */
 #define LSCQP_GEN_BVC   2          /* generateBVC  :708-736 */
+#define LSCQP_GEN_RSFC  3          /* generateReciprocalRSFC :581-609 (obstacle sizes: lscqp_set_obstacle_sizes) */
 
 /* The fields of Param / Mission the QP reads (src/param.cpp:5-173). */
 typedef struct lscqp_config {
@@ -113,6 +117,11 @@ int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents,
         double* normals_out,        /* [sum K][M][3]                                             */
         double* rhs_out,            /* [sum K][M][6]                                             */
         void* stream);
+
+/* Predicted obstacle sizes for LSCQP_GEN_RSFC (obs_pred_sizes of obstacleSizePredictionWithConstAcc,
+ * src/traj_planner.cpp:321-358): DEVICE array [sum K][M][6], or NULL = every obstacle's radius (obs/size_prediction off).
+ * Kept by the handle until set again. */
+int lscqp_set_obstacle_sizes(lscqp_handle* h, const double* obs_size);
 
 /* Fused variant for obstacles that are agents of the same population (what MultiSyncSimulator::broadcastMsgs hands
  * to every planner, src/multi_sync_simulator.cpp:305-352): the obstacles' trajectories / radii / goals / positions are

@@ -218,6 +218,11 @@ inline lscqp_config make_lscqp_config(const Param& p, const Mission& m, int max_
     c.dt = p.dt; c.w_control = p.control_input_weight; c.w_terminal = p.terminal_weight;
     c.planner_mode = (int) p.planner_mode; c.use_sfc = p.world_use_octomap ? 1 : 0;
     c.comm_range = p.communication_range;      // rows of traj_optimizer.cpp:477-500, every planner mode
+    // SlackMode (sp_const.hpp:43-47): CONTINUITY adds neither variables nor rows in populatebyrow (it only moves the column
+    // offset of slacks that do not exist, traj_optimizer.cpp:227-231); COLLISIONCONSTRAINT is what mode reciprocal_rsfc
+    // selects (param.cpp:157-161) and is handled there; any other combination is not a model the reference builds
+    if (p.slack_mode == SlackMode::COLLISIONCONSTRAINT && p.planner_mode != PlannerMode::RECIPROCALRSFC)
+        throw std::invalid_argument("[lscqp] SlackMode::COLLISIONCONSTRAINT is only built for PlannerMode::RECIPROCALRSFC");
     for (int k = 0; k < 3; k++) { c.world_min[k] = (double) m.world_min(k); c.world_max[k] = (double) m.world_max(k); }
     c.z_2d = p.world_z_2d; c.max_obs = max_obs; c.max_agents = 1; c.max_iter = 0; c.tol = 0; c.presolve = 1;
     return c;

@@ -15,8 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblscqp.so")
 
-MODE_DLSC, MODE_LSC, MODE_BVC = 0, 1, 2
-GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
+MODE_DLSC, MODE_LSC, MODE_BVC, MODE_RECIPROCALRSFC = 0, 1, 2, 4
+GEN_LSC, GEN_CLSC, GEN_BVC, GEN_RSFC = 0, 1, 2, 3
 SFC_INIT, SFC_FROM_POINT, SFC_FROM_HULL = 0, 1, 2
 STATUS_OK, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL, STATUS_CAPACITY = 0, 1, 2, 3, 4
 
@@ -60,7 +60,7 @@ def load():
                      "lscqp_goal_host", "lscqp_measure_fp64_peak", "lscqp_select_neighbours", "lscqp_assemble_lsc_fused", "lscqp_validate_batch",
                      "lscqp_last_instances", "lscqp_exchange_create", "lscqp_exchange_connect", "lscqp_exchange_begin",
                      "lscqp_step_exchange", "lscqp_exchange_status", "lscqp_exchange_destroy", "lscqp_exchange_connect_ptrs",
-                     "lscqp_map_set", "lscqp_map_get", "lscqp_sfc_batch"):
+                     "lscqp_map_set", "lscqp_map_get", "lscqp_sfc_batch", "lscqp_sfc_host", "lscqp_set_obstacle_sizes"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -160,6 +160,11 @@ class LscQp:
         self._check(self.lib.lscqp_assemble_lsc_batch(self.h, generator, n, _dp(own_traj), _dp(agent_meta), _dp(agent_goal),
                                                       _dp(obs_offsets), _dp(obs_traj), _dp(obs_meta), _dp(obs_goal),
                                                       _dp(obs_position), _dp(normals), _dp(rhs), C.c_void_p(stream)))
+
+    def set_obstacle_sizes(self, obs_size):
+        """predicted obstacle sizes [sumK][M][6] (device tensor) for GEN_RSFC, or None = the obstacles' radii"""
+        self._obs_size_keep = obs_size
+        self._check(self.lib.lscqp_set_obstacle_sizes(self.h, _dp(obs_size)))
 
     def assemble_lsc_fused(self, generator, prune, n, own_traj, agent_meta, agent_goal, state, limits, obs_offsets, obs_index,
                            all_traj, all_meta, all_goal, all_state, normals, rhs, stream=0):

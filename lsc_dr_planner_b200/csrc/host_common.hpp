@@ -55,7 +55,8 @@ inline int validate_config(const lscqp_config& c) {
     if (c.n != 5 || c.phi != 3) return LSCQP_E_INVALID;          // traj_optimizer.cpp:198-201
     if (!(c.M == 5 || c.M == 10)) return LSCQP_E_INVALID;
     if (!(c.dim == 2 || c.dim == 3)) return LSCQP_E_INVALID;
-    if (!(c.planner_mode == LSCQP_MODE_DLSC || c.planner_mode == LSCQP_MODE_LSC || c.planner_mode == LSCQP_MODE_BVC))
+    if (!(c.planner_mode == LSCQP_MODE_DLSC || c.planner_mode == LSCQP_MODE_LSC || c.planner_mode == LSCQP_MODE_BVC ||
+          c.planner_mode == LSCQP_MODE_RECIPROCALRSFC))
         return LSCQP_E_INVALID;
     if (c.max_obs < 0 || c.max_obs > 40) return LSCQP_E_INVALID;
     if (!(c.dt > 0) || !(c.w_control > 0) || !(c.w_terminal >= 0)) return LSCQP_E_INVALID;
@@ -77,6 +78,7 @@ inline void fill_solve_params(const lscqp_config& c, SolveParams& p) {
     p.use_sfc = c.use_sfc;
     p.presolve = c.presolve & 1;
     p.max_obs = c.max_obs;
+    p.rsfc = c.planner_mode == LSCQP_MODE_RECIPROCALRSFC;
     p.klass = nullptr; p.klass_mode = 0;
     p.comm_range = c.comm_range;
     double Q[36];

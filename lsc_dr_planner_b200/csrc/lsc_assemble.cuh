@@ -38,6 +38,7 @@ struct AssembleParams {
     const double* all_meta;      // [n_total][2]
     const float*  all_goal;      // [n_total][3]
     const float*  all_state;     // [n_total][9]
+    const double* obs_size;      // [sumK][M][6] predicted obstacle sizes (generator 3; null: the obstacle radius)
     int prune;
     const float*  state;         // [n][9]   (prune)
     const double* limits;        // [n][8]   (prune)
@@ -262,7 +263,7 @@ lsc_assemble_kernel(const AssembleParams p) {
     for (int e = threadIdx.x; e < M * 18; e += blockDim.x) s_own[e] = p.own_traj[(size_t) agent * M * 18 + e];
     const int obs0 = p.obs_offsets[agent], K = p.obs_offsets[agent + 1] - obs0;
     const double a_r = p.agent_meta[agent * 2 + 0], a_dw = p.agent_meta[agent * 2 + 1];
-    const bool prune = p.prune && p.dim == 3 && p.generator != 2 && K * M <= 40 * M;
+    const bool prune = p.prune && p.dim == 3 && p.generator < 2 && K * M <= 40 * M;
     if (prune && threadIdx.x < 3) {
         // the same fixed third control point and velocity step the solve kernel's presolve uses
         const int k = threadIdx.x;
@@ -363,6 +364,40 @@ lsc_assemble_kernel(const AssembleParams p) {
         f3 normal;
         double d[6];
         f3 pt[6];
+        if (p.generator == 3) {                                                     // generateReciprocalRSFC :581-609
+            // normalVectorBetweenLines (:1157-1177) on closestPointsBetweenLinePaths (geometry.hpp:104-127): the paths
+            // first -> last control point of the obstacle and of the agent, in the original coordinates
+            const f3 rs = f3_sub(own[0], obs[0]), re = f3_sub(own[5], obs[5]);
+            const ClosestPts rc = closest_point_segment(f3_make(0.f, 0.f, 0.f), rs, re);
+            const double len = f3_distance(rs, re);
+            double alpha = 0.0;
+            if (len > 0) alpha = f3_norm(f3_sub(rc.cp2, rs)) / len;
+            const f3 cp1 = f3_add(obs[0], f3_scale(f3_sub(obs[5], obs[0]), alpha));
+            const f3 cp2 = f3_add(own[0], f3_scale(f3_sub(own[5], own[0]), alpha));
+            normal = f3_normalized(f3_sub(cp2, cp1));
+            if (f3_norm(normal) == 0) {
+                if (f3_norm(rs) == 0 && f3_norm(re) == 0) normal = f3_make(1.f, 0.f, 0.f);
+                else normal = f3_cross(f3_sub(re, rs), f3_make(0.f, 0.f, 1.f));
+            }
+            normal.z = (float) ((double) normal.z / (downwash * downwash));         // :603-604
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const double size = p.obs_size ? p.obs_size[(j * M + m) * 6 + i] : o_r;
+                d[i] = rc.dist < size + a_r ? 0.5 * (size + a_r + rc.dist) : size + a_r;     // :593-600
+                pt[i] = obs[i];
+            }
+            const double nx3 = (double) normal.x, ny3 = (double) normal.y, nz3 = (double) normal.z;
+            double* no3 = p.normals + (j * M + m) * 3;
+            no3[0] = nx3; no3[1] = ny3; no3[2] = nz3;
+            double* ro3 = p.rhs + (j * M + m) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double b = nx3 * (double) pt[i].x + ny3 * (double) pt[i].y;
+                if (p.dim == 3) b += nz3 * (double) pt[i].z;
+                ro3[i] = b + d[i];
+            }
+            continue;
+        }
         if (p.generator == 2) {                                                     // generateBVC :708-736
             f3 a0 = f3_make(s_own[0], s_own[1], __fdiv_rn(s_own[2], dwf));
             const float* o0p = obase + src * M * 18;

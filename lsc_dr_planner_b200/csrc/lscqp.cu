@@ -60,6 +60,7 @@ struct lscqp_handle {
     DevBuf d_occ, d_closest, d_boxes;   // static map (lscqp_map_set)
     MapView map{};
     bool has_map = false;
+    const double* obs_size = nullptr;   // lscqp_set_obstacle_sizes (generateReciprocalRSFC)
     Exchange* xchg = nullptr;          // peer exchange of the sharded closed loop (lscqp_exchange_*)
 };
 
@@ -174,13 +175,19 @@ extern "C" int lscqp_last_instances(lscqp_handle* h, int n_agents, int* klass_ou
     return 0;
 }
 
+extern "C" int lscqp_set_obstacle_sizes(lscqp_handle* h, const double* obs_size) {
+    if (!h) return fail(LSCQP_E_INVALID, "null handle");
+    h->obs_size = obs_size;
+    return 0;
+}
+
 extern "C" int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_agents, const float* own_traj,
                                         const double* agent_meta, const float* agent_goal, const int* obs_offsets,
                                         const float* obs_traj, const float* obs_meta, const float* obs_goal,
                                         const float* obs_position, double* normals_out, double* rhs_out, void* stream) {
     if (!h || n_agents < 0 || !own_traj || !agent_meta || !obs_offsets || !obs_traj || !obs_meta || !normals_out || !rhs_out)
         return fail(LSCQP_E_INVALID, "null argument");
-    if (generator < 0 || generator > 2) return fail(LSCQP_E_INVALID, "unknown generator");
+    if (generator < 0 || generator > 3) return fail(LSCQP_E_INVALID, "unknown generator");
     if ((generator == LSCQP_GEN_CLSC && (!obs_goal || !agent_goal)) || (generator == LSCQP_GEN_LSC && (!obs_position || !agent_goal)))
         return fail(LSCQP_E_INVALID, "generator needs goal / position arrays");
     if (n_agents == 0) return 0;
@@ -188,7 +195,7 @@ extern "C" int lscqp_assemble_lsc_batch(lscqp_handle* h, int generator, int n_ag
     p.n_agents = n_agents; p.generator = generator; p.dim = h->cfg.dim;
     p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
     p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;
-    p.normals = normals_out; p.rhs = rhs_out;
+    p.normals = normals_out; p.rhs = rhs_out; p.obs_size = h->obs_size;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
     else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
@@ -205,7 +212,7 @@ extern "C" int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prun
     if (!h || n_agents < 0 || !own_traj || !agent_meta || !agent_goal || !obs_offsets || !obs_index || !all_traj || !all_meta ||
         !all_goal || !all_state || !normals_out || !rhs_out)
         return fail(LSCQP_E_INVALID, "null argument");
-    if (generator < 0 || generator > 2) return fail(LSCQP_E_INVALID, "unknown generator");
+    if (generator < 0 || generator > 3) return fail(LSCQP_E_INVALID, "unknown generator");
     if (prune && (!state || !limits)) return fail(LSCQP_E_INVALID, "prune needs state and limits");
     if (n_agents == 0) return 0;
     AssembleParams p{};
@@ -213,7 +220,7 @@ extern "C" int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prun
     p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
     p.obs_index = obs_index; p.all_traj = all_traj; p.all_meta = all_meta; p.all_goal = all_goal; p.all_state = all_state;
     p.prune = prune ? 1 : 0; p.state = state; p.limits = limits; p.dt = h->cfg.dt;
-    p.normals = normals_out; p.rhs = rhs_out;
+    p.normals = normals_out; p.rhs = rhs_out; p.obs_size = h->obs_size;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
     else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);

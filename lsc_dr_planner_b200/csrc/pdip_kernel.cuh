@@ -58,6 +58,10 @@ struct SolveParams {
     double world_min[3], world_max[3];
     int use_sfc;
     int presolve;               // drop obstacles whose rows are all proven inactive by velocity-bound propagation (exact)
+    int rsfc;                   // PlannerMode::RECIPROCALRSFC: its SlackMode::COLLISIONCONSTRAINT gives every LSC row a free slack
+                                // epsilon <= 0 without a cost term (traj_optimizer.cpp:272-283, :423-425; slack_collision_weight is
+                                // never read), so no LSC row can bind: the x-part of the minimiser is that of the model without
+                                // them; and the z bounds of segment 0 are relaxed to +-100 (:255-258)
     int max_obs;                // lscqp_config.max_obs: a longer obstacle list is reported as ST_CAPACITY, never truncated
     const float*  state;        // [n][9]   position, velocity, acceleration
     const float*  goal;         // [n][3]   current_goal_point
@@ -649,6 +653,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         if (p.klass_mode == 1) { if (tid == 0) p.klass[agent] = 1; return; }   // the full-capacity pass reports it
         K = 0;
     }
+    if (p.rsfc) K = 0;                                                    // (rows with a free, cost-less slack: see SolveParams::rsfc)
 
     // ---- Cholesky trailing-update pair assignment (fixed per lane)
     int pr_i[C::NPR], pr_k[C::NPR];
@@ -679,6 +684,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
         s_goal[k] = (double) p.goal[agent * 3 + k] - pos;
         for (int m = 0; m < M; m++) {
             double lo = p.world_min[k], hi = p.world_max[k];              // :252-253
+            if (p.rsfc && k == 2 && m == 0) { lo = -100.0; hi = 100.0; }  // :255-258
             if (p.use_sfc) {                                               // :372-397, Box::convertToLSCs
                 lo = fmax(lo, (double) p.sfc[((size_t) agent * M + m) * 6 + k]);
                 hi = fmin(hi, (double) p.sfc[((size_t) agent * M + m) * 6 + 3 + k]);

@@ -141,6 +141,9 @@ static int lsc_row_active(const float *nrm) {  /* :409-411, Vector3::norm() */
 void orc_qp_sizes(const orc_config *cfg, int K, const float *lsc_normal, int *nv, int *ne, int *ni) {
     int M = cfg->M, n = cfg->n, phi = cfg->phi, dim = cfg->dim;
     *nv = dim * M * (n + 1);
+    /* slack variables, :272-283: one per (obstacle, segment) in SlackMode::COLLISIONCONSTRAINT, which is what
+     * mode reciprocal_rsfc selects (src/param.cpp:157-161); dynamic_obstacle_indices is never populated */
+    if (cfg->planner_mode == ORC_MODE_RECIPROCALRSFC) *nv += K * M;
     int e = dim * 6 + dim * (M - 2) * phi;                       /* :319-368 */
     if (cfg->planner_mode == ORC_MODE_LSC) e += dim * (phi - 1); /* :504-511 */
     *ne = e;
@@ -190,6 +193,10 @@ int orc_qp_build(const orc_config *cfg, const orc_agent *ag, int K,
                 if (m == 0 && i < 3) { lb[row] = -ORC_INF; ub[row] = ORC_INF; }
                 else { lb[row] = lower; ub[row] = upper; }
             }
+
+    /* epsilon_slack_col_oi_m in (-inf, 0], no cost term anywhere (:272-283; slack_collision_weight is never read) */
+    if (cfg->planner_mode == ORC_MODE_RECIPROCALRSFC)
+        for (int j = dim * M * N; j < nv; j++) { lb[j] = -ORC_INF; ub[j] = 0.0; }
 
     /* cost 1: jerk, :286-299 */
     double Q[36];
@@ -275,6 +282,8 @@ int orc_qp_build(const orc_config *cfg, const orc_agent *ag, int K,
                     G[(size_t) g * nv + k * offset_dim + m * offset_seg + i] = (double) nr[k];
                     cst += (double) nr[k] * (double) pt[k];
                 }
+                if (cfg->planner_mode == ORC_MODE_RECIPROCALRSFC)          /* expr += -(lsc.d + x[offset_slack_col + M oi + m]), :423-425 */
+                    G[(size_t) g * nv + dim * M * N + M * oi + m] = -1.0;
                 rlo[g] = cst + lsc_d[rec]; rhi[g] = ORC_INF;
                 g++;
             }
@@ -535,6 +544,42 @@ static v3 normal_between_polys(const v3 *own, const v3 *obs, int N, double *dist
     return v3_normalized(cp2);
 }
 
+/* obstacleSizePredictionWithConstAcc, src/traj_planner.cpp:321-358, for one obstacle in mode reciprocal_rsfc with
+ * obs/size_prediction on: size[m][i] = radius + velocity_guard + Bernstein control points of 1/2 a (m dt + tau dt)^2 for
+ * the first M_u = (int)((uncertainty_horizon + 1e-9) / dt) segments, the value at M_u dt afterwards.
+ * velocity_guard = ratio |v_agent|^2 / max_acc_agent[0] (0 when use_velocity_guard is off). */
+void orc_obstacle_sizes(int M, int n, double dt, double obs_radius, double obs_max_acc, double uncertainty_horizon,
+                        double velocity_guard, double *size /* [M][n+1] */) {
+    const int N = n + 1;
+    double B[36], Binv[36];
+    orc_bernstein_basis(n, B);
+    /* B_inv: monomial -> Bernstein (polynomial.hpp:281-294 builds B and its inverse); B is upper triangular */
+    for (int c = 0; c < N; c++) {                      /* solve X B = I row by row: Binv = B^-1 */
+        for (int r = 0; r < N; r++) Binv[r * N + c] = 0;
+    }
+    for (int r = 0; r < N; r++)
+        for (int c = 0; c < N; c++) {
+            double v = (r == c) ? 1.0 : 0.0;
+            for (int k = 0; k < c; k++) v -= Binv[r * N + k] * B[k * N + c];
+            Binv[r * N + c] = v / B[c * N + c];
+        }
+    const int Mu = (int) ((uncertainty_horizon + 1e-9) / dt);
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < N; i++) {
+            if (m < Mu) {
+                double coef[3] = {0.5 * obs_max_acc * pow(m * dt, 2), obs_max_acc * m * dt * dt, 0.5 * obs_max_acc * pow(dt, 2)};
+                double cp = 0;
+                for (int k = 0; k < 3; k++) cp += coef[k] * Binv[k * N + i];
+                size[m * N + i] = obs_radius + velocity_guard + cp;
+            } else {
+                size[m * N + i] = obs_radius + velocity_guard + 0.5 * obs_max_acc * pow(Mu * dt, 2);
+            }
+        }
+}
+
+/* optional [K][M][n+1] obstacle sizes for ORC_GEN_RSFC (set before the call, reset to NULL after; test infrastructure) */
+const double *orc_rsfc_sizes = 0;
+
 void orc_generate_lsc(const orc_config *cfg, int generator, const orc_agent *ag, double agent_downwash,
                       const float *own_traj, int K, const float *obs_traj,
                       const float *obs_radius, const float *obs_downwash,
@@ -550,6 +595,37 @@ void orc_generate_lsc(const orc_config *cfg, int generator, const orc_agent *ag,
         int transform = !(generator == ORC_GEN_CLSC && cfg->dim == 2);             /* :666-672 */
         const float *ot = obs_traj + (size_t) oi * M * N * 3;
 
+        if (generator == ORC_GEN_RSFC) {                                           /* generateReciprocalRSFC :581-609 */
+            for (int m = 0; m < M; m++) {
+                for (int i = 0; i < N; i++) {
+                    own[i] = v3_load(own_traj + ((size_t) m * N + i) * 3);
+                    obs[i] = v3_load(ot + ((size_t) m * N + i) * 3);
+                }
+                /* normalVectorBetweenLines :1157-1177 on closestPointsBetweenLinePaths (geometry.hpp:104-127) */
+                v3 rs = v3_sub(own[0], obs[0]), re = v3_sub(own[N - 1], obs[N - 1]);          /* rel_path = line2 - line1 */
+                closest_t rc = closest_point_segment(v3_make(0, 0, 0), rs, re);
+                double len = v3_distance(rs, re), alpha = 0;
+                if (len > 0) alpha = v3_norm(v3_sub(rc.cp2, rs)) / len;
+                v3 cp1 = v3_add(obs[0], v3_scale(v3_sub(obs[N - 1], obs[0]), alpha));
+                v3 cp2 = v3_add(own[0], v3_scale(v3_sub(own[N - 1], own[0]), alpha));
+                double closest_dist = rc.dist;
+                v3 normal = v3_normalized(v3_sub(cp2, cp1));
+                if (v3_norm(normal) == 0) {
+                    if (v3_norm(rs) == 0 && v3_norm(re) == 0) normal = v3_make(1, 0, 0);
+                    else normal = v3_cross(v3_sub(re, rs), v3_make(0, 0, 1));
+                }
+                normal.z = (float) ((double) normal.z / (downwash * downwash));   /* :603-604 */
+                size_t rec0 = ((size_t) oi * M + m) * N;
+                for (int i = 0; i < N; i++) {
+                    /* obs_pred_sizes (orc_obstacle_sizes); without it the obstacle's radius (obs/size_prediction off) */
+                    const double size = orc_rsfc_sizes ? orc_rsfc_sizes[rec0 + i] : o_r;
+                    lsc_d[rec0 + i] = closest_dist < size + ag->radius ? 0.5 * (size + ag->radius + closest_dist) : size + ag->radius;
+                    v3_store(lsc_point + (rec0 + i) * 3, obs[i]);
+                    v3_store(lsc_normal + (rec0 + i) * 3, normal);
+                }
+            }
+            continue;
+        }
         v3 bvc_normal = v3_make(0, 0, 0); double bvc_d = 0;
         if (generator == ORC_GEN_BVC) {                                            /* :708-736 */
             v3 a0 = v3_load(own_traj), o0 = v3_load(ot);

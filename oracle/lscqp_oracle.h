@@ -89,7 +89,10 @@ void orc_closest_points_segments(const float *l1s, const float *l1e, const float
  *   own_traj [M][n+1][3], obs_traj [K][M][n+1][3], obs_radius/obs_downwash [K],
  *   obs_goal [K][3] (CLSC), obs_position [K][3] (LSC zero-normal fallback)
  * out: lsc_point/lsc_normal [K][M][n+1][3] float, lsc_d [K][M][n+1] double */
-enum { ORC_GEN_LSC = 0, ORC_GEN_CLSC = 1, ORC_GEN_BVC = 2 };
+enum { ORC_GEN_LSC = 0, ORC_GEN_CLSC = 1, ORC_GEN_BVC = 2, ORC_GEN_RSFC = 3 /* generateReciprocalRSFC :581-609 */ };
+void orc_obstacle_sizes(int M, int n, double dt, double obs_radius, double obs_max_acc, double uncertainty_horizon,
+                        double velocity_guard, double *size /* [M][n+1] */);
+extern const double *orc_rsfc_sizes;   /* [K][M][n+1] sizes used by ORC_GEN_RSFC (NULL: the obstacle radius) */
 void orc_generate_lsc(const orc_config *cfg, int generator, const orc_agent *ag, double agent_downwash,
                       const float *own_traj, int K, const float *obs_traj,
                       const float *obs_radius, const float *obs_downwash,

@@ -28,7 +28,7 @@ _REF = os.path.join(_HERE, "_ref", "libopengjk_ref.so")
 INF = 1e30
 
 MODE_DLSC, MODE_LSC, MODE_BVC, MODE_ORCA, MODE_RECIPROCALRSFC = 0, 1, 2, 3, 4
-GEN_LSC, GEN_CLSC, GEN_BVC = 0, 1, 2
+GEN_LSC, GEN_CLSC, GEN_BVC, GEN_RSFC = 0, 1, 2, 3
 
 
 def build(force: bool = False) -> None:
@@ -275,9 +275,18 @@ def closest_points_segments(l1s, l1e, l2s, l2e):
     return cp1, cp2, dist.value
 
 
+def obstacle_sizes(cfg: Config, obs_radius: float, obs_max_acc: float, uncertainty_horizon: float = 1.0, velocity_guard: float = 0.0):
+    """obstacleSizePredictionWithConstAcc (src/traj_planner.cpp:321-358) for one obstacle: [M, n+1] predicted sizes"""
+    out = np.zeros((cfg.M, cfg.n + 1))
+    lib().orc_obstacle_sizes(cfg.M, cfg.n, C.c_double(cfg.dt), C.c_double(obs_radius), C.c_double(obs_max_acc),
+                             C.c_double(uncertainty_horizon), C.c_double(velocity_guard), _p(out, C.c_double))
+    return out
+
+
 def generate_lsc(cfg: Config, generator: int, ag: Agent, own_traj, obs_traj, obs_radius, obs_downwash,
-                 obs_goal=None, obs_position=None):
-    """generateLSC / generateCLSC / generateBVC (src/traj_planner.cpp:611-736).
+                 obs_goal=None, obs_position=None, obs_size=None):
+    """generateLSC / generateCLSC / generateBVC / generateReciprocalRSFC (src/traj_planner.cpp:581-736).
+    obs_size [K, M, n+1]: predicted obstacle sizes (GEN_RSFC; None: the obstacle radius).
     Returns (point[K,M,6,3] f32, normal[K,M,6,3] f32, d[K,M,6] f64)."""
     own_traj, obs_traj = _f32(own_traj), _f32(obs_traj)
     K = obs_traj.shape[0]
@@ -288,10 +297,18 @@ def generate_lsc(cfg: Config, generator: int, ag: Agent, own_traj, obs_traj, obs
     pt = np.zeros((K, cfg.M, N, 3), np.float32); nr = np.zeros((K, cfg.M, N, 3), np.float32)
     d = np.zeros((K, cfg.M, N))
     cc, ca = cfg.c(), ag.c()
-    lib().orc_generate_lsc(C.byref(cc), generator, C.byref(ca), C.c_double(ag.downwash), _p(own_traj, C.c_float), K,
-                           _p(obs_traj, C.c_float), _p(obs_radius, C.c_float), _p(obs_downwash, C.c_float),
-                           _p(obs_goal, C.c_float), _p(obs_position, C.c_float),
-                           _p(pt, C.c_float), _p(nr, C.c_float), _p(d, C.c_double))
+    slot = C.c_void_p.in_dll(lib(), "orc_rsfc_sizes")
+    sizes = None
+    if obs_size is not None:
+        sizes = np.ascontiguousarray(obs_size, np.float64).reshape(K, cfg.M, N)
+        slot.value = sizes.ctypes.data
+    try:
+        lib().orc_generate_lsc(C.byref(cc), generator, C.byref(ca), C.c_double(ag.downwash), _p(own_traj, C.c_float), K,
+                               _p(obs_traj, C.c_float), _p(obs_radius, C.c_float), _p(obs_downwash, C.c_float),
+                               _p(obs_goal, C.c_float), _p(obs_position, C.c_float),
+                               _p(pt, C.c_float), _p(nr, C.c_float), _p(d, C.c_double))
+    finally:
+        slot.value = None
     return pt, nr, d
 
 

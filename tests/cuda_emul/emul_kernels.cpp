@@ -61,11 +61,14 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     return LSCQP_E_INVALID;
 }
 
+static const double* g_emul_obs_size = nullptr;
+extern "C" void emul_set_obstacle_sizes(const double* s) { g_emul_obs_size = s; }
 extern "C" int emul_assemble_lsc_batch(const lscqp_config* cfg, int generator, int n_agents, const float* own_traj,
                                        const double* agent_meta, const float* agent_goal, const int* obs_offsets,
                                        const float* obs_traj, const float* obs_meta, const float* obs_goal,
                                        const float* obs_position, double* normals_out, double* rhs_out) {
     AssembleParams p{};
+    p.obs_size = g_emul_obs_size;
     p.n_agents = n_agents; p.generator = generator; p.dim = cfg->dim;
     p.own_traj = own_traj; p.agent_meta = agent_meta; p.agent_goal = agent_goal; p.obs_offsets = obs_offsets;
     p.obs_traj = obs_traj; p.obs_meta = obs_meta; p.obs_goal = obs_goal; p.obs_position = obs_position;

@@ -41,14 +41,16 @@ def solve_batch(cfg, n, state, goal, limits, sfc, off, normals, rhs, want_dual=F
     return ctrl, cost, status, iters, kkt, dual
 
 
-def assemble(cfg, generator, n, own_traj, agent_meta, agent_goal, off, obs_traj, obs_meta, obs_goal, obs_position):
+def assemble(cfg, generator, n, own_traj, agent_meta, agent_goal, off, obs_traj, obs_meta, obs_goal, obs_position, obs_size=None):
     cc = capi.make_config(cfg)
+    lib().emul_set_obstacle_sizes(_p(obs_size, np.float64))
     sk = int(off[n])
     normals = np.zeros((sk, cfg.M, 3)); rhs = np.zeros((sk, cfg.M, 6))
     rc = lib().emul_assemble_lsc_batch(C.byref(cc), generator, n, _p(own_traj, np.float32), _p(agent_meta, np.float64),
                                        _p(agent_goal, np.float32), _p(off, np.int32), _p(obs_traj, np.float32),
                                        _p(obs_meta, np.float32), _p(obs_goal, np.float32), _p(obs_position, np.float32),
                                        _p(normals, np.float64), _p(rhs, np.float64))
+    lib().emul_set_obstacle_sizes(C.c_void_p(0))
     assert rc == 0, rc
     return normals, rhs
 

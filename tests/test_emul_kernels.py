@@ -104,6 +104,43 @@ def test_assembly_kernel_matches_oracle(generator, M, dim):
     assert (normals == n_ref).mean() > 0.99
 
 
+def test_reciprocal_rsfc_generator_and_slack_mode():
+    """a8': generateReciprocalRSFC (traj_planner.cpp:581-609, with obstacleSizePredictionWithConstAcc :321-358) on the
+    emulator against the oracle, and the QP of mode reciprocal_rsfc: its SlackMode::COLLISIONCONSTRAINT gives every LSC row
+    a free slack without a cost term (traj_optimizer.cpp:272-283, 423-425), so the oracle's model WITH the slack columns has
+    the same control points as the kernel, which drops the rows; z bounds of segment 0 are +-100 (:255-258)"""
+    cfg = W.PlannerConfig(M=5, dim=3, planner_mode=4)
+    b = W.make_forest_batch(32, K=6, cfg=cfg)
+    cfgo = oracle_config(cfg)
+    n = 4
+    off = np.ascontiguousarray(b.obs_offsets[:n + 1]); sk = off[n]
+    # predicted sizes: every obstacle with max_acc 2, uncertainty horizon 1 s, velocity guard of the agent
+    sizes = np.zeros((sk, cfg.M, 6))
+    for a in range(n):
+        vg = 1.0 * float((b.state[a, 3:6].astype(np.float64) ** 2).sum()) / b.limits[a, 3]
+        for j in range(off[a], off[a + 1]):
+            sizes[j] = orc.obstacle_sizes(cfgo, float(b.obs_meta()[j, 0]), 2.0, 1.0, vg)
+    assert sizes[0, 0, 0] > 0.15 and sizes[0, 4, 5] > sizes[0, 0, 0] + 0.5        # grows by 1/2 a t^2 over the horizon
+    normals, rhs = emul.assemble(cfg, 3, n, b.own_traj[:n].copy(), b.agent_meta[:n].copy(), b.goal[:n].copy(), off,
+                                 b.obs_traj()[:sk].copy(), b.obs_meta()[:sk].copy(), b.obs_goal()[:sk].copy(),
+                                 b.obs_position()[:sk].copy(), obs_size=sizes)
+    from common import oracle_agent
+    for a in range(n):
+        sl = slice(off[a], off[a + 1])
+        pt, nr, d = orc.generate_lsc(cfgo, orc.GEN_RSFC, oracle_agent(b, a), b.own_traj[a], b.obs_traj()[sl], b.obs_meta()[sl, 0],
+                                     b.obs_meta()[sl, 1], b.obs_goal()[sl], b.obs_position()[sl], obs_size=sizes[sl])
+        n_ref, r_ref = orc.pack_planes(cfgo, pt, nr, d)
+        assert np.abs(normals[sl] - n_ref).max() <= 2.4e-7 and np.abs(rhs[sl] - r_ref).max() <= 2e-6
+        # the QP: oracle model with K * M slack columns vs the kernel
+        qp = orc.qp_build(cfgo, oracle_agent(b, a), pt, nr, d)
+        assert qp.q.size == 90 + (off[a + 1] - off[a]) * cfg.M
+        xe, ok = oracle_solution(qp)
+        ctrl, cost, status, iters, kkt, _ = emul.solve_batch(cfg, 1, b.state[a:a + 1].copy(), b.goal[a:a + 1].copy(), b.limits[a:a + 1].copy(), None,
+                                                             np.array([0, off[a + 1] - off[a]], np.int32), np.ascontiguousarray(normals[sl]),
+                                                             np.ascontiguousarray(rhs[sl]))
+        assert status[0] == 0 and np.abs(ctrl[0] - xe[:90]).max() < (1e-5 if ok else 1e-4), (a, np.abs(ctrl[0] - xe[:90]).max())
+
+
 def test_step_kernel_matches_oracle():
     for M, dim in ((5, 3), (10, 2)):
         cfg = W.PlannerConfig(M=M, dim=dim)

@@ -193,7 +193,8 @@ def test_infeasible_is_reported_not_nan():
     assert np.isfinite(ctrl[1]).all()
 
 
-@pytest.mark.parametrize("generator,M,dim", [(capi.GEN_LSC, 5, 3), (capi.GEN_CLSC, 10, 2), (capi.GEN_CLSC, 5, 3), (capi.GEN_BVC, 5, 3)])
+@pytest.mark.parametrize("generator,M,dim", [(capi.GEN_LSC, 5, 3), (capi.GEN_CLSC, 10, 2), (capi.GEN_CLSC, 5, 3), (capi.GEN_BVC, 5, 3),
+                                             (capi.GEN_RSFC, 5, 3)])
 def test_assembly_parity(generator, M, dim):
     """device LSC assembly vs the oracle's restatement of generateLSC / generateCLSC / generateBVC"""
     import torch
