@@ -38,6 +38,12 @@ struct AssembleParams {
     const double* all_meta;      // [n_total][2]
     const float*  all_goal;      // [n_total][3]
     const float*  all_state;     // [n_total][9]
+    // split dispatch of the pruned path (lscqp_assemble_lsc_fused at throughput batch sizes): lsc_assemble_kernel only
+    // prunes and appends the surviving pairs to a global work list, lsc_pairs_kernel then computes their planes with
+    // every thread of the grid busy (in one kernel the ~15 % surviving pairs leave most threads of a CTA idle while a few
+    // run the long fp64 hull enumeration)
+    int2* work_list;             // [sum K * M] (agent, pair row j * M + m); null: planes computed in the same kernel
+    int*  work_count;            // [1] zeroed before the launch
     const double* obs_size;      // [sumK][M][6] predicted obstacle sizes (generator 3; null: the obstacle radius)
     int prune;
     const float*  state;         // [n][9]   (prune)
@@ -233,6 +239,125 @@ __device__ __forceinline__ ClosestPts closest_points_segments(f3 l1s, f3 l1e, f3
 }
 
 // ---------------------------------------------------------------------------------------------
+// One (obstacle, segment) pair: the plane of the selected generator, packed (normal, rhs_i = n . p_i + d_i).
+// own_traj_: the agent's initial trajectory [M][6][3] (shared or global memory); j: row of the obstacle in the CSR arrays.
+template <int M>
+__device__ __forceinline__ void assemble_pair(const AssembleParams& p, int agent, size_t j, int m, const float* own_traj_,
+                                              double a_r, double a_dw) {
+    double o_r, o_dw;
+    size_t src = j;
+if (p.obs_index) {
+    src = (size_t) p.obs_index[j];
+    o_r = (double) (float) p.all_meta[src * 2 + 0]; o_dw = (double) (float) p.all_meta[src * 2 + 1];   // agent_manager.cpp:184-199
+} else { o_r = (double) p.obs_meta[j * 4 + 0]; o_dw = (double) p.obs_meta[j * 4 + 1]; }
+    const double collision_dist = o_r + a_r;                                    // traj_planner.cpp:642, :661
+    const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);            // downwashBetween :1229-1240
+    const float dwf = (float) downwash;
+    const bool transform = !(p.generator == 1 && p.dim == 2);                   // :666-672
+    const float* obase = p.obs_index ? p.all_traj : p.obs_traj;
+    const float* ot = obase + (src * M + m) * 18;
+    const float* ogoal = p.obs_index ? p.all_goal + src * 3 : p.obs_goal + j * 3;
+    const float* opos = p.obs_index ? p.all_state + src * 9 : p.obs_position + j * 3;
+
+    f3 own[6], obs[6], own_t[6], obs_t[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        own[i] = f3_make(own_traj_[m * 18 + i * 3], own_traj_[m * 18 + i * 3 + 1], own_traj_[m * 18 + i * 3 + 2]);
+        obs[i] = f3_make(ot[i * 3], ot[i * 3 + 1], ot[i * 3 + 2]);
+        own_t[i] = own[i]; obs_t[i] = obs[i];
+        if (transform) {                                                        // trajectory.cpp:207-219
+            own_t[i].z = __fdiv_rn(own[i].z, dwf); obs_t[i].z = __fdiv_rn(obs[i].z, dwf);
+        }
+    }
+    f3 normal;
+    double d[6];
+    f3 pt[6];
+    if (p.generator == 3) {                                                     // generateReciprocalRSFC :581-609
+        // normalVectorBetweenLines (:1157-1177) on closestPointsBetweenLinePaths (geometry.hpp:104-127): the paths
+        // first -> last control point of the obstacle and of the agent, in the original coordinates
+        const f3 rs = f3_sub(own[0], obs[0]), re = f3_sub(own[5], obs[5]);
+        const ClosestPts rc = closest_point_segment(f3_make(0.f, 0.f, 0.f), rs, re);
+        const double len = f3_distance(rs, re);
+        double alpha = 0.0;
+        if (len > 0) alpha = f3_norm(f3_sub(rc.cp2, rs)) / len;
+        const f3 cp1 = f3_add(obs[0], f3_scale(f3_sub(obs[5], obs[0]), alpha));
+        const f3 cp2 = f3_add(own[0], f3_scale(f3_sub(own[5], own[0]), alpha));
+        normal = f3_normalized(f3_sub(cp2, cp1));
+        if (f3_norm(normal) == 0) {
+            if (f3_norm(rs) == 0 && f3_norm(re) == 0) normal = f3_make(1.f, 0.f, 0.f);
+            else normal = f3_cross(f3_sub(re, rs), f3_make(0.f, 0.f, 1.f));
+        }
+        normal.z = (float) ((double) normal.z / (downwash * downwash));         // :603-604
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double size = p.obs_size ? p.obs_size[(j * M + m) * 6 + i] : o_r;
+            d[i] = rc.dist < size + a_r ? 0.5 * (size + a_r + rc.dist) : size + a_r;     // :593-600
+            pt[i] = obs[i];
+        }
+        const double nx3 = (double) normal.x, ny3 = (double) normal.y, nz3 = (double) normal.z;
+        double* no3 = p.normals + (j * M + m) * 3;
+        no3[0] = nx3; no3[1] = ny3; no3[2] = nz3;
+        double* ro3 = p.rhs + (j * M + m) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            double b = nx3 * (double) pt[i].x + ny3 * (double) pt[i].y;
+            if (p.dim == 3) b += nz3 * (double) pt[i].z;
+            ro3[i] = b + d[i];
+        }
+        return;
+    }
+    if (p.generator == 2) {                                                     // generateBVC :708-736
+        f3 a0 = f3_make(own_traj_[0], own_traj_[1], __fdiv_rn(own_traj_[2], dwf));
+        const float* o0p = obase + src * M * 18;
+        f3 o0 = f3_make(o0p[0], o0p[1], __fdiv_rn(o0p[2], dwf));
+        const f3 diff = f3_sub(a0, o0);
+        normal = f3_normalized(diff);
+        const double dd = 0.5 * (collision_dist + f3_dot(diff, normal));
+#pragma unroll
+        for (int i = 0; i < 6; i++) { d[i] = dd; pt[i] = obs[i]; }
+    } else if (p.generator == 1 && m == M - 1) {                                // generateCLSC :691-703
+        const f3 og = f3_make(ogoal[0], ogoal[1], ogoal[2]);
+        const f3 ag = f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]);
+        const ClosestPts cp = closest_points_segments(obs_t[5], og, own_t[5], ag);
+        normal = f3_normalized(f3_sub(cp.cp2, cp.cp1));
+        const double dd = 0.5 * (collision_dist + cp.dist);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { d[i] = dd; pt[i] = cp.cp1; }
+    } else {                                                                    // :625 / :678
+        double rel[6][3], v[3];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const f3 r = f3_sub(own_t[i], obs_t[i]);                            // :1186
+            rel[i][0] = (double) r.x; rel[i][1] = (double) r.y; rel[i][2] = (double) r.z;
+        }
+        min_norm_hull6(rel, v);
+        normal = f3_normalized(f3_make((float) v[0], (float) v[1], (float) v[2]));   // geometry.hpp:292, :1196
+        if (p.generator == 0 && f3_norm(normal) < 1e-5) {                       // :626-634
+            f3 vec = f3_sub(f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]),
+                            f3_make(opos[0], opos[1], opos[2]));
+            vec.z = (float) ((double) vec.z / downwash);                        // coordinateTransform :1262-1266
+            normal = f3_normalized(vec);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {                                           // :640-645 / :683-686
+            d[i] = 0.5 * (collision_dist + f3_dot(f3_sub(own_t[i], obs_t[i]), normal));
+            pt[i] = obs[i];
+        }
+    }
+    normal.z = (float) ((double) normal.z / downwash);                          // :653 / :689 / :701 / :730
+    const double nx = (double) normal.x, ny = (double) normal.y, nz = (double) normal.z;
+    double* no = p.normals + (j * M + m) * 3;
+    no[0] = nx; no[1] = ny; no[2] = nz;
+    double* ro = p.rhs + (j * M + m) * 6;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double b = nx * (double) pt[i].x + ny * (double) pt[i].y;               // traj_optimizer.cpp:414-421
+        if (p.dim == 3) b += nz * (double) pt[i].z;
+        ro[i] = b + d[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // one CTA per agent; threads stride over that agent's (obstacle, segment) pairs
 #ifdef LSCQP_CUDA_EMUL
 #define LSCQP_ASM_SMEM(name, count) float* name = reinterpret_cast<float*>(emu_dyn_smem)
@@ -334,119 +459,35 @@ lsc_assemble_kernel(const AssembleParams p) {
         }
         __syncthreads();
         n_work = s_cnt[0];
+        if (p.work_list) {
+            if (threadIdx.x == 0) s_cnt[1] = atomicAdd(p.work_count, n_work);
+            __syncthreads();
+            const int base = s_cnt[1];
+            for (int w = threadIdx.x; w < n_work; w += blockDim.x) {
+                const int e = (int) s_list[w];
+                int2 item; item.x = agent; item.y = (obs0 + e / M) * M + e % M;
+                p.work_list[base + w] = item;
+            }
+            return;
+        }
     }
 
     for (int w = threadIdx.x; w < n_work; w += blockDim.x) {
         const int e = prune ? (int) s_list[w] : w;
-        const int oi = e / M, m = e % M;
-        const size_t j = (size_t) obs0 + oi;
-        double o_r, o_dw;
-        const size_t src = obstacle(j, o_r, o_dw);
-        const double collision_dist = o_r + a_r;                                    // traj_planner.cpp:642, :661
-        const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);            // downwashBetween :1229-1240
-        const float dwf = (float) downwash;
-        const bool transform = !(p.generator == 1 && p.dim == 2);                   // :666-672
-        const float* obase = p.obs_index ? p.all_traj : p.obs_traj;
-        const float* ot = obase + (src * M + m) * 18;
-        const float* ogoal = p.obs_index ? p.all_goal + src * 3 : p.obs_goal + j * 3;
-        const float* opos = p.obs_index ? p.all_state + src * 9 : p.obs_position + j * 3;
+        assemble_pair<M>(p, agent, (size_t) obs0 + e / M, e % M, s_own, a_r, a_dw);
+    }
+}
 
-        f3 own[6], obs[6], own_t[6], obs_t[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            own[i] = f3_make(s_own[m * 18 + i * 3], s_own[m * 18 + i * 3 + 1], s_own[m * 18 + i * 3 + 2]);
-            obs[i] = f3_make(ot[i * 3], ot[i * 3 + 1], ot[i * 3 + 2]);
-            own_t[i] = own[i]; obs_t[i] = obs[i];
-            if (transform) {                                                        // trajectory.cpp:207-219
-                own_t[i].z = __fdiv_rn(own[i].z, dwf); obs_t[i].z = __fdiv_rn(obs[i].z, dwf);
-            }
-        }
-        f3 normal;
-        double d[6];
-        f3 pt[6];
-        if (p.generator == 3) {                                                     // generateReciprocalRSFC :581-609
-            // normalVectorBetweenLines (:1157-1177) on closestPointsBetweenLinePaths (geometry.hpp:104-127): the paths
-            // first -> last control point of the obstacle and of the agent, in the original coordinates
-            const f3 rs = f3_sub(own[0], obs[0]), re = f3_sub(own[5], obs[5]);
-            const ClosestPts rc = closest_point_segment(f3_make(0.f, 0.f, 0.f), rs, re);
-            const double len = f3_distance(rs, re);
-            double alpha = 0.0;
-            if (len > 0) alpha = f3_norm(f3_sub(rc.cp2, rs)) / len;
-            const f3 cp1 = f3_add(obs[0], f3_scale(f3_sub(obs[5], obs[0]), alpha));
-            const f3 cp2 = f3_add(own[0], f3_scale(f3_sub(own[5], own[0]), alpha));
-            normal = f3_normalized(f3_sub(cp2, cp1));
-            if (f3_norm(normal) == 0) {
-                if (f3_norm(rs) == 0 && f3_norm(re) == 0) normal = f3_make(1.f, 0.f, 0.f);
-                else normal = f3_cross(f3_sub(re, rs), f3_make(0.f, 0.f, 1.f));
-            }
-            normal.z = (float) ((double) normal.z / (downwash * downwash));         // :603-604
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const double size = p.obs_size ? p.obs_size[(j * M + m) * 6 + i] : o_r;
-                d[i] = rc.dist < size + a_r ? 0.5 * (size + a_r + rc.dist) : size + a_r;     // :593-600
-                pt[i] = obs[i];
-            }
-            const double nx3 = (double) normal.x, ny3 = (double) normal.y, nz3 = (double) normal.z;
-            double* no3 = p.normals + (j * M + m) * 3;
-            no3[0] = nx3; no3[1] = ny3; no3[2] = nz3;
-            double* ro3 = p.rhs + (j * M + m) * 6;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                double b = nx3 * (double) pt[i].x + ny3 * (double) pt[i].y;
-                if (p.dim == 3) b += nz3 * (double) pt[i].z;
-                ro3[i] = b + d[i];
-            }
-            continue;
-        }
-        if (p.generator == 2) {                                                     // generateBVC :708-736
-            f3 a0 = f3_make(s_own[0], s_own[1], __fdiv_rn(s_own[2], dwf));
-            const float* o0p = obase + src * M * 18;
-            f3 o0 = f3_make(o0p[0], o0p[1], __fdiv_rn(o0p[2], dwf));
-            const f3 diff = f3_sub(a0, o0);
-            normal = f3_normalized(diff);
-            const double dd = 0.5 * (collision_dist + f3_dot(diff, normal));
-#pragma unroll
-            for (int i = 0; i < 6; i++) { d[i] = dd; pt[i] = obs[i]; }
-        } else if (p.generator == 1 && m == M - 1) {                                // generateCLSC :691-703
-            const f3 og = f3_make(ogoal[0], ogoal[1], ogoal[2]);
-            const f3 ag = f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]);
-            const ClosestPts cp = closest_points_segments(obs_t[5], og, own_t[5], ag);
-            normal = f3_normalized(f3_sub(cp.cp2, cp.cp1));
-            const double dd = 0.5 * (collision_dist + cp.dist);
-#pragma unroll
-            for (int i = 0; i < 6; i++) { d[i] = dd; pt[i] = cp.cp1; }
-        } else {                                                                    // :625 / :678
-            double rel[6][3], v[3];
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const f3 r = f3_sub(own_t[i], obs_t[i]);                            // :1186
-                rel[i][0] = (double) r.x; rel[i][1] = (double) r.y; rel[i][2] = (double) r.z;
-            }
-            min_norm_hull6(rel, v);
-            normal = f3_normalized(f3_make((float) v[0], (float) v[1], (float) v[2]));   // geometry.hpp:292, :1196
-            if (p.generator == 0 && f3_norm(normal) < 1e-5) {                       // :626-634
-                f3 vec = f3_sub(f3_make(p.agent_goal[agent * 3], p.agent_goal[agent * 3 + 1], p.agent_goal[agent * 3 + 2]),
-                                f3_make(opos[0], opos[1], opos[2]));
-                vec.z = (float) ((double) vec.z / downwash);                        // coordinateTransform :1262-1266
-                normal = f3_normalized(vec);
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) {                                           // :640-645 / :683-686
-                d[i] = 0.5 * (collision_dist + f3_dot(f3_sub(own_t[i], obs_t[i]), normal));
-                pt[i] = obs[i];
-            }
-        }
-        normal.z = (float) ((double) normal.z / downwash);                          // :653 / :689 / :701 / :730
-        const double nx = (double) normal.x, ny = (double) normal.y, nz = (double) normal.z;
-        double* no = p.normals + (j * M + m) * 3;
-        no[0] = nx; no[1] = ny; no[2] = nz;
-        double* ro = p.rhs + (j * M + m) * 6;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            double b = nx * (double) pt[i].x + ny * (double) pt[i].y;               // traj_optimizer.cpp:414-421
-            if (p.dim == 3) b += nz * (double) pt[i].z;
-            ro[i] = b + d[i];
-        }
+// second half of the split dispatch: one thread per surviving (obstacle, segment) pair of the whole batch
+template <int M>
+__global__ void __launch_bounds__(128, 4)
+lsc_pairs_kernel(const AssembleParams p) {
+    const int n = *p.work_count;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        const int2 item = p.work_list[w];
+        const int agent = item.x;
+        assemble_pair<M>(p, agent, (size_t) (item.y / M), item.y % M, p.own_traj + (size_t) agent * M * 18,
+                         p.agent_meta[agent * 2 + 0], p.agent_meta[agent * 2 + 1]);
     }
 }
 

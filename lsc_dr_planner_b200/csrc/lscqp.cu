@@ -57,6 +57,8 @@ struct lscqp_handle {
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
+    DevBuf d_work;                      // global work list of the split LSC assembly
+    int asm_split_min = 256;            // batch size from which lscqp_assemble_lsc_fused prunes and enumerates in two kernels
     DevBuf d_occ, d_closest, d_boxes;   // static map (lscqp_map_set)
     MapView map{};
     bool has_map = false;
@@ -93,6 +95,7 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     h->two_pass = info.has_light && (cfg->presolve & 1) && !(cfg->presolve & 2);
     if (cfg->presolve & 4) h->two_pass_min = 0;            // light first pass at any batch size
     if (const char* e = std::getenv("LSCQP_TWO_PASS_MIN")) h->two_pass_min = std::atoi(e);
+    if (const char* e = std::getenv("LSCQP_ASM_SPLIT_MIN")) h->asm_split_min = std::atoi(e);
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
     if (h->d_proj_ent.reserve(tab.term.size() * sizeof(ProjTerm)) || h->d_proj_term.reserve((tabl.term.size() + 1) * sizeof(ProjTerm)) ||
@@ -117,7 +120,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes};
+                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes, &h->d_work};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -222,9 +225,25 @@ extern "C" int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prun
     p.prune = prune ? 1 : 0; p.state = state; p.limits = limits; p.dt = h->cfg.dt;
     p.normals = normals_out; p.rhs = rhs_out; p.obs_size = h->obs_size;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // Pruned path at throughput batch sizes: prune + global work list, then one thread per surviving pair (split dispatch,
+    // lsc_assemble.cuh).  The list is sized for max_obs pairs per agent; it must exist before a stream capture starts.
+    const bool split = p.prune && h->cfg.dim == 3 && generator < 2 && n_agents >= h->asm_split_min;
+    if (split) {
+        const size_t cap = (size_t) n_agents * (size_t) h->cfg.max_obs * h->cfg.M;
+        if (h->d_work.reserve(cap * sizeof(int2) + 16)) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
+        p.work_count = h->d_work.as<int>();
+        p.work_list = reinterpret_cast<int2*>(h->d_work.as<char>() + 16);
+        CK(cudaMemsetAsync(p.work_count, 0, sizeof(int), st));
+    }
     if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
     else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
     h->launches++;
+    if (split) {
+        const int blocks = 148 * 4;
+        if (h->cfg.M == 5) lsc_pairs_kernel<5><<<blocks, 128, 0, st>>>(p);
+        else lsc_pairs_kernel<10><<<blocks, 128, 0, st>>>(p);
+        h->launches++;
+    }
     CK(cudaGetLastError());
     return 0;
 }

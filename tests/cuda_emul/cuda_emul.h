@@ -24,6 +24,7 @@
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 struct double2 { double x, y; };
 namespace emu {
 struct Thread {

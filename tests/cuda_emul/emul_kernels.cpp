@@ -89,9 +89,18 @@ extern "C" int emul_assemble_lsc_fused(const lscqp_config* cfg, int generator, i
     p.obs_index = obs_index; p.all_traj = all_traj; p.all_meta = all_meta; p.all_goal = all_goal; p.all_state = all_state;
     p.prune = prune; p.state = state; p.limits = limits; p.dt = cfg->dt;
     p.normals = normals_out; p.rhs = rhs_out;
+    // prune > 1: the split dispatch (prune kernel + global work list + one thread per surviving pair)
+    std::vector<int2> work((size_t) obs_offsets[n_agents] * cfg->M + 1);
+    int count = 0;
+    const bool split = prune > 1;
+    if (split) { p.work_list = work.data(); p.work_count = &count; p.prune = 1; }
     if (cfg->M == 5) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<5>(p); });
     else if (cfg->M == 10) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<10>(p); });
     else return LSCQP_E_INVALID;
+    if (split) {
+        if (cfg->M == 5) emu::launch(3, 128, 64, [&]() { lsc_pairs_kernel<5>(p); });
+        else emu::launch(3, 128, 64, [&]() { lsc_pairs_kernel<10>(p); });
+    }
     return 0;
 }
 

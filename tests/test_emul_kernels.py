@@ -316,6 +316,9 @@ def test_fused_assembly_reads_in_place_and_prunes_exactly(generator, M, dim):
     n0, r0 = emul.assemble_fused(cfg, generator, False, full)
     assert np.array_equal(n0, n_ref) and np.array_equal(r0, r_ref)
     n1, r1 = emul.assemble_fused(cfg, generator, True, full)
+    # the split dispatch (prune kernel -> global work list -> one thread per surviving pair) writes the same planes
+    n2, r2 = emul.assemble_fused(cfg, generator, 2, full)
+    assert np.array_equal(n1, n2) and np.array_equal(r1, r2)
     dropped = (n1 == 0).all(axis=2) & ~(n_ref == 0).all(axis=2)
     kept = ~dropped
     assert np.array_equal(n1[kept], n_ref[kept]) and np.array_equal(r1[kept], r_ref[kept]) and (r1[dropped] == 0).all()
