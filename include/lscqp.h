@@ -75,7 +75,9 @@ typedef struct lscqp_config {
                                       bit 1: keep every agent on the full-capacity kernel
                                       instance (no light-instance first pass);
                                       bit 2: light first pass at any batch size (default: only
-                                      from 1536 agents, below that a batch is latency bound)    */
+                                      from 1536 agents, below that a batch is latency bound);
+                                      bit 3: no dual active-set first pass (das_kernel.cuh): the
+                                      interior-point instances alone                            */
 } lscqp_config;
 
 typedef struct lscqp_handle lscqp_handle;

@@ -136,7 +136,9 @@ class LscQp:
         return int(self.lib.lscqp_launch_count(self.h))
 
     def last_instances(self, n, stream=0) -> np.ndarray:
-        """kernel instance of every agent in the last two-pass solve_batch: 0 = light (one warp per QP), 1 = full capacity"""
+        """which pass solved every agent in the last two-pass solve_batch: 0 = the first pass (dual active-set kernel, or the
+        light interior-point instance when that is the first pass), otherwise the full-capacity interior-point instance
+        (after the active-set pass the value is its reason for deferring, das_kernel.cuh)"""
         out = np.zeros(n, np.int32)
         self._check(self.lib.lscqp_last_instances(self.h, n, _hp(out, np.int32), C.c_void_p(stream)))
         return out

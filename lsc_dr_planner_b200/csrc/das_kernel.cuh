@@ -1,0 +1,690 @@
+// das_kernel.cuh -- batched dual active-set solve of the per-agent trajectory QP: the first pass of lscqp_solve_batch.
+//
+// Same model as pdip_kernel.cuh (the QP TrajOptimizer::populatebyrow builds, src/traj_optimizer.cpp:216-514, solved by the
+// CPLEX call :66), same analytic elimination of the equalities, same exact presolve, same agent-local coordinates -- but
+// solved by the Goldfarb-Idnani dual active-set method (Math. Programming 27, 1983) instead of an interior point:
+//   * The reduced Hessian H = Z'(blkdiag 2 w_c Q_base + terminal weights)Z does not depend on the agent: it is block
+//     diagonal over the dimensions and has one value per number of terminal segments (traj_optimizer.cpp:530-538), so its
+//     inverse and the inverse Cholesky factor J = L^-T come from a host-built table (host_common.hpp:build_das_tables).
+//   * Start at the unconstrained minimiser y = -H^-1 g.  Each iteration evaluates every row q_r(c) >= 0 at the current
+//     point (no per-row state: the rows are recomputed from the control points), takes the most violated one, and moves
+//     along z = J2 J2' n in the primal / r = R^-1 J1' n in the dual space until the row is satisfied (add it to the active
+//     set: one Householder reflection on J2, one new column of S = R^-1 -- the inverse factor is what is stored, so r is
+//     a lane-parallel matrix-vector product instead of a sequential back-substitution) or a multiplier reaches zero
+//     (drop that row: Givens rotations on the columns of S and J).  On the trajectory QPs of the forest workload 13-30 rows end up active (of 39 variables) and almost
+//     every iteration is an add: ~23 iterations of ~40 flops per lane instead of ~9 interior-point iterations of a
+//     full row sweep x4 + factorisation.
+//   * The result is checked before it is accepted: primal feasibility of every row at the returned point (the loop's
+//     exit test), multipliers >= 0 (invariant of the method), stationarity recomputed from scratch.  Anything else --
+//     more kept obstacles than this kernel holds, an iteration cap, a dependent / infeasible row, a stationarity residual
+//     above tolerance -- flags the agent in klass[] and leaves it to the interior-point pass (pdip_kernel.cuh, klass_mode 2).
+// One warp per agent, 32 threads per CTA, no CTA barrier, no atomics: results are bit-reproducible.
+#pragma once
+#include "pdip_kernel.cuh"
+
+#ifndef LSCQP_DAS_MINCTAS
+#define LSCQP_DAS_MINCTAS 9
+#endif
+
+namespace lscqp {
+
+template <class C>
+struct Das {
+    static constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, NZS = C::NZS;
+    static constexpr int N1 = NR / D;                       // reduced variables per dimension
+    static constexpr int RPL = (NR + 31) / 32;              // reduced variables per lane
+    static constexpr int VPT = (NV + 31) / 32;              // full-space variables (box-row owners) per lane
+    static constexpr int CPL = (NCP + 31) / 32;             // control points (LSC-row owners) per lane
+    static constexpr int KPT = 10;                          // kept obstacles this kernel holds
+    static constexpr int NLSC = CPL * KPT;                  // row slots of a lane: LSC rows first, then 6 per variable
+    static constexpr int NSLOT = NLSC + VPT * 6;
+    static constexpr int LDJ = NR | 1;
+    static constexpr int KRAW = C::KRAW;
+    static_assert(NSLOT <= 64, "row slots do not fit the 64-bit masks");
+    static_assert(NR * (NR | 1) >= NV, "full-space scratch does not fit under J");
+    // shared memory (doubles)
+    static constexpr int O_Q2 = 0;
+    static constexpr int O_C = O_Q2 + 36;
+    static constexpr int O_Y = O_C + NV;
+    static constexpr int O_X0 = O_Y + NR;
+    static constexpr int O_VLIM = O_X0 + 3 * D;
+    static constexpr int O_ALIM = O_VLIM + D;
+    static constexpr int O_GOAL = O_ALIM + D;
+    static constexpr int O_ORG = O_GOAL + D;
+    static constexpr int O_LB = O_ORG + D;
+    static constexpr int O_UB = O_LB + D * M;
+    static constexpr int O_TERMW = O_UB + D * M;            // [M] terminal weights, [M] the number of terminal segments
+    static constexpr int O_NRM = O_TERMW + M + 1;           // [KPT][M][3]
+    static constexpr int O_D = O_NRM + KPT * M * 3;         // d = J'n
+    static constexpr int O_Z = O_D + NR;                    // Householder row factors beta (J2 v)_r
+    static constexpr int O_RV = O_Z + NR;                   // r = S d1
+    static constexpr int O_U = O_RV + NR;                   // multipliers of the active rows (in active-set order)
+    static constexpr int O_J = O_U + NR;                    // J [NR][LDJ]  (start-up and epilogue: full-space scratch [NV])
+    static constexpr int O_R = O_J + NR * LDJ;              // S = R^-1, upper triangular, packed by columns: S(j, k) at k (k + 1) / 2 + j
+    static constexpr int O_INT = O_R + NR * (NR + 1) / 2;   // int ids[NR] (active rows: slot * 32 + lane), act[KRAW], keep[KRAW + 2]
+    static constexpr int O_END = O_INT + (NR + 2 * KRAW + 2 + 1) / 2;
+    static constexpr int SMEM_BYTES = O_END * 8;
+};
+
+// reduced index <-> (dimension, index within the dimension)
+template <class C>
+__device__ __forceinline__ void das_decode(int r, int& k, int& r1) {
+    if (C::TERM && r >= (C::M - 1) * C::NZS) { k = r - (C::M - 1) * C::NZS; r1 = 3 * (C::M - 1); }
+    else { k = (r % C::NZS) / 3; r1 = 3 * (r / C::NZS) + r % 3; }
+}
+template <class C>
+__device__ __forceinline__ int das_encode(int k, int r1) {
+    if (C::TERM && r1 == 3 * (C::M - 1)) return (C::M - 1) * C::NZS + k;
+    return (r1 / 3) * C::NZS + k * 3 + r1 % 3;
+}
+
+// Row (owner lane lp, slot) in the full space: at most three (dimension, control point, coefficient) entries, unused ones
+// with a zero coefficient.  LSC row of control point cp and kept obstacle j: normal n on (k, cp), k < D
+// (traj_optimizer.cpp:414-421); box rows of variable v: 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc- with unit-coefficient
+// stencils (:238-270, :440-474).
+template <class C>
+__device__ __forceinline__ void das_row_full(int lp, int slot, const double* s_nrm, int* fk, int* fcp, double* fa) {
+    using A = Das<C>;
+    constexpr int M = C::M, D = C::D, NCP = C::NCP;
+    if (slot < A::NLSC) {
+        const int cp = lp + 32 * (slot / A::KPT), j = slot % A::KPT;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { fk[k] = k < D ? k : 0; fcp[k] = cp; fa[k] = k < D ? s_nrm[(j * M + cp / 6) * 3 + k] : 0.0; }
+    } else {
+        const int b = slot - A::NLSC, u = b / 6, e = b % 6;
+        const int v = lp + 32 * u, k = v / NCP, cp = v % NCP;
+        const double sg = (e & 1) ? -1.0 : 1.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { fk[i] = k; fcp[i] = cp; fa[i] = 0.0; }
+        if (e < 2) { fa[0] = sg; }                                                       // c - lb >= 0, ub - c >= 0
+        else if (e < 4) { fa[0] = sg; fa[1] = -sg; fcp[1] = cp + 1; }                     // vlim -+ (c[i+1] - c[i]) >= 0
+        else { fa[0] = -sg; fa[1] = 2.0 * sg; fa[2] = -sg; fcp[1] = cp + 1; fcp[2] = cp + 2; }   // alim -+ (c[i+2] - 2 c[i+1] + c[i]) >= 0
+    }
+}
+
+// ... and in the reduced space: at most 9 (reduced variable, coefficient) pairs through the continuity map
+template <class C>
+__device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_nrm, int* pr, double* pv) {
+    int fk[3], fcp[3];
+    double fa[3];
+    das_row_full<C>(lp, slot, s_nrm, fk, fcp, fa);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+        const int m = fcp[f] / 6, i = fcp[f] % 6;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { pr[f * 3 + j] = 0; pv[f * 3 + j] = 0.0; }
+        if (i >= 3) { pr[f * 3] = ridx<C>(m, fk[f], i - 3); pv[f * 3] = fa[f]; }
+        else if (m >= 1) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) { pr[f * 3 + j] = ridx<C>(m - 1, fk[f], j); pv[f * 3 + j] = fa[f] * tcoef(i, j); }
+        }
+    }
+}
+
+// exact warp arg-min of a double per lane (ties: the lowest lane): two redux.sync.min passes over the halves of an
+// order-preserving 64-bit key.  Returns the winning lane.
+__device__ __forceinline__ int warp_argmin(double v) {
+    long long b = __double_as_longlong(v);
+    const unsigned long long key = (unsigned long long) b ^ ((unsigned long long) (b >> 63) | 0x8000000000000000ull);
+    const unsigned hi = (unsigned) (key >> 32), lo = (unsigned) key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+}
+
+template <class C>
+__global__ void __launch_bounds__(32, LSCQP_DAS_MINCTAS)
+das_solve_kernel(const SolveParams p) {
+    using A = Das<C>;
+    constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR;
+    constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1;
+    constexpr unsigned FULL = 0xffffffffu;
+    LSCQP_DYN_SMEM(sm);
+    const int lane = threadIdx.x & 31;
+    const int agent = blockIdx.x;
+    if (agent >= p.n_agents) return;
+
+    double* sQ2 = sm + A::O_Q2;
+    double* s_c = sm + A::O_C;
+    double* s_y = sm + A::O_Y;
+    double* s_x0 = sm + A::O_X0;
+    double* s_vlim = sm + A::O_VLIM;
+    double* s_alim = sm + A::O_ALIM;
+    double* s_goal = sm + A::O_GOAL;
+    double* s_org = sm + A::O_ORG;
+    double* s_lb = sm + A::O_LB;
+    double* s_ub = sm + A::O_UB;
+    double* s_termw = sm + A::O_TERMW;
+    double* s_nrm = sm + A::O_NRM;
+    double* s_d = sm + A::O_D;
+    double* s_z = sm + A::O_Z;
+    double* s_rv = sm + A::O_RV;
+    double* s_u = sm + A::O_U;
+    double* s_J = sm + A::O_J;
+    double* s_S = sm + A::O_R;
+    double* s_full = s_J;                                   // [NV] full-space scratch (start-up and epilogue only)
+    int* s_ids = reinterpret_cast<int*>(sm + A::O_INT);
+    int* s_act = s_ids + NR;
+    int* s_keep = s_act + A::KRAW;
+
+    // every exit that does not deliver a checked solution leaves the agent to the interior-point pass
+    // (klass: 0 solved here; else the reason -- 1 obstacle list beyond the ABI capacity, 2 more kept obstacles than KPT,
+    //  3 iteration cap, 4 dependent / infeasible row, 5 NaN, 6 stationarity or multiplier check failed)
+    auto defer = [&](int why) { if (lane == 0) p.klass[agent] = why; };
+
+    const int obs0 = p.obs_offsets[agent];
+    int K = p.obs_offsets[agent + 1] - obs0;
+    if (K < 0 || K > A::KRAW || K > p.max_obs) { defer(1); return; }      // (reported as ST_CAPACITY by the other pass)
+    if (p.rsfc) K = 0;                                                     // see SolveParams::rsfc
+
+    // ---- per-agent constants (as pdip_kernel.cuh: local coordinates, unit-coefficient velocity / acceleration rows)
+    for (int e = lane; e < 36; e += 32) sQ2[e] = p.Q2[e];
+    if (lane < D) {
+        const int k = lane;
+        const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
+                     acc = (double) p.state[agent * 9 + 6 + k];
+        const double c0 = 0.0, c1 = vel * p.dt / 5.0, c2 = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - c0;   // traj_optimizer.cpp:321-338
+        s_org[k] = pos;
+        s_x0[k * 3 + 0] = c0; s_x0[k * 3 + 1] = c1; s_x0[k * 3 + 2] = c2;
+        s_vlim[k] = p.limits[agent * 8 + k] * p.dt / 5.0;                 // :448-453
+        s_alim[k] = p.limits[agent * 8 + 3 + k] * p.dt * p.dt / 20.0;     // :462-471
+        s_goal[k] = (double) p.goal[agent * 3 + k] - pos;
+        for (int m = 0; m < M; m++) {
+            double lo = p.world_min[k], hi = p.world_max[k];              // :252-253
+            if (p.rsfc && k == 2 && m == 0) { lo = -100.0; hi = 100.0; }  // :255-258
+            if (p.use_sfc) {                                               // :372-397
+                lo = fmax(lo, (double) p.sfc[((size_t) agent * M + m) * 6 + k]);
+                hi = fmin(hi, (double) p.sfc[((size_t) agent * M + m) * 6 + 3 + k]);
+            }
+            s_lb[k * M + m] = lo - pos; s_ub[k * M + m] = hi - pos;
+        }
+    }
+    if (lane == 8) {
+        // getTerminalSegments_old, traj_optimizer.cpp:530-538 (float norm of the point3d difference)
+        const float dx = p.goal[agent * 3 + 0] - p.state[agent * 9 + 0], dy = p.goal[agent * 3 + 1] - p.state[agent * 9 + 1],
+                    dz = p.goal[agent * 3 + 2] - p.state[agent * 9 + 2];
+        const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const double flight = sqrt((double) nsq) / p.limits[agent * 8 + 7];
+        int ts = (int) ((M * p.dt - flight + 1e-9) / p.dt);
+        if (ts < 1) ts = 1;
+        if (ts > M) ts = M;
+        for (int m = 0; m < M; m++) s_termw[m] = (m >= M - ts) ? 2.0 * p.w_t : 0.0;
+        s_termw[M] = (double) ts;
+    }
+    for (int e = lane; e < A::KRAW; e += 32) s_keep[e] = (e < K && !p.presolve) ? 1 : 0;
+    __syncwarp();
+    const int ts = (int) s_termw[M];
+
+    // ---- rows of this lane.  Slot s < NLSC: LSC row of control point lane + 32 (s / KPT), kept obstacle s % KPT;
+    // slot NLSC + 6 u + e: box row e of variable lane + 32 u.  rmask: the rows that exist.
+    unsigned long long rmask = 0, amask = 0;                 // existing rows / rows in the active set
+    unsigned bmask[VPT];
+#pragma unroll
+    for (int u = 0; u < VPT; u++) {
+        const int v = lane + u * 32, m_v = (v % NCP) / 6, i_v = v % 6;
+        const bool on = v < NV;
+        const bool has_bnd = on && !(m_v == 0 && i_v < 3);              // :260-265
+        const bool has_vel = on && i_v < 5 && !(m_v == 0 && i_v < 2);   // :444
+        const bool has_acc = on && i_v < 4 && !(m_v == 0 && i_v < 1);   // :458
+        bmask[u] = (has_bnd ? 3u : 0u) | (has_vel ? 12u : 0u) | (has_acc ? 48u : 0u);
+        if (p.presolve && has_bnd) {
+            // exact presolve of the bound rows (pdip_kernel.cuh): the reach box of the velocity rows lies strictly inside
+            const int k_v = v / NCP;
+            const double reach = (double) (5 * m_v + i_v - 2) * s_vlim[k_v];
+            if (s_x0[k_v * 3 + 2] - reach - s_lb[k_v * M + m_v] > 1e-6 && s_ub[k_v * M + m_v] - (s_x0[k_v * 3 + 2] + reach) > 1e-6)
+                bmask[u] &= ~3u;
+        }
+        rmask |= (unsigned long long) bmask[u] << (A::NLSC + 6 * u);
+    }
+    // exact presolve of the obstacles (pdip_kernel.cuh): dropped when no point the velocity rows allow can activate a row
+    if (p.presolve) {
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int cp = lane + 32 * c, m_cp = cp / 6, i_cp = cp % 6;
+            if (cp >= NCP || (m_cp == 0 && i_cp < 3)) continue;
+            const double steps = (double) (5 * m_cp + i_cp - 2);
+            for (int oi = 0; oi < K; oi++) {
+                const double* g = p.normals + ((size_t) (obs0 + oi) * M + m_cp) * 3;
+                const double nx = g[0], ny = g[1], nz = (D == 3) ? g[2] : 0.0;
+                double b = p.rhs[((size_t) (obs0 + oi) * M + m_cp) * 6 + i_cp] - (nx * s_org[0] + ny * s_org[1]);
+                if (D == 3) b -= nz * s_org[2];
+                double lo = nx * s_x0[2] + ny * s_x0[5] - steps * (fabs(nx) * s_vlim[0] + fabs(ny) * s_vlim[1]);
+                if (D == 3) lo += nz * s_x0[8] - steps * fabs(nz) * s_vlim[2];
+                const bool zero_normal = (float) nx == 0.0f && (float) ny == 0.0f && (D == 2 || (float) nz == 0.0f);
+                if (!(lo - b > 1e-6) && !zero_normal) s_keep[oi] = 1;      // benign race: every writer stores 1
+            }
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < K; e += 32) {
+        if (!s_keep[e]) continue;
+        int pos = 0;
+        for (int u = 0; u < e; u++) pos += s_keep[u];
+        if (pos < KPT) s_act[pos] = e;
+    }
+    if (lane == 0) {
+        int n = 0;
+        for (int u = 0; u < K; u++) n += s_keep[u];
+        s_keep[A::KRAW] = n;
+    }
+    __syncwarp();
+    K = s_keep[A::KRAW];
+    if (K > KPT) { defer(2); return; }
+    for (int e = lane; e < K * M; e += 32) {
+        // rows with a (float) normal shorter than SP_EPSILON_FLOAT are skipped by the reference (traj_optimizer.cpp:409-411)
+        const double* g = p.normals + ((size_t) (obs0 + s_act[e / M]) * M + e % M) * 3;
+        double nx = g[0], ny = g[1], nz = g[2];
+        const float fx = (float) nx, fy = (float) ny, fz = (float) nz;
+        const float nsq = __fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz));
+        if (sqrt((double) nsq) < 1e-5) { nx = 0.0; ny = 0.0; nz = 0.0; }
+        s_nrm[e * 3] = nx; s_nrm[e * 3 + 1] = ny; s_nrm[e * 3 + 2] = nz;
+    }
+    __syncwarp();
+    double rb[CPL][KPT];                                      // row constants in local coordinates: n . c - rb >= 0
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        const int cp = lane + 32 * c, m_cp = cp / 6, i_cp = cp % 6;
+        const bool lsc = cp < NCP && !(m_cp == 0 && i_cp < 3);          // :404
+#pragma unroll
+        for (int j = 0; j < KPT; j++) {
+            rb[c][j] = 0.0;
+            if (!lsc || j >= K) continue;
+            const double* n = s_nrm + (j * M + m_cp) * 3;
+            if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) continue;
+            double b = p.rhs[((size_t) (obs0 + s_act[j]) * M + m_cp) * 6 + i_cp] - (n[0] * s_org[0] + n[1] * s_org[1]);
+            if (D == 3) b -= n[2] * s_org[2];
+            rb[c][j] = b;
+            rmask |= 1ull << (c * KPT + j);
+        }
+    }
+
+    auto expand = [&]() {
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = lane + u * 32;
+            if (v < NV) s_c[v] = full_from_reduced<C>(s_y, s_x0, v / NCP, (v % NCP) / 6, v % 6);
+        }
+    };
+    // full-space gradient of the objective at s_c:  (2 w_c Q) c + terminal terms (traj_optimizer.cpp:294-315)
+    auto grad_full = [&](double* out) {
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = lane + u * 32;
+            if (v >= NV) continue;
+            const int k_v = v / NCP, m_v = (v % NCP) / 6, a = v % 6, v0 = k_v * NCP + m_v * 6;
+            double gr = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; b++) gr += sQ2[a * 6 + b] * s_c[v0 + b];
+            if (a == 5) gr += s_termw[m_v] * (s_c[v0 + 5] - s_goal[k_v]);
+            out[v] = gr;
+        }
+    };
+
+    // ---- unconstrained minimiser y = -H^-1 g and J = L^-T from the table of this agent's terminal-segment count
+    const double* Hinv = p.das_tab + (size_t) (ts - 1) * 2 * N1 * N1;
+    const double* J1 = Hinv + N1 * N1;
+#pragma unroll
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_y[r] = 0.0; }
+    __syncwarp();
+    expand();
+    __syncwarp();
+    grad_full(s_full);
+    __syncwarp();
+    double g0[RPL];
+#pragma unroll
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; g0[t] = r < NR ? reduce_from_full<C>(s_full, r) : 0.0; }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_u[r] = g0[t]; }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < RPL; t++) {
+        const int r = lane + 32 * t;
+        if (r >= NR) continue;
+        int k, r1;
+        das_decode<C>(r, k, r1);
+        double y = 0.0;
+        for (int c1 = 0; c1 < N1; c1++) y -= Hinv[r1 * N1 + c1] * s_u[das_encode<C>(k, c1)];
+        s_y[r] = y;
+        for (int cc = 0; cc < NR; cc++) {
+            int k2, c1;
+            das_decode<C>(cc, k2, c1);
+            s_J[r * LDJ + cc] = (k2 == k) ? J1[r1 * N1 + c1] : 0.0;
+        }
+    }
+    __syncwarp();
+
+    // ---- row evaluation at s_c.  only < 0: every existing row outside the active set, result = the most violated one
+    // (smallest slack in the reference's row scaling: velocity rows carry 5/dt, acceleration rows 20/dt^2) of this lane;
+    // only >= 0: that slot alone; only == -2: nothing.
+    const double wv = 5.0 / p.dt, wa = 20.0 / (p.dt * p.dt);
+    auto sweep = [&](int only, double& best, double& best_raw, int& best_slot) {
+        best = INFINITY; best_raw = 0.0; best_slot = 0;
+        const unsigned long long live = only == -1 ? (rmask & ~amask) : (only >= 0 ? 1ull << only : 0ull);
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int cp = lane + 32 * c;
+            if (cp >= NCP || !((live >> (c * KPT)) & ((1ull << KPT) - 1))) continue;
+            const int m_cp = cp / 6;
+            const double cx = s_c[cp], cy = s_c[NCP + cp], cz = (D == 3) ? s_c[2 * NCP + cp] : 0.0;
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                if (!(live >> (c * KPT + j) & 1ull)) continue;
+                const double* n = s_nrm + (j * M + m_cp) * 3;
+                double q = n[0] * cx + n[1] * cy - rb[c][j];
+                if (D == 3) q += n[2] * cz;
+                if (q < best) { best = q; best_raw = q; best_slot = c * KPT + j; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = lane + u * 32;
+            const unsigned bits = (unsigned) (live >> (A::NLSC + 6 * u)) & 63u;
+            if (v >= NV || !bits) continue;
+            const int k_v = v / NCP, m_v = (v % NCP) / 6;
+            const double* cc = s_c + v;
+            const double c0 = cc[0];
+            double dv = 0.0, da = 0.0;
+            if (bmask[u] & 4u) dv = cc[1] - c0;
+            if (bmask[u] & 16u) da = cc[2] - 2.0 * cc[1] + c0;
+            double q[6];
+            q[0] = c0 - s_lb[k_v * M + m_v]; q[1] = s_ub[k_v * M + m_v] - c0;
+            q[2] = s_vlim[k_v] - dv; q[3] = s_vlim[k_v] + dv; q[4] = s_alim[k_v] - da; q[5] = s_alim[k_v] + da;
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                if (!(bits >> e & 1u)) continue;
+                const double w = e < 2 ? 1.0 : (e < 4 ? wv : wa);
+                if (q[e] * w < best) { best = q[e] * w; best_raw = q[e]; best_slot = A::NLSC + 6 * u + e; }
+            }
+        }
+    };
+
+    // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l
+    // of S becomes zero left of the last column; the new inverse factor is S without row l and without its last column,
+    // and J follows with the same column rotations (its column q-1 thereby returns to J2).
+    int q = 0;                                                // size of the active set
+    auto drop = [&](int l) {
+        const int id = s_ids[l];
+        if (lane == (id & 31)) amask &= ~(1ull << (id >> 5));
+        for (int j = l; j < q - 1; j++) {
+            double* cj = s_S + j * (j + 1) / 2;               // column j: rows 0 .. j (unshifted: row l still present)
+            double* cn = s_S + (j + 1) * (j + 2) / 2;         // column j + 1: rows 0 .. j + 1
+            const double a = cj[l], b = cn[l];
+            const double h = sqrt(a * a + b * b);
+            double cs = 1.0, sn = 0.0;
+            if (h > 0.0) { cs = b / h; sn = a / h; }
+            double xs[RPL], ys[RPL];
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int i = lane + 32 * t;
+                xs[t] = i <= j ? cj[i] : 0.0; ys[t] = i <= j + 1 ? cn[i] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int i = lane + 32 * t;
+                if (i > j + 1) continue;
+                cn[i] = sn * xs[t] + cs * ys[t];                               // stays in place for the next rotation
+                if (i != l) cj[i < l ? i : i - 1] = cs * xs[t] - sn * ys[t];   // final: row l (now zero) removed
+            }
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int r = lane + 32 * t;
+                if (r >= NR) continue;
+                const double x = s_J[r * LDJ + j], yv = s_J[r * LDJ + j + 1];
+                s_J[r * LDJ + j] = cs * x - sn * yv; s_J[r * LDJ + j + 1] = sn * x + cs * yv;
+            }
+            __syncwarp();
+        }
+        double un[RPL]; int idn[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; t++) {
+            const int j = lane + 32 * t;
+            un[t] = (j >= l && j < q) ? s_u[j + 1] : 0.0;     // (u[q] is the multiplier of the row being added)
+            idn[t] = (j >= l && j < q - 1) ? s_ids[j + 1] : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < RPL; t++) {
+            const int j = lane + 32 * t;
+            if (j >= l && j < q) s_u[j] = un[t];
+            if (j >= l && j < q - 1) s_ids[j] = idn[t];
+        }
+        q--;
+        __syncwarp();
+    };
+
+    // ---- main loop
+    int it = 0, why = 5;
+    const int it_max = 4 * NR + 40;
+    bool ok = false;
+    double viol = 0.0;
+    while (true) {
+        expand();
+        __syncwarp();
+        double best, best_raw; int best_slot;
+        sweep(-1, best, best_raw, best_slot);
+        const int lp = warp_argmin(best);
+        const int slot = __shfl_sync(FULL, best_slot, lp);
+        best = __shfl_sync(FULL, best, lp);
+        if (!(best == best)) break;                           // NaN: leave it to the other pass
+        if (!(best < -1e-10)) { ok = true; viol = fmax(0.0, -best); break; }
+        const int pid = slot * 32 + lp;
+        double sp = __shfl_sync(FULL, best_raw, lp);          // slack of the row being added (negative)
+        int pr[9]; double pv[9];
+        das_row_pairs<C>(lp, slot, s_nrm, pr, pv);
+        if (lane == 0) s_u[q] = 0.0;
+        bool fail = false;
+        while (true) {                                         // until row p is added (or the model is found infeasible)
+            if (++it > it_max) { fail = true; why = 3; break; }
+            // d = J'n, z = J2 d2, r = R^-1 d1
+            double d2p = 0.0, dnp = 0.0;
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int k = lane + 32 * t;
+                double d = 0.0;
+                if (k < NR) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) if (pv[i] != 0.0) d += pv[i] * s_J[pr[i] * LDJ + k];
+                    s_d[k] = d;
+                    dnp += d * d;
+                    if (k >= q) d2p += d * d;
+                }
+            }
+            const double d2n = warp_sum(d2p), dn = warp_sum(dnp);   // (the shuffles order the stores of s_d before the reads below)
+            __syncwarp();
+            double zz[RPL];
+#pragma unroll
+            for (int t = 0; t < RPL; t++) zz[t] = 0.0;
+            {
+                double za[RPL], zb[RPL];
+#pragma unroll
+                for (int t = 0; t < RPL; t++) { za[t] = 0.0; zb[t] = 0.0; }
+                int k = q;
+                for (; k + 1 < NR; k += 2) {
+                    const double d0 = s_d[k], d1 = s_d[k + 1];
+#pragma unroll
+                    for (int t = 0; t < RPL; t++) {
+                        const int r = lane + 32 * t;
+                        if (r < NR) { za[t] += s_J[r * LDJ + k] * d0; zb[t] += s_J[r * LDJ + k + 1] * d1; }
+                    }
+                }
+                if (k < NR) {
+                    const double d0 = s_d[k];
+#pragma unroll
+                    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) za[t] += s_J[r * LDJ + k] * d0; }
+                }
+#pragma unroll
+                for (int t = 0; t < RPL; t++) zz[t] = za[t] + zb[t];
+            }
+            {
+                double ra[RPL], rb2[RPL];
+#pragma unroll
+                for (int t = 0; t < RPL; t++) { ra[t] = 0.0; rb2[t] = 0.0; }
+                int k = 0;
+                for (; k + 1 < q; k += 2) {
+                    const double d0 = s_d[k], d1 = s_d[k + 1];
+                    const double* c0 = s_S + k * (k + 1) / 2;
+                    const double* c1 = c0 + k + 1;
+#pragma unroll
+                    for (int t = 0; t < RPL; t++) {
+                        const int j = lane + 32 * t;
+                        if (j <= k) ra[t] += c0[j] * d0;
+                        if (j <= k + 1) rb2[t] += c1[j] * d1;
+                    }
+                }
+                if (k < q) {
+                    const double d0 = s_d[k];
+                    const double* c0 = s_S + k * (k + 1) / 2;
+#pragma unroll
+                    for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j <= k) ra[t] += c0[j] * d0; }
+                }
+#pragma unroll
+                for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j < q) s_rv[j] = ra[t] + rb2[t]; }
+            }
+            __syncwarp();
+            // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible
+            double t1 = INFINITY; int l = 0x7fffffff;
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int j = lane + 32 * t;
+                if (j < q && s_rv[j] > 0.0) { const double ra = s_u[j] / s_rv[j]; if (ra < t1) { t1 = ra; l = j; } }
+            }
+            {
+                const int wl = warp_argmin(t1);
+                t1 = __shfl_sync(FULL, t1, wl);
+                l = __shfl_sync(FULL, l, wl);
+            }
+            const bool dependent = !(d2n > 1e-24 * dn) || q >= NR;      // n in the span of the active normals: no primal step
+            const double t2 = dependent ? INFINITY : -sp / d2n;
+            const double tt = fmin(t1, t2);
+            if (tt == INFINITY) { fail = true; why = 4; break; }         // infeasible (or numerically so): the other pass decides
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                const int j = lane + 32 * t;
+                if (!dependent && j < NR) s_y[j] += tt * zz[t];
+                if (j < q) s_u[j] -= tt * s_rv[j];
+            }
+            if (lane == 0) s_u[q] += tt;
+            __syncwarp();
+            if (t2 <= t1) {
+                // full step: row p joins the active set.  One Householder reflection (I - beta v v') with v = d2 + sign ||d2|| e1
+                // maps d2 onto a multiple of e1; J2 <- J2 (I - beta v v') with J2 v = z + (v0 - d_q) J(:, q).
+                const double dq = s_d[q], nr2 = sqrt(d2n), sg = dq >= 0.0 ? 1.0 : -1.0;
+                const double v0 = dq + sg * nr2, beta = 1.0 / (nr2 * (nr2 + fabs(dq)));
+#pragma unroll
+                for (int t = 0; t < RPL; t++) {
+                    const int r = lane + 32 * t;
+                    if (r < NR) s_z[r] = beta * (zz[t] + (v0 - dq) * s_J[r * LDJ + q]);
+                }
+                __syncwarp();
+                for (int kb = q; kb < NR; kb += 32) {            // lane = column of J2, loop over the rows
+                    const int k = kb + lane;
+                    if (k >= NR) continue;
+                    const double vk = k == q ? v0 : s_d[k];
+                    double* jc = s_J + k;
+#pragma unroll 3
+                    for (int r = 0; r < NR; r++) jc[r * LDJ] -= s_z[r] * vk;
+                }
+                // R gains the column (d1; rho), rho = -sign ||d2||:  S gains (-S d1 / rho; 1 / rho) = (-r / rho; 1 / rho)
+                const double rinv = -sg / nr2;
+                double* cq = s_S + q * (q + 1) / 2;
+#pragma unroll
+                for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j < q) cq[j] = -s_rv[j] * rinv; }
+                if (lane == 0) { cq[q] = rinv; s_ids[q] = pid; }
+                if (lane == lp) amask |= 1ull << slot;
+                q++;
+                __syncwarp();
+                break;
+            }
+            // partial step: the multiplier of active row l reached zero before row p became feasible
+            drop(l);
+            if (!dependent) {
+                expand();
+                __syncwarp();
+                double b2, raw2; int s2;
+                sweep(lane == lp ? slot : -2, b2, raw2, s2);     // (-2: the other lanes evaluate nothing)
+                sp = __shfl_sync(FULL, raw2, lp);
+                if (!(sp < 0.0)) sp = -1e-300;                   // (rounding: the step length was t1 < t2)
+            }
+        }
+        if (fail) break;
+    }
+    if (!ok) { defer(why); return; }
+
+    // ---- verification and outputs.  s_c holds the final point; stationarity Z'(grad f - sum u_j n_j) from scratch
+    // (J is dead: its storage is the full-space scratch).
+    __syncwarp();
+    grad_full(s_full);
+    __syncwarp();
+    double gscale = 0.0;
+#pragma unroll
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) gscale = fmax(gscale, fabs(reduce_from_full<C>(s_full, r))); }
+    for (int j = 0; j < q; j++) {                             // one active row at a time: its <= 3 full-space entries
+        const int id = s_ids[j];
+        int fk[3], fcp[3]; double fa[3];
+        das_row_full<C>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
+        const double uj = s_u[j];
+#pragma unroll
+        for (int t = 0; t < 3; t++) if (lane == t && fa[t] != 0.0) s_full[fk[t] * NCP + fcp[t]] -= uj * fa[t];
+        __syncwarp();
+    }
+    double rd = 0.0, umin = 0.0;
+#pragma unroll
+    for (int t = 0; t < RPL; t++) {
+        const int r = lane + 32 * t;
+        if (r < NR) rd = fmax(rd, fabs(reduce_from_full<C>(s_full, r)));
+        if (r < q) umin = fmin(umin, s_u[r]);
+    }
+    rd = warp_max(rd); gscale = warp_max(gscale); umin = warp_min(umin);
+#ifdef LSCQP_CUDA_EMUL
+    if (lane == 0 && getenv("LSCQP_DAS_DEBUG")) fprintf(stderr, "das agent %d: it %d q %d rd %.3e gscale %.3e umin %.3e\n", agent, it, q, rd, gscale, umin);
+#endif
+    if (!(rd <= 1e-7 * fmax(1.0, gscale)) || !(umin >= -1e-9 * fmax(1.0, gscale))) { defer(6); return; }
+
+    double cost = 0.0;
+#pragma unroll
+    for (int u = 0; u < VPT; u++) {
+        const int v = lane + u * 32;
+        if (v >= NV) continue;
+        // objective x'Px + q'x + c0 with P = w_c Q (no 1/2, traj_optimizer.cpp:294) + terminal terms (:301-315)
+        const int k_v = v / NCP, m_v = (v % NCP) / 6, i_v = v % 6, v0 = k_v * NCP + m_v * 6;
+        double qc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) qc += sQ2[i_v * 6 + b] * s_c[v0 + b];
+        cost += 0.5 * s_c[v] * qc;
+        if (i_v == 5) { const double e = s_c[v] - s_goal[k_v]; cost += 0.5 * s_termw[m_v] * e * e; }
+        p.ctrl_out[(size_t) agent * NV + v] = s_c[v] + s_org[k_v];
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) {
+        p.cost_out[agent] = cost;
+        p.status_out[agent] = ST_OK;
+        p.klass[agent] = 0;
+        if (p.iters_out) p.iters_out[agent] = it;
+        if (p.kkt_out) {
+            p.kkt_out[agent * 4 + 0] = rd; p.kkt_out[agent * 4 + 1] = viol;
+            p.kkt_out[agent * 4 + 2] = 0.0; p.kkt_out[agent * 4 + 3] = 0.0;
+        }
+    }
+    if (p.dual_out) {
+        // layout of pdip_kernel.cuh: [KRAW][M][6] LSC rows, then [NV][6] box rows in the reference's row scaling
+        double* du = p.dual_out + (size_t) agent * p.dual_stride;
+        for (int e = lane; e < p.dual_stride; e += 32) du[e] = 0.0;
+        __syncwarp();
+        const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
+        for (int j = lane; j < q; j += 32) {
+            const int id = s_ids[j], lo = id & 31, slot = id >> 5;
+            if (slot < A::NLSC) {
+                const int cp = lo + 32 * (slot / KPT);
+                du[(s_act[slot % KPT] * M + cp / 6) * 6 + cp % 6] = s_u[j];
+            } else {
+                const int b = slot - A::NLSC, e = b % 6, v = lo + 32 * (b / 6);
+                du[A::KRAW * M * 6 + v * 6 + e] = s_u[j] * (e < 2 ? 1.0 : (e < 4 ? sv : sa));
+            }
+        }
+    }
+}
+
+}  // namespace lscqp

@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../include/lscqp.h"
 #include "pdip_kernel.cuh"
+#include "das_kernel.cuh"
 
 namespace lscqp {
 
@@ -182,6 +183,65 @@ inline ProjTable build_projection(int nt = C::NT) {
     return out;
 }
 
+// Table of the dual active-set first pass (das_kernel.cuh).  The reduced Hessian of the objective is the same for every
+// agent up to the number of terminal segments ts (traj_optimizer.cpp:301-315, :530-538) and block diagonal over the
+// dimensions: H1(ts) = Z1' (blkdiag_m 2 w_c Q_base + 2 w_t e5 e5' for m >= M - ts) Z1 with Z1 the continuity map of one
+// dimension.  For ts = 1..M: [N1][N1] H1^-1, then [N1][N1] J = L^-T (H1 = L L').  Empty when a factorisation fails.
+template <class C>
+inline std::vector<double> build_das_table(const double* Q2, double w_t) {
+    constexpr int M = C::M, N1 = C::NR / C::D, NF = 6 * M;
+    static const double T[3][3] = {{0, 0, 1}, {0, -1, 2}, {1, -4, 4}};
+    std::vector<double> Z((size_t) NF * N1, 0.0);
+    for (int m = 0; m < M; m++)
+        for (int i = 0; i < 6; i++) {
+            const int f = m * 6 + i;
+            if (i >= 3) Z[(size_t) f * N1 + ((C::TERM && m == M - 1) ? 3 * (M - 1) : 3 * m + i - 3)] = 1.0;
+            else if (m >= 1) for (int j = 0; j < 3; j++) Z[(size_t) f * N1 + 3 * (m - 1) + j] = T[i][j];
+        }
+    std::vector<double> out((size_t) M * 2 * N1 * N1, 0.0);
+    for (int ts = 1; ts <= M; ts++) {
+        std::vector<double> P((size_t) NF * NF, 0.0), PZ((size_t) NF * N1, 0.0), H((size_t) N1 * N1, 0.0);
+        for (int m = 0; m < M; m++) {
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) P[(size_t) (m * 6 + a) * NF + m * 6 + b] = Q2[a * 6 + b];
+            if (m >= M - ts) P[(size_t) (m * 6 + 5) * NF + m * 6 + 5] += 2.0 * w_t;
+        }
+        for (int f = 0; f < NF; f++) for (int r = 0; r < N1; r++) {
+            double a = 0; for (int g = 0; g < NF; g++) a += P[(size_t) f * NF + g] * Z[(size_t) g * N1 + r];
+            PZ[(size_t) f * N1 + r] = a;
+        }
+        for (int r = 0; r < N1; r++) for (int c = 0; c < N1; c++) {
+            double a = 0; for (int f = 0; f < NF; f++) a += Z[(size_t) f * N1 + r] * PZ[(size_t) f * N1 + c];
+            H[(size_t) r * N1 + c] = a;
+        }
+        std::vector<double> L((size_t) N1 * N1, 0.0), Li((size_t) N1 * N1, 0.0);
+        for (int j = 0; j < N1; j++) {
+            double d = 0.5 * (H[(size_t) j * N1 + j] + H[(size_t) j * N1 + j]);
+            for (int k = 0; k < j; k++) d -= L[(size_t) j * N1 + k] * L[(size_t) j * N1 + k];
+            if (!(d > 0.0)) return {};
+            L[(size_t) j * N1 + j] = std::sqrt(d);
+            for (int i = j + 1; i < N1; i++) {
+                double a = 0.5 * (H[(size_t) i * N1 + j] + H[(size_t) j * N1 + i]);
+                for (int k = 0; k < j; k++) a -= L[(size_t) i * N1 + k] * L[(size_t) j * N1 + k];
+                L[(size_t) i * N1 + j] = a / L[(size_t) j * N1 + j];
+            }
+        }
+        for (int c = 0; c < N1; c++)                       // L Li = I, column by column (forward substitution)
+            for (int i = c; i < N1; i++) {
+                double a = (i == c) ? 1.0 : 0.0;
+                for (int k = c; k < i; k++) a -= L[(size_t) i * N1 + k] * Li[(size_t) k * N1 + c];
+                Li[(size_t) i * N1 + c] = a / L[(size_t) i * N1 + i];
+            }
+        double* Hinv = out.data() + (size_t) (ts - 1) * 2 * N1 * N1;
+        double* J = Hinv + (size_t) N1 * N1;
+        for (int r = 0; r < N1; r++) for (int c = 0; c < N1; c++) {
+            J[(size_t) r * N1 + c] = Li[(size_t) c * N1 + r];                       // J = Li'
+            double a = 0; for (int k = 0; k < N1; k++) a += Li[(size_t) k * N1 + r] * Li[(size_t) k * N1 + c];
+            Hinv[(size_t) r * N1 + c] = a;                                           // H^-1 = Li' Li
+        }
+    }
+    return out;
+}
+
 // Light instances (two-pass dispatch, SolveParams::klass_mode): one obstacle group, LSCQP_LIGHT_KPT kept obstacles at
 // most, a quarter of the threads -- so the serial factorisation of one QP overlaps the row sweeps of many others on the
 // same SM.  Agents whose presolve keeps more obstacles fall through to the full-capacity instance.
@@ -196,6 +256,8 @@ struct Instance {
     using Full = Cfg<M_, D_, T_, 4, 10, COMM_>;
     using Light = Cfg<M_, D_, T_, LSCQP_LIGHT_G, LSCQP_LIGHT_KPT, false>;
     static constexpr bool HAS_LIGHT = !COMM_;
+    // dual active-set first pass (das_kernel.cuh): banded models of at most 64 reduced variables (two per lane)
+    static constexpr bool HAS_DAS = !COMM_ && Full::NR <= 64;
     // Communication-range configurations with few neighbours (the shipped 10-agent missions: K <= 9): half the threads
     // (2 obstacle groups x 5 rows), so twice as many CTAs share an SM while the dense factorisation of each runs.
     // Only where one variable per thread and one comm pair per thread still fit.

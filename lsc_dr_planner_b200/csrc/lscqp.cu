@@ -54,6 +54,8 @@ struct lscqp_handle {
     DevBuf d_own, d_ameta, d_index;
     DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout, d_knn;
     bool two_pass = false, last_two_pass = false;
+    bool das = false;                   // dual active-set first pass available and enabled (das_kernel.cuh)
+    DevBuf d_das;
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
@@ -96,6 +98,17 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
     if (cfg->presolve & 4) h->two_pass_min = 0;            // light first pass at any batch size
     if (const char* e = std::getenv("LSCQP_TWO_PASS_MIN")) h->two_pass_min = std::atoi(e);
     if (const char* e = std::getenv("LSCQP_ASM_SPLIT_MIN")) h->asm_split_min = std::atoi(e);
+    // dual active-set first pass: every banded configuration it is instantiated for, unless switched off (presolve bit 8,
+    // LSCQP_DAS=0: the interior-point instances alone, as before)
+    h->das = info.has_das && !(cfg->presolve & 8);
+    if (const char* e = std::getenv("LSCQP_DAS")) h->das = h->das && std::atoi(e) != 0;
+    if (h->das) {
+        if (h->d_das.reserve(info.das_tab.size() * sizeof(double)) ||
+            cudaMemcpy(h->d_das.p, info.das_tab.data(), info.das_tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete h; return fail(LSCQP_E_CUDA, "active-set table upload failed");
+        }
+        h->base.das_tab = h->d_das.as<double>();
+    }
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
     if (h->d_proj_ent.reserve(tab.term.size() * sizeof(ProjTerm)) || h->d_proj_term.reserve((tabl.term.size() + 1) * sizeof(ProjTerm)) ||
@@ -120,7 +133,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes, &h->d_work};
+                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes, &h->d_work, &h->d_das};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -150,7 +163,10 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // The light first pass pays off in the throughput regime (several waves of one-warp CTAs); a small batch is
     // latency bound and finishes sooner on the 128-thread instance alone.
-    const bool two_pass = h->two_pass && n_agents >= h->two_pass_min;
+    // first pass: the dual active-set kernel when available (any batch size: its per-QP latency is below that of the
+    // 128-thread interior-point instance), else the light interior-point instance in the throughput regime
+    const int first_pass = h->das ? 2 : ((h->two_pass && n_agents >= h->two_pass_min) ? 1 : 0);
+    const bool two_pass = first_pass != 0;
     h->last_two_pass = two_pass;
     if (two_pass) {
         if (h->d_klass.reserve((size_t) n_agents * sizeof(int))) return fail(LSCQP_E_CUDA, "cudaMalloc failed");
@@ -158,11 +174,11 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
         // (routing the remainder of the light pass's last round to the full-capacity pass was measured: 1.65 vs 1.52 ms
         //  per 4096 QPs -- the QPs' durations spread over 8..11 iterations, so the rounds do not end together)
     }
-    int launched = inst_launch_0(h->cfg, p, n_agents, two_pass, st);
-    if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, two_pass, st);
-    if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, two_pass, st);
-    if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, two_pass, st);
-    if (!launched) launched = inst_launch_4(h->cfg, p, n_agents, two_pass, st);
+    int launched = inst_launch_0(h->cfg, p, n_agents, first_pass, st);
+    if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, first_pass, st);
+    if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, first_pass, st);
+    if (!launched) launched = inst_launch_3(h->cfg, p, n_agents, first_pass, st);
+    if (!launched) launched = inst_launch_4(h->cfg, p, n_agents, first_pass, st);
     h->launches += launched;
     CK(cudaGetLastError());
     return 0;

@@ -93,6 +93,9 @@ struct SolveParams {
     // instance then runs with klass_mode 2 and solves only the flagged agents.  0: solve every agent.
     int*    klass;              // [n]
     int     klass_mode;
+    // dual active-set first pass (das_kernel.cuh): per terminal-segment count ts = 1..M the inverse reduced Hessian of one
+    // dimension and its inverse Cholesky factor, [M][2][N1][N1] (host_common.hpp:build_das_table)
+    const double* das_tab;
 };
 
 enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3, ST_CAPACITY = 4 };

@@ -8,7 +8,8 @@ namespace lscqp {
 
 struct InstanceInfo {
     int dual_stride = 0, kmax = 0, nv = 0;
-    bool has_light = false;
+    bool has_light = false, has_das = false;
+    std::vector<double> das_tab;   // host_common.hpp:build_das_table (empty: no dual active-set pass)
     ProjTable tab, tab_light;      // projection term streams of the full-capacity / light instance
 };
 
@@ -19,12 +20,14 @@ int inst_query_1(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_2(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_3(const lscqp_config& cfg, InstanceInfo* info);
 int inst_query_4(const lscqp_config& cfg, InstanceInfo* info);
-// Launches the instance (light pass first when two_pass); returns the number of kernels launched, 0 when not here.
-int inst_launch_0(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
-int inst_launch_1(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
-int inst_launch_2(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
-int inst_launch_3(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
-int inst_launch_4(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st);
+// Launches the instance; first_pass 0: the full-capacity interior-point instance alone, 1: the light interior-point
+// instance first, 2: the dual active-set kernel first (the full-capacity instance then solves only the agents the first
+// pass flagged).  Returns the number of kernels launched, 0 when the instance lives elsewhere.
+int inst_launch_0(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st);
+int inst_launch_1(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st);
+int inst_launch_2(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st);
+int inst_launch_3(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st);
+int inst_launch_4(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st);
 
 #ifdef LSCQP_TU
 #if LSCQP_TU == 0
@@ -48,6 +51,10 @@ template <class C>
 static int set_smem_attr() {
     return cudaFuncSetAttribute(pdip_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess ? 0 : -1;
 }
+template <class C>
+static int set_smem_attr_das() {
+    return cudaFuncSetAttribute(das_solve_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Das<C>::SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
 
 int LSCQP_TU_NAME(inst_query)(const lscqp_config& cfg, InstanceInfo* info) {
     const bool term = cfg.planner_mode == LSCQP_MODE_LSC, comm = cfg.comm_range > 0;
@@ -64,6 +71,13 @@ int LSCQP_TU_NAME(inst_query)(const lscqp_config& cfg, InstanceInfo* info) {
         if (I::HAS_COMPACT && cfg.max_obs <= I::COMPACT_KMAX)                       \
             info->tab = build_projection<typename I::Compact>();                    \
         if (I::HAS_LIGHT) info->tab_light = build_projection<C>(I::Light::NT);      \
+        if constexpr (I::HAS_DAS) {                                                 \
+            SolveParams sp;                                                         \
+            fill_solve_params(cfg, sp);                                             \
+            info->das_tab = build_das_table<C>(sp.Q2, cfg.w_terminal);              \
+            info->has_das = !info->das_tab.empty();                                 \
+            if (info->has_das && set_smem_attr_das<C>()) return -1;                 \
+        }                                                                           \
         return 1;                                                                   \
     }
     LSCQP_TU_INSTANCES(X)
@@ -71,7 +85,7 @@ int LSCQP_TU_NAME(inst_query)(const lscqp_config& cfg, InstanceInfo* info) {
     return 0;
 }
 
-int LSCQP_TU_NAME(inst_launch)(const lscqp_config& cfg, SolveParams& p, int n_agents, bool two_pass, cudaStream_t st) {
+int LSCQP_TU_NAME(inst_launch)(const lscqp_config& cfg, SolveParams& p, int n_agents, int first_pass, cudaStream_t st) {
     const bool term = cfg.planner_mode == LSCQP_MODE_LSC, comm = cfg.comm_range > 0;
 #define X(M_, D_, T_, C_)                                                           \
     if (cfg.M == M_ && cfg.dim == D_ && term == T_ && comm == C_) {                 \
@@ -84,7 +98,15 @@ int LSCQP_TU_NAME(inst_launch)(const lscqp_config& cfg, SolveParams& p, int n_ag
             pdip_solve_kernel<K><<<n_agents, K::NT, K::SMEM_BYTES, st>>>(p);        \
             return launched;                                                        \
         }                                                                           \
-        if (I::HAS_LIGHT && two_pass) {                                             \
+        if constexpr (I::HAS_DAS) {                                                 \
+            if (first_pass == 2) {                                                  \
+                p.klass_mode = 1;                                                   \
+                das_solve_kernel<C><<<n_agents, 32, Das<C>::SMEM_BYTES, st>>>(p);   \
+                p.klass_mode = 2;                                                   \
+                launched = 2;                                                       \
+            }                                                                       \
+        }                                                                           \
+        if (I::HAS_LIGHT && first_pass == 1) {                                      \
             using L = typename I::Light;                                            \
             p.klass_mode = 1;                                                       \
             pdip_solve_kernel<L><<<n_agents, L::NT, L::SMEM_BYTES, st>>>(p);        \

@@ -146,6 +146,18 @@ inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); r
 inline float __fdividef(float a, float b) { return a / b; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
+inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = (double) v;
+    __syncwarp();
+    const int w0 = s.cur & ~31, wn = std::min(32, s.nthreads - w0);
+    double r = s.slot_d[w0];
+    for (int i = 1; i < wn; i++) r = std::min(r, s.slot_d[w0 + i]);
+    __syncwarp();
+    return (unsigned) r;
+}
 #undef __launch_bounds__
 #define __launch_bounds__(...)
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

@@ -1,3 +1,4 @@
+#include <cstdio>
 // tests/cuda_emul/emul_pdip.cpp -- runs the unmodified PDIP kernel source on the CPU emulator.
 // TEST INFRASTRUCTURE ONLY (see cuda_emul.h).  Built by tests/cuda_emul/build.sh with g++.
 #define CUDA_EMUL_IMPL
@@ -14,6 +15,8 @@ using namespace lscqp;
 
 extern "C" int emul_dual_stride(int M, int D, int comm) { return 40 * M * 6 + D * M * 6 * 6 + (comm ? 2 * D * (M * (M - 1) / 2 + M) : 0); }
 
+static int g_emul_das_solved = -1;      // agents the dual active-set pass solved in the last emul_solve_batch (-1: it did not run)
+extern "C" int emul_das_solved() { return g_emul_das_solved; }
 extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
                                 const float* state, const float* goal, const double* limits, const float* sfc,
                                 const float* next_waypoint, const int* obs_offsets, const double* normals, const double* rhs,
@@ -28,6 +31,7 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
     p.obs_offsets = obs_offsets; p.normals = normals; p.rhs = rhs; p.warm_traj = initial_traj;
     p.ctrl_out = ctrl_out; p.cost_out = cost_out; p.status_out = status_out; p.iters_out = iters_out;
     p.kkt_out = kkt_out; p.dual_out = dual_out;
+    g_emul_das_solved = -1;
     const bool term = cfg->planner_mode == LSCQP_MODE_LSC;
     const bool comm = cfg->comm_range > 0;
 #define X(M_, D_, T_, C_)                                                                   \
@@ -47,7 +51,16 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
             return 0;                                                                       \
         }                                                                                   \
         std::vector<int> klass(n_agents + 1, 0);                                            \
-        if (I::HAS_LIGHT && (cfg->presolve & 1) && !(cfg->presolve & 2)) {                  \
+        const std::vector<double> dtab = I::HAS_DAS ? build_das_table<C>(p.Q2, cfg->w_terminal) : std::vector<double>(); \
+        if (I::HAS_DAS && !dtab.empty() && !(cfg->presolve & 8) && !std::getenv("LSCQP_DAS_OFF")) { \
+            p.das_tab = dtab.data();                                                        \
+            p.klass = klass.data(); p.klass_mode = 1;                                       \
+            emu::launch(n_agents, 32, Das<C>::SMEM_BYTES, [&]() { das_solve_kernel<C>(p); }); \
+            g_emul_das_solved = 0;                                                          \
+            for (int a = 0; a < n_agents; a++) g_emul_das_solved += klass[a] == 0;          \
+            if (std::getenv("LSCQP_DAS_DEBUG")) for (int a = 0; a < n_agents; a++) if (klass[a]) fprintf(stderr, "das: agent %d deferred, reason %d\n", a, klass[a]); \
+            p.klass_mode = 2;                                                               \
+        } else if (I::HAS_LIGHT && (cfg->presolve & 1) && !(cfg->presolve & 2)) {           \
             using L = typename I::Light;                                                    \
             p.klass = klass.data(); p.klass_mode = 1;                                       \
             emu::launch(n_agents, L::NT, L::SMEM_BYTES, [&]() { pdip_solve_kernel<L>(p); }); \

@@ -56,11 +56,17 @@ def _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, 
     return np.array(errs)
 
 
+PDIP_ONLY = 9          # lscqp_config.presolve: presolve on (bit 0), dual active-set first pass off (bit 3)
+
+
+@pytest.mark.parametrize("solver", ["das", "pdip"])
 @pytest.mark.parametrize("M,dim,mode,K", [(5, 3, capi.MODE_LSC, 40), (5, 3, capi.MODE_DLSC, 40), (10, 2, capi.MODE_LSC, 9),
                                           (5, 2, capi.MODE_LSC, 12), (10, 3, capi.MODE_DLSC, 40), (5, 3, capi.MODE_BVC, 7)])
-def test_solve_parity_real_rule(M, dim, mode, K):
-    """config 2 shape (and the launch-file shape M=10/D=2): oracle-generated planes, GPU solve vs oracle optimum"""
-    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode)
+def test_solve_parity_real_rule(M, dim, mode, K, solver):
+    """config 2 shape (and the launch-file shape M=10/D=2): oracle-generated planes, GPU solve vs oracle optimum; once
+    through the default dispatch (dual active-set first pass, interior point for what it defers) and once through the
+    interior-point instances alone"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode, presolve=1 if solver == "das" else PDIP_ONLY)
     batch = W.make_forest_batch(64, K=K, cfg=cfg)
     agents = list(range(0, 64, 4))
     gen = orc.GEN_BVC if mode == capi.MODE_BVC else orc.GEN_LSC
@@ -69,13 +75,15 @@ def test_solve_parity_real_rule(M, dim, mode, K):
     ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
     errs = _check_against_oracle(batch, agents, off, normals, rhs, ctrl, cost, status, min_checked=8)
     assert np.median(errs) < 1e-7
-    assert iters.max() < 40
+    # interior point: a few dozen iterations at most; active set: one row enters or leaves per iteration, capped at 4 NR + 40
+    assert iters.max() < (40 if solver == "pdip" else 4 * dim * 3 * M + 40)
 
 
 @pytest.mark.parametrize("M,dim,mode,K", [(5, 3, capi.MODE_LSC, 40), (10, 2, capi.MODE_LSC, 9), (5, 3, capi.MODE_DLSC, 24)])
 def test_warm_start_parity(M, dim, mode, K):
-    """initial_traj as the solver's starting point: same optimum, fewer iterations than the cold start"""
-    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode)
+    """initial_traj as the interior-point solver's starting point: same optimum, fewer iterations than the cold start
+    (the dual active-set pass starts from the unconstrained minimiser and ignores it: switched off here)"""
+    cfg = W.PlannerConfig(M=M, dim=dim, planner_mode=mode, presolve=PDIP_ONLY)
     batch = W.make_forest_batch(64, K=K, cfg=cfg)
     agents = list(range(1, 64, 4))
     off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
@@ -570,46 +578,53 @@ def test_validate_batch_gpu():
 
 
 def test_light_and_full_instances_agree_at_full_size():
-    """BASELINE's 4096-agent batch: the two-pass dispatch (one-warp light instance first) and the one-pass full-capacity
-    instance return the same solutions, statuses and (to the last iterations' noise) objective values"""
+    """BASELINE's 4096-agent batch: the interior-point two-pass dispatch (one-warp light instance first), the one-pass
+    full-capacity instance and the default dispatch (dual active-set first pass) return the same solutions, statuses and
+    (to the last iterations' noise) objective values"""
     import copy
     import torch
     batch = W.make_forest_batch(4096, K=40)
     outs = []
-    for presolve in (1, 3):                                  # 3 = presolve on, light instances off
+    for presolve in (9, 11, 1):                              # 9 = light + full, 11 = full only, 1 = default (active set first)
         cfg = copy.copy(batch.cfg); cfg.presolve = presolve
         planner = _planner(cfg)
         d = planner.upload(batch)
         planner.replan_device(d)
         torch.cuda.synchronize()
         outs.append((d.ctrl.clone(), d.status.clone(), d.cost.clone(), d.iters.clone()))
-    (c1, s1, f1, i1), (c3, s3, f3, i3) = outs
-    assert int((s1 != 0).sum()) == 0 and int((s3 != 0).sum()) == 0
+    (c1, s1, f1, i1), (c3, s3, f3, i3), (ca, sa, fa, ia) = outs
+    assert int((s1 != 0).sum()) == 0 and int((s3 != 0).sum()) == 0 and int((sa != 0).sum()) == 0
+    assert float((ca - c3).abs().max()) < 2e-6
+    assert float(((fa - f3).abs() / f3.abs().clamp(min=1.0)).max()) < 1e-8
     assert float((c1 - c3).abs().max()) < 2e-6
     assert float(((f1 - f3).abs() / f3.abs().clamp(min=1.0)).max()) < 1e-8
     assert abs(float(i1.float().mean()) - float(i3.float().mean())) < 0.2
 
 
-def test_bench_batch_light_instance_and_pruned_assembly_against_oracle():
+@pytest.mark.parametrize("solver", ["das", "pdip"])
+def test_bench_batch_light_instance_and_pruned_assembly_against_oracle(solver):
     """The kernels the bench number is made of, against the oracle on hardware: BASELINE's 4096-agent batch through the
-    fused pruned assembly and the two-pass solve; 64 sampled agents that the one-warp *light* instance solved
+    fused pruned assembly and the two-pass solve; 64 sampled agents that the first pass solved -- the dual active-set
+    kernel of the default dispatch ("das"), or the one-warp *light* interior-point instance with it switched off ("pdip")
     (lscqp_last_instances) are compared with the oracle's optimum of the reference's full model (all 40 obstacles, all
     rows) at 1e-5 m, and their pruned planes with the oracle's planes: a kept (obstacle, segment) pair carries the
     reference's normal (<= 1 float ulp) and constants, a dropped pair (zero normal) is strictly inactive at the optimum."""
     import torch
     batch = W.make_forest_batch(4096, K=40)
+    if solver == "pdip":
+        batch.cfg.presolve = PDIP_ONLY
     planner = _planner(batch.cfg)
     d = planner.upload(batch)
     planner.replan_device(d)
     torch.cuda.synchronize()
     klass = planner.qp.last_instances(4096)
-    assert (klass == 0).mean() > 0.9                          # the light instance is what the bench measures
+    assert (klass == 0).mean() > 0.9                          # the first pass is what the bench measures
     status = d.status.cpu().numpy(); ctrl = d.ctrl.cpu().numpy(); cost = d.cost.cpu().numpy()
     normals_d = d.normals.cpu().numpy(); rhs_d = d.rhs.cpu().numpy()
     assert (status == 0).all()
     rng = np.random.default_rng(64)
     agents = [int(a) for a in rng.choice(np.where(klass == 0)[0], 64, replace=False)]
-    agents += [int(a) for a in np.where(klass == 1)[0][:4]]   # and a few the full-capacity pass took over
+    agents += [int(a) for a in np.where(klass != 0)[0][:4]]   # and a few the full-capacity pass took over
     off, normals, rhs = oracle_planes(batch, agents, orc.GEN_LSC)
     errs = _check_against_oracle(batch, agents, off, normals, rhs, ctrl[agents], cost[agents], status[agents], min_checked=60)
     print("light-instance parity: max |ctrl - oracle| = %.2e, median %.2e over %d agents" % (errs.max(), np.median(errs), len(errs)))
