@@ -7,23 +7,27 @@
 //     diagonal over the dimensions and has one value per number of terminal segments (traj_optimizer.cpp:530-538), so its
 //     inverse and the inverse Cholesky factor J = L^-T come from a host-built table (host_common.hpp:build_das_tables).
 //   * Start at the unconstrained minimiser y = -H^-1 g.  Each iteration evaluates every row q_r(c) >= 0 at the current
-//     point (no per-row state: the rows are recomputed from the control points), takes the most violated one, and moves
-//     along z = J2 J2' n in the primal / r = R^-1 J1' n in the dual space until the row is satisfied (add it to the active
-//     set: one Householder reflection on J2, one new column of S = R^-1 -- the inverse factor is what is stored, so r is
-//     a lane-parallel matrix-vector product instead of a sequential back-substitution) or a multiplier reaches zero
-//     (drop that row: Givens rotations on the columns of S and J).  On the trajectory QPs of the forest workload 13-30 rows end up active (of 39 variables) and almost
-//     every iteration is an add: ~23 iterations of ~40 flops per lane instead of ~9 interior-point iterations of a
-//     full row sweep x4 + factorisation.
+//     point (no per-row state: the rows are recomputed from the control points), takes the most violated one (normal n)
+//     and moves along z = (H^-1 - J1 J1') n in the primal / r = S J1' n in the dual space, where the columns of J1 are
+//     H-orthonormal and span H^-1 x the active normals and S = R^-1 is the inverse of their triangular factor
+//     (J1' N = R).  Either the row becomes feasible -- it joins the active set: J1 gains the column z / sqrt(n'z), S
+//     the column (-r, 1) / sqrt(n'z) -- or a multiplier reaches zero first: that row leaves (Givens rotations on the
+//     columns of S and J1).  Only J1 is stored (the complement J2 of the textbook method never is: J2 J2' = H^-1 - J1 J1'),
+//     the dual direction is a lane-parallel product with the stored inverse factor, and lane j owns active row j.
+//     On the trajectory QPs of the forest workload 13-30 rows end up active (of 39 variables) and almost every
+//     iteration is an add: ~24 iterations of a row sweep and a few short dot products, instead of ~9 interior-point
+//     iterations of four row sweeps, a Hessian assembly, a factorisation and two solves.
 //   * The result is checked before it is accepted: primal feasibility of every row at the returned point (the loop's
-//     exit test), multipliers >= 0 (invariant of the method), stationarity recomputed from scratch.  Anything else --
-//     more kept obstacles than this kernel holds, an iteration cap, a dependent / infeasible row, a stationarity residual
-//     above tolerance -- flags the agent in klass[] and leaves it to the interior-point pass (pdip_kernel.cuh, klass_mode 2).
+//     exit test; the active rows, which the method keeps at zero only up to rounding, are re-evaluated too), multipliers
+//     >= 0 (invariant of the method), stationarity recomputed from scratch.  Anything else -- more kept obstacles or
+//     active rows than this kernel holds, an iteration cap, an infeasible row, a residual above tolerance -- flags the
+//     agent in klass[] and leaves it to the interior-point pass (pdip_kernel.cuh, klass_mode 2).
 // One warp per agent, 32 threads per CTA, no CTA barrier, no atomics: results are bit-reproducible.
 #pragma once
 #include "pdip_kernel.cuh"
 
 #ifndef LSCQP_DAS_MINCTAS
-#define LSCQP_DAS_MINCTAS 9
+#define LSCQP_DAS_MINCTAS 12
 #endif
 
 namespace lscqp {
@@ -38,13 +42,13 @@ struct Das {
     static constexpr int KPT = 10;                          // kept obstacles this kernel holds
     static constexpr int NLSC = CPL * KPT;                  // row slots of a lane: LSC rows first, then 6 per variable
     static constexpr int NSLOT = NLSC + VPT * 6;
-    static constexpr int LDJ = NR | 1;
+    static constexpr int QMAX = 32;                         // active rows this kernel holds (one lane each)
+    static constexpr int LDJ = QMAX + 1;
     static constexpr int KRAW = C::KRAW;
     static_assert(NSLOT <= 64, "row slots do not fit the 64-bit masks");
-    static_assert(NR * (NR | 1) >= NV, "full-space scratch does not fit under J");
+    static_assert(NR * LDJ >= NV, "full-space scratch does not fit under J1");
     // shared memory (doubles)
-    static constexpr int O_Q2 = 0;
-    static constexpr int O_C = O_Q2 + 36;
+    static constexpr int O_C = 0;
     static constexpr int O_Y = O_C + NV;
     static constexpr int O_X0 = O_Y + NR;
     static constexpr int O_VLIM = O_X0 + 3 * D;
@@ -55,14 +59,11 @@ struct Das {
     static constexpr int O_UB = O_LB + D * M;
     static constexpr int O_TERMW = O_UB + D * M;            // [M] terminal weights, [M] the number of terminal segments
     static constexpr int O_NRM = O_TERMW + M + 1;           // [KPT][M][3]
-    static constexpr int O_D = O_NRM + KPT * M * 3;         // d = J'n
-    static constexpr int O_Z = O_D + NR;                    // Householder row factors beta (J2 v)_r
-    static constexpr int O_RV = O_Z + NR;                   // r = S d1
-    static constexpr int O_U = O_RV + NR;                   // multipliers of the active rows (in active-set order)
-    static constexpr int O_J = O_U + NR;                    // J [NR][LDJ]  (start-up and epilogue: full-space scratch [NV])
+    static constexpr int O_D = O_NRM + KPT * M * 3;         // d1 = J1'n [QMAX]
+    static constexpr int O_J = O_D + QMAX;                  // J1 [NR][LDJ]  (start-up and epilogue: full-space scratch [NV])
     static constexpr int O_R = O_J + NR * LDJ;              // S = R^-1, upper triangular, packed by columns: S(j, k) at k (k + 1) / 2 + j
-    static constexpr int O_INT = O_R + NR * (NR + 1) / 2;   // int ids[NR] (active rows: slot * 32 + lane), act[KRAW], keep[KRAW + 2]
-    static constexpr int O_END = O_INT + (NR + 2 * KRAW + 2 + 1) / 2;
+    static constexpr int O_INT = O_R + QMAX * (QMAX + 1) / 2;   // int ids[QMAX] (active rows: slot * 32 + lane), act[KRAW], keep[KRAW + 2]
+    static constexpr int O_END = O_INT + (QMAX + 2 * KRAW + 2 + 1) / 2;
     static constexpr int SMEM_BYTES = O_END * 8;
 };
 
@@ -137,14 +138,13 @@ __global__ void __launch_bounds__(32, LSCQP_DAS_MINCTAS)
 das_solve_kernel(const SolveParams p) {
     using A = Das<C>;
     constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR;
-    constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1;
+    constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1, QMAX = A::QMAX;
     constexpr unsigned FULL = 0xffffffffu;
     LSCQP_DYN_SMEM(sm);
     const int lane = threadIdx.x & 31;
     const int agent = blockIdx.x;
     if (agent >= p.n_agents) return;
 
-    double* sQ2 = sm + A::O_Q2;
     double* s_c = sm + A::O_C;
     double* s_y = sm + A::O_Y;
     double* s_x0 = sm + A::O_X0;
@@ -157,19 +157,17 @@ das_solve_kernel(const SolveParams p) {
     double* s_termw = sm + A::O_TERMW;
     double* s_nrm = sm + A::O_NRM;
     double* s_d = sm + A::O_D;
-    double* s_z = sm + A::O_Z;
-    double* s_rv = sm + A::O_RV;
-    double* s_u = sm + A::O_U;
     double* s_J = sm + A::O_J;
     double* s_S = sm + A::O_R;
     double* s_full = s_J;                                   // [NV] full-space scratch (start-up and epilogue only)
     int* s_ids = reinterpret_cast<int*>(sm + A::O_INT);
-    int* s_act = s_ids + NR;
+    int* s_act = s_ids + A::QMAX;
     int* s_keep = s_act + A::KRAW;
+    const double* sQ2 = p.Q2;                               // (kernel parameter: constant bank)
 
     // every exit that does not deliver a checked solution leaves the agent to the interior-point pass
     // (klass: 0 solved here; else the reason -- 1 obstacle list beyond the ABI capacity, 2 more kept obstacles than KPT,
-    //  3 iteration cap, 4 dependent / infeasible row, 5 NaN, 6 stationarity or multiplier check failed)
+    //  3 iteration cap, 4 infeasible row, 5 NaN, 6 feasibility / stationarity / multiplier check failed, 7 more active rows than QMAX)
     auto defer = [&](int why) { if (lane == 0) p.klass[agent] = why; };
 
     const int obs0 = p.obs_offsets[agent];
@@ -178,7 +176,6 @@ das_solve_kernel(const SolveParams p) {
     if (p.rsfc) K = 0;                                                     // see SolveParams::rsfc
 
     // ---- per-agent constants (as pdip_kernel.cuh: local coordinates, unit-coefficient velocity / acceleration rows)
-    for (int e = lane; e < 36; e += 32) sQ2[e] = p.Q2[e];
     if (lane < D) {
         const int k = lane;
         const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k],
@@ -320,9 +317,8 @@ das_solve_kernel(const SolveParams p) {
         }
     };
 
-    // ---- unconstrained minimiser y = -H^-1 g and J = L^-T from the table of this agent's terminal-segment count
+    // ---- unconstrained minimiser y = -H^-1 g, H^-1 from the table of this agent's terminal-segment count
     const double* Hinv = p.das_tab + (size_t) (ts - 1) * 2 * N1 * N1;
-    const double* J1 = Hinv + N1 * N1;
 #pragma unroll
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_y[r] = 0.0; }
     __syncwarp();
@@ -335,32 +331,28 @@ das_solve_kernel(const SolveParams p) {
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; g0[t] = r < NR ? reduce_from_full<C>(s_full, r) : 0.0; }
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_u[r] = g0[t]; }
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_full[r] = g0[t]; }
     __syncwarp();
+    int my_k[RPL], my_r1[RPL];                               // dimension / index within the dimension of this lane's variables
 #pragma unroll
     for (int t = 0; t < RPL; t++) {
         const int r = lane + 32 * t;
+        my_k[t] = -1; my_r1[t] = 0;
         if (r >= NR) continue;
-        int k, r1;
-        das_decode<C>(r, k, r1);
+        das_decode<C>(r, my_k[t], my_r1[t]);
         double y = 0.0;
-        for (int c1 = 0; c1 < N1; c1++) y -= Hinv[r1 * N1 + c1] * s_u[das_encode<C>(k, c1)];
+        for (int c1 = 0; c1 < N1; c1++) y -= Hinv[c1 * N1 + my_r1[t]] * s_full[das_encode<C>(my_k[t], c1)];
         s_y[r] = y;
-        for (int cc = 0; cc < NR; cc++) {
-            int k2, c1;
-            das_decode<C>(cc, k2, c1);
-            s_J[r * LDJ + cc] = (k2 == k) ? J1[r1 * N1 + c1] : 0.0;
-        }
     }
     __syncwarp();
 
     // ---- row evaluation at s_c.  only < 0: every existing row outside the active set, result = the most violated one
     // (smallest slack in the reference's row scaling: velocity rows carry 5/dt, acceleration rows 20/dt^2) of this lane;
-    // only >= 0: that slot alone; only == -2: nothing.
+    // only >= 0: that slot alone; only == -2: nothing; only == -3: the rows of the active set.
     const double wv = 5.0 / p.dt, wa = 20.0 / (p.dt * p.dt);
     auto sweep = [&](int only, double& best, double& best_raw, int& best_slot) {
         best = INFINITY; best_raw = 0.0; best_slot = 0;
-        const unsigned long long live = only == -1 ? (rmask & ~amask) : (only >= 0 ? 1ull << only : 0ull);
+        const unsigned long long live = only == -1 ? (rmask & ~amask) : (only == -3 ? amask : (only >= 0 ? 1ull << only : 0ull));
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const int cp = lane + 32 * c;
@@ -401,8 +393,9 @@ das_solve_kernel(const SolveParams p) {
 
     // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l
     // of S becomes zero left of the last column; the new inverse factor is S without row l and without its last column,
-    // and J follows with the same column rotations (its column q-1 thereby returns to J2).
-    int q = 0;                                                // size of the active set
+    // and J1 follows with the same column rotations (its last column leaves the span).
+    int q = 0;                                                // size of the active set; lane j < q owns active row j
+    double u_own = 0.0;                                       // multiplier of this lane's active row
     auto drop = [&](int l) {
         const int id = s_ids[l];
         if (lane == (id & 31)) amask &= ~(1ull << (id >> 5));
@@ -413,19 +406,11 @@ das_solve_kernel(const SolveParams p) {
             const double h = sqrt(a * a + b * b);
             double cs = 1.0, sn = 0.0;
             if (h > 0.0) { cs = b / h; sn = a / h; }
-            double xs[RPL], ys[RPL];
-#pragma unroll
-            for (int t = 0; t < RPL; t++) {
-                const int i = lane + 32 * t;
-                xs[t] = i <= j ? cj[i] : 0.0; ys[t] = i <= j + 1 ? cn[i] : 0.0;
-            }
+            const double xs = lane <= j ? cj[lane] : 0.0, ys = lane <= j + 1 ? cn[lane] : 0.0;
             __syncwarp();
-#pragma unroll
-            for (int t = 0; t < RPL; t++) {
-                const int i = lane + 32 * t;
-                if (i > j + 1) continue;
-                cn[i] = sn * xs[t] + cs * ys[t];                               // stays in place for the next rotation
-                if (i != l) cj[i < l ? i : i - 1] = cs * xs[t] - sn * ys[t];   // final: row l (now zero) removed
+            if (lane <= j + 1) {
+                cn[lane] = sn * xs + cs * ys;                                      // stays in place for the next rotation
+                if (lane != l) cj[lane < l ? lane : lane - 1] = cs * xs - sn * ys; // final: row l (now zero) removed
             }
 #pragma unroll
             for (int t = 0; t < RPL; t++) {
@@ -436,20 +421,11 @@ das_solve_kernel(const SolveParams p) {
             }
             __syncwarp();
         }
-        double un[RPL]; int idn[RPL];
-#pragma unroll
-        for (int t = 0; t < RPL; t++) {
-            const int j = lane + 32 * t;
-            un[t] = (j >= l && j < q) ? s_u[j + 1] : 0.0;     // (u[q] is the multiplier of the row being added)
-            idn[t] = (j >= l && j < q - 1) ? s_ids[j + 1] : 0;
-        }
+        const double un = __shfl_down_sync(FULL, u_own, 1);
+        const int idn = (lane >= l && lane < q - 1) ? s_ids[lane + 1] : 0;
         __syncwarp();
-#pragma unroll
-        for (int t = 0; t < RPL; t++) {
-            const int j = lane + 32 * t;
-            if (j >= l && j < q) s_u[j] = un[t];
-            if (j >= l && j < q - 1) s_ids[j] = idn[t];
-        }
+        if (lane >= l && lane < q - 1) { u_own = un; s_ids[lane] = idn; }
+        if (lane == q - 1) u_own = 0.0;
         q--;
         __syncwarp();
     };
@@ -473,35 +449,44 @@ das_solve_kernel(const SolveParams p) {
         double sp = __shfl_sync(FULL, best_raw, lp);          // slack of the row being added (negative)
         int pr[9]; double pv[9];
         das_row_pairs<C>(lp, slot, s_nrm, pr, pv);
-        if (lane == 0) s_u[q] = 0.0;
+        // this lane's entries of n and of w = H^-1 n (H^-1 is block diagonal over the dimensions)
+        double nr[RPL], w[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; t++) { nr[t] = 0.0; w[t] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            if (pv[i] == 0.0) continue;
+            int ki, ci;
+            das_decode<C>(pr[i], ki, ci);
+#pragma unroll
+            for (int t = 0; t < RPL; t++) {
+                if (pr[i] == lane + 32 * t) nr[t] += pv[i];
+                if (ki == my_k[t]) w[t] += Hinv[ci * N1 + my_r1[t]] * pv[i];
+            }
+        }
+        double nwp = 0.0;
+#pragma unroll
+        for (int t = 0; t < RPL; t++) nwp += nr[t] * w[t];
+        const double nw = warp_sum(nwp);                      // n' H^-1 n
+        double u_new = 0.0;                                   // multiplier of row p
         bool fail = false;
         while (true) {                                         // until row p is added (or the model is found infeasible)
             if (++it > it_max) { fail = true; why = 3; break; }
-            // d = J'n, z = J2 d2, r = R^-1 d1
-            double d2p = 0.0, dnp = 0.0;
+            // d1 = J1'n (lane = active row), z = w - J1 d1, r = S d1
+            double dk = 0.0;
+            if (lane < q) {
 #pragma unroll
-            for (int t = 0; t < RPL; t++) {
-                const int k = lane + 32 * t;
-                double d = 0.0;
-                if (k < NR) {
-#pragma unroll
-                    for (int i = 0; i < 9; i++) if (pv[i] != 0.0) d += pv[i] * s_J[pr[i] * LDJ + k];
-                    s_d[k] = d;
-                    dnp += d * d;
-                    if (k >= q) d2p += d * d;
-                }
+                for (int i = 0; i < 9; i++) if (pv[i] != 0.0) dk += pv[i] * s_J[pr[i] * LDJ + lane];
             }
-            const double d2n = warp_sum(d2p), dn = warp_sum(dnp);   // (the shuffles order the stores of s_d before the reads below)
+            s_d[lane] = dk;
             __syncwarp();
             double zz[RPL];
-#pragma unroll
-            for (int t = 0; t < RPL; t++) zz[t] = 0.0;
             {
                 double za[RPL], zb[RPL];
 #pragma unroll
                 for (int t = 0; t < RPL; t++) { za[t] = 0.0; zb[t] = 0.0; }
-                int k = q;
-                for (; k + 1 < NR; k += 2) {
+                int k = 0;
+                for (; k + 1 < q; k += 2) {
                     const double d0 = s_d[k], d1 = s_d[k + 1];
 #pragma unroll
                     for (int t = 0; t < RPL; t++) {
@@ -509,90 +494,60 @@ das_solve_kernel(const SolveParams p) {
                         if (r < NR) { za[t] += s_J[r * LDJ + k] * d0; zb[t] += s_J[r * LDJ + k + 1] * d1; }
                     }
                 }
-                if (k < NR) {
+                if (k < q) {
                     const double d0 = s_d[k];
 #pragma unroll
                     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) za[t] += s_J[r * LDJ + k] * d0; }
                 }
 #pragma unroll
-                for (int t = 0; t < RPL; t++) zz[t] = za[t] + zb[t];
+                for (int t = 0; t < RPL; t++) zz[t] = w[t] - (za[t] + zb[t]);
             }
-            {
-                double ra[RPL], rb2[RPL];
+            double nzp = 0.0;
 #pragma unroll
-                for (int t = 0; t < RPL; t++) { ra[t] = 0.0; rb2[t] = 0.0; }
+            for (int t = 0; t < RPL; t++) nzp += nr[t] * zz[t];
+            const double nz = warp_sum(nzp);                   // n'z = n'(H^-1 - J1 J1')n >= 0: the curvature along z
+            double rj = 0.0;
+            {
+                double ra = 0.0, rb2 = 0.0;
                 int k = 0;
                 for (; k + 1 < q; k += 2) {
-                    const double d0 = s_d[k], d1 = s_d[k + 1];
                     const double* c0 = s_S + k * (k + 1) / 2;
-                    const double* c1 = c0 + k + 1;
-#pragma unroll
-                    for (int t = 0; t < RPL; t++) {
-                        const int j = lane + 32 * t;
-                        if (j <= k) ra[t] += c0[j] * d0;
-                        if (j <= k + 1) rb2[t] += c1[j] * d1;
-                    }
+                    if (lane <= k) ra += c0[lane] * s_d[k];
+                    if (lane <= k + 1) rb2 += c0[k + 1 + lane] * s_d[k + 1];
                 }
-                if (k < q) {
-                    const double d0 = s_d[k];
-                    const double* c0 = s_S + k * (k + 1) / 2;
-#pragma unroll
-                    for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j <= k) ra[t] += c0[j] * d0; }
-                }
-#pragma unroll
-                for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j < q) s_rv[j] = ra[t] + rb2[t]; }
+                if (k < q && lane <= k) ra += s_S[k * (k + 1) / 2 + lane] * s_d[k];
+                rj = ra + rb2;
             }
-            __syncwarp();
             // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible
-            double t1 = INFINITY; int l = 0x7fffffff;
-#pragma unroll
-            for (int t = 0; t < RPL; t++) {
-                const int j = lane + 32 * t;
-                if (j < q && s_rv[j] > 0.0) { const double ra = s_u[j] / s_rv[j]; if (ra < t1) { t1 = ra; l = j; } }
-            }
+            double t1 = (lane < q && rj > 0.0) ? u_own / rj : INFINITY;
+            int l;
             {
                 const int wl = warp_argmin(t1);
                 t1 = __shfl_sync(FULL, t1, wl);
-                l = __shfl_sync(FULL, l, wl);
+                l = wl;
             }
-            const bool dependent = !(d2n > 1e-24 * dn) || q >= NR;      // n in the span of the active normals: no primal step
-            const double t2 = dependent ? INFINITY : -sp / d2n;
+            const bool dependent = !(nz > 1e-24 * nw);         // n in the span of the active normals: no primal step
+            const double t2 = dependent ? INFINITY : -sp / nz;
             const double tt = fmin(t1, t2);
             if (tt == INFINITY) { fail = true; why = 4; break; }         // infeasible (or numerically so): the other pass decides
-            __syncwarp();
 #pragma unroll
             for (int t = 0; t < RPL; t++) {
                 const int j = lane + 32 * t;
                 if (!dependent && j < NR) s_y[j] += tt * zz[t];
-                if (j < q) s_u[j] -= tt * s_rv[j];
             }
-            if (lane == 0) s_u[q] += tt;
+            if (lane < q) u_own -= tt * rj;
+            u_new += tt;
             __syncwarp();
             if (t2 <= t1) {
-                // full step: row p joins the active set.  One Householder reflection (I - beta v v') with v = d2 + sign ||d2|| e1
-                // maps d2 onto a multiple of e1; J2 <- J2 (I - beta v v') with J2 v = z + (v0 - d_q) J(:, q).
-                const double dq = s_d[q], nr2 = sqrt(d2n), sg = dq >= 0.0 ? 1.0 : -1.0;
-                const double v0 = dq + sg * nr2, beta = 1.0 / (nr2 * (nr2 + fabs(dq)));
+                // full step: row p joins the active set
+                if (q >= QMAX) { fail = true; why = 7; break; }
+                const double rinv = 1.0 / sqrt(nz);
 #pragma unroll
-                for (int t = 0; t < RPL; t++) {
-                    const int r = lane + 32 * t;
-                    if (r < NR) s_z[r] = beta * (zz[t] + (v0 - dq) * s_J[r * LDJ + q]);
-                }
-                __syncwarp();
-                for (int kb = q; kb < NR; kb += 32) {            // lane = column of J2, loop over the rows
-                    const int k = kb + lane;
-                    if (k >= NR) continue;
-                    const double vk = k == q ? v0 : s_d[k];
-                    double* jc = s_J + k;
-#pragma unroll 3
-                    for (int r = 0; r < NR; r++) jc[r * LDJ] -= s_z[r] * vk;
-                }
-                // R gains the column (d1; rho), rho = -sign ||d2||:  S gains (-S d1 / rho; 1 / rho) = (-r / rho; 1 / rho)
-                const double rinv = -sg / nr2;
+                for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_J[r * LDJ + q] = zz[t] * rinv; }
+                // R gains the column (d1; rho), rho = sqrt(n'z):  S gains (-S d1; 1) / rho = (-r; 1) / rho
                 double* cq = s_S + q * (q + 1) / 2;
-#pragma unroll
-                for (int t = 0; t < RPL; t++) { const int j = lane + 32 * t; if (j < q) cq[j] = -s_rv[j] * rinv; }
-                if (lane == 0) { cq[q] = rinv; s_ids[q] = pid; }
+                if (lane < q) cq[lane] = -rj * rinv;
+                if (lane == q) { cq[q] = rinv; u_own = u_new; s_ids[q] = pid; }
                 if (lane == lp) amask |= 1ull << slot;
                 q++;
                 __syncwarp();
@@ -613,8 +568,14 @@ das_solve_kernel(const SolveParams p) {
     }
     if (!ok) { defer(why); return; }
 
-    // ---- verification and outputs.  s_c holds the final point; stationarity Z'(grad f - sum u_j n_j) from scratch
-    // (J is dead: its storage is the full-space scratch).
+    // ---- verification and outputs.  s_c holds the final point.  The active rows are zero only up to the rounding of the
+    // updates: re-evaluated like the others.  Stationarity Z'(grad f - sum u_j n_j) from scratch (J1 is dead: its storage is
+    // the full-space scratch).
+    {
+        double b3, raw3; int s3;
+        sweep(-3, b3, raw3, s3);
+        viol = fmax(viol, -warp_min(b3));
+    }
     __syncwarp();
     grad_full(s_full);
     __syncwarp();
@@ -625,23 +586,20 @@ das_solve_kernel(const SolveParams p) {
         const int id = s_ids[j];
         int fk[3], fcp[3]; double fa[3];
         das_row_full<C>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
-        const double uj = s_u[j];
+        const double uj = __shfl_sync(FULL, u_own, j);
 #pragma unroll
         for (int t = 0; t < 3; t++) if (lane == t && fa[t] != 0.0) s_full[fk[t] * NCP + fcp[t]] -= uj * fa[t];
         __syncwarp();
     }
-    double rd = 0.0, umin = 0.0;
+    double rd = 0.0;
 #pragma unroll
-    for (int t = 0; t < RPL; t++) {
-        const int r = lane + 32 * t;
-        if (r < NR) rd = fmax(rd, fabs(reduce_from_full<C>(s_full, r)));
-        if (r < q) umin = fmin(umin, s_u[r]);
-    }
-    rd = warp_max(rd); gscale = warp_max(gscale); umin = warp_min(umin);
+    for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) rd = fmax(rd, fabs(reduce_from_full<C>(s_full, r))); }
+    rd = warp_max(rd); gscale = warp_max(gscale);
+    const double umin = warp_min(lane < q ? u_own : 0.0);
 #ifdef LSCQP_CUDA_EMUL
-    if (lane == 0 && getenv("LSCQP_DAS_DEBUG")) fprintf(stderr, "das agent %d: it %d q %d rd %.3e gscale %.3e umin %.3e\n", agent, it, q, rd, gscale, umin);
+    if (lane == 0 && getenv("LSCQP_DAS_DEBUG")) fprintf(stderr, "das agent %d: it %d q %d rd %.3e gscale %.3e umin %.3e viol %.3e\n", agent, it, q, rd, gscale, umin, viol);
 #endif
-    if (!(rd <= 1e-7 * fmax(1.0, gscale)) || !(umin >= -1e-9 * fmax(1.0, gscale))) { defer(6); return; }
+    if (!(rd <= 1e-7 * fmax(1.0, gscale)) || !(umin >= -1e-9 * fmax(1.0, gscale)) || !(viol <= 1e-9)) { defer(6); return; }
 
     double cost = 0.0;
 #pragma unroll
@@ -674,14 +632,14 @@ das_solve_kernel(const SolveParams p) {
         for (int e = lane; e < p.dual_stride; e += 32) du[e] = 0.0;
         __syncwarp();
         const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
-        for (int j = lane; j < q; j += 32) {
-            const int id = s_ids[j], lo = id & 31, slot = id >> 5;
+        if (lane < q) {
+            const int id = s_ids[lane], lo = id & 31, slot = id >> 5;
             if (slot < A::NLSC) {
                 const int cp = lo + 32 * (slot / KPT);
-                du[(s_act[slot % KPT] * M + cp / 6) * 6 + cp % 6] = s_u[j];
+                du[(s_act[slot % KPT] * M + cp / 6) * 6 + cp % 6] = u_own;
             } else {
                 const int b = slot - A::NLSC, e = b % 6, v = lo + 32 * (b / 6);
-                du[A::KRAW * M * 6 + v * 6 + e] = s_u[j] * (e < 2 ? 1.0 : (e < 4 ? sv : sa));
+                du[A::KRAW * M * 6 + v * 6 + e] = u_own * (e < 2 ? 1.0 : (e < 4 ? sv : sa));
             }
         }
     }

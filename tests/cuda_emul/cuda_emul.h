@@ -93,6 +93,15 @@ inline double __shfl_sync(unsigned, double v, int src_lane) {
     __syncwarp();
     return r;
 }
+inline double __shfl_down_sync(unsigned, double v, int delta) {
+    emu::State& s = emu::st();
+    s.slot_d[s.cur] = v;
+    __syncwarp();
+    const int lane = s.cur & 31;
+    const double r = lane + delta < 32 ? s.slot_d[s.cur + delta] : v;
+    __syncwarp();
+    return r;
+}
 inline int __shfl_up_sync(unsigned, int v, int delta) {
     emu::State& s = emu::st();
     s.slot_d[s.cur] = (double) v;
