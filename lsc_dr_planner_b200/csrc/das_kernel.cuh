@@ -103,9 +103,10 @@ __device__ __forceinline__ void das_row_full(int lp, int slot, const double* s_n
     }
 }
 
-// ... and in the reduced space: at most 9 (reduced variable, coefficient) pairs through the continuity map
+// ... and in the reduced space: at most 9 (reduced variable pr, coefficient pv) pairs through the continuity map, with
+// the variable's dimension pk and index pc within the dimension (das_decode)
 template <class C>
-__device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_nrm, int* pr, double* pv) {
+__device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_nrm, int* pr, double* pv, int* pk, int* pc) {
     int fk[3], fcp[3];
     double fa[3];
     das_row_full<C>(lp, slot, s_nrm, fk, fcp, fa);
@@ -113,11 +114,15 @@ __device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_
     for (int f = 0; f < 3; f++) {
         const int m = fcp[f] / 6, i = fcp[f] % 6;
 #pragma unroll
-        for (int j = 0; j < 3; j++) { pr[f * 3 + j] = 0; pv[f * 3 + j] = 0.0; }
-        if (i >= 3) { pr[f * 3] = ridx<C>(m, fk[f], i - 3); pv[f * 3] = fa[f]; }
-        else if (m >= 1) {
+        for (int j = 0; j < 3; j++) { pr[f * 3 + j] = 0; pv[f * 3 + j] = 0.0; pk[f * 3 + j] = fk[f]; pc[f * 3 + j] = 0; }
+        if (i >= 3) {
+            pr[f * 3] = ridx<C>(m, fk[f], i - 3); pv[f * 3] = fa[f];
+            pc[f * 3] = (C::TERM && m == C::M - 1) ? 3 * (C::M - 1) : 3 * m + i - 3;
+        } else if (m >= 1) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) { pr[f * 3 + j] = ridx<C>(m - 1, fk[f], j); pv[f * 3 + j] = fa[f] * tcoef(i, j); }
+            for (int j = 0; j < 3; j++) {
+                pr[f * 3 + j] = ridx<C>(m - 1, fk[f], j); pv[f * 3 + j] = fa[f] * tcoef(i, j); pc[f * 3 + j] = 3 * (m - 1) + j;
+            }
         }
     }
 }
@@ -240,6 +245,7 @@ das_solve_kernel(const SolveParams p) {
             const int cp = lane + 32 * c, m_cp = cp / 6, i_cp = cp % 6;
             if (cp >= NCP || (m_cp == 0 && i_cp < 3)) continue;
             const double steps = (double) (5 * m_cp + i_cp - 2);
+#pragma unroll 4
             for (int oi = 0; oi < K; oi++) {
                 const double* g = p.normals + ((size_t) (obs0 + oi) * M + m_cp) * 3;
                 const double nx = g[0], ny = g[1], nz = (D == 3) ? g[2] : 0.0;
@@ -391,6 +397,61 @@ das_solve_kernel(const SolveParams p) {
         }
     };
 
+    // ---- the same over every live row, cheaper: the two rows of a bound / velocity / acceleration pair share one evaluation
+    // (lim - |x| is the smaller of the two slacks; with one of them in the active set the other cannot be violated), no
+    // per-row branches.  Returns the lane's smallest scaled slack and its slot; the raw slack is best * row_unscale(slot).
+    int kv_[VPT];
+#pragma unroll
+    for (int u = 0; u < VPT; u++) kv_[u] = (lane + 32 * u) / NCP;
+    const bool any_bnd = __any_sync(FULL, [&]() { unsigned b = 0;
+#pragma unroll
+        for (int u = 0; u < VPT; u++) b |= bmask[u] & 3u;
+        return b != 0; }());
+    auto sweep_fast = [&](double& best, int& best_slot) {
+        best = INFINITY; best_slot = 0;
+        const unsigned long long live = rmask & ~amask;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const int cp = lane + 32 * c;
+            if (cp >= NCP) continue;
+            const int m_cp = cp / 6;
+            const double cx = s_c[cp], cy = s_c[NCP + cp], cz = (D == 3) ? s_c[2 * NCP + cp] : 0.0;
+#pragma unroll
+            for (int j = 0; j < KPT; j++) {
+                if (j >= K) break;                                        // (warp uniform)
+                const double* n = s_nrm + (j * M + m_cp) * 3;
+                double q = n[0] * cx + n[1] * cy - rb[c][j];
+                if (D == 3) q += n[2] * cz;
+                q = (live >> (c * KPT + j) & 1ull) ? q : INFINITY;
+                if (q < best) { best = q; best_slot = c * KPT + j; }
+            }
+        }
+        const unsigned long long both = live & (live >> 1);               // bit 2i: rows 2i and 2i + 1 both live (NLSC is even)
+#pragma unroll
+        for (int u = 0; u < VPT; u++) {
+            const int v = lane + u * 32;
+            if (v >= NV) continue;
+            const unsigned bits = (unsigned) (both >> (A::NLSC + 6 * u));
+            const double* cc = s_c + v;                                    // (cc[1], cc[2] may lie past the array: masked rows)
+            const double c0 = cc[0], c1 = cc[1], c2 = cc[2];
+            const double dv = c1 - c0, da = c2 - 2.0 * c1 + c0;
+            double qv = (s_vlim[kv_[u]] - fabs(dv)) * wv, qa = (s_alim[kv_[u]] - fabs(da)) * wa;
+            qv = (bits & 4u) ? qv : INFINITY; qa = (bits & 16u) ? qa : INFINITY;
+            if (qv < best) { best = qv; best_slot = A::NLSC + 6 * u + (dv > 0.0 ? 2 : 3); }
+            if (qa < best) { best = qa; best_slot = A::NLSC + 6 * u + (da > 0.0 ? 4 : 5); }
+            if (any_bnd) {                                                 // (warp uniform)
+                const int m_v = (v % NCP) / 6;
+                const double ql = c0 - s_lb[kv_[u] * M + m_v], qu = s_ub[kv_[u] * M + m_v] - c0;
+                const double qb = (bits & 1u) ? fmin(ql, qu) : INFINITY;
+                if (qb < best) { best = qb; best_slot = A::NLSC + 6 * u + (ql <= qu ? 0 : 1); }
+            }
+        }
+    };
+    auto row_unscale = [&](int slot) {
+        const int e = slot < A::NLSC ? 0 : (slot - A::NLSC) % 6;
+        return e < 2 ? 1.0 : (e < 4 ? p.dt / 5.0 : p.dt * p.dt / 20.0);
+    };
+
     // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l
     // of S becomes zero left of the last column; the new inverse factor is S without row l and without its last column,
     // and J1 follows with the same column rotations (its last column leaves the span).
@@ -438,17 +499,17 @@ das_solve_kernel(const SolveParams p) {
     while (true) {
         expand();
         __syncwarp();
-        double best, best_raw; int best_slot;
-        sweep(-1, best, best_raw, best_slot);
+        double best; int best_slot;
+        sweep_fast(best, best_slot);
         const int lp = warp_argmin(best);
         const int slot = __shfl_sync(FULL, best_slot, lp);
         best = __shfl_sync(FULL, best, lp);
         if (!(best == best)) break;                           // NaN: leave it to the other pass
         if (!(best < -1e-10)) { ok = true; viol = fmax(0.0, -best); break; }
         const int pid = slot * 32 + lp;
-        double sp = __shfl_sync(FULL, best_raw, lp);          // slack of the row being added (negative)
-        int pr[9]; double pv[9];
-        das_row_pairs<C>(lp, slot, s_nrm, pr, pv);
+        double sp = best * row_unscale(slot);                 // slack of the row being added (negative)
+        int pr[9], pk[9], pc[9]; double pv[9];
+        das_row_pairs<C>(lp, slot, s_nrm, pr, pv, pk, pc);
         // this lane's entries of n and of w = H^-1 n (H^-1 is block diagonal over the dimensions)
         double nr[RPL], w[RPL];
 #pragma unroll
@@ -456,12 +517,10 @@ das_solve_kernel(const SolveParams p) {
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             if (pv[i] == 0.0) continue;
-            int ki, ci;
-            das_decode<C>(pr[i], ki, ci);
 #pragma unroll
             for (int t = 0; t < RPL; t++) {
                 if (pr[i] == lane + 32 * t) nr[t] += pv[i];
-                if (ki == my_k[t]) w[t] += Hinv[ci * N1 + my_r1[t]] * pv[i];
+                if (pk[i] == my_k[t]) w[t] += Hinv[pc[i] * N1 + my_r1[t]] * pv[i];
             }
         }
         double nwp = 0.0;
