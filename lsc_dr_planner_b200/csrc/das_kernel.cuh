@@ -539,11 +539,13 @@ das_solve_kernel(const SolveParams p) {
             }
             s_d[lane] = dk;
             __syncwarp();
-            double zz[RPL];
+            // one pass over the active columns k: z = w - J1 d1 (this lane's RPL rows) and r_j = sum_{k >= j} S(j, k) d1_k
+            double zz[RPL], rj = 0.0;
             {
-                double za[RPL], zb[RPL];
+                double za[RPL], zb[RPL], ra = 0.0, rb2 = 0.0;
 #pragma unroll
                 for (int t = 0; t < RPL; t++) { za[t] = 0.0; zb[t] = 0.0; }
+                const double* col = s_S;                        // column k of S starts at k (k + 1) / 2
                 int k = 0;
                 for (; k + 1 < q; k += 2) {
                     const double d0 = s_d[k], d1 = s_d[k + 1];
@@ -552,31 +554,25 @@ das_solve_kernel(const SolveParams p) {
                         const int r = lane + 32 * t;
                         if (r < NR) { za[t] += s_J[r * LDJ + k] * d0; zb[t] += s_J[r * LDJ + k + 1] * d1; }
                     }
+                    if (lane <= k) ra += col[lane] * d0;
+                    col += k + 1;
+                    if (lane <= k + 1) rb2 += col[lane] * d1;
+                    col += k + 2;
                 }
                 if (k < q) {
                     const double d0 = s_d[k];
 #pragma unroll
                     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) za[t] += s_J[r * LDJ + k] * d0; }
+                    if (lane <= k) ra += col[lane] * d0;
                 }
 #pragma unroll
                 for (int t = 0; t < RPL; t++) zz[t] = w[t] - (za[t] + zb[t]);
+                rj = ra + rb2;
             }
             double nzp = 0.0;
 #pragma unroll
             for (int t = 0; t < RPL; t++) nzp += nr[t] * zz[t];
             const double nz = warp_sum(nzp);                   // n'z = n'(H^-1 - J1 J1')n >= 0: the curvature along z
-            double rj = 0.0;
-            {
-                double ra = 0.0, rb2 = 0.0;
-                int k = 0;
-                for (; k + 1 < q; k += 2) {
-                    const double* c0 = s_S + k * (k + 1) / 2;
-                    if (lane <= k) ra += c0[lane] * s_d[k];
-                    if (lane <= k + 1) rb2 += c0[k + 1 + lane] * s_d[k + 1];
-                }
-                if (k < q && lane <= k) ra += s_S[k * (k + 1) / 2 + lane] * s_d[k];
-                rj = ra + rb2;
-            }
             // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible
             double t1 = (lane < q && rj > 0.0) ? u_own / rj : INFINITY;
             int l;
@@ -641,15 +637,16 @@ das_solve_kernel(const SolveParams p) {
     double gscale = 0.0;
 #pragma unroll
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) gscale = fmax(gscale, fabs(reduce_from_full<C>(s_full, r))); }
-    for (int j = 0; j < q; j++) {                             // one active row at a time: its <= 3 full-space entries
+    for (int j = 0; j < q; j++) {                             // the active rows in order: <= 3 full-space entries each
         const int id = s_ids[j];
         int fk[3], fcp[3]; double fa[3];
         das_row_full<C>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
         const double uj = __shfl_sync(FULL, u_own, j);
+        // lane k applies the entries of dimension k, in program order: no two lanes ever touch the same address
 #pragma unroll
-        for (int t = 0; t < 3; t++) if (lane == t && fa[t] != 0.0) s_full[fk[t] * NCP + fcp[t]] -= uj * fa[t];
-        __syncwarp();
+        for (int t = 0; t < 3; t++) if (lane == fk[t] && fa[t] != 0.0) s_full[fk[t] * NCP + fcp[t]] -= uj * fa[t];
     }
+    __syncwarp();
     double rd = 0.0;
 #pragma unroll
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) rd = fmax(rd, fabs(reduce_from_full<C>(s_full, r))); }
