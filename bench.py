@@ -4,9 +4,9 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic agents: gather the neighbours'
-trajectories, assemble every LSC half-space (constructLSC), solve every agent's QP
-(trajOptimization).  Workload: random forest, 4096 agents per GPU, M=5 segments of degree 5, 3-D,
+A "step" is one pass of the hot path over one batch of synthetic agents: read the neighbours'
+trajectories in place, assemble every LSC half-space (constructLSC), solve every agent's QP
+(trajOptimization: dual active-set first pass, interior point for what it defers).  Workload: random forest, 4096 agents per GPU, M=5 segments of degree 5, 3-D,
 K=40 neighbours (1080 LSC rows + 414 box/velocity/acceleration rows per QP), planes from the
 reference's real rule.  Agents are independent, so ranks hold disjoint batches (weak scaling) and
 there is no data-path collective.
@@ -188,10 +188,12 @@ def run_reference(args):
 
 
 def workload_config(args, n_agents):
-    return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (LSC assembly + PDIP solve)",
+    return {"workload": f"forest{n_agents}_K{args.K}_M5_D3 replan step (LSC assembly + QP solve)",
             "agents_per_gpu": n_agents, "K": args.K, "M": 5, "degree": 5, "dim": 3, "rows_per_qp": 27 * args.K + 414,
             "planner_mode": "lsc", "generator": "generateLSC", "l2": "flushed between timed steps (256 MiB write)",
-            "solver": "warm start from initial_traj, exact presolve (velocity-bound row pruning, in assembly and solve) on; see `variants` for off",
+            "solver": "dual active-set first pass (das_solve_kernel, verified result) + interior-point pass for the agents it defers; "
+                      "exact presolve (velocity-bound row pruning, in assembly and solve) on; see `variants` for the interior-point "
+                      "instances alone and for presolve off",
             "parallelism": f"agents sharded over {args.gpus} rank(s), no data-path collective"}
 
 
@@ -397,6 +399,10 @@ def run_ours(args):
     t_sol = np.array([e[1].elapsed_time(e[2]) for e in ev])
     t_step = t_asm + t_sol
     iters_mean = float(d.iters.float().mean().item())
+    try:
+        first_pass_share = float((planner.qp.last_instances(n_agents) == 0).mean())   # agents the first pass solved
+    except Exception:
+        first_pass_share = 0.0
 
     # ---- end-to-end through the host-buffer entry point (pinned host memory, copies inside)
     for _ in range(max(1, args.warmup // 2)):
@@ -438,11 +444,12 @@ def run_ours(args):
         achieved = n_agents * ab["solve"] / (sol_ms * 1e-3) / 1e9
         traffic = None
         fp64_view = None
+        solve_kernel = "das_solve_kernel" if first_pass_share > 0.5 else "pdip_solve_kernel"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic = tj.get("pdip_solve_kernel_bytes_per_launch")
-            flops = tj.get("pdip_solve_kernel_fp64_flops_per_launch")
+            traffic = tj.get(solve_kernel + "_bytes_per_launch")
+            flops = tj.get(solve_kernel + "_fp64_flops_per_launch")
             if flops:
                 # FP64 view: flops of one 4096-agent launch counted by ncu (2 dfma + dadd + dmul thread
                 # instructions, profiles/), scaled to this batch, over the live kernel time; peak from the on-box DFMA
@@ -455,16 +462,17 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_agents),
                 "clocks": clocks, "gpu_launches": int(launches),
-                "kernel_ms": {"assemble": asm_ms, "solve": sol_ms}, "pdip_iterations_mean": iters_mean,
+                "kernel_ms": {"assemble": asm_ms, "solve": sol_ms}, "solver_iterations_mean": iters_mean,
+                "first_pass_share": first_pass_share,
                 "e2e": {"value": world * n_agents / e2e_s, "unit": UNIT, "h2d_bytes_per_step": planner.h2d_bytes(hb),
                         "d2h_bytes_per_step": planner.d2h_bytes(hb), "ms_per_step": 1e3 * e2e_s,
                         "api": "lscqp_replan_host (C ABI, pinned host buffers: inputs copied host->device inside the call, "
                                "outputs stored by the solve kernel straight into the pinned result arrays)"},
-                "roofline": {"kernel": "pdip_solve_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "roofline": {"kernel": solve_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                              "frac": achieved / hbm, "traffic": traffic, "peak_source": how,
                              "algorithmic_bytes_per_qp": ab["solve"],
-                             "note": "latency/FP64-issue bound by design (SURVEY 8(d)): the HBM fraction is reported as required, "
-                                     "see DESIGN.md for the FP64 view",
+                             "note": "dependency-latency bound by design (SURVEY 8(d): the solve reads its 15.6 KB once and iterates on "
+                                     "chip): the HBM fraction is reported as required, see DESIGN.md section 3 for what bounds it",
                              "fp64": fp64_view,
                              "assemble": {"achieved": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9,
                                           "frac": n_agents * ab["assemble"] / (asm_ms * 1e-3) / 1e9 / hbm,
@@ -491,11 +499,16 @@ def run_ours(args):
             ms = timed(lambda: planner.assemble_device(d, capi.GEN_LSC, stream))
             variants["assemble_gathered_unpruned"] = {"ms": ms, "note": "gather kernel + every (obstacle, segment) plane, as lscqp_assemble_lsc_batch returns them"}
             planner.assemble_fused_device(d, capi.GEN_LSC, stream)
-            cfg3 = copy.copy(batch.cfg); cfg3.presolve = 3        # presolve on, light instances off (one pass, 128-thread CTAs)
+            cfg9 = copy.copy(batch.cfg); cfg9.presolve = 9        # presolve on, no active-set pass: light + full interior-point instances
+            planner9 = BatchPlanner(cfg9, device=local)
+            ms = timed(lambda: planner9.solve_device(d, stream=stream))
+            variants["solve_interior_point_two_pass"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item()),
+                                                         "note": "the round-1 dispatch: one-warp light PDIP instance, then the 128-thread instance; warm start from initial_traj"}
+            cfg3 = copy.copy(batch.cfg); cfg3.presolve = 11       # ... and the 128-thread interior-point instance alone
             planner3 = BatchPlanner(cfg3, device=local)
             ms = timed(lambda: planner3.solve_device(d, stream=stream))
             variants["solve_full_instance_only"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
-            cfg2 = copy.copy(batch.cfg); cfg2.presolve = False
+            cfg2 = copy.copy(batch.cfg); cfg2.presolve = 8        # presolve off (every obstacle kept: interior point only)
             planner2 = BatchPlanner(cfg2, device=local)
             ms = timed(lambda: planner2.solve_device(d, stream=stream))
             variants["solve_no_presolve"] = {"ms": ms, "qp_per_s": n_agents / (ms * 1e-3), "iters_mean": float(d.iters.float().mean().item())}
@@ -549,8 +562,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=4096, help="agents per GPU")
     ap.add_argument("--K", type=int, default=40)

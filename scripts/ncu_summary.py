@@ -24,7 +24,8 @@ def unit_bytes(v, u):
     return float(v) * m.get(u, 1)
 
 traffic = {}
-for name, rep in (("pdip_solve_kernel", "prof_solve.ncu-rep"), ("lsc_assemble_kernel", "prof_asm.ncu-rep")):
+for name, rep in (("das_solve_kernel", "prof_das.ncu-rep"), ("pdip_solve_kernel", "prof_solve.ncu-rep"),
+                  ("lsc_assemble_kernel", "prof_asm.ncu-rep"), ("lsc_pairs_kernel", "prof_pairs.ncu-rep")):
     path = os.path.join(root, "gpurun_out", rep)
     if not os.path.exists(path):
         continue
