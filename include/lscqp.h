@@ -160,12 +160,15 @@ int lscqp_solve_batch(lscqp_handle* h, int n_agents,
         double* cost_out,           /* [n_agents]  objective incl. constant (cplex.getObjValue) */
         int*    status_out,         /* [n_agents]  LSCQP_OK | MAX_ITER | INFEASIBLE | NUMERICAL */
         int*    iters_out,          /* [n_agents]  optional                                      */
-        double* kkt_out,            /* [n_agents][4] optional: stationarity, primal, guarded pivots, gap */
+        double* kkt_out,            /* [n_agents][4] optional: stationarity, primal, guarded pivots (interior point) or
+                                       64 * largest + final active-set size (active set), gap (0 for the active set) */
         double* dual_out,           /* [n_agents][lscqp_dual_stride] optional                   */
         void* stream);
 
-/* Diagnostics: which kernel instance solved each agent in the last lscqp_solve_batch call on this handle (0 = light
- * one-warp instance, 1 = full-capacity instance); klass_out is a HOST array [n_agents]; synchronises `stream`.
+/* Diagnostics: which pass solved each agent in the last lscqp_solve_batch call on this handle (0 = the first pass: the
+ * dual active-set kernel, or the light one-warp interior-point instance when that pass is switched off; otherwise the
+ * full-capacity interior-point instance -- after an active-set first pass the value is its reason for deferring,
+ * das_kernel.cuh); klass_out is a HOST array [n_agents]; synchronises `stream`.
  * LSCQP_E_INVALID when that call ran the full-capacity instance alone. */
 int lscqp_last_instances(lscqp_handle* h, int n_agents, int* klass_out, void* stream);
 

@@ -29,6 +29,12 @@
 #ifndef LSCQP_DAS_MINCTAS
 #define LSCQP_DAS_MINCTAS 12
 #endif
+#ifndef LSCQP_DAS_QMAX
+#define LSCQP_DAS_QMAX 32
+#endif
+#ifndef LSCQP_DAS_KPT
+#define LSCQP_DAS_KPT 10
+#endif
 
 namespace lscqp {
 
@@ -39,10 +45,10 @@ struct Das {
     static constexpr int RPL = (NR + 31) / 32;              // reduced variables per lane
     static constexpr int VPT = (NV + 31) / 32;              // full-space variables (box-row owners) per lane
     static constexpr int CPL = (NCP + 31) / 32;             // control points (LSC-row owners) per lane
-    static constexpr int KPT = 10;                          // kept obstacles this kernel holds
+    static constexpr int KPT = LSCQP_DAS_KPT;               // kept obstacles this kernel holds
     static constexpr int NLSC = CPL * KPT;                  // row slots of a lane: LSC rows first, then 6 per variable
     static constexpr int NSLOT = NLSC + VPT * 6;
-    static constexpr int QMAX = 32;                         // active rows this kernel holds (one lane each)
+    static constexpr int QMAX = LSCQP_DAS_QMAX;             // active rows this kernel holds (one lane each, <= 32)
     static constexpr int LDJ = QMAX + 1;
     static constexpr int KRAW = C::KRAW;
     static_assert(NSLOT <= 64, "row slots do not fit the 64-bit masks");
@@ -492,7 +498,7 @@ das_solve_kernel(const SolveParams p) {
     };
 
     // ---- main loop
-    int it = 0, why = 5;
+    int it = 0, why = 5, q_top = 0;
     const int it_max = 4 * NR + 40;
     bool ok = false;
     double viol = 0.0;
@@ -605,6 +611,7 @@ das_solve_kernel(const SolveParams p) {
                 if (lane == q) { cq[q] = rinv; u_own = u_new; s_ids[q] = pid; }
                 if (lane == lp) amask |= 1ull << slot;
                 q++;
+                q_top = q > q_top ? q : q_top;
                 __syncwarp();
                 break;
             }
@@ -679,7 +686,7 @@ das_solve_kernel(const SolveParams p) {
         if (p.iters_out) p.iters_out[agent] = it;
         if (p.kkt_out) {
             p.kkt_out[agent * 4 + 0] = rd; p.kkt_out[agent * 4 + 1] = viol;
-            p.kkt_out[agent * 4 + 2] = 0.0; p.kkt_out[agent * 4 + 3] = 0.0;
+            p.kkt_out[agent * 4 + 2] = (double) (q_top * 64 + q); p.kkt_out[agent * 4 + 3] = 0.0;   // (largest, final active set)
         }
     }
     if (p.dual_out) {
