@@ -38,14 +38,18 @@
 
 namespace lscqp {
 
-template <class C>
+// KPT_: kept obstacles the instance holds.  Up to 16 their row constants live in registers (the throughput instance);
+// the large instance (host_common.hpp:Instance::DAS_BIG_KPT) keeps them in shared memory and is run second, over the
+// agents the first flagged with "more kept obstacles than I hold" only.
+template <class C, int KPT_ = LSCQP_DAS_KPT>
 struct Das {
     static constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR, NZS = C::NZS;
     static constexpr int N1 = NR / D;                       // reduced variables per dimension
     static constexpr int RPL = (NR + 31) / 32;              // reduced variables per lane
     static constexpr int VPT = (NV + 31) / 32;              // full-space variables (box-row owners) per lane
     static constexpr int CPL = (NCP + 31) / 32;             // control points (LSC-row owners) per lane
-    static constexpr int KPT = LSCQP_DAS_KPT;               // kept obstacles this kernel holds
+    static constexpr int KPT = KPT_;                        // kept obstacles this kernel holds
+    static constexpr bool BIG = KPT_ > 16;                  // row constants in shared memory
     static constexpr int NLSC = CPL * KPT;                  // row slots of a lane: LSC rows first, then 6 per variable
     static constexpr int NSLOT = NLSC + VPT * 6;
     static constexpr int QMAX = LSCQP_DAS_QMAX;             // active rows this kernel holds (one lane each, <= 32)
@@ -65,7 +69,8 @@ struct Das {
     static constexpr int O_UB = O_LB + D * M;
     static constexpr int O_TERMW = O_UB + D * M;            // [M] terminal weights, [M] the number of terminal segments
     static constexpr int O_NRM = O_TERMW + M + 1;           // [KPT][M][3]
-    static constexpr int O_D = O_NRM + KPT * M * 3;         // d1 = J1'n [QMAX]
+    static constexpr int O_RB = O_NRM + KPT * M * 3;        // [KPT][CPL][32] row constants (BIG only)
+    static constexpr int O_D = O_RB + (BIG ? KPT * CPL * 32 : 0);   // d1 = J1'n [QMAX]
     static constexpr int O_J = O_D + QMAX;                  // J1 [NR][LDJ]  (start-up and epilogue: full-space scratch [NV])
     static constexpr int O_R = O_J + NR * LDJ;              // S = R^-1, upper triangular, packed by columns: S(j, k) at k (k + 1) / 2 + j
     static constexpr int O_INT = O_R + QMAX * (QMAX + 1) / 2;   // int ids[QMAX] (active rows: slot * 32 + lane), act[KRAW], keep[KRAW + 2]
@@ -89,9 +94,9 @@ __device__ __forceinline__ int das_encode(int k, int r1) {
 // with a zero coefficient.  LSC row of control point cp and kept obstacle j: normal n on (k, cp), k < D
 // (traj_optimizer.cpp:414-421); box rows of variable v: 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc- with unit-coefficient
 // stencils (:238-270, :440-474).
-template <class C>
+template <class C, int KPT_>
 __device__ __forceinline__ void das_row_full(int lp, int slot, const double* s_nrm, int* fk, int* fcp, double* fa) {
-    using A = Das<C>;
+    using A = Das<C, KPT_>;
     constexpr int M = C::M, D = C::D, NCP = C::NCP;
     if (slot < A::NLSC) {
         const int cp = lp + 32 * (slot / A::KPT), j = slot % A::KPT;
@@ -111,11 +116,11 @@ __device__ __forceinline__ void das_row_full(int lp, int slot, const double* s_n
 
 // ... and in the reduced space: at most 9 (reduced variable pr, coefficient pv) pairs through the continuity map, with
 // the variable's dimension pk and index pc within the dimension (das_decode)
-template <class C>
+template <class C, int KPT_>
 __device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_nrm, int* pr, double* pv, int* pk, int* pc) {
     int fk[3], fcp[3];
     double fa[3];
-    das_row_full<C>(lp, slot, s_nrm, fk, fcp, fa);
+    das_row_full<C, KPT_>(lp, slot, s_nrm, fk, fcp, fa);
 #pragma unroll
     for (int f = 0; f < 3; f++) {
         const int m = fcp[f] / 6, i = fcp[f] % 6;
@@ -144,10 +149,10 @@ __device__ __forceinline__ int warp_argmin(double v) {
     return __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
 }
 
-template <class C>
-__global__ void __launch_bounds__(32, LSCQP_DAS_MINCTAS)
+template <class C, int KPT_ = LSCQP_DAS_KPT>
+__global__ void __launch_bounds__(32, (KPT_ > 16 ? 6 : LSCQP_DAS_MINCTAS))
 das_solve_kernel(const SolveParams p) {
-    using A = Das<C>;
+    using A = Das<C, KPT_>;
     constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR;
     constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1, QMAX = A::QMAX;
     constexpr unsigned FULL = 0xffffffffu;
@@ -181,6 +186,7 @@ das_solve_kernel(const SolveParams p) {
     //  3 iteration cap, 4 infeasible row, 5 NaN, 6 feasibility / stationarity / multiplier check failed, 7 more active rows than QMAX)
     auto defer = [&](int why) { if (lane == 0) p.klass[agent] = why; };
 
+    if (p.klass_mode == 3 && p.klass[agent] != 2) return;                 // large instance: only what the first pass could not hold
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
     if (K < 0 || K > A::KRAW || K > p.max_obs) { defer(1); return; }      // (reported as ST_CAPACITY by the other pass)
@@ -289,20 +295,24 @@ das_solve_kernel(const SolveParams p) {
         s_nrm[e * 3] = nx; s_nrm[e * 3 + 1] = ny; s_nrm[e * 3 + 2] = nz;
     }
     __syncwarp();
-    double rb[CPL][KPT];                                      // row constants in local coordinates: n . c - rb >= 0
+    // row constants in local coordinates (n . c - rb >= 0): registers, or shared memory [j][c][lane] in the large instance
+    double rb_reg[A::BIG ? 1 : CPL][A::BIG ? 1 : KPT];
+    double* s_rb = sm + A::O_RB;
+#define LSCQP_RB(c, j) (A::BIG ? s_rb[((j) * CPL + (c)) * 32 + lane] : rb_reg[A::BIG ? 0 : (c)][A::BIG ? 0 : (j)])
 #pragma unroll
     for (int c = 0; c < CPL; c++) {
         const int cp = lane + 32 * c, m_cp = cp / 6, i_cp = cp % 6;
         const bool lsc = cp < NCP && !(m_cp == 0 && i_cp < 3);          // :404
 #pragma unroll
         for (int j = 0; j < KPT; j++) {
-            rb[c][j] = 0.0;
+            if (A::BIG && j >= K) break;
+            if (A::BIG) s_rb[(j * CPL + c) * 32 + lane] = 0.0; else rb_reg[A::BIG ? 0 : c][A::BIG ? 0 : j] = 0.0;
             if (!lsc || j >= K) continue;
             const double* n = s_nrm + (j * M + m_cp) * 3;
             if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) continue;
             double b = p.rhs[((size_t) (obs0 + s_act[j]) * M + m_cp) * 6 + i_cp] - (n[0] * s_org[0] + n[1] * s_org[1]);
             if (D == 3) b -= n[2] * s_org[2];
-            rb[c][j] = b;
+            if (A::BIG) s_rb[(j * CPL + c) * 32 + lane] = b; else rb_reg[A::BIG ? 0 : c][A::BIG ? 0 : j] = b;
             rmask |= 1ull << (c * KPT + j);
         }
     }
@@ -373,9 +383,10 @@ das_solve_kernel(const SolveParams p) {
             const double cx = s_c[cp], cy = s_c[NCP + cp], cz = (D == 3) ? s_c[2 * NCP + cp] : 0.0;
 #pragma unroll
             for (int j = 0; j < KPT; j++) {
+                if (A::BIG && j >= K) break;
                 if (!(live >> (c * KPT + j) & 1ull)) continue;
                 const double* n = s_nrm + (j * M + m_cp) * 3;
-                double q = n[0] * cx + n[1] * cy - rb[c][j];
+                double q = n[0] * cx + n[1] * cy - LSCQP_RB(c, j);
                 if (D == 3) q += n[2] * cz;
                 if (q < best) { best = q; best_raw = q; best_slot = c * KPT + j; }
             }
@@ -426,7 +437,7 @@ das_solve_kernel(const SolveParams p) {
             for (int j = 0; j < KPT; j++) {
                 if (j >= K) break;                                        // (warp uniform)
                 const double* n = s_nrm + (j * M + m_cp) * 3;
-                double q = n[0] * cx + n[1] * cy - rb[c][j];
+                double q = n[0] * cx + n[1] * cy - LSCQP_RB(c, j);
                 if (D == 3) q += n[2] * cz;
                 q = (live >> (c * KPT + j) & 1ull) ? q : INFINITY;
                 if (q < best) { best = q; best_slot = c * KPT + j; }
@@ -515,7 +526,7 @@ das_solve_kernel(const SolveParams p) {
         const int pid = slot * 32 + lp;
         double sp = best * row_unscale(slot);                 // slack of the row being added (negative)
         int pr[9], pk[9], pc[9]; double pv[9];
-        das_row_pairs<C>(lp, slot, s_nrm, pr, pv, pk, pc);
+        das_row_pairs<C, KPT_>(lp, slot, s_nrm, pr, pv, pk, pc);
         // this lane's entries of n and of w = H^-1 n (H^-1 is block diagonal over the dimensions)
         double nr[RPL], w[RPL];
 #pragma unroll
@@ -647,7 +658,7 @@ das_solve_kernel(const SolveParams p) {
     for (int j = 0; j < q; j++) {                             // the active rows in order: <= 3 full-space entries each
         const int id = s_ids[j];
         int fk[3], fcp[3]; double fa[3];
-        das_row_full<C>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
+        das_row_full<C, KPT_>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
         const double uj = __shfl_sync(FULL, u_own, j);
         // lane k applies the entries of dimension k, in program order: no two lanes ever touch the same address
 #pragma unroll
@@ -707,5 +718,7 @@ das_solve_kernel(const SolveParams p) {
         }
     }
 }
+
+#undef LSCQP_RB
 
 }  // namespace lscqp

@@ -55,6 +55,7 @@ struct lscqp_handle {
     DevBuf d_proj_ent, d_proj_term, d_wp, d_klass, d_gout, d_knn;
     bool two_pass = false, last_two_pass = false;
     bool das = false;                   // dual active-set first pass available and enabled (das_kernel.cuh)
+    int das_big_slots = 0;              // batch size up to which the large active-set instance alone is the first pass
     DevBuf d_das;
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
@@ -108,6 +109,7 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
             delete h; return fail(LSCQP_E_CUDA, "active-set table upload failed");
         }
         h->base.das_tab = h->d_das.as<double>();
+        h->das_big_slots = info.das_big_slots;
     }
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
@@ -165,7 +167,7 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
     // latency bound and finishes sooner on the 128-thread instance alone.
     // first pass: the dual active-set kernel when available (any batch size: its per-QP latency is below that of the
     // 128-thread interior-point instance), else the light interior-point instance in the throughput regime
-    const int first_pass = h->das ? 2 : ((h->two_pass && n_agents >= h->two_pass_min) ? 1 : 0);
+    const int first_pass = h->das ? (n_agents <= h->das_big_slots ? 3 : 2) : ((h->two_pass && n_agents >= h->two_pass_min) ? 1 : 0);
     const bool two_pass = first_pass != 0;
     h->last_two_pass = two_pass;
     if (two_pass) {

@@ -30,3 +30,17 @@ print("assemble (fused) %.3f ms" % timed(lambda: qp.assemble_lsc_fused(sim.gener
 print("solve            %.3f ms" % timed(lambda: qp.solve_batch(n, sim.state, sim.goal, sim.limits, None, sim.obs_offsets, sim.normals, sim.rhs, sim.ctrl, sim.cost, sim.status, sim.iters, initial_traj=own)))
 print("iters mean %.2f  status!=0: %d" % (float(sim.iters.float().mean()), int((sim.status != 0).sum())))
 print("step kernel      %.3f ms" % timed(lambda: qp.step_batch(n, sim.ctrl, sim.cfg.dt, sim.traj_out, sim.state_out, sim.shifted)))
+# which pass solved the agents (0 = dual active set; otherwise its reason for deferring to the interior point), over a fresh run
+import numpy as np
+sim2 = ClosedLoopSim(batch, device=0, comm_range=3.0)
+hist = np.zeros(8, int)
+for s in range(args.steps):
+    sim2.step()
+    if s % 5 == 0:
+        torch.cuda.synchronize()
+        kl = sim2.planner.qp.last_instances(sim2.n_local)
+        hist += np.bincount(kl, minlength=8)[:8]
+        if (kl != 0).any() and s < 30:
+            a = int(np.where(kl != 0)[0][0])
+            print("  step", s, "deferred", int((kl != 0).sum()), "first agent", a, "reason", kl[a], "K", int(sim2.obs_offsets[a + 1] - sim2.obs_offsets[a]), "iters", int(sim2.iters[a]))
+print("pass histogram over the run (comm_range 3.0):", hist)

@@ -15,7 +15,30 @@ using namespace lscqp;
 
 extern "C" int emul_dual_stride(int M, int D, int comm) { return 40 * M * 6 + D * M * 6 * 6 + (comm ? 2 * D * (M * (M - 1) / 2 + M) : 0); }
 
-static int g_emul_das_solved = -1;      // agents the dual active-set pass solved in the last emul_solve_batch (-1: it did not run)
+static int g_emul_das_solved = -1;
+// dual active-set first pass on the emulator (the dispatch of solve_instances.hpp:das_launch); false: not available
+template <class I>
+static bool emul_das(const lscqp_config* cfg, SolveParams& p, int n_agents, std::vector<int>& klass) {
+    if constexpr (I::HAS_DAS) {
+        using C = typename I::Full;
+        static std::vector<double> dtab;
+        dtab = build_das_table<C>(p.Q2, cfg->w_terminal);
+        if (dtab.empty()) return false;
+        p.das_tab = dtab.data();
+        p.klass = klass.data(); p.klass_mode = 1;
+        emu::launch(n_agents, 32, Das<C, LSCQP_DAS_KPT>::SMEM_BYTES, [&]() { das_solve_kernel<C, LSCQP_DAS_KPT>(p); });
+        if (std::getenv("LSCQP_DAS_DEBUG")) for (int a = 0; a < n_agents; a++) if (klass[a]) fprintf(stderr, "das: agent %d deferred, reason %d\n", a, klass[a]);
+        if constexpr (I::HAS_DAS_BIG) {
+            p.klass_mode = 3;
+            emu::launch(n_agents, 32, Das<C, I::DAS_BIG_KPT>::SMEM_BYTES, [&]() { das_solve_kernel<C, I::DAS_BIG_KPT>(p); });
+        }
+        g_emul_das_solved = 0;
+        for (int a = 0; a < n_agents; a++) g_emul_das_solved += klass[a] == 0;
+        p.klass_mode = 2;
+        return true;
+    }
+    return false;
+}      // agents the dual active-set pass solved in the last emul_solve_batch (-1: it did not run)
 extern "C" int emul_das_solved() { return g_emul_das_solved; }
 extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
                                 const float* state, const float* goal, const double* limits, const float* sfc,
@@ -51,15 +74,7 @@ extern "C" int emul_solve_batch(const lscqp_config* cfg, int n_agents,
             return 0;                                                                       \
         }                                                                                   \
         std::vector<int> klass(n_agents + 1, 0);                                            \
-        const std::vector<double> dtab = I::HAS_DAS ? build_das_table<C>(p.Q2, cfg->w_terminal) : std::vector<double>(); \
-        if (I::HAS_DAS && !dtab.empty() && !(cfg->presolve & 8) && !std::getenv("LSCQP_DAS_OFF")) { \
-            p.das_tab = dtab.data();                                                        \
-            p.klass = klass.data(); p.klass_mode = 1;                                       \
-            emu::launch(n_agents, 32, Das<C>::SMEM_BYTES, [&]() { das_solve_kernel<C>(p); }); \
-            g_emul_das_solved = 0;                                                          \
-            for (int a = 0; a < n_agents; a++) g_emul_das_solved += klass[a] == 0;          \
-            if (std::getenv("LSCQP_DAS_DEBUG")) for (int a = 0; a < n_agents; a++) if (klass[a]) fprintf(stderr, "das: agent %d deferred, reason %d\n", a, klass[a]); \
-            p.klass_mode = 2;                                                               \
+        if (!(cfg->presolve & 8) && !std::getenv("LSCQP_DAS_OFF") && emul_das<I>(cfg, p, n_agents, klass)) {   \
         } else if (I::HAS_LIGHT && (cfg->presolve & 1) && !(cfg->presolve & 2)) {           \
             using L = typename I::Light;                                                    \
             p.klass = klass.data(); p.klass_mode = 1;                                       \

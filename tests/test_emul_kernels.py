@@ -35,6 +35,26 @@ def test_solve_kernel_matches_golden_solutions(name, cfg, K):
         assert kkt[:, 1].max() < 1e-9 and kkt[:, 3].max() < 1e-10
 
 
+def test_active_set_instances_by_kept_obstacles():
+    """dispatch of the dual active-set kernel on the emulator: up to 10 kept obstacles the throughput instance, 11..20 the
+    large instance (row constants in shared memory), beyond that the interior point -- the same optimum on every route"""
+    from common import oracle_qp_from_planes, oracle_solution
+    batch = W.make_forest_batch(64, K=40)
+    agents = [0, 7, 12, 33]
+    st = np.ascontiguousarray(batch.state[agents]); goal = np.ascontiguousarray(batch.goal[agents]); lim = np.ascontiguousarray(batch.limits[agents])
+    for K, solved_by_das in ((8, 4), (16, 4), (30, 0)):
+        off, nrm, rhs = W.make_synthetic_planes(batch, K=K)
+        sel_off = np.array([0] + list(np.cumsum([off[a + 1] - off[a] for a in agents])), np.int32)
+        sn = np.ascontiguousarray(np.concatenate([nrm[off[a]:off[a + 1]] for a in agents]))
+        sr = np.ascontiguousarray(np.concatenate([rhs[off[a]:off[a + 1]] for a in agents]))
+        ctrl, cost, status, iters, kkt, _ = emul.solve_batch(batch.cfg, len(agents), st, goal, lim, None, sel_off, sn, sr)
+        assert (status == 0).all()
+        assert emul.lib().emul_das_solved() == solved_by_das, (K, emul.lib().emul_das_solved())
+        for i, a in enumerate(agents):
+            xe, ok = oracle_solution(oracle_qp_from_planes(batch, a, sn[sel_off[i]:sel_off[i + 1]], sr[sel_off[i]:sel_off[i + 1]]))
+            assert ok and np.abs(ctrl[i] - xe).max() < 1e-5, (K, a, np.abs(ctrl[i] - xe).max())
+
+
 def test_solve_kernel_duals_give_a_kkt_certificate():
     """the multipliers returned in dual_out (reference row scaling) certify stationarity of the restated model"""
     cfg = W.PlannerConfig()

@@ -141,6 +141,29 @@ def test_solve_parity_synthetic_planes():
     _check_against_oracle(batch, agents, sel_off, sel_n, sel_r, ctrl, cost, status, min_checked=12)
 
 
+def test_active_set_large_instance_takes_dense_neighbourhoods():
+    """11..20 kept obstacles per agent (the dense spots of a closed loop): beyond the throughput active-set instance's
+    capacity, solved by its large instance (row constants in shared memory), never by silently dropping rows; beyond 20
+    the interior point takes over.  Both against the oracle."""
+    batch = W.make_forest_batch(128, K=40, seed=20260004)
+    for K, by_active_set in ((16, True), (28, False)):
+        off, normals, rhs = W.make_synthetic_planes(batch, K=K)
+        n = batch.n_agents
+        planner = _planner(batch.cfg)
+        agents = list(range(n))
+        ctrl, cost, status, iters, kkt, _ = _solve_host(planner, batch, agents, off, normals, rhs)
+        klass = planner.qp.last_instances(n)
+        assert (status == 0).all()
+        if by_active_set:
+            assert (klass == 0).mean() > 0.9, np.bincount(klass)       # (a few may exceed 32 active rows: interior point)
+        else:
+            assert (klass == 2).mean() > 0.5, np.bincount(klass)       # reason 2: more kept obstacles than the instance holds
+        sub = list(range(0, n, 8))
+        sel_off = np.array([0] + list(np.cumsum([off[a + 1] - off[a] for a in sub])), np.int32)
+        sel_n = np.concatenate([normals[off[a]:off[a + 1]] for a in sub]); sel_r = np.concatenate([rhs[off[a]:off[a + 1]] for a in sub])
+        _check_against_oracle(batch, sub, sel_off, sel_n, sel_r, ctrl[sub], cost[sub], status[sub], min_checked=12)
+
+
 def test_solve_with_sfc_boxes():
     """SFC rows (world_use_octomap): per-segment boxes around the previous solution"""
     cfg = W.PlannerConfig(use_sfc=True)
