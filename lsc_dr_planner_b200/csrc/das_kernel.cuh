@@ -52,8 +52,10 @@ struct Das {
     static constexpr bool BIG = KPT_ > 16;                  // row constants in shared memory
     static constexpr int NLSC = CPL * KPT;                  // row slots of a lane: LSC rows first, then 6 per variable
     static constexpr int NSLOT = NLSC + VPT * 6;
-    static constexpr int QMAX = LSCQP_DAS_QMAX;             // active rows this kernel holds (one lane each, <= 32)
-    static constexpr int LDJ = QMAX + 1;
+    // active rows the instance holds: one lane each in the throughput instance, every reduced variable (two per lane) in the large one
+    static constexpr int QMAX = BIG ? (NR < 64 ? NR : 64) : LSCQP_DAS_QMAX;
+    static constexpr int QSL = (QMAX + 31) / 32;            // active rows per lane
+    static constexpr int LDJ = QMAX | 1;
     static constexpr int KRAW = C::KRAW;
     static_assert(NSLOT <= 64, "row slots do not fit the 64-bit masks");
     static_assert(NR * LDJ >= NV, "full-space scratch does not fit under J1");
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(32, (KPT_ > 16 ? 6 : LSCQP_DAS_MINCTAS))
 das_solve_kernel(const SolveParams p) {
     using A = Das<C, KPT_>;
     constexpr int M = C::M, D = C::D, NCP = C::NCP, NV = C::NV, NR = C::NR;
-    constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1, QMAX = A::QMAX;
+    constexpr int RPL = A::RPL, VPT = A::VPT, CPL = A::CPL, KPT = A::KPT, LDJ = A::LDJ, N1 = A::N1, QMAX = A::QMAX, QSL = A::QSL;
     constexpr unsigned FULL = 0xffffffffu;
     LSCQP_DYN_SMEM(sm);
     const int lane = threadIdx.x & 31;
@@ -186,7 +188,7 @@ das_solve_kernel(const SolveParams p) {
     //  3 iteration cap, 4 infeasible row, 5 NaN, 6 feasibility / stationarity / multiplier check failed, 7 more active rows than QMAX)
     auto defer = [&](int why) { if (lane == 0) p.klass[agent] = why; };
 
-    if (p.klass_mode == 3 && p.klass[agent] != 2) return;                 // large instance: only what the first pass could not hold
+    if (p.klass_mode == 3 && p.klass[agent] != 2 && p.klass[agent] != 7) return;   // large instance: only what the first pass could not hold
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
     if (K < 0 || K > A::KRAW || K > p.max_obs) { defer(1); return; }      // (reported as ST_CAPACITY by the other pass)
@@ -472,8 +474,10 @@ das_solve_kernel(const SolveParams p) {
     // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l
     // of S becomes zero left of the last column; the new inverse factor is S without row l and without its last column,
     // and J1 follows with the same column rotations (its last column leaves the span).
-    int q = 0;                                                // size of the active set; lane j < q owns active row j
-    double u_own = 0.0;                                       // multiplier of this lane's active row
+    int q = 0;                                                // size of the active set; active row j is owned by lane j % 32, slot j / 32
+    double u_own[QSL];                                        // multipliers of this lane's active rows
+#pragma unroll
+    for (int t = 0; t < QSL; t++) u_own[t] = 0.0;
     auto drop = [&](int l) {
         const int id = s_ids[l];
         if (lane == (id & 31)) amask &= ~(1ull << (id >> 5));
@@ -484,11 +488,19 @@ das_solve_kernel(const SolveParams p) {
             const double h = sqrt(a * a + b * b);
             double cs = 1.0, sn = 0.0;
             if (h > 0.0) { cs = b / h; sn = a / h; }
-            const double xs = lane <= j ? cj[lane] : 0.0, ys = lane <= j + 1 ? cn[lane] : 0.0;
+            double xs[QSL], ys[QSL];
+#pragma unroll
+            for (int t = 0; t < QSL; t++) {
+                const int i = lane + 32 * t;
+                xs[t] = i <= j ? cj[i] : 0.0; ys[t] = i <= j + 1 ? cn[i] : 0.0;
+            }
             __syncwarp();
-            if (lane <= j + 1) {
-                cn[lane] = sn * xs + cs * ys;                                      // stays in place for the next rotation
-                if (lane != l) cj[lane < l ? lane : lane - 1] = cs * xs - sn * ys; // final: row l (now zero) removed
+#pragma unroll
+            for (int t = 0; t < QSL; t++) {
+                const int i = lane + 32 * t;
+                if (i > j + 1) continue;
+                cn[i] = sn * xs[t] + cs * ys[t];                                    // stays in place for the next rotation
+                if (i != l) cj[i < l ? i : i - 1] = cs * xs[t] - sn * ys[t];        // final: row l (now zero) removed
             }
 #pragma unroll
             for (int t = 0; t < RPL; t++) {
@@ -499,11 +511,21 @@ das_solve_kernel(const SolveParams p) {
             }
             __syncwarp();
         }
-        const double un = __shfl_down_sync(FULL, u_own, 1);
-        const int idn = (lane >= l && lane < q - 1) ? s_ids[lane + 1] : 0;
+        // the multipliers and ids behind position l move up by one (through s_d: dead until the next d1)
+#pragma unroll
+        for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j < q) s_d[j] = u_own[t]; }
         __syncwarp();
-        if (lane >= l && lane < q - 1) { u_own = un; s_ids[lane] = idn; }
-        if (lane == q - 1) u_own = 0.0;
+        int idn[QSL];
+#pragma unroll
+        for (int t = 0; t < QSL; t++) {
+            const int j = lane + 32 * t;
+            idn[t] = (j >= l && j < q - 1) ? s_ids[j + 1] : 0;
+            if (j >= l && j < q - 1) u_own[t] = s_d[j + 1];
+            if (j == q - 1) u_own[t] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j >= l && j < q - 1) s_ids[j] = idn[t]; }
         q--;
         __syncwarp();
     };
@@ -549,19 +571,25 @@ das_solve_kernel(const SolveParams p) {
         while (true) {                                         // until row p is added (or the model is found infeasible)
             if (++it > it_max) { fail = true; why = 3; break; }
             // d1 = J1'n (lane = active row), z = w - J1 d1, r = S d1
-            double dk = 0.0;
-            if (lane < q) {
 #pragma unroll
-                for (int i = 0; i < 9; i++) if (pv[i] != 0.0) dk += pv[i] * s_J[pr[i] * LDJ + lane];
+            for (int t = 0; t < QSL; t++) {
+                const int j = lane + 32 * t;
+                double dk = 0.0;
+                if (j < q) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) if (pv[i] != 0.0) dk += pv[i] * s_J[pr[i] * LDJ + j];
+                }
+                if (j < QMAX) s_d[j] = dk;
             }
-            s_d[lane] = dk;
             __syncwarp();
             // one pass over the active columns k: z = w - J1 d1 (this lane's RPL rows) and r_j = sum_{k >= j} S(j, k) d1_k
-            double zz[RPL], rj = 0.0;
+            double zz[RPL], rj[QSL];
             {
-                double za[RPL], zb[RPL], ra = 0.0, rb2 = 0.0;
+                double za[RPL], zb[RPL], ra[QSL], rb2[QSL];
 #pragma unroll
                 for (int t = 0; t < RPL; t++) { za[t] = 0.0; zb[t] = 0.0; }
+#pragma unroll
+                for (int t = 0; t < QSL; t++) { ra[t] = 0.0; rb2[t] = 0.0; }
                 const double* col = s_S;                        // column k of S starts at k (k + 1) / 2
                 int k = 0;
                 for (; k + 1 < q; k += 2) {
@@ -571,32 +599,41 @@ das_solve_kernel(const SolveParams p) {
                         const int r = lane + 32 * t;
                         if (r < NR) { za[t] += s_J[r * LDJ + k] * d0; zb[t] += s_J[r * LDJ + k + 1] * d1; }
                     }
-                    if (lane <= k) ra += col[lane] * d0;
+#pragma unroll
+                    for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j <= k) ra[t] += col[j] * d0; }
                     col += k + 1;
-                    if (lane <= k + 1) rb2 += col[lane] * d1;
+#pragma unroll
+                    for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j <= k + 1) rb2[t] += col[j] * d1; }
                     col += k + 2;
                 }
                 if (k < q) {
                     const double d0 = s_d[k];
 #pragma unroll
                     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) za[t] += s_J[r * LDJ + k] * d0; }
-                    if (lane <= k) ra += col[lane] * d0;
+#pragma unroll
+                    for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j <= k) ra[t] += col[j] * d0; }
                 }
 #pragma unroll
                 for (int t = 0; t < RPL; t++) zz[t] = w[t] - (za[t] + zb[t]);
-                rj = ra + rb2;
+#pragma unroll
+                for (int t = 0; t < QSL; t++) rj[t] = ra[t] + rb2[t];
             }
             double nzp = 0.0;
 #pragma unroll
             for (int t = 0; t < RPL; t++) nzp += nr[t] * zz[t];
             const double nz = warp_sum(nzp);                   // n'z = n'(H^-1 - J1 J1')n >= 0: the curvature along z
             // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible
-            double t1 = (lane < q && rj > 0.0) ? u_own / rj : INFINITY;
-            int l;
+            double t1 = INFINITY;
+            int l = 0;
+#pragma unroll
+            for (int t = 0; t < QSL; t++) {
+                const int j = lane + 32 * t;
+                if (j < q && rj[t] > 0.0) { const double ra = u_own[t] / rj[t]; if (ra < t1) { t1 = ra; l = j; } }
+            }
             {
                 const int wl = warp_argmin(t1);
                 t1 = __shfl_sync(FULL, t1, wl);
-                l = wl;
+                l = __shfl_sync(FULL, l, wl);
             }
             const bool dependent = !(nz > 1e-24 * nw);         // n in the span of the active normals: no primal step
             const double t2 = dependent ? INFINITY : -sp / nz;
@@ -607,7 +644,8 @@ das_solve_kernel(const SolveParams p) {
                 const int j = lane + 32 * t;
                 if (!dependent && j < NR) s_y[j] += tt * zz[t];
             }
-            if (lane < q) u_own -= tt * rj;
+#pragma unroll
+            for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j < q) u_own[t] -= tt * rj[t]; }
             u_new += tt;
             __syncwarp();
             if (t2 <= t1) {
@@ -618,8 +656,12 @@ das_solve_kernel(const SolveParams p) {
                 for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_J[r * LDJ + q] = zz[t] * rinv; }
                 // R gains the column (d1; rho), rho = sqrt(n'z):  S gains (-S d1; 1) / rho = (-r; 1) / rho
                 double* cq = s_S + q * (q + 1) / 2;
-                if (lane < q) cq[lane] = -rj * rinv;
-                if (lane == q) { cq[q] = rinv; u_own = u_new; s_ids[q] = pid; }
+#pragma unroll
+                for (int t = 0; t < QSL; t++) {
+                    const int j = lane + 32 * t;
+                    if (j < q) cq[j] = -rj[t] * rinv;
+                    if (j == q) { cq[q] = rinv; u_own[t] = u_new; s_ids[q] = pid; }
+                }
                 if (lane == lp) amask |= 1ull << slot;
                 q++;
                 q_top = q > q_top ? q : q_top;
@@ -659,7 +701,10 @@ das_solve_kernel(const SolveParams p) {
         const int id = s_ids[j];
         int fk[3], fcp[3]; double fa[3];
         das_row_full<C, KPT_>(id & 31, id >> 5, s_nrm, fk, fcp, fa);
-        const double uj = __shfl_sync(FULL, u_own, j);
+        double um = 0.0;
+#pragma unroll
+        for (int t = 0; t < QSL; t++) if ((j >> 5) == t) um = u_own[t];
+        const double uj = __shfl_sync(FULL, um, j & 31);
         // lane k applies the entries of dimension k, in program order: no two lanes ever touch the same address
 #pragma unroll
         for (int t = 0; t < 3; t++) if (lane == fk[t] && fa[t] != 0.0) s_full[fk[t] * NCP + fcp[t]] -= uj * fa[t];
@@ -669,7 +714,10 @@ das_solve_kernel(const SolveParams p) {
 #pragma unroll
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) rd = fmax(rd, fabs(reduce_from_full<C>(s_full, r))); }
     rd = warp_max(rd); gscale = warp_max(gscale);
-    const double umin = warp_min(lane < q ? u_own : 0.0);
+    double um_ = 0.0;
+#pragma unroll
+    for (int t = 0; t < QSL; t++) if (lane + 32 * t < q) um_ = fmin(um_, u_own[t]);
+    const double umin = warp_min(um_);
 #ifdef LSCQP_CUDA_EMUL
     if (lane == 0 && getenv("LSCQP_DAS_DEBUG")) fprintf(stderr, "das agent %d: it %d q %d rd %.3e gscale %.3e umin %.3e viol %.3e\n", agent, it, q, rd, gscale, umin, viol);
 #endif
@@ -706,14 +754,17 @@ das_solve_kernel(const SolveParams p) {
         for (int e = lane; e < p.dual_stride; e += 32) du[e] = 0.0;
         __syncwarp();
         const double sv = p.dt / 5.0, sa = p.dt * p.dt / 20.0;
-        if (lane < q) {
-            const int id = s_ids[lane], lo = id & 31, slot = id >> 5;
+#pragma unroll
+        for (int t = 0; t < QSL; t++) {
+            const int j = lane + 32 * t;
+            if (j >= q) continue;
+            const int id = s_ids[j], lo = id & 31, slot = id >> 5;
             if (slot < A::NLSC) {
                 const int cp = lo + 32 * (slot / KPT);
-                du[(s_act[slot % KPT] * M + cp / 6) * 6 + cp % 6] = u_own;
+                du[(s_act[slot % KPT] * M + cp / 6) * 6 + cp % 6] = u_own[t];
             } else {
                 const int b = slot - A::NLSC, e = b % 6, v = lo + 32 * (b / 6);
-                du[A::KRAW * M * 6 + v * 6 + e] = u_own * (e < 2 ? 1.0 : (e < 4 ? sv : sa));
+                du[A::KRAW * M * 6 + v * 6 + e] = u_own[t] * (e < 2 ? 1.0 : (e < 4 ? sv : sa));
             }
         }
     }

@@ -258,11 +258,11 @@ struct Instance {
     static constexpr bool HAS_LIGHT = !COMM_;
     // dual active-set first pass (das_kernel.cuh): banded models of at most 64 reduced variables (two per lane)
     static constexpr bool HAS_DAS = !COMM_ && Full::NR <= 64;
-    // ... and its large instance (up to 20 kept obstacles, row constants in shared memory) for the agents whose presolve keeps
-    // more obstacles than the throughput instance holds -- the dense spots of a closed loop; one control point per lane
-    // only (M = 5).  Beyond 20 kept obstacles the interior point is the better method (measured on config 4's synthetic
+    // ... and its large instance (up to 20 kept obstacles, row constants in shared memory, as many active rows as there are
+    // reduced variables) for the agents whose presolve keeps more obstacles, or whose optimum has more active rows, than
+    // the throughput instance holds -- the dense spots of a closed loop, near-vertex solutions.  Beyond 20 kept obstacles the interior point is the better method (measured on config 4's synthetic
     // planes, 30-40 kept: ~79 active-set iterations with many drops, 3.05 ms per 4096 QPs against 2.75 ms)
-    static constexpr bool HAS_DAS_BIG = HAS_DAS && M_ == 5;
+    static constexpr bool HAS_DAS_BIG = HAS_DAS;
     static constexpr int DAS_BIG_KPT = 20;
     // Communication-range configurations with few neighbours (the shipped 10-agent missions: K <= 9): half the threads
     // (2 obstacle groups x 5 rows), so twice as many CTAs share an SM while the dense factorisation of each runs.

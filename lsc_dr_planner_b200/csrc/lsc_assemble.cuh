@@ -238,6 +238,19 @@ __device__ __forceinline__ ClosestPts closest_points_segments(f3 l1s, f3 l1e, f3
     return r;
 }
 
+// one segment of a trajectory -- 6 control points x 3 floats = 72 bytes, 8-byte aligned -- as nine 64-bit read-only loads
+__device__ __forceinline__ void load_record(const float* rec, float* out /* [18] */) {
+    const float2* r2 = reinterpret_cast<const float2*>(rec);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const float2 v = __ldg(r2 + i); out[2 * i] = v.x; out[2 * i + 1] = v.y; }
+}
+// six row constants (48 bytes, 16-byte aligned) as three 128-bit stores
+__device__ __forceinline__ void store_rhs(double* ro, const double* v /* [6] */) {
+    double2* r2 = reinterpret_cast<double2*>(ro);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { double2 t; t.x = v[2 * i]; t.y = v[2 * i + 1]; r2[i] = t; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One (obstacle, segment) pair: the plane of the selected generator, packed (normal, rhs_i = n . p_i + d_i).
 // own_traj_: the agent's initial trajectory [M][6][3] (shared or global memory); j: row of the obstacle in the CSR arrays.
@@ -260,10 +273,12 @@ if (p.obs_index) {
     const float* opos = p.obs_index ? p.all_state + src * 9 : p.obs_position + j * 3;
 
     f3 own[6], obs[6], own_t[6], obs_t[6];
+    float orec[18];
+    load_record(ot, orec);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         own[i] = f3_make(own_traj_[m * 18 + i * 3], own_traj_[m * 18 + i * 3 + 1], own_traj_[m * 18 + i * 3 + 2]);
-        obs[i] = f3_make(ot[i * 3], ot[i * 3 + 1], ot[i * 3 + 2]);
+        obs[i] = f3_make(orec[i * 3], orec[i * 3 + 1], orec[i * 3 + 2]);
         own_t[i] = own[i]; obs_t[i] = obs[i];
         if (transform) {                                                        // trajectory.cpp:207-219
             own_t[i].z = __fdiv_rn(own[i].z, dwf); obs_t[i].z = __fdiv_rn(obs[i].z, dwf);
@@ -297,13 +312,14 @@ if (p.obs_index) {
         const double nx3 = (double) normal.x, ny3 = (double) normal.y, nz3 = (double) normal.z;
         double* no3 = p.normals + (j * M + m) * 3;
         no3[0] = nx3; no3[1] = ny3; no3[2] = nz3;
-        double* ro3 = p.rhs + (j * M + m) * 6;
+        double rv3[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             double b = nx3 * (double) pt[i].x + ny3 * (double) pt[i].y;
             if (p.dim == 3) b += nz3 * (double) pt[i].z;
-            ro3[i] = b + d[i];
+            rv3[i] = b + d[i];
         }
+        store_rhs(p.rhs + (j * M + m) * 6, rv3);
         return;
     }
     if (p.generator == 2) {                                                     // generateBVC :708-736
@@ -348,13 +364,14 @@ if (p.obs_index) {
     const double nx = (double) normal.x, ny = (double) normal.y, nz = (double) normal.z;
     double* no = p.normals + (j * M + m) * 3;
     no[0] = nx; no[1] = ny; no[2] = nz;
-    double* ro = p.rhs + (j * M + m) * 6;
+    double rv[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         double b = nx * (double) pt[i].x + ny * (double) pt[i].y;               // traj_optimizer.cpp:414-421
         if (p.dim == 3) b += nz * (double) pt[i].z;
-        ro[i] = b + d[i];
+        rv[i] = b + d[i];
     }
+    store_rhs(p.rhs + (j * M + m) * 6, rv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,12 +445,14 @@ lsc_assemble_kernel(const AssembleParams p) {
                 const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);
                 const double iz = 1.0 / downwash;
                 const float* ot = (p.obs_index ? p.all_traj : p.obs_traj) + (src * M + m) * 18;
+                float orec[18];
+                load_record(ot, orec);
                 double r[6][3], cx = 0, cy = 0, cz = 0, emax = 0;
                 const double vstep = sqrt(s_x0[3] * s_x0[3] + s_x0[4] * s_x0[4] + s_x0[5] * s_x0[5] * iz * iz);
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     const double ox = (double) s_own[m * 18 + i * 3], oy = (double) s_own[m * 18 + i * 3 + 1], oz = (double) s_own[m * 18 + i * 3 + 2];
-                    r[i][0] = ox - (double) ot[i * 3]; r[i][1] = oy - (double) ot[i * 3 + 1]; r[i][2] = (oz - (double) ot[i * 3 + 2]) * iz;
+                    r[i][0] = ox - (double) orec[i * 3]; r[i][1] = oy - (double) orec[i * 3 + 1]; r[i][2] = (oz - (double) orec[i * 3 + 2]) * iz;
                     cx += r[i][0]; cy += r[i][1]; cz += r[i][2];
                     if (m == 0 && i < 3) continue;                                      // no such rows (traj_optimizer.cpp:404)
                     const double ex = s_x0[0] - ox, ey = s_x0[1] - oy, ez = (s_x0[2] - oz) * iz;
@@ -450,9 +469,8 @@ lsc_assemble_kernel(const AssembleParams p) {
             if (drop) {
                 double* no = p.normals + (j * M + m) * 3;
                 no[0] = 0.0; no[1] = 0.0; no[2] = 0.0;
-                double* ro = p.rhs + (j * M + m) * 6;
-#pragma unroll
-                for (int i = 0; i < 6; i++) ro[i] = 0.0;
+                const double zero6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                store_rhs(p.rhs + (j * M + m) * 6, zero6);
             } else {
                 s_list[atomicAdd(&s_cnt[0], 1)] = (unsigned short) e;      // (order does not matter: pairs are independent)
             }

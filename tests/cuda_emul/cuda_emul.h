@@ -26,6 +26,8 @@ struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 struct double2 { double x, y; };
+struct float2 { float x, y; };
+template <class T> inline T __ldg(const T* p) { return *p; }
 namespace emu {
 struct Thread {
     ucontext_t ctx;

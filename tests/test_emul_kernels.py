@@ -55,6 +55,21 @@ def test_active_set_instances_by_kept_obstacles():
             assert ok and np.abs(ctrl[i] - xe).max() < 1e-5, (K, a, np.abs(ctrl[i] - xe).max())
 
 
+def test_active_set_many_active_rows_case():
+    """tests/golden/many_active_rows_case.npz: the agent of the 8-GPU bench batches (seed 20260007, agent 2515) whose optimum
+    has 35 active rows -- more than the throughput active-set instance holds (32): taken over by the large instance
+    (two active rows per lane), not by the slower interior point; same optimum as the oracle's"""
+    g = np.load(os.path.join(GOLDEN, "many_active_rows_case.npz"))
+    cfg = W.make_forest_batch(8, K=4).cfg
+    cfg.world_min = (-66.0, -66.0, 0.0); cfg.world_max = (66.0, 66.0, 2.5)
+    off = np.array([0, g["normals"].shape[0]], np.int32)
+    ctrl, cost, status, iters, kkt, _ = emul.solve_batch(cfg, 1, g["state"][None].copy(), g["goal"][None].copy(), g["limits"][None].copy(),
+                                                         None, off, np.ascontiguousarray(g["normals"]), np.ascontiguousarray(g["rhs"]))
+    assert status[0] == 0 and emul.lib().emul_das_solved() == 1
+    assert int(kkt[0, 2]) // 64 > 32                                  # largest active set of the run
+    assert np.abs(ctrl[0] - g["x"]).max() < 1e-8
+
+
 def test_solve_kernel_duals_give_a_kkt_certificate():
     """the multipliers returned in dual_out (reference row scaling) certify stationarity of the restated model"""
     cfg = W.PlannerConfig()
