@@ -77,6 +77,9 @@ struct Das {
     static constexpr int O_R = O_J + NR * LDJ;              // S = R^-1, upper triangular, packed by columns: S(j, k) at k (k + 1) / 2 + j
     static constexpr int O_INT = O_R + QMAX * (QMAX + 1) / 2;   // int ids[QMAX] (active rows: slot * 32 + lane), act[KRAW], keep[KRAW + 2]
     static constexpr int O_END = O_INT + (QMAX + 2 * KRAW + 2 + 1) / 2;
+    // checkpoint of the throughput instance (SolveParams::das_ckpt), in doubles: q, it, y[NR], u[QF], ids[QF], J1[NR][QF], S packed
+    static constexpr int QF = LSCQP_DAS_QMAX, KF = LSCQP_DAS_KPT;
+    static constexpr int CK_Y = 2, CK_U = CK_Y + NR, CK_ID = CK_U + QF, CK_J = CK_ID + QF, CK_S = CK_J + NR * QF, CK_STRIDE = CK_S + QF * (QF + 1) / 2;
     static constexpr int SMEM_BYTES = O_END * 8;
 };
 
@@ -187,8 +190,9 @@ das_solve_kernel(const SolveParams p) {
     // (klass: 0 solved here; else the reason -- 1 obstacle list beyond the ABI capacity, 2 more kept obstacles than KPT,
     //  3 iteration cap, 4 infeasible row, 5 NaN, 6 feasibility / stationarity / multiplier check failed, 7 more active rows than QMAX)
     auto defer = [&](int why) { if (lane == 0) p.klass[agent] = why; };
+    const int kl_in = p.klass_mode == 3 ? p.klass[agent] : 0;            // (large instance: the first pass's verdict, + checkpoint slot)
 
-    if (p.klass_mode == 3 && p.klass[agent] != 2 && p.klass[agent] != 7) return;   // large instance: only what the first pass could not hold
+    if (p.klass_mode == 3 && (kl_in & 15) != 2 && (kl_in & 15) != 7) return;   // large instance: only what the first pass could not hold
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
     if (K < 0 || K > A::KRAW || K > p.max_obs) { defer(1); return; }      // (reported as ST_CAPACITY by the other pass)
@@ -343,6 +347,7 @@ das_solve_kernel(const SolveParams p) {
 
     // ---- unconstrained minimiser y = -H^-1 g, H^-1 from the table of this agent's terminal-segment count
     const double* Hinv = p.das_tab + (size_t) (ts - 1) * 2 * N1 * N1;
+    const int ck_slot = A::BIG ? (kl_in >> 4) : 0;                        // > 0: resume from the throughput instance's checkpoint
 #pragma unroll
     for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_y[r] = 0.0; }
     __syncwarp();
@@ -532,6 +537,29 @@ das_solve_kernel(const SolveParams p) {
 
     // ---- main loop
     int it = 0, why = 5, q_top = 0;
+    bool ck_ok = false;                                       // the state at the point of failure can be handed over
+    if (A::BIG && ck_slot > 0) {
+        // resume: the state the throughput instance left when it needed one more active row than it holds
+        const double* ck = p.das_ckpt + (size_t) (ck_slot - 1) * A::CK_STRIDE;
+        q = (int) ck[0]; it = (int) ck[1]; q_top = q;
+#pragma unroll
+        for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_y[r] = ck[A::CK_Y + r]; }
+#pragma unroll
+        for (int t = 0; t < QSL; t++) {
+            const int j = lane + 32 * t;
+            u_own[t] = j < q ? ck[A::CK_U + j] : 0.0;
+            if (j < q) {
+                // row ids are (slot, lane) pairs and the slot numbering depends on the instance's obstacle capacity
+                const int idf = (int) ck[A::CK_ID + j], lo = idf & 31, sf = idf >> 5;
+                const int sb = sf < CPL * A::KF ? (sf / A::KF) * KPT + sf % A::KF : sf - CPL * A::KF + A::NLSC;
+                s_ids[j] = sb * 32 + lo;
+            }
+        }
+        for (int e = lane; e < NR * q; e += 32) { const int r = e / q, k = e % q; s_J[r * LDJ + k] = ck[A::CK_J + r * A::QF + k]; }
+        for (int e = lane; e < q * (q + 1) / 2; e += 32) s_S[e] = ck[A::CK_S + e];
+        __syncwarp();
+        for (int j = 0; j < q; j++) { const int id = s_ids[j]; if (lane == (id & 31)) amask |= 1ull << (id >> 5); }
+    }
     const int it_max = 4 * NR + 40;
     bool ok = false;
     double viol = 0.0;
@@ -639,6 +667,12 @@ das_solve_kernel(const SolveParams p) {
             const double t2 = dependent ? INFINITY : -sp / nz;
             const double tt = fmin(t1, t2);
             if (tt == INFINITY) { fail = true; why = 4; break; }         // infeasible (or numerically so): the other pass decides
+            if (t2 <= t1 && q >= QMAX) {
+                // a full step would add a row this instance cannot hold.  Nothing of row p has been applied yet when its
+                // multiplier is still zero: (y, active set, u) is then a consistent pair the large instance can resume from.
+                fail = true; why = 7; ck_ok = u_new == 0.0; it--;
+                break;
+            }
 #pragma unroll
             for (int t = 0; t < RPL; t++) {
                 const int j = lane + 32 * t;
@@ -650,7 +684,6 @@ das_solve_kernel(const SolveParams p) {
             __syncwarp();
             if (t2 <= t1) {
                 // full step: row p joins the active set
-                if (q >= QMAX) { fail = true; why = 7; break; }
                 const double rinv = 1.0 / sqrt(nz);
 #pragma unroll
                 for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_J[r * LDJ + q] = zz[t] * rinv; }
@@ -681,7 +714,28 @@ das_solve_kernel(const SolveParams p) {
         }
         if (fail) break;
     }
-    if (!ok) { defer(why); return; }
+    if (!ok) {
+#ifndef LSCQP_DAS_NO_CKPT
+        if (!A::BIG && why == 7 && ck_ok && p.das_ckpt) {
+            // hand-over to the large instance (SolveParams::das_ckpt): the state goes into a pool slot, the slot number into
+            // klass[] (bits 4 and up) beside the reason
+            int slot_ck = 0;
+            if (lane == 0) slot_ck = atomicAdd(p.das_ckpt_count, 1);
+            slot_ck = __shfl_sync(FULL, slot_ck, 0);
+            if (slot_ck < p.das_ckpt_slots) {
+                double* ck = p.das_ckpt + (size_t) slot_ck * A::CK_STRIDE;
+                if (lane == 0) { ck[0] = (double) q; ck[1] = (double) it; }
+                for (int r = lane; r < NR; r += 32) ck[A::CK_Y + r] = s_y[r];
+#pragma unroll
+                for (int t = 0; t < QSL; t++) { const int j = lane + 32 * t; if (j < q) { ck[A::CK_U + j] = u_own[t]; ck[A::CK_ID + j] = (double) s_ids[j]; } }
+                for (int e = lane; e < NR * q; e += 32) { const int r = e / q, k = e % q; ck[A::CK_J + r * A::QF + k] = s_J[r * LDJ + k]; }
+                for (int e = lane; e < q * (q + 1) / 2; e += 32) ck[A::CK_S + e] = s_S[e];
+                why = 7 | ((slot_ck + 1) << 4);
+            }
+        }
+#endif
+        defer(why); return;
+    }
 
     // ---- verification and outputs.  s_c holds the final point.  The active rows are zero only up to the rounding of the
     // updates: re-evaluated like the others.  Stationarity Z'(grad f - sum u_j n_j) from scratch (J1 is dead: its storage is

@@ -56,7 +56,7 @@ struct lscqp_handle {
     bool two_pass = false, last_two_pass = false;
     bool das = false;                   // dual active-set first pass available and enabled (das_kernel.cuh)
     int das_big_slots = 0;              // batch size up to which the large active-set instance alone is the first pass
-    DevBuf d_das;
+    DevBuf d_das, d_ckpt;               // active-set table; checkpoint pool of the instance hand-over (+ its counter)
     size_t knn_smem = 0;
     int two_pass_min = 1536;       // batch size from which the light first pass is used (LSCQP_TWO_PASS_MIN overrides)
     unsigned long long launches = 0;
@@ -110,6 +110,13 @@ extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** 
         }
         h->base.das_tab = h->d_das.as<double>();
         h->das_big_slots = info.das_big_slots;
+        if (info.das_ckpt_stride > 0) {
+            const int slots = 64;
+            if (h->d_ckpt.reserve(16 + (size_t) slots * info.das_ckpt_stride * sizeof(double))) { delete h; return fail(LSCQP_E_CUDA, "cudaMalloc failed"); }
+            h->base.das_ckpt_count = h->d_ckpt.as<int>();
+            h->base.das_ckpt = reinterpret_cast<double*>(h->d_ckpt.as<char>() + 16);
+            h->base.das_ckpt_slots = slots;
+        }
     }
     const ProjTable& tab = info.tab;
     const ProjTable& tabl = info.tab_light;
@@ -135,7 +142,7 @@ extern "C" int lscqp_destroy(lscqp_handle* h) {
     DevBuf* bufs[] = {&h->d_state, &h->d_goal, &h->d_limits, &h->d_sfc, &h->d_off, &h->d_normals, &h->d_rhs, &h->d_ctrl,
                       &h->d_cost, &h->d_status, &h->d_iters, &h->d_kkt, &h->d_dual, &h->d_own, &h->d_ameta, &h->d_index,
                       &h->d_proj_ent, &h->d_proj_term, &h->d_wp,
-                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes, &h->d_work, &h->d_das};
+                      &h->d_klass, &h->d_gout, &h->d_knn, &h->d_occ, &h->d_closest, &h->d_boxes, &h->d_work, &h->d_das, &h->d_ckpt};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -176,6 +183,7 @@ extern "C" int lscqp_solve_batch(lscqp_handle* h, int n_agents, const float* sta
         // (routing the remainder of the light pass's last round to the full-capacity pass was measured: 1.65 vs 1.52 ms
         //  per 4096 QPs -- the QPs' durations spread over 8..11 iterations, so the rounds do not end together)
     }
+    if (first_pass == 2 && p.das_ckpt) CK(cudaMemsetAsync(p.das_ckpt_count, 0, sizeof(int), st));
     int launched = inst_launch_0(h->cfg, p, n_agents, first_pass, st);
     if (!launched) launched = inst_launch_1(h->cfg, p, n_agents, first_pass, st);
     if (!launched) launched = inst_launch_2(h->cfg, p, n_agents, first_pass, st);

@@ -96,6 +96,12 @@ struct SolveParams {
     // dual active-set first pass (das_kernel.cuh): per terminal-segment count ts = 1..M the inverse reduced Hessian of one
     // dimension and its inverse Cholesky factor, [M][2][N1][N1] (host_common.hpp:build_das_table)
     const double* das_tab;
+    // hand-over from the throughput active-set instance to the large one: an agent that needs a 33rd active row writes its
+    // state (iterate, multipliers, active rows, J1, S) into a slot of this pool and passes the slot number in klass[]
+    // (bits 4 and up), so the large instance resumes instead of starting over.  Null / exhausted pool: it starts over.
+    double* das_ckpt;
+    int*    das_ckpt_count;
+    int     das_ckpt_slots;
 };
 
 enum { ST_OK = 0, ST_MAX_ITER = 1, ST_INFEASIBLE = 2, ST_NUMERICAL = 3, ST_CAPACITY = 4 };

@@ -10,6 +10,7 @@ struct InstanceInfo {
     int dual_stride = 0, kmax = 0, nv = 0;
     bool has_light = false, has_das = false;
     int das_big_slots = 0;         // CTAs of the large active-set instance the device holds at once (0: no such instance)
+    int das_ckpt_stride = 0;       // doubles per checkpoint slot of the hand-over between the two instances (0: none)
     std::vector<double> das_tab;   // host_common.hpp:build_das_table (empty: no dual active-set pass)
     ProjTable tab, tab_light;      // projection term streams of the full-capacity / light instance
 };
@@ -77,6 +78,7 @@ static int das_prepare(const lscqp_config& cfg, InstanceInfo* info) {
                                                                   Das<C, I::DAS_BIG_KPT>::SMEM_BYTES) != cudaSuccess) return -1;
                 if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
                 info->das_big_slots = per_sm * sms;
+                info->das_ckpt_stride = Das<C, LSCQP_DAS_KPT>::CK_STRIDE;
             }
         }
     }

@@ -21,3 +21,10 @@ print("active rows: final mean %.1f max %d; largest during the run max %d (capac
 print("stationarity max", kkt[kl == 0, 0].max(), "primal max", kkt[kl == 0, 1].max())
 for a in np.where(kl != 0)[0][:10]:
     print("  agent", a, "klass", kl[a], "status", st[a], "iters", it[a])
+
+stream = torch.cuda.current_stream().cuda_stream
+ts = []
+for rep in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); pl.solve_device(d, stream=stream); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+print("solve ms (L2 warm): min %.4f median %.4f" % (min(ts), sorted(ts)[2]))

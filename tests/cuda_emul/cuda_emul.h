@@ -18,6 +18,7 @@
 #define __global__
 #define __device__
 #define __host__
+#define __noinline__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__

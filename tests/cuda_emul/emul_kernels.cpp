@@ -25,6 +25,9 @@ static bool emul_das(const lscqp_config* cfg, SolveParams& p, int n_agents, std:
         dtab = build_das_table<C>(p.Q2, cfg->w_terminal);
         if (dtab.empty()) return false;
         p.das_tab = dtab.data();
+        static std::vector<double> ckpt; static int ckpt_count;
+        ckpt.assign((size_t) 8 * Das<C, LSCQP_DAS_KPT>::CK_STRIDE, 0.0); ckpt_count = 0;
+        if (I::HAS_DAS_BIG && !std::getenv("LSCQP_DAS_NO_CKPT")) { p.das_ckpt = ckpt.data(); p.das_ckpt_count = &ckpt_count; p.das_ckpt_slots = 8; }
         p.klass = klass.data(); p.klass_mode = 1;
         emu::launch(n_agents, 32, Das<C, LSCQP_DAS_KPT>::SMEM_BYTES, [&]() { das_solve_kernel<C, LSCQP_DAS_KPT>(p); });
         if (std::getenv("LSCQP_DAS_DEBUG")) for (int a = 0; a < n_agents; a++) if (klass[a]) fprintf(stderr, "das: agent %d deferred, reason %d\n", a, klass[a]);
