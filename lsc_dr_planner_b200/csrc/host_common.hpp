@@ -256,8 +256,11 @@ struct Instance {
     using Full = Cfg<M_, D_, T_, 4, 10, COMM_>;
     using Light = Cfg<M_, D_, T_, LSCQP_LIGHT_G, LSCQP_LIGHT_KPT, false>;
     static constexpr bool HAS_LIGHT = !COMM_;
-    // dual active-set first pass (das_kernel.cuh): banded models of at most 64 reduced variables (two per lane)
-    static constexpr bool HAS_DAS = !COMM_ && Full::NR <= 64;
+    // dual active-set first pass (das_kernel.cuh): the M = 5 models without communication-range rows.  For M = 10 the
+    // randomised sweep (scripts/gpu_fuzz.py) shows the method at a disadvantage on both counts: 90-170 iterations (60
+    // variables, many drops) against 10-14 interior-point iterations, and a reduced Hessian with nearly flat directions,
+    // where its 4e-8 stationarity residual leaves a few agents per thousand up to 6e-5 m from the optimum.
+    static constexpr bool HAS_DAS = !COMM_ && M_ == 5;
     // ... and its large instance (up to 20 kept obstacles, row constants in shared memory, as many active rows as there are
     // reduced variables) for the agents whose presolve keeps more obstacles, or whose optimum has more active rows, than
     // the throughput instance holds -- the dense spots of a closed loop, near-vertex solutions.  Beyond 20 kept obstacles the interior point is the better method (measured on config 4's synthetic

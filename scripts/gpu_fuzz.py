@@ -1,5 +1,6 @@
-"""Randomised robustness sweep on the GPU (development aid): many workload shapes through both dispatch modes; reports
-failures, self-certified KKT residuals and light-vs-full agreement.  python scripts/gpu_fuzz.py [n_rounds]"""
+"""Randomised robustness sweep on the GPU (development aid): many workload shapes through three dispatches -- the default
+(dual active-set passes first), the interior-point instances alone, and those without presolve; reports failures,
+self-certified KKT residuals, the share of agents the active-set passes solved and the agreement between the dispatches.  python scripts/gpu_fuzz.py [n_rounds]"""
 import copy, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,13 +27,19 @@ for r in range(rounds):
         batch.goal = g.astype(np.float32)
     gen = capi.GEN_LSC if (mode == 0 or rng.random() < 0.5) else capi.GEN_CLSC
     res = []
-    for presolve in (1, 3, 0):
+    share = 0.0
+    for presolve in (1, 9, 8):
         c = copy.copy(batch.cfg); c.presolve = presolve
         pl = BatchPlanner(c, device=0)
         d = pl.upload(batch)
         pl.assemble_fused_device(d, gen)
         pl.solve_device(d, want_kkt=True, warm=bool(r % 3))
         torch.cuda.synchronize()
+        if presolve == 1:
+            try:
+                share = float((pl.qp.last_instances(n) == 0).mean())
+            except Exception:
+                share = -1.0
         res.append((d.ctrl.clone(), d.status.clone(), d.kkt.clone(), float(d.iters.float().mean())))
     s = [x[1] for x in res]
     ok = (s[0] == 0) & (s[1] == 0) & (s[2] == 0)
@@ -49,6 +56,6 @@ for r in range(rounds):
         i = int(torch.nonzero(big)[0])
         print(f"    {int(big.sum())} agents differ by > 1e-5 (vs full: {int((ok & (dfull > 1e-5)).sum())}, vs no-presolve: {int((ok & (dnop > 1e-5)).sum())}); "
               f"agent {i}: kkt two-pass {res[0][2][i].tolist()} no-presolve {res[2][2][i].tolist()}")
-    print(f"round {r:2d} M{M} D{dim} mode{mode} gen{gen} K{K:2d} n{n}: not-ok {nbad} (statuses two-pass/full/no-presolve "
+    print(f"round {r:2d} M{M} D{dim} mode{mode} gen{gen} K{K:2d} n{n}: active-set share {share:.3f}, not-ok {nbad} (statuses default/interior-point/no-presolve "
           f"{[int((x != 0).sum()) for x in s]}), iters {res[0][3]:.2f}/{res[1][3]:.2f}/{res[2][3]:.2f}, max diff {dd:.2e}, finite {fin}")
 print("total agents", tot, "not ok", bad, "worst", worst)
