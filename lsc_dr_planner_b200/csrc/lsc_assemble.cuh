@@ -448,7 +448,9 @@ lsc_assemble_kernel(const AssembleParams p) {
                 float orec[18];
                 load_record(ot, orec);
                 double r[6][3], cx = 0, cy = 0, cz = 0, emax = 0;
-                const double vstep = sqrt(s_x0[3] * s_x0[3] + s_x0[4] * s_x0[4] + s_x0[5] * s_x0[5] * iz * iz);
+                // (square roots in float: their 6e-8 relative error on lengths of a few metres is far inside the 1e-3 margin;
+                //  one division for the whole pair: min_i (r_i . c) / |c|)
+                const double vstep = (double) sqrtf((float) (s_x0[3] * s_x0[3] + s_x0[4] * s_x0[4] + s_x0[5] * s_x0[5] * iz * iz));
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     const double ox = (double) s_own[m * 18 + i * 3], oy = (double) s_own[m * 18 + i * 3 + 1], oz = (double) s_own[m * 18 + i * 3 + 2];
@@ -456,13 +458,14 @@ lsc_assemble_kernel(const AssembleParams p) {
                     cx += r[i][0]; cy += r[i][1]; cz += r[i][2];
                     if (m == 0 && i < 3) continue;                                      // no such rows (traj_optimizer.cpp:404)
                     const double ex = s_x0[0] - ox, ey = s_x0[1] - oy, ez = (s_x0[2] - oz) * iz;
-                    emax = fmax(emax, sqrt(ex * ex + ey * ey + ez * ez) + (double) (5 * m + i - 2) * vstep);
+                    emax = fmax(emax, (double) sqrtf((float) (ex * ex + ey * ey + ez * ez)) + (double) (5 * m + i - 2) * vstep);
                 }
-                const double cn = sqrt(cx * cx + cy * cy + cz * cz);
+                const double cn = (double) sqrtf((float) (cx * cx + cy * cy + cz * cz));
                 if (cn > 0.0) {
                     double lb = 1e300;
 #pragma unroll
-                    for (int i = 0; i < 6; i++) lb = fmin(lb, (r[i][0] * cx + r[i][1] * cy + r[i][2] * cz) / cn);
+                    for (int i = 0; i < 6; i++) lb = fmin(lb, r[i][0] * cx + r[i][1] * cy + r[i][2] * cz);
+                    lb /= cn;
                     drop = lb > (o_r + a_r) + 2.0 * emax + 1e-3;
                 }
             }

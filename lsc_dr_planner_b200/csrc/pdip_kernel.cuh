@@ -578,6 +578,7 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
     const int tid = threadIdx.x, lane = tid & 31;
     const int agent = blockIdx.x;
     if (agent >= p.n_agents) return;
+    if (p.klass_mode == 2 && p.klass[agent] == 0) return;                // solved by the first pass already
 
     double* sQ2 = sm + C::O_Q2;
     double* s_c = sm + C::O_C;
@@ -654,7 +655,6 @@ pdip_solve_kernel(const SolveParams p) {   // @phase setup
 
     const int obs0 = p.obs_offsets[agent];
     int K = p.obs_offsets[agent + 1] - obs0;
-    if (p.klass_mode == 2 && p.klass[agent] == 0) return;                // solved by the light instance already
     // The reference's model takes every obstacle it is handed (traj_optimizer.cpp:400-437 loops over getObsSize()):
     // a list this instance cannot hold is reported through status_out (LSCQP_CAPACITY), never silently shortened.
     bool cap_fail = K < 0 || K > C::KRAW || K > p.max_obs;
