@@ -480,22 +480,98 @@ lsc_assemble_kernel(const AssembleParams p) {
         }
         __syncthreads();
         n_work = s_cnt[0];
-        if (p.work_list) {
-            if (threadIdx.x == 0) s_cnt[1] = atomicAdd(p.work_count, n_work);
-            __syncthreads();
-            const int base = s_cnt[1];
-            for (int w = threadIdx.x; w < n_work; w += blockDim.x) {
-                const int e = (int) s_list[w];
-                int2 item; item.x = agent; item.y = (obs0 + e / M) * M + e % M;
-                p.work_list[base + w] = item;
-            }
-            return;
-        }
     }
 
     for (int w = threadIdx.x; w < n_work; w += blockDim.x) {
         const int e = prune ? (int) s_list[w] : w;
         assemble_pair<M>(p, agent, (size_t) obs0 + e / M, e % M, s_own, a_r, a_dw);
+    }
+}
+
+// first half of the split dispatch (lscqp_assemble_lsc_fused at throughput batch sizes): the pruning test alone, one CTA per
+// agent, no shared memory and no CTA barrier -- every warp runs on its own: the agent's constants and trajectory come
+// through L1 (broadcast loads), a dropped pair is zeroed at once, the surviving pairs of a warp are appended to the global
+// work list with one atomicAdd per warp (ballot + prefix).  Without the hull enumeration in the same kernel the register
+// budget allows twice the resident warps, which is what hides the cold-cache latency of the neighbours' records.
+template <int M>
+__global__ void __launch_bounds__(128, 8)
+lsc_prune_kernel(const AssembleParams p) {
+    const int agent = blockIdx.x;
+    if (agent >= p.n_agents) return;
+    const int lane = threadIdx.x & 31;
+    const int obs0 = p.obs_offsets[agent], K = p.obs_offsets[agent + 1] - obs0;
+    const double a_r = p.agent_meta[agent * 2 + 0], a_dw = p.agent_meta[agent * 2 + 1];
+    // the same fixed third control point and velocity step the solve kernels' presolve uses
+    double x0[3], vl[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double pos = (double) p.state[agent * 9 + k], vel = (double) p.state[agent * 9 + 3 + k], acc = (double) p.state[agent * 9 + 6 + k];
+        const double c1 = pos + vel * p.dt / 5.0;
+        x0[k] = acc * p.dt * p.dt / 20.0 + 2.0 * c1 - pos;
+        vl[k] = p.limits[agent * 8 + k] * p.dt / 5.0;
+    }
+    const float* own_traj = p.own_traj + (size_t) agent * M * 18;
+    for (int e0 = 0; e0 < K * M; e0 += blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        const bool valid = e < K * M;
+        bool drop = false;
+        size_t j = 0;
+        int m = 0;
+        if (valid) {
+            const int oi = e / M;
+            m = e % M;
+            j = (size_t) obs0 + oi;
+            double o_r, o_dw;
+            size_t src = j;
+            if (p.obs_index) {
+                src = (size_t) p.obs_index[j];
+                o_r = (double) (float) p.all_meta[src * 2 + 0]; o_dw = (double) (float) p.all_meta[src * 2 + 1];   // agent_manager.cpp:184-199
+            } else { o_r = (double) p.obs_meta[j * 4 + 0]; o_dw = (double) p.obs_meta[j * 4 + 1]; }
+            if (!(p.generator == 1 && m == M - 1)) {
+                // the sufficient condition of lsc_assemble_kernel's phase 1 (see there)
+                const double downwash = (a_dw * a_r + o_dw * o_r) / (a_r + o_r);
+                const double iz = 1.0 / downwash;
+                float orec[18], arec[18];
+                load_record((p.obs_index ? p.all_traj : p.obs_traj) + (src * M + m) * 18, orec);
+                load_record(own_traj + m * 18, arec);
+                double r[6][3], cx = 0, cy = 0, cz = 0, emax = 0;
+                const double vstep = (double) sqrtf((float) (vl[0] * vl[0] + vl[1] * vl[1] + vl[2] * vl[2] * iz * iz));
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const double ox = (double) arec[i * 3], oy = (double) arec[i * 3 + 1], oz = (double) arec[i * 3 + 2];
+                    r[i][0] = ox - (double) orec[i * 3]; r[i][1] = oy - (double) orec[i * 3 + 1]; r[i][2] = (oz - (double) orec[i * 3 + 2]) * iz;
+                    cx += r[i][0]; cy += r[i][1]; cz += r[i][2];
+                    if (m == 0 && i < 3) continue;                                      // no such rows (traj_optimizer.cpp:404)
+                    const double ex = x0[0] - ox, ey = x0[1] - oy, ez = (x0[2] - oz) * iz;
+                    emax = fmax(emax, (double) sqrtf((float) (ex * ex + ey * ey + ez * ez)) + (double) (5 * m + i - 2) * vstep);
+                }
+                const double cn = (double) sqrtf((float) (cx * cx + cy * cy + cz * cz));
+                if (cn > 0.0) {
+                    double lb = 1e300;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) lb = fmin(lb, r[i][0] * cx + r[i][1] * cy + r[i][2] * cz);
+                    lb /= cn;
+                    drop = lb > (o_r + a_r) + 2.0 * emax + 1e-3;
+                }
+            }
+            if (drop) {
+                double* no = p.normals + (j * M + m) * 3;
+                no[0] = 0.0; no[1] = 0.0; no[2] = 0.0;
+                const double zero6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                store_rhs(p.rhs + (j * M + m) * 6, zero6);
+            }
+        }
+        const unsigned keep = __ballot_sync(0xffffffffu, valid && !drop);
+        if (keep) {
+            const int leader = __ffs(keep) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.work_count, __popc(keep));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid && !drop) {
+                int2 item; item.x = agent; item.y = (int) j * M + m;
+                p.work_list[base + __popc(keep & ((1u << lane) - 1u))] = item;      // (order does not matter: pairs are independent)
+            }
+        }
     }
 }
 

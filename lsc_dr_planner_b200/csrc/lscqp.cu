@@ -261,8 +261,13 @@ extern "C" int lscqp_assemble_lsc_fused(lscqp_handle* h, int generator, int prun
         p.work_list = reinterpret_cast<int2*>(h->d_work.as<char>() + 16);
         CK(cudaMemsetAsync(p.work_count, 0, sizeof(int), st));
     }
-    if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
-    else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
+    if (split) {
+        if (h->cfg.M == 5) lsc_prune_kernel<5><<<n_agents, 128, 0, st>>>(p);
+        else lsc_prune_kernel<10><<<n_agents, 128, 0, st>>>(p);
+    } else {
+        if (h->cfg.M == 5) lsc_assemble_kernel<5><<<n_agents, 128, 0, st>>>(p);
+        else lsc_assemble_kernel<10><<<n_agents, 128, 0, st>>>(p);
+    }
     h->launches++;
     if (split) {
         const int blocks = 148 * 4;

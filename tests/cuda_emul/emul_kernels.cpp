@@ -123,11 +123,17 @@ extern "C" int emul_assemble_lsc_fused(const lscqp_config* cfg, int generator, i
     // prune > 1: the split dispatch (prune kernel + global work list + one thread per surviving pair)
     std::vector<int2> work((size_t) obs_offsets[n_agents] * cfg->M + 1);
     int count = 0;
-    const bool split = prune > 1;
-    if (split) { p.work_list = work.data(); p.work_count = &count; p.prune = 1; }
-    if (cfg->M == 5) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<5>(p); });
-    else if (cfg->M == 10) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<10>(p); });
-    else return LSCQP_E_INVALID;
+    const bool split = prune > 1 && cfg->dim == 3 && generator < 2;      // (the condition of lscqp_assemble_lsc_fused)
+    if (prune > 1) p.prune = 1;
+    if (split) { p.work_list = work.data(); p.work_count = &count; }
+    if (cfg->M != 5 && cfg->M != 10) return LSCQP_E_INVALID;
+    if (split) {
+        if (cfg->M == 5) emu::launch(n_agents, 128, 64, [&]() { lsc_prune_kernel<5>(p); });
+        else emu::launch(n_agents, 128, 64, [&]() { lsc_prune_kernel<10>(p); });
+    } else {
+        if (cfg->M == 5) emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<5>(p); });
+        else emu::launch(n_agents, 128, 4096, [&]() { lsc_assemble_kernel<10>(p); });
+    }
     if (split) {
         if (cfg->M == 5) emu::launch(3, 128, 64, [&]() { lsc_pairs_kernel<5>(p); });
         else emu::launch(3, 128, 64, [&]() { lsc_pairs_kernel<10>(p); });
