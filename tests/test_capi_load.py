@@ -81,3 +81,10 @@ def test_cpp_shim_compiles():
     """include/lscqp_shim.hpp (TrajOptimizer / CollisionConstraints / BatchTrajOptimizer) is valid C++17 on its own"""
     src = os.path.join(ROOT, "tests", "shim", "shim_smoke.cpp")
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", src], check=True)
+
+
+def test_cpp_shim_compiles_against_project_types():
+    """... and in LSCQP_SHIM_EXTERNAL_TYPES mode, where Param / Mission / Agent / point3d / Trajectory come from the host
+    project (the way it is used inside the reference tree): compiled against stand-ins with the reference's member lists"""
+    src = os.path.join(ROOT, "tests", "shim", "shim_external.cpp")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", src], check=True)
