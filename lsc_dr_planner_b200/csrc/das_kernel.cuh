@@ -95,7 +95,7 @@ __device__ __forceinline__ int das_encode(int k, int r1) {
     return (r1 / 3) * C::NZS + k * 3 + r1 % 3;
 }
 
-// Row (owner lane lp, slot) in the full space: at most three (dimension, control point, coefficient) entries, unused ones
+// Row (owner lane lp, slot) in the full space: at most three (dimension, control point, coefficient) entries, unused ones   // @phase row_decode
 // with a zero coefficient.  LSC row of control point cp and kept obstacle j: normal n on (k, cp), k < D
 // (traj_optimizer.cpp:414-421); box rows of variable v: 0 lb, 1 ub, 2 vel+, 3 vel-, 4 acc+, 5 acc- with unit-coefficient
 // stencils (:238-270, :440-474).
@@ -143,7 +143,7 @@ __device__ __forceinline__ void das_row_pairs(int lp, int slot, const double* s_
     }
 }
 
-// exact warp arg-min of a double per lane (ties: the lowest lane): two redux.sync.min passes over the halves of an
+// exact warp arg-min of a double per lane (ties: the lowest lane): two redux.sync.min passes over the halves of an   // @phase argmin
 // order-preserving 64-bit key.  Returns the winning lane.
 __device__ __forceinline__ int warp_argmin(double v) {
     long long b = __double_as_longlong(v);
@@ -154,7 +154,7 @@ __device__ __forceinline__ int warp_argmin(double v) {
     return __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
 }
 
-template <class C, int KPT_ = LSCQP_DAS_KPT>
+template <class C, int KPT_ = LSCQP_DAS_KPT>   // @phase setup
 __global__ void __launch_bounds__(32, (KPT_ > 16 ? 6 : LSCQP_DAS_MINCTAS))
 das_solve_kernel(const SolveParams p) {
     using A = Das<C, KPT_>;
@@ -235,7 +235,7 @@ das_solve_kernel(const SolveParams p) {
     __syncwarp();
     const int ts = (int) s_termw[M];
 
-    // ---- rows of this lane.  Slot s < NLSC: LSC row of control point lane + 32 (s / KPT), kept obstacle s % KPT;
+    // ---- rows of this lane.  Slot s < NLSC: LSC row of control point lane + 32 (s / KPT), kept obstacle s % KPT;   // @phase rows_presolve
     // slot NLSC + 6 u + e: box row e of variable lane + 32 u.  rmask: the rows that exist.
     unsigned long long rmask = 0, amask = 0;                 // existing rows / rows in the active set
     unsigned bmask[VPT];
@@ -345,7 +345,7 @@ das_solve_kernel(const SolveParams p) {
         }
     };
 
-    // ---- unconstrained minimiser y = -H^-1 g, H^-1 from the table of this agent's terminal-segment count
+    // ---- unconstrained minimiser y = -H^-1 g, H^-1 from the table of this agent's terminal-segment count   // @phase start_point
     const double* Hinv = p.das_tab + (size_t) (ts - 1) * 2 * N1 * N1;
     const int ck_slot = A::BIG ? (kl_in >> 4) : 0;                        // > 0: resume from the throughput instance's checkpoint
 #pragma unroll
@@ -375,7 +375,7 @@ das_solve_kernel(const SolveParams p) {
     }
     __syncwarp();
 
-    // ---- row evaluation at s_c.  only < 0: every existing row outside the active set, result = the most violated one
+    // ---- row evaluation at s_c.  only < 0: every existing row outside the active set, result = the most violated one   // @phase sweep_general
     // (smallest slack in the reference's row scaling: velocity rows carry 5/dt, acceleration rows 20/dt^2) of this lane;
     // only >= 0: that slot alone; only == -2: nothing; only == -3: the rows of the active set.
     const double wv = 5.0 / p.dt, wa = 20.0 / (p.dt * p.dt);
@@ -421,7 +421,7 @@ das_solve_kernel(const SolveParams p) {
         }
     };
 
-    // ---- the same over every live row, cheaper: the two rows of a bound / velocity / acceleration pair share one evaluation
+    // ---- the same over every live row, cheaper: the two rows of a bound / velocity / acceleration pair share one evaluation   // @phase sweep_fast
     // (lim - |x| is the smaller of the two slacks; with one of them in the active set the other cannot be violated), no
     // per-row branches.  Returns the lane's smallest scaled slack and its slot; the raw slack is best * row_unscale(slot).
     int kv_[VPT];
@@ -476,7 +476,7 @@ das_solve_kernel(const SolveParams p) {
         return e < 2 ? 1.0 : (e < 4 ? p.dt / 5.0 : p.dt * p.dt / 20.0);
     };
 
-    // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l
+    // ---- drop the active row at position l.  With S = R^-1: rotate the columns (j, j+1), j = l .. q-2, of S so that row l   // @phase drop
     // of S becomes zero left of the last column; the new inverse factor is S without row l and without its last column,
     // and J1 follows with the same column rotations (its last column leaves the span).
     int q = 0;                                                // size of the active set; active row j is owned by lane j % 32, slot j / 32
@@ -535,7 +535,7 @@ das_solve_kernel(const SolveParams p) {
         __syncwarp();
     };
 
-    // ---- main loop
+    // ---- main loop   // @phase select_row
     int it = 0, why = 5, q_top = 0;
     bool ck_ok = false;                                       // the state at the point of failure can be handed over
     if (A::BIG && ck_slot > 0) {
@@ -598,7 +598,7 @@ das_solve_kernel(const SolveParams p) {
         bool fail = false;
         while (true) {                                         // until row p is added (or the model is found infeasible)
             if (++it > it_max) { fail = true; why = 3; break; }
-            // d1 = J1'n (lane = active row), z = w - J1 d1, r = S d1
+            // d1 = J1'n (lane = active row), z = w - J1 d1, r = S d1   // @phase directions
 #pragma unroll
             for (int t = 0; t < QSL; t++) {
                 const int j = lane + 32 * t;
@@ -650,7 +650,7 @@ das_solve_kernel(const SolveParams p) {
 #pragma unroll
             for (int t = 0; t < RPL; t++) nzp += nr[t] * zz[t];
             const double nz = warp_sum(nzp);                   // n'z = n'(H^-1 - J1 J1')n >= 0: the curvature along z
-            // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible
+            // step lengths: t1 keeps the multipliers non-negative, t2 makes row p feasible   // @phase step_lengths
             double t1 = INFINITY;
             int l = 0;
 #pragma unroll
@@ -683,7 +683,7 @@ das_solve_kernel(const SolveParams p) {
             u_new += tt;
             __syncwarp();
             if (t2 <= t1) {
-                // full step: row p joins the active set
+                // full step: row p joins the active set   // @phase add_row
                 const double rinv = 1.0 / sqrt(nz);
 #pragma unroll
                 for (int t = 0; t < RPL; t++) { const int r = lane + 32 * t; if (r < NR) s_J[r * LDJ + q] = zz[t] * rinv; }
@@ -701,7 +701,7 @@ das_solve_kernel(const SolveParams p) {
                 __syncwarp();
                 break;
             }
-            // partial step: the multiplier of active row l reached zero before row p became feasible
+            // partial step: the multiplier of active row l reached zero before row p became feasible   // @phase partial_step
             drop(l);
             if (!dependent) {
                 expand();
@@ -737,7 +737,7 @@ das_solve_kernel(const SolveParams p) {
         defer(why); return;
     }
 
-    // ---- verification and outputs.  s_c holds the final point.  The active rows are zero only up to the rounding of the
+    // ---- verification and outputs.  s_c holds the final point.  The active rows are zero only up to the rounding of the   // @phase verify_output
     // updates: re-evaluated like the others.  Stationarity Z'(grad f - sum u_j n_j) from scratch (J1 is dead: its storage is
     // the full-space scratch).
     {

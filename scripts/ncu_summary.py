@@ -25,7 +25,7 @@ def unit_bytes(v, u):
 
 traffic = {}
 for name, rep in (("das_solve_kernel", "prof_das.ncu-rep"), ("pdip_solve_kernel", "prof_solve.ncu-rep"),
-                  ("lsc_assemble_kernel", "prof_asm.ncu-rep"), ("lsc_pairs_kernel", "prof_pairs.ncu-rep")):
+                  ("lsc_prune_kernel", "prof_asm.ncu-rep"), ("lsc_pairs_kernel", "prof_pairs.ncu-rep")):
     path = os.path.join(root, "gpurun_out", rep)
     if not os.path.exists(path):
         continue
