@@ -19,7 +19,7 @@ VARIANTS = {
     "occ4": ("-DLSCQP_LIGHT_EXTRA_SMEM=4300",),
     "g2k4c4": ("-DLSCQP_LIGHT_G=2", "-DLSCQP_LIGHT_KPT=4", "-DLSCQP_LIGHT_MINCTAS=4"),
 }
-VARIANTS.update({"nockpt": ("-DLSCQP_DAS_NO_CKPT",), "das14": ("-DLSCQP_DAS_MINCTAS=14", "-DLSCQP_DAS_QMAX=28", "-DLSCQP_DAS_KPT=8"), "das13": ("-DLSCQP_DAS_MINCTAS=13", "-DLSCQP_DAS_QMAX=30", "-DLSCQP_DAS_KPT=8"),
+VARIANTS.update({"kpt8": ("-DLSCQP_DAS_KPT=8",), "nockpt": ("-DLSCQP_DAS_NO_CKPT",), "das14": ("-DLSCQP_DAS_MINCTAS=14", "-DLSCQP_DAS_QMAX=28", "-DLSCQP_DAS_KPT=8"), "das13": ("-DLSCQP_DAS_MINCTAS=13", "-DLSCQP_DAS_QMAX=30", "-DLSCQP_DAS_KPT=8"),
                  "c12": ("-DLSCQP_LIGHT_MINCTAS=12",), "c16": ("-DLSCQP_LIGHT_MINCTAS=16",)})
 import shutil
 for tag in sys.argv[1:]:
