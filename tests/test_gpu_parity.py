@@ -164,6 +164,31 @@ def test_active_set_large_instance_takes_dense_neighbourhoods():
         _check_against_oracle(batch, sub, sel_off, sel_n, sel_r, ctrl[sub], cost[sub], status[sub], min_checked=12)
 
 
+def test_active_set_hand_over_on_hardware():
+    """tests/golden/many_active_rows_case.npz (35 active rows at the optimum) replicated 1400 times: above the one-wave
+    regime, so the throughput active-set instance runs first, stops at its 32-row capacity and hands its state over; the
+    pool has 64 slots, so 64 copies are resumed by the large instance and the rest restarted by it -- every copy must
+    land on the oracle's optimum, solved by the active-set passes"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "many_active_rows_case.npz"))
+    n = 1400
+    cfg = W.make_forest_batch(8, K=4).cfg
+    cfg.world_min = (-66.0, -66.0, 0.0); cfg.world_max = (66.0, 66.0, 2.5)
+    K = g["normals"].shape[0]
+    qp = capi.LscQp(cfg, device=0)
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[None], n, axis=0))
+    off = (np.arange(n + 1) * K).astype(np.int32)
+    normals = np.ascontiguousarray(np.tile(g["normals"], (n, 1, 1))); rhs = np.ascontiguousarray(np.tile(g["rhs"], (n, 1, 1)))
+    nv = cfg.dim * cfg.M * 6
+    ctrl = np.zeros((n, nv)); cost = np.zeros(n); status = np.zeros(n, np.int32); iters = np.zeros(n, np.int32); kkt = np.zeros((n, 4))
+    qp.solve_host(n, rep(g["state"]), rep(g["goal"]), rep(g["limits"]), None, off, normals, rhs, ctrl, cost, status, iters=iters, kkt=kkt)
+    klass = qp.last_instances(n)
+    assert (status == 0).all() and (klass == 0).all(), (np.bincount(status), np.bincount(klass))
+    assert np.abs(ctrl - g["x"][None]).max() < 1e-8
+    assert (kkt[:, 2].astype(int) // 64 > 32).all()           # every copy went beyond the throughput instance's 32 rows
+    assert len(np.unique(iters)) == 1                          # resumed and restarted copies count the same iterations
+
+
 def test_solve_with_sfc_boxes():
     """SFC rows (world_use_octomap): per-segment boxes around the previous solution"""
     cfg = W.PlannerConfig(use_sfc=True)
