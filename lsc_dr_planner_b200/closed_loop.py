@@ -151,8 +151,8 @@ class ClosedLoopSim:
         # goalPlanning (src/traj_planner.cpp:433-477): static goal, or the right-hand rule -- an agent that is slower than
         # deadlock/velocity_threshold (0.1) after deadlock/seq_threshold (5) replans and still more than 0.2 m from its
         # goal (isDeadlock, :904-923) aims at position + (desired - position) x e_z instead
-        self._seq += 1
         if self.goal_mode == "righthand":
+            self._seq += 1                                             # (planner_seq: only the deadlock rule reads it)
             pos, vel = self.state[:, 0:3], self.state[:, 3:6]
             to_goal = self.desired_goal - pos
             dead = (self._seq > 5) & (vel.norm(dim=1) < 0.1) & (to_goal.norm(dim=1) > 0.2)
@@ -174,7 +174,7 @@ class ClosedLoopSim:
                 qp.sfc_batch(capi.SFC_FROM_POINT, n, own[:, M_ - 1, 5].contiguous(), goal, None, lim, self.sfc, self.sfc_status, stream)
         qp.solve_batch(n, st, goal, lim, self.sfc, self.obs_offsets, self.normals, self.rhs, self.ctrl, self.cost,
                        self.status, self.iters, stream=stream, initial_traj=own)
-        self._overflowed += (self.overflow[:n] > 0).sum()
+        self._overflowed += torch.count_nonzero(self.overflow[:n])    # (one reduction launch; overflow holds 0 or the count)
         if p2p:
             # failsafe (keep initial_traj where the QP did not converge, traj_planner.cpp:795-797) + doStep + shift +
             # publish to every rank, one kernel
