@@ -69,7 +69,7 @@ struct lscqp_handle {
     Exchange* xchg = nullptr;          // peer exchange of the sharded closed loop (lscqp_exchange_*)
 };
 
-extern "C" const char* lscqp_version(void) { return "lscqp-b200 0.1 (sm_100a)"; }
+extern "C" const char* lscqp_version(void) { return "lscqp-b200 0.2 (sm_100a)"; }
 extern "C" const char* lscqp_last_error(void) { return g_err.c_str(); }
 
 extern "C" int lscqp_create(const lscqp_config* cfg, int device, lscqp_handle** out) {
