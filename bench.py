@@ -213,7 +213,7 @@ def closed_loop_batch(W, n_agents, K=40):
 
 def run_strong(args, torch, dist, W, capi, rank, world, local, flush):
     """BASELINE config 4: 4096 agents with synthetic random LSC half-spaces, N fixed, agents sharded over the ranks
-    (strong scaling).  One step = PDIP solve of the rank's shard + the exchange of the solved trajectories with every
+    (strong scaling).  One step = QP solve of the rank's shard + the exchange of the solved trajectories with every
     rank (lscqp_step_exchange stores them into all ranks' blocks over NVLink, lscqp_exchange_begin waits for everyone's
     flag and copies them out) -- the gather is inside the timed region."""
     from lsc_dr_planner_b200.planner import BatchPlanner
@@ -279,7 +279,7 @@ def run_strong(args, torch, dist, W, capi, rank, world, local, flush):
         same = True
     ms_step = float(tt[0]) / args.steps
     return {"workload": f"config 4: {N} agents total, synthetic random LSC half-spaces (K={args.K}, M=5, D=3), agents sharded "
-                        f"over {world} rank(s); step = PDIP solve of the shard + exchange of the solved trajectories with every rank",
+                        f"over {world} rank(s); step = QP solve of the shard (30-40 kept obstacles per agent: interior-point pass) + exchange of the solved trajectories with every rank",
             "scaling": "strong", "agents_total": N, "agents_per_rank": n, "ms_per_step": ms_step,
             "value": N / (ms_step * 1e-3), "unit": UNIT, "exchange": "p2p stores into every rank's block over NVLink (CUDA IPC) + flag wait"
             if p2p else "nccl all_gather_into_tensor", "exchange_in_timed_region": True, "bytes_published_per_rank_per_step": n * (90 + 9) * 4 * world,
@@ -288,7 +288,7 @@ def run_strong(args, torch, dist, W, capi, rank, world, local, flush):
 
 def run_closed_loop(args, torch, dist, W, capi, rank, world, local, exchange, graph=True):
     """BASELINE config 5: 1024 agents x 200 closed-loop replans, agents sharded over the ranks; per replan: neighbour
-    selection, LSC assembly, PDIP solve, failsafe + doStep + shift, exchange of the new trajectories with every rank."""
+    selection, LSC assembly, QP solve, failsafe + doStep + shift, exchange of the new trajectories with every rank."""
     from lsc_dr_planner_b200.closed_loop import ClosedLoopSim
     N, T = args.loop_agents, args.loop_steps
     b = closed_loop_batch(W, N)
